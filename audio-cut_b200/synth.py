@@ -1,0 +1,63 @@
+"""Seeded synthetic test audio (there is no network access for real tracks).
+
+The signal follows SURVEY.md section 8(d) config 1: a "vocal" made of 8 harmonic
+partials with vibrato under a 2 Hz on/off phrase gate, band-limited pink noise and a
+120 BPM click track, peak-normalised to 0.5; the right channel is the left one
+delayed by 3 samples at 0.9 gain so that L and R are decorrelated.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SR = 44100
+
+
+def synth_track(seconds: float, *, sr: int = SR, seed: int = 0, stereo: bool = True) -> np.ndarray:
+    """Return float32 audio, shape (2, N) when ``stereo`` else (N,)."""
+    n = int(round(seconds * sr))
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / sr
+
+    # vocal-like: 8 partials of a slowly gliding f0 with 5.5 Hz vibrato, gated in phrases
+    f0 = 220.0 * 2.0 ** (np.sin(2 * np.pi * 0.11 * t) * 0.25)
+    vib = 1.0 + 0.01 * np.sin(2 * np.pi * 5.5 * t)
+    phase = 2 * np.pi * np.cumsum(f0 * vib) / sr
+    voc = np.zeros(n)
+    for k in range(1, 9):
+        voc += np.sin(k * phase + rng.uniform(0, 2 * np.pi)) / k**1.2
+    gate_raw = (np.sin(2 * np.pi * 0.5 * t + 0.3) > -0.2).astype(np.float64)  # 2 s phrases with gaps
+    ramp = int(0.02 * sr)
+    kern = np.hanning(2 * ramp + 1)
+    kern /= kern.sum()
+    gate = np.convolve(gate_raw, kern, mode="same")
+    voc *= gate
+
+    # band-limited pink-ish noise: white noise shaped by 1/sqrt(f) between 60 Hz and 12 kHz
+    m = 1
+    while m < n:
+        m *= 2
+    spec = np.fft.rfft(rng.standard_normal(m))
+    freqs = np.fft.rfftfreq(m, 1.0 / sr)
+    shape = np.zeros_like(freqs)
+    band = (freqs >= 60.0) & (freqs <= 12000.0)
+    shape[band] = 1.0 / np.sqrt(freqs[band])
+    noise = np.fft.irfft(spec * shape, m)[:n]
+    noise /= np.max(np.abs(noise)) + 1e-12
+
+    # 120 BPM click track: 5 ms decaying 1 kHz bursts
+    clicks = np.zeros(n)
+    burst_len = int(0.03 * sr)
+    bt = np.arange(burst_len) / sr
+    burst = np.sin(2 * np.pi * 1000.0 * bt) * np.exp(-bt / 0.005)
+    for pos in range(0, n, int(0.5 * sr)):
+        seg = min(burst_len, n - pos)
+        clicks[pos : pos + seg] += burst[:seg]
+
+    mix = 0.6 * voc / (np.max(np.abs(voc)) + 1e-12) + 0.25 * noise + 0.35 * clicks
+    mix *= 0.5 / (np.max(np.abs(mix)) + 1e-12)
+    left = mix
+    if not stereo:
+        return left.astype(np.float32)
+    right = np.zeros(n)
+    right[3:] = 0.9 * left[:-3]
+    return np.stack([left, right]).astype(np.float32)

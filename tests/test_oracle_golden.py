@@ -1,0 +1,113 @@
+"""The oracle restatement against fixtures produced by the reference's own code
+(tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import mdx, pipeline, planner
+from oracle import features as OF
+
+
+def test_chunk_schedule_matches_reference(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "chunk_schedule.json")))
+    assert len(cases) >= 16
+    for case in cases:
+        plans = planner.chunk_schedule(*case["args"])
+        assert len(plans) == len(case["plans"]), case["args"]
+        for p, ref in zip(plans, case["plans"]):
+            assert p.index == ref[0]
+            # bit-exact floats (repr round-trips)
+            assert [repr(p.start_s), repr(p.end_s), repr(p.halo_left_s), repr(p.halo_right_s)] == ref[1:], case["args"]
+
+
+def test_chunk_counts_from_survey():
+    # 30 s -> 4 chunks, 240 s -> 32, 3600 s -> 480
+    assert [len(planner.chunk_schedule(t)) for t in (30.0, 240.0, 3600.0)] == [4, 32, 480]
+
+
+SMALL = mdx.MdxGeometry(n_fft=512, hop=128, dim_f=224, dim_t=32)
+CH_GAIN = torch.tensor([0.5, 0.4, 0.3, 0.45])
+
+
+def _fake_net(spec):
+    return spec * CH_GAIN[None, :, None, None]
+
+
+def test_infer_chunk_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "infer_chunk.npz"))
+    for tag in ("mono", "stereo", "short"):
+        v, i = mdx.infer_chunk(z[f"{tag}_in"], _fake_net, SMALL, align_hop=256, output_type=str(z[f"{tag}_otype"]))
+        assert v.shape == z[f"{tag}_vocal"].shape
+        np.testing.assert_array_equal(v, z[f"{tag}_vocal"])
+        np.testing.assert_array_equal(i, z[f"{tag}_instr"])
+
+
+def test_window_counts_full_geometry():
+    # 10 s chunk -> L=442368, B=2; last 7.5 s chunk -> L=331776, B=2 (both n_fft)
+    for n_fft in (6144, 7680):
+        g = mdx.MdxGeometry(n_fft=n_fft)
+        assert g.chunk_size == 261120 and g.gen == 261120 - n_fft
+        assert mdx.n_windows(441000, g) == 2 and mdx.n_windows(330750, g) == 2
+
+
+def _fake_infer_factory():
+    state = {"k": 0}
+
+    def infer(chunk):
+        k = state["k"]
+        state["k"] += 1
+        ramp = np.linspace(0.0, 1.0, chunk.shape[-1], dtype=np.float32)
+        v = (0.7 * chunk + np.float32(0.01 * (k + 1)) * ramp).astype(np.float32)
+        return v, (chunk - v).astype(np.float32)
+
+    return infer
+
+
+def test_pipeline_stitch_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    sr = int(z["sr"])
+    vocal, instr = pipeline.separate_track(z["audio"], _fake_infer_factory(), sr=sr)
+    np.testing.assert_array_equal(vocal, z["vocal"])
+    np.testing.assert_array_equal(instr, z["instr"])
+
+
+def test_chunk_feature_builder_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    sr = int(z["sr"])
+    audio = z["audio"]
+    cf = pipeline.ChunkFeatures(sr)
+    assert cf.hop_length == int(z["hop_length"])
+    plans = planner.chunk_schedule(len(audio) / float(sr))
+    assert len(plans) == int(z["n_chunks"])
+    for p in plans:
+        cs, ce, _, _ = planner.sample_bounds(p, sr, len(audio))
+        cf.add_chunk(p, audio[cs:ce])
+    out = cf.finalize()
+    for k in ("rms_series", "spectral_flatness", "onset_envelope", "mdd_series"):
+        np.testing.assert_array_equal(out[k], z[k], err_msg=k)
+    np.testing.assert_array_equal(out["onset_frames"], z["onset_frames"])
+    assert out["global_mdd"] == float(z["global_mdd"])
+
+
+def test_stft_istft_roundtrip_and_crop():
+    g = mdx.MdxGeometry(n_fft=512, hop=128, dim_f=257 - 1, dim_t=32)
+    x = torch.randn(3, 2, g.chunk_size)
+    y = mdx.istft(mdx.stft(x, g), g)
+    # only the Nyquist bin is dropped; interior samples reconstruct closely
+    err = (x - y)[..., g.trim : -g.trim].abs().max()
+    assert err < 0.2
+
+
+def test_rms_frame_count_odd_and_even():
+    y = np.random.default_rng(0).standard_normal(10000).astype(np.float32)
+    assert len(OF.rms(y, 2048, 441)) == 1 + 10000 // 441
+    assert len(OF.rms(y, 2205, 882)) == 1 + (10000 + 2 * 1102 - 2205) // 882
+    np.testing.assert_allclose(OF.rms(np.ones(5000, np.float32), 100, 50)[5:-5], 1.0, rtol=1e-6)
+
+
+def test_mel_filterbank_matches_torchaudio_slaney():
+    ta = __import__("pytest").importorskip("torchaudio")
+    fb = ta.functional.melscale_fbanks(1025, 0.0, 22050.0, 128, 44100, norm="slaney", mel_scale="slaney").T.numpy()
+    np.testing.assert_allclose(OF.mel_filterbank(44100, 2048, 128), fb, rtol=2e-5, atol=3e-7)
