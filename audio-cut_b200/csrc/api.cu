@@ -1,0 +1,106 @@
+// Library bring-up, error reporting, cached FFT tables.
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ac {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+static int g_sm_count = 0;
+static std::mutex g_plan_mu;
+static std::map<int, FftPlan*> g_plans;
+
+void set_error(const std::string& msg) { t_error = msg; }
+int device_sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+const FftPlan* get_fft_plan(int n) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  auto it = g_plans.find(n);
+  if (it != g_plans.end()) return it->second;
+  FftPlan* p = new FftPlan();
+  p->n = n;
+  int m = n, c3 = 0, c5 = 0, c2 = 0;
+  while (m % 3 == 0) { m /= 3; ++c3; }
+  while (m % 5 == 0) { m /= 5; ++c5; }
+  while (m % 2 == 0) { m /= 2; ++c2; }
+  if (m != 1 || n < 2) {
+    set_error("fft length " + std::to_string(n) + " is not of the form 2^a 3^b 5^c");
+    delete p;
+    return nullptr;
+  }
+  // odd radices first: their Ns=1 pass writes with an odd stride (no smem bank conflicts)
+  int k = 0;
+  for (int i = 0; i < c3; ++i) p->radix[k++] = 3;
+  for (int i = 0; i < c5; ++i) p->radix[k++] = 5;
+  while (c2 >= 3) { p->radix[k++] = 8; c2 -= 3; }
+  if (c2 == 2) p->radix[k++] = 4;
+  if (c2 == 1) p->radix[k++] = 2;
+  p->n_radix = k;
+  if (k > 12) {
+    set_error("fft length too large");
+    delete p;
+    return nullptr;
+  }
+  std::vector<float2> tw(n);
+  std::vector<float> hann(n);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int i = 0; i < n; ++i) {
+    double a = -two_pi * (double)i / (double)n;
+    tw[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+    hann[i] = (float)(0.5 - 0.5 * std::cos(two_pi * (double)i / (double)n));
+  }
+  float2* d_tw = nullptr;
+  float* d_h = nullptr;
+  if (cudaMalloc(&d_tw, sizeof(float2) * n) != cudaSuccess || cudaMalloc(&d_h, sizeof(float) * n) != cudaSuccess ||
+      cudaMemcpy(d_tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d_h, hann.data(), sizeof(float) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error(std::string("fft plan upload: ") + cudaGetErrorString(cudaGetLastError()));
+    delete p;
+    return nullptr;
+  }
+  p->d_twiddle = d_tw;
+  p->d_hann = d_h;
+  g_plans[n] = p;
+  return p;
+}
+
+}  // namespace ac
+
+extern "C" {
+
+int ac_abi_version(void) { return 1; }
+const char* ac_last_error(void) { return ac::t_error.c_str(); }
+long long ac_launch_count(void) { return ac::g_launches.load(); }
+
+int ac_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    ac::set_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return AC_E_NODEVICE;
+  }
+  AC_REQUIRE(device >= 0 && device < n, "device index out of range");
+  AC_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AC_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    ac::set_error(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    return AC_E_NODEVICE;
+  }
+  ac::g_sm_count = prop.multiProcessorCount;
+  return AC_OK;
+}
+
+long long ac_frame_count(long long n, int frame, int hop, int center) {
+  if (frame <= 0 || hop <= 0 || n < 0) return 0;
+  long long padded = center ? n + 2LL * (frame / 2) : n;
+  if (padded < frame) return 0;
+  return 1 + (padded - frame) / hop;
+}
+
+}  // extern "C"

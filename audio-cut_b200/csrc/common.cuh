@@ -1,0 +1,88 @@
+// Shared helpers for libaudiocut_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/audiocut_b200.h"
+
+namespace ac {
+
+void set_error(const std::string& msg);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define AC_CHECK_CUDA(expr)                                                                             \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      ac::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" +        \
+                    std::to_string(__LINE__) + ")");                                                    \
+      return AC_E_CUDA;                                                                                 \
+    }                                                                                                   \
+  } while (0)
+
+#define AC_REQUIRE(cond, msg)                   \
+  do {                                          \
+    if (!(cond)) {                              \
+      ac::set_error(std::string("invalid: ") + (msg)); \
+      return AC_E_INVALID;                      \
+    }                                           \
+  } while (0)
+
+#define AC_LAUNCH_CHECK()                  \
+  do {                                     \
+    ac::count_launch();                    \
+    AC_CHECK_CUDA(cudaPeekAtLastError());  \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// storage type helpers: activations are float or __nv_bfloat16, math is always fp32
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// streaming 128-bit global load (read once: keep it out of L1)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+int device_sm_count();
+
+// ---- per-geometry FFT tables (device resident, cached) ------------------------------------
+struct FftPlan {
+  int n = 0;
+  int n_radix = 0;
+  int radix[16];
+  const float2* d_twiddle = nullptr;  // exp(-2*pi*i*k/n), k in [0,n)
+  const float* d_hann = nullptr;      // periodic hann, n values
+};
+// returns nullptr (and sets the error) when n has a prime factor other than 2,3,5
+const FftPlan* get_fft_plan(int n);
+
+}  // namespace ac

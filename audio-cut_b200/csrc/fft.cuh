@@ -1,0 +1,148 @@
+// Shared-memory mixed-radix (2,3,4,5,8) Stockham FFT, complex fp32, one transform per CTA.
+// Ping-pong between two padded smem buffers; twiddles come from a device table
+// exp(-2*pi*i*k/n) computed in double on the host (ac::get_fft_plan).
+#pragma once
+#include "common.cuh"
+
+namespace ac {
+
+struct FftDev {
+  int n;
+  int n_radix;
+  int radix[12];
+  const float2* tw;
+};
+
+inline FftDev make_fft_dev(const FftPlan* p) {
+  FftDev d;
+  d.n = p->n;
+  d.n_radix = p->n_radix;
+  for (int i = 0; i < 12; ++i) d.radix[i] = i < p->n_radix ? p->radix[i] : 1;
+  d.tw = p->d_twiddle;
+  return d;
+}
+
+// padded smem index: one extra float2 every 32 keeps strided butterfly writes off one bank
+__device__ __host__ __forceinline__ int fpad(int i) { return i + (i >> 5); }
+inline size_t fft_smem_floats2(int n) { return (size_t)fpad(n) + 1; }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by -i (forward) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft_small(float2* v) {
+  if constexpr (R == 2) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  } else if constexpr (R == 3) {
+    const float s60 = 0.86602540378443864676f;
+    float2 t1 = cadd(v[1], v[2]);
+    float2 m = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+    float2 d = csub(v[1], v[2]);
+    float2 s = make_float2(s60 * d.x, s60 * d.y);
+    float2 ms = mul_mi<INV>(s);  // -i*s forward
+    v[0] = cadd(v[0], t1);
+    v[1] = cadd(m, ms);
+    v[2] = csub(m, ms);
+  } else if constexpr (R == 4) {
+    float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    float2 t2 = cadd(v[1], v[3]), t3 = mul_mi<INV>(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[2] = csub(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[3] = csub(t1, t3);
+  } else if constexpr (R == 5) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+    float2 b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    float2 m1 = make_float2(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+    float2 m2 = make_float2(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    float2 n1 = mul_mi<INV>(make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y));
+    float2 n2 = mul_mi<INV>(make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y));
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = cadd(m1, n1);
+    v[4] = csub(m1, n1);
+    v[2] = cadd(m2, n2);
+    v[3] = csub(m2, n2);
+  } else if constexpr (R == 8) {
+    const float h = 0.70710678118654752440f;
+    float2 e[4] = {v[0], v[2], v[4], v[6]};
+    float2 o[4] = {v[1], v[3], v[5], v[7]};
+    dft_small<4, INV>(e);
+    dft_small<4, INV>(o);
+    // o[k] *= w8^k ; w8 = exp(-+ 2*pi*i/8)
+    float2 w1 = INV ? make_float2(h, h) : make_float2(h, -h);
+    float2 w3 = INV ? make_float2(-h, h) : make_float2(-h, -h);
+    o[1] = cmul(o[1], w1);
+    o[2] = mul_mi<INV>(o[2]);
+    o[3] = cmul(o[3], w3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = cadd(e[k], o[k]);
+      v[k + 4] = csub(e[k], o[k]);
+    }
+  }
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* __restrict__ out, int n, int Ns,
+                                         const float2* __restrict__ tw) {
+  const int nb = n / R;
+  const int tmul = n / (Ns * R);
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    const int k = j % Ns;
+    const int ts = k * tmul;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in[fpad(j + r * nb)];
+    if (k != 0) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        float2 w = __ldg(&tw[r * ts]);
+        if (INV) w.y = -w.y;
+        v[r] = cmul(v[r], w);
+      }
+    }
+    dft_small<R, INV>(v);
+    const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[fpad(j0 + r * Ns)] = v[r];
+  }
+}
+
+// Transforms the n points in buf0 (index through fpad); returns the buffer holding the result
+// in natural order.  All threads of the CTA must call it; ends with a __syncthreads().
+template <bool INV>
+__device__ __forceinline__ float2* fft_smem(float2* buf0, float2* buf1, const FftDev& p) {
+  float2* in = buf0;
+  float2* out = buf1;
+  int Ns = 1;
+  for (int s = 0; s < p.n_radix; ++s) {
+    const int R = p.radix[s];
+    switch (R) {
+      case 2: fft_pass<2, INV>(in, out, p.n, Ns, p.tw); break;
+      case 3: fft_pass<3, INV>(in, out, p.n, Ns, p.tw); break;
+      case 4: fft_pass<4, INV>(in, out, p.n, Ns, p.tw); break;
+      case 5: fft_pass<5, INV>(in, out, p.n, Ns, p.tw); break;
+      default: fft_pass<8, INV>(in, out, p.n, Ns, p.tw); break;
+    }
+    __syncthreads();
+    float2* t = in;
+    in = out;
+    out = t;
+    Ns *= R;
+  }
+  return in;
+}
+
+}  // namespace ac

@@ -1,0 +1,113 @@
+// Framewise RMS and zero-crossing rate: one HBM pass, frames cut out of a shared-memory tile.
+//
+// librosa.feature.rms(y, frame_length, hop_length, center=True, pad_mode="constant"):
+//   features_cache.py:182 (4410/2205), pure_vocal_pause_detector.py:1111-1113 (1102/441), :1397 (2048/441),
+//   seamless_splitter.py:1714, :1848 (2048/441), vocal_separator.py:483 (2205/882).
+// librosa.feature.zero_crossing_rate(y, frame_length, hop_length, center=True): pure_vocal_pause_detector.py:444.
+//
+// A CTA stages the samples of FR consecutive frames (one coalesced 128-bit sweep; each sample
+// is read from HBM ~once even though frames overlap frame/hop times) and every warp reduces
+// whole frames out of shared memory with lane-strided, conflict-free reads + a shuffle tree.
+#include "common.cuh"
+
+namespace ac {
+
+constexpr int kRmsThreads = 256;
+constexpr int kRmsMaxTileFloats = 24064;  // 94 KB -> two CTAs per SM
+
+// MODE 0: rms (zero padding)   MODE 1: zero-crossing rate (edge padding, |y|<=1e-10 -> 0)
+template <int MODE>
+__global__ void __launch_bounds__(kRmsThreads) frame_reduce_kernel(const float* __restrict__ x, long long n, int frame,
+                                                                   int hop, int pad, int frames_per_cta,
+                                                                   long long n_frames, float* __restrict__ out) {
+  extern __shared__ float tile[];
+  const long long t0 = (long long)blockIdx.x * frames_per_cta;
+  const int nf = (int)min((long long)frames_per_cta, n_frames - t0);
+  const long long start = t0 * hop - pad;                         // first sample of the tile (may be < 0)
+  const long long end = start + (long long)(nf - 1) * hop + frame;  // one past the last
+  const long long a0 = (start >= 0 ? start / 4 : -((-start + 3) / 4)) * 4;  // floor to a multiple of 4
+  const int len4 = (int)((end - a0 + 3) / 4);
+  const bool aligned = (((uintptr_t)x) & 15) == 0;
+  for (int i = threadIdx.x; i < len4; i += kRmsThreads) {
+    const long long idx = a0 + 4LL * i;
+    float4 v;
+    if (aligned && idx >= 0 && idx + 3 < n) {
+      v = ldg_stream_f4(reinterpret_cast<const float4*>(x + idx));
+    } else {
+      float e[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        long long j = idx + k;
+        if (MODE == 1) {
+          j = j < 0 ? 0 : (j >= n ? n - 1 : j);
+          e[k] = x[j];
+        } else {
+          e[k] = (j >= 0 && j < n) ? x[j] : 0.f;
+        }
+      }
+      v = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    reinterpret_cast<float4*>(tile)[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int off0 = (int)(start - a0);
+  for (int f = warp; f < nf; f += kRmsThreads / 32) {
+    const float* fr = tile + off0 + f * hop;
+    float acc = 0.f;
+    if (MODE == 0) {
+      for (int j = lane; j < frame; j += 32) {
+        float v = fr[j];
+        acc = fmaf(v, v, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[t0 + f] = sqrtf(acc / (float)frame);
+    } else {
+      for (int j = lane + 1; j < frame; j += 32) {
+        float a = fr[j - 1], b = fr[j];
+        a = fabsf(a) <= 1e-10f ? 0.f : a;
+        b = fabsf(b) <= 1e-10f ? 0.f : b;
+        acc += (signbit(a) != signbit(b)) ? 1.f : 0.f;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[t0 + f] = acc / (float)frame;
+    }
+  }
+}
+
+template <int MODE>
+static int launch_frame_reduce(const float* d_x, long long n, int frame, int hop, int center, float* d_out,
+                               cudaStream_t st) {
+  AC_REQUIRE(d_x && d_out, "null pointer");
+  AC_REQUIRE(frame > 0 && hop > 0 && n > 0, "frame, hop and n must be positive");
+  AC_REQUIRE(frame + 8 <= kRmsMaxTileFloats, "frame too long");
+  const long long n_frames = ac_frame_count(n, frame, hop, center);
+  if (n_frames <= 0) return AC_OK;
+  int fr = 1 + (kRmsMaxTileFloats - 8 - frame) / hop;
+  if (fr > 64) fr = 64;
+  // keep at least ~4 CTAs per SM worth of work when the signal is short
+  const long long want = 4LL * device_sm_count();
+  while (fr > 8 && (n_frames + fr - 1) / fr < want) fr /= 2;
+  const size_t smem = sizeof(float) * (size_t)((fr - 1) * hop + frame + 8);
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[MODE]) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(frame_reduce_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(float) * kRmsMaxTileFloats)));
+    attr_done[MODE] = true;
+  }
+  const long long grid = (n_frames + fr - 1) / fr;
+  frame_reduce_kernel<MODE><<<(unsigned)grid, kRmsThreads, smem, st>>>(d_x, n, frame, hop, center ? frame / 2 : 0, fr,
+                                                                        n_frames, d_out);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac
+
+extern "C" int ac_frame_rms(const float* d_x, long long n, int frame, int hop, int center, float* d_out, void* stream) {
+  return ac::launch_frame_reduce<0>(d_x, n, frame, hop, center, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int ac_zero_crossing_rate(const float* d_x, long long n, int frame, int hop, float* d_out, void* stream) {
+  return ac::launch_frame_reduce<1>(d_x, n, frame, hop, 1, d_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,363 @@
+// MDX23 window STFT and the fused inverse path (iFFT + window + overlap-add + envelope
+// normalise + trim + stem arithmetic + accumulate).
+//
+// Replaces Conv_TDF_net_trim_model.stft/.istft (external MVSEP-MDX23 inference.py; called at
+// backends.py:355, :376) and, in stems mode, backends.py:377 (trim/concat), :389-406 (crop, mix
+// subtraction, mono mean) plus enhanced_vocal_separator.py:423-437 (effective-region accumulate).
+//
+// STFT: one CTA per (frame, window).  Left and right are packed as re/im of ONE complex FFT of
+// length n_fft (two real transforms for the price of one); the Hermitian split yields
+// {L_re,L_im,R_re,R_im}, written as one 16-byte (f32) / 8-byte (bf16) store per bin into the
+// [win][t][f][4] layout, i.e. every frame is a contiguous 48 KB run in HBM.
+//
+// iSTFT: one CTA per (strip of consecutive frames, window).  The CTA walks its frames in order,
+// keeps the ceil(n_fft/hop) hop-blocks that are still receiving contributions in a shared-memory
+// ring, and emits a hop-block as soon as its last frame has been added - the overlap-add never
+// touches HBM.  Strips re-compute nb-1 warm-up frames.
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "fft.cuh"
+#include "stft_mdx.cuh"
+
+namespace ac {
+
+constexpr int kFftThreads = 512;
+
+static std::mutex g_mdx_mu;
+static std::map<std::vector<int>, MdxPlan*> g_mdx_plans;
+
+const MdxPlan* get_mdx_plan(const ac_mdx_geom& g) {
+  std::lock_guard<std::mutex> lk(g_mdx_mu);
+  std::vector<int> key = {g.n_fft, g.hop, g.dim_f, g.dim_t};
+  auto it = g_mdx_plans.find(key);
+  if (it != g_mdx_plans.end()) return it->second;
+  if (g.n_fft < 16 || g.hop <= 0 || g.dim_t < 2 || g.dim_f <= 0 || g.dim_f > g.n_fft / 2 || (g.n_fft & 1)) {
+    set_error("bad mdx geometry");
+    return nullptr;
+  }
+  const int W = g.hop * (g.dim_t - 1);
+  if (W <= g.n_fft) {
+    set_error("mdx geometry: window shorter than n_fft");
+    return nullptr;
+  }
+  const FftPlan* fft = get_fft_plan(g.n_fft);
+  if (!fft) return nullptr;
+  const int plen = W + g.n_fft;
+  std::vector<double> env(plen, 0.0);
+  std::vector<float> w2(g.n_fft);
+  for (int j = 0; j < g.n_fft; ++j) {
+    float w = (float)(0.5 - 0.5 * std::cos(6.283185307179586476925286766559 * (double)j / (double)g.n_fft));
+    w2[j] = w * w;
+  }
+  for (int t = 0; t < g.dim_t; ++t)
+    for (int j = 0; j < g.n_fft; ++j) env[(size_t)t * g.hop + j] += (double)w2[j];
+  std::vector<float> envf(plen);
+  for (int i = 0; i < plen; ++i) envf[i] = (float)env[i];
+  float* d_env = nullptr;
+  if (cudaMalloc(&d_env, sizeof(float) * plen) != cudaSuccess ||
+      cudaMemcpy(d_env, envf.data(), sizeof(float) * plen, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("mdx plan upload failed");
+    return nullptr;
+  }
+  MdxPlan* p = new MdxPlan{g, W, fft, d_env};
+  g_mdx_plans[key] = p;
+  return p;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_spec4(T* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store_spec4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store_spec4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<uint32_t*>(&lo);
+  v.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+__device__ __forceinline__ float4 load_spec4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load_spec4(const __nv_bfloat16* p) {
+  uint2 v = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&v.x), hi = *reinterpret_cast<__nv_bfloat162*>(&v.y);
+  float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFftThreads) stft_mdx_kernel(const float* __restrict__ src, long long ch_stride,
+                                                               int n_ch, const WinDesc* __restrict__ wins, FftDev fft,
+                                                               const float* __restrict__ hann, int hop, int dim_f,
+                                                               int dim_t, int W, T* __restrict__ spec) {
+  extern __shared__ float2 smem_f2[];
+  const int N = fft.n;
+  float2* buf0 = smem_f2;
+  float2* buf1 = smem_f2 + fpad(N) + 1;
+  const int t = blockIdx.x;
+  const WinDesc wd = wins[blockIdx.y];
+  const float* s0 = src + wd.base;
+  const float* s1 = src + (n_ch > 1 ? ch_stride : 0) + wd.base;
+  const int p0 = t * hop - N / 2;
+  for (int j = threadIdx.x; j < N; j += kFftThreads) {
+    int p = p0 + j;
+    p = p < 0 ? -p : p;
+    p = p >= W ? 2 * (W - 1) - p : p;  // torch.stft center=True, pad_mode="reflect"
+    float l = 0.f, r = 0.f;
+    if (p >= wd.p_lo && p < wd.p_hi) {
+      l = __ldg(s0 + p);
+      r = __ldg(s1 + p);
+    }
+    const float w = __ldg(hann + j);
+    buf0[fpad(j)] = make_float2(l * w, r * w);
+  }
+  __syncthreads();
+  const float2* Z = fft_smem<false>(buf0, buf1, fft);
+  T* out = spec + ((size_t)blockIdx.y * dim_t + t) * (size_t)dim_f * 4;
+  for (int k = threadIdx.x; k < dim_f; k += kFftThreads) {
+    const float2 a = Z[fpad(k)];
+    const float2 b = Z[fpad(k == 0 ? 0 : N - k)];
+    store_spec4<T>(out + (size_t)k * 4, 0.5f * (a.x + b.x), 0.5f * (a.y - b.y), 0.5f * (a.y + b.y),
+                   -0.5f * (a.x - b.x));
+  }
+}
+
+struct IstftArgs {
+  const WinDesc* wins;
+  FftDev fft;
+  const float* hann;
+  const float* env;
+  int hop, dim_f, dim_t, W;
+  int nb;              // ring blocks = ceil(n_fft/hop)
+  int blk_lo, blk_hi;  // hop-blocks (padded coordinates) to emit
+  int strip;           // blocks per CTA
+  int mode;
+  float* wave;  // mode 0
+  const float* mix;  // mode 1
+  long long mix_stride;
+  int n_ch;
+  int output_is_vocal;
+  float* vocal;
+  float* instr;
+  float* weight;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kFftThreads) istft_mdx_kernel(const T* __restrict__ spec, IstftArgs a) {
+  extern __shared__ float2 smem_f2[];
+  const int N = a.fft.n;
+  float2* buf0 = smem_f2;
+  float2* buf1 = buf0 + fpad(N) + 1;
+  float2* ring = buf1 + fpad(N) + 1;  // [nb][hop]
+  const int hop = a.hop;
+  const int e0 = a.blk_lo + blockIdx.x * a.strip;
+  const int e1 = min(a.blk_hi, e0 + a.strip);
+  if (e0 >= e1) return;
+  const WinDesc wd = a.wins[blockIdx.y];
+  const int half = N / 2;
+  const float inv_n = 1.0f / (float)N;
+  for (int i = threadIdx.x; i < a.nb * hop; i += kFftThreads) ring[i] = make_float2(0.f, 0.f);
+  const int t_first = max(0, e0 - a.nb + 1);
+  for (int t = t_first; t < e1; ++t) {
+    if (t < a.dim_t) {
+      // ---- build the full-length spectrum of z = L + iR from the kept bins (Hermitian extension)
+      const T* in = spec + ((size_t)blockIdx.y * a.dim_t + t) * (size_t)a.dim_f * 4;
+      for (int k = a.dim_f + threadIdx.x; k <= N - a.dim_f; k += kFftThreads) buf0[fpad(k)] = make_float2(0.f, 0.f);
+      for (int k = threadIdx.x; k < a.dim_f; k += kFftThreads) {
+        const float4 v = load_spec4(in + (size_t)k * 4);  // L_re, L_im, R_re, R_im
+        if (k == 0) {
+          buf0[0] = make_float2(v.x, v.z);  // c2r ignores the imaginary part of DC
+        } else {
+          buf0[fpad(k)] = make_float2(v.x - v.w, v.y + v.z);
+          buf0[fpad(N - k)] = make_float2(v.x + v.w, v.z - v.y);
+        }
+      }
+      __syncthreads();
+      const float2* z = fft_smem<true>(buf0, buf1, a.fft);
+      // ---- windowed overlap-add into the ring (frame t covers padded positions [t*hop, t*hop+N))
+      for (int j = threadIdx.x; j < N; j += kFftThreads) {
+        const float w = __ldg(a.hann + j) * inv_n;
+        const float2 v = z[fpad(j)];
+        const int blk = t + j / hop;
+        float2* dst = ring + (blk % a.nb) * hop + (j % hop);
+        float2 acc = *dst;
+        acc.x = fmaf(v.x, w, acc.x);
+        acc.y = fmaf(v.y, w, acc.y);
+        *dst = acc;
+      }
+      __syncthreads();
+    }
+    // ---- hop-block t is complete: emit (or discard during warm-up) and recycle its slot
+    float2* blk = ring + (t % a.nb) * hop;
+    if (t >= e0) {
+      for (int i = threadIdx.x; i < hop; i += kFftThreads) {
+        const int pos = t * hop + i;
+        const int n = pos - half;  // sample index in the torch.istft output
+        if (n < 0 || n >= a.W) continue;
+        const float e = __ldg(a.env + pos);
+        const float2 acc = blk[i];
+        const float y0 = acc.x / e, y1 = acc.y / e;
+        if (a.mode == 0) {
+          float* w0 = a.wave + (size_t)blockIdx.y * 2 * a.W;
+          w0[n] = y0;
+          w0[a.W + n] = y1;
+        } else {
+          const int o = n - half;  // trim = n_fft/2 on both sides (backends.py:377)
+          if (o < 0 || o >= wd.out_len || n >= a.W - half) continue;
+          const long long tp = wd.out_base + o;
+          if (tp < wd.eff_start || tp >= wd.eff_end) continue;
+          const float m0 = __ldg(a.mix + tp);
+          const float m1 = __ldg(a.mix + (a.n_ch > 1 ? a.mix_stride : 0) + tp);
+          float v, ins;
+          if (a.output_is_vocal) {
+            v = (y0 + y1) * 0.5f;
+            ins = ((m0 - y0) + (m1 - y1)) * 0.5f;
+          } else {
+            ins = (y0 + y1) * 0.5f;
+            v = ((m0 - y0) + (m1 - y1)) * 0.5f;
+          }
+          atomicAdd(a.vocal + tp, v);
+          atomicAdd(a.instr + tp, ins);
+          atomicAdd(a.weight + tp, 1.0f);
+        }
+      }
+    }
+    for (int i = threadIdx.x; i < hop; i += kFftThreads) blk[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+  }
+}
+
+static size_t stft_smem_bytes(int n_fft) { return sizeof(float2) * 2 * (fft_smem_floats2(n_fft)); }
+
+int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, int n_ch, const WinDesc* d_wins,
+                int n_win, void* d_spec, int dtype, cudaStream_t st) {
+  if (n_win <= 0) return AC_OK;
+  const ac_mdx_geom& g = plan->g;
+  const size_t smem = stft_smem_bytes(g.n_fft);
+  AC_REQUIRE(smem <= 227 * 1024, "n_fft too large for shared memory");
+  FftDev fd = make_fft_dev(plan->fft);
+  dim3 grid(g.dim_t, n_win);
+  if (dtype == AC_F32) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(stft_mdx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_mdx_kernel<float><<<grid, kFftThreads, smem, st>>>(d_src, ch_stride, n_ch, d_wins, fd, plan->fft->d_hann,
+                                                            g.hop, g.dim_f, g.dim_t, plan->W, (float*)d_spec);
+  } else {
+    AC_CHECK_CUDA(
+        cudaFuncSetAttribute(stft_mdx_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_mdx_kernel<__nv_bfloat16><<<grid, kFftThreads, smem, st>>>(
+        d_src, ch_stride, n_ch, d_wins, fd, plan->fft->d_hann, g.hop, g.dim_f, g.dim_t, plan->W, (__nv_bfloat16*)d_spec);
+  }
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDesc* d_wins, int n_win, int mode,
+                 float* d_wave, const float* d_mix, long long mix_stride, int n_ch, int output_is_vocal,
+                 float* d_vocal, float* d_instr, float* d_weight, cudaStream_t st) {
+  if (n_win <= 0) return AC_OK;
+  const ac_mdx_geom& g = plan->g;
+  IstftArgs a;
+  a.wins = d_wins;
+  a.fft = make_fft_dev(plan->fft);
+  a.hann = plan->fft->d_hann;
+  a.env = plan->d_env;
+  a.hop = g.hop;
+  a.dim_f = g.dim_f;
+  a.dim_t = g.dim_t;
+  a.W = plan->W;
+  a.nb = (g.n_fft + g.hop - 1) / g.hop;
+  const int half = g.n_fft / 2;
+  const int pos_lo = mode == 0 ? half : g.n_fft;        // first padded position needed
+  const int pos_hi = mode == 0 ? plan->W + half : plan->W;  // one past the last
+  a.blk_lo = pos_lo / g.hop;
+  a.blk_hi = (pos_hi + g.hop - 1) / g.hop;
+  const int n_blk = a.blk_hi - a.blk_lo;
+  // enough CTAs for ~2 waves, but strips no shorter than 4x the warm-up
+  int strips = (2 * device_sm_count() + n_win - 1) / n_win;
+  int max_strips = n_blk / (4 * a.nb);
+  if (max_strips < 1) max_strips = 1;
+  if (strips > max_strips) strips = max_strips;
+  if (strips < 1) strips = 1;
+  a.strip = (n_blk + strips - 1) / strips;
+  strips = (n_blk + a.strip - 1) / a.strip;
+  a.mode = mode;
+  a.wave = d_wave;
+  a.mix = d_mix;
+  a.mix_stride = mix_stride;
+  a.n_ch = n_ch;
+  a.output_is_vocal = output_is_vocal;
+  a.vocal = d_vocal;
+  a.instr = d_instr;
+  a.weight = d_weight;
+  const size_t smem = stft_smem_bytes(g.n_fft) + sizeof(float2) * (size_t)a.nb * g.hop;
+  AC_REQUIRE(smem <= 227 * 1024, "n_fft too large for shared memory");
+  dim3 grid(strips, n_win);
+  if (dtype == AC_F32) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(istft_mdx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    istft_mdx_kernel<float><<<grid, kFftThreads, smem, st>>>((const float*)d_spec, a);
+  } else {
+    AC_CHECK_CUDA(
+        cudaFuncSetAttribute(istft_mdx_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    istft_mdx_kernel<__nv_bfloat16><<<grid, kFftThreads, smem, st>>>((const __nv_bfloat16*)d_spec, a);
+  }
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac
+
+// ---- C ABI: standalone batch forms ([B][2][W] waves) ------------------------------------------
+namespace {
+struct WinCache {  // identity window descriptors for the [B][2][W] layout, grown on demand
+  ac::WinDesc* d = nullptr;
+  int cap = 0;
+  int W = 0;
+};
+WinCache g_wc;
+std::mutex g_wc_mu;
+
+const ac::WinDesc* batch_windows(int B, int W) {
+  std::lock_guard<std::mutex> lk(g_wc_mu);
+  if (g_wc.cap < B || g_wc.W != W) {
+    if (g_wc.d) cudaFree(g_wc.d);
+    int cap = B < 64 ? 64 : B;
+    std::vector<ac::WinDesc> h(cap);
+    for (int b = 0; b < cap; ++b) {
+      h[b] = ac::WinDesc{(long long)b * 2 * W, 0, 0, 0, 0, W, 0, 0};
+    }
+    if (cudaMalloc(&g_wc.d, sizeof(ac::WinDesc) * cap) != cudaSuccess ||
+        cudaMemcpy(g_wc.d, h.data(), sizeof(ac::WinDesc) * cap, cudaMemcpyHostToDevice) != cudaSuccess) {
+      g_wc = WinCache();
+      ac::set_error("window descriptor upload failed");
+      return nullptr;
+    }
+    g_wc.cap = cap;
+    g_wc.W = W;
+  }
+  return g_wc.d;
+}
+}  // namespace
+
+extern "C" int ac_stft_mdx(const float* d_wave, void* d_spec, int B, const ac_mdx_geom* g, int dtype, void* stream) {
+  AC_REQUIRE(d_wave && d_spec && g && B >= 0, "null pointer");
+  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16, "dtype");
+  const ac::MdxPlan* plan = ac::get_mdx_plan(*g);
+  if (!plan) return AC_E_INVALID;
+  const ac::WinDesc* w = batch_windows(B, plan->W);
+  if (!w) return AC_E_CUDA;
+  return ac::launch_stft(plan, d_wave, plan->W, 2, w, B, d_spec, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int ac_istft_mdx(const void* d_spec, float* d_wave, int B, const ac_mdx_geom* g, int dtype, void* stream) {
+  AC_REQUIRE(d_wave && d_spec && g && B >= 0, "null pointer");
+  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16, "dtype");
+  const ac::MdxPlan* plan = ac::get_mdx_plan(*g);
+  if (!plan) return AC_E_INVALID;
+  const ac::WinDesc* w = batch_windows(B, plan->W);
+  if (!w) return AC_E_CUDA;
+  return ac::launch_istft(plan, d_spec, dtype, w, B, 0, d_wave, nullptr, 0, 2, 1, nullptr, nullptr, nullptr,
+                          (cudaStream_t)stream);
+}

@@ -1,0 +1,37 @@
+// Internal interface of the MDX STFT / fused iSTFT-OLA kernels (shared with track.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ac {
+
+// One model window (261120 samples at Kim_Vocal geometry) cut out of a signal buffer.
+struct WinDesc {
+  long long base;       // index (per channel) of window position p = 0 in the source buffer
+  long long out_base;   // stems mode: track sample that window output n = trim maps to
+  long long eff_start;  // stems mode: only track samples in [eff_start, eff_end) are written
+  long long eff_end;
+  int p_lo, p_hi;       // window positions holding real samples; outside -> 0 (zero padding)
+  int out_len;          // stems mode: outputs n = trim .. trim+out_len-1 are valid (<= gen)
+  int pad_;
+};
+
+struct MdxPlan {
+  ac_mdx_geom g;
+  int W;               // hop*(dim_t-1)
+  const FftPlan* fft;  // length n_fft
+  const float* d_env;  // sum of squared windows per padded position, (dim_t-1)*hop + n_fft values
+};
+const MdxPlan* get_mdx_plan(const ac_mdx_geom& g);
+
+// src: [n_ch][ch_stride] (n_ch 1 or 2).  spec: [n_win][dim_t][dim_f][4] of T (float / bf16).
+int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, int n_ch, const WinDesc* d_wins,
+                int n_win, void* d_spec, int dtype, cudaStream_t st);
+
+// mode 0: raw torch.istft output into d_wave [n_win][2][W].
+// mode 1: stems: trims n_fft/2 per side, maps to the track through WinDesc, subtracts from the
+//         mix, averages the two channels and atomically accumulates vocal / instrumental / weight.
+int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDesc* d_wins, int n_win, int mode,
+                 float* d_wave, const float* d_mix, long long mix_stride, int n_ch, int output_is_vocal,
+                 float* d_vocal, float* d_instr, float* d_weight, cudaStream_t st);
+
+}  // namespace ac

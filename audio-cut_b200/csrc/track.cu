@@ -1,0 +1,144 @@
+// Whole-track chunked separation: the device side of EnhancedVocalSeparator._separate_with_pipeline
+// (enhanced_vocal_separator.py:366-458) + MDX23OnnxBackend.infer_chunk (backends.py:299-406).
+//
+// The track is uploaded once; every model window of every chunk is described by a WinDesc that
+// the STFT kernel reads straight out of the track buffer (window build, align_hop / gen / trim
+// zero padding are index arithmetic, not copies) and that the fused iSTFT kernel uses to map its
+// output back to track samples (trim, concat, crop, halo trim).  Windows are independent, so they
+// are simply batched through STFT -> U-Net -> iSTFT max_batch at a time.
+#include <vector>
+
+#include "stft_mdx.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+static int chunk_windows(int chunk_len, const ac_track_params& p) {
+  const int hop = p.align_hop > 0 ? p.align_hop : 1;
+  const long long L = (long long)chunk_len + ((hop - chunk_len % hop) % hop);
+  const int W = p.mdx.hop * (p.mdx.dim_t - 1);
+  const int gen = W - p.mdx.n_fft;
+  const long long pad = (gen - L % gen) % gen;
+  return (int)((L + pad) / gen);
+}
+
+static void build_windows(const ac_chunk_desc* ch, int n_chunks, const ac_track_params& p, std::vector<WinDesc>& out) {
+  const int W = p.mdx.hop * (p.mdx.dim_t - 1);
+  const int trim = p.mdx.n_fft / 2;
+  const int gen = W - p.mdx.n_fft;
+  out.clear();
+  for (int c = 0; c < n_chunks; ++c) {
+    if (ch[c].chunk_len <= 0) continue;
+    const int nw = chunk_windows(ch[c].chunk_len, p);
+    for (int w = 0; w < nw; ++w) {
+      const long long q0 = (long long)w * gen - trim;  // chunk-local index of window position 0
+      WinDesc d;
+      d.base = ch[c].chunk_start + q0;
+      long long lo = -q0, hi = (long long)ch[c].chunk_len - q0;
+      if (lo < 0) lo = 0;
+      if (hi > W) hi = W;
+      if (hi < lo) hi = lo;
+      d.p_lo = (int)lo;
+      d.p_hi = (int)hi;
+      d.out_base = ch[c].chunk_start + (long long)w * gen;
+      long long ol = (long long)ch[c].chunk_len - (long long)w * gen;
+      if (ol > gen) ol = gen;
+      if (ol <= 0) continue;  // window made only of alignment padding: its output is cropped away
+      d.out_len = (int)ol;
+      d.eff_start = ch[c].eff_start;
+      d.eff_end = ch[c].eff_end;
+      d.pad_ = 0;
+      out.push_back(d);
+    }
+  }
+}
+
+__global__ void finalize_stems_kernel(float* __restrict__ vocal, float* __restrict__ instr,
+                                      const float* __restrict__ weight, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float w = weight[i];
+  w = w == 0.f ? 1.f : w;
+  vocal[i] = vocal[i] / w;
+  instr[i] = instr[i] / w;
+}
+
+static int default_batch(int dtype) { return dtype == AC_F32 ? 8 : 16; }
+
+}  // namespace ac
+
+extern "C" int ac_track_window_count(const ac_chunk_desc* h_chunks, int n_chunks, const ac_track_params* p) {
+  if (!h_chunks || !p || n_chunks < 0) return -1;
+  std::vector<ac::WinDesc> w;
+  ac::build_windows(h_chunks, n_chunks, *p, w);
+  return (int)w.size();
+}
+
+extern "C" size_t ac_track_workspace_bytes(const ac_unet* net, const ac_chunk_desc* h_chunks, int n_chunks,
+                                           const ac_track_params* p) {
+  if (!net || !h_chunks || !p) return 0;
+  const int nw = ac_track_window_count(h_chunks, n_chunks, p);
+  if (nw < 0) return 0;
+  int mb = p->max_batch > 0 ? p->max_batch : ac::default_batch(p->dtype);
+  if (mb > nw) mb = nw > 0 ? nw : 1;
+  const size_t es = p->dtype == AC_F32 ? 4 : 2;
+  const size_t spec = (size_t)mb * p->mdx.dim_t * p->mdx.dim_f * 4 * es;
+  return ac::align_up(sizeof(ac::WinDesc) * (size_t)(nw > 0 ? nw : 1), 256) + ac::align_up(spec, 256) +
+         ac_unet_workspace_bytes(net, mb, p->dtype) + 1024;
+}
+
+extern "C" int ac_separate_track(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
+                                 int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr,
+                                 float* d_weight, void* d_ws, size_t ws_bytes, void* stream) {
+  using namespace ac;
+  AC_REQUIRE(net && d_mix && h_chunks && p && d_vocal && d_instr && d_weight && d_ws, "null pointer");
+  AC_REQUIRE(n_samples > 0 && n_chunks >= 0, "bad sizes");
+  AC_REQUIRE(p->n_channels == 1 || p->n_channels == 2, "n_channels must be 1 or 2");
+  AC_REQUIRE(p->dtype == AC_F32 || p->dtype == AC_BF16, "dtype");
+  for (int c = 0; c < n_chunks; ++c) {
+    AC_REQUIRE(h_chunks[c].chunk_start >= 0 && h_chunks[c].chunk_start + h_chunks[c].chunk_len <= n_samples,
+               "chunk outside the track");
+    AC_REQUIRE(h_chunks[c].eff_start >= 0 && h_chunks[c].eff_end <= n_samples, "effective region outside the track");
+  }
+  if (ws_bytes < ac_track_workspace_bytes(net, h_chunks, n_chunks, p)) {
+    set_error("track workspace too small");
+    return AC_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const MdxPlan* plan = get_mdx_plan(p->mdx);
+  if (!plan) return AC_E_INVALID;
+  std::vector<WinDesc> wins;
+  build_windows(h_chunks, n_chunks, *p, wins);
+  const int nw = (int)wins.size();
+  int mb = p->max_batch > 0 ? p->max_batch : default_batch(p->dtype);
+  if (mb > nw) mb = nw > 0 ? nw : 1;
+  const size_t es = p->dtype == AC_F32 ? 4 : 2;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~uintptr_t(255));
+  WinDesc* d_wins = reinterpret_cast<WinDesc*>(base);
+  char* d_spec = base + align_up(sizeof(WinDesc) * (size_t)(nw > 0 ? nw : 1), 256);
+  const size_t spec_bytes = align_up((size_t)mb * p->mdx.dim_t * p->mdx.dim_f * 4 * es, 256);
+  char* d_uws = d_spec + spec_bytes;
+  const size_t uws_bytes = ws_bytes - (size_t)(d_uws - reinterpret_cast<char*>(d_ws));
+
+  AC_CHECK_CUDA(cudaMemsetAsync(d_vocal, 0, sizeof(float) * n_samples, st));
+  AC_CHECK_CUDA(cudaMemsetAsync(d_instr, 0, sizeof(float) * n_samples, st));
+  AC_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, sizeof(float) * n_samples, st));
+  if (nw > 0) {
+    AC_CHECK_CUDA(cudaMemcpyAsync(d_wins, wins.data(), sizeof(WinDesc) * nw, cudaMemcpyHostToDevice, st));
+    // wins is a host temporary: the copy above must have consumed it before we return
+    AC_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+  for (int w0 = 0; w0 < nw; w0 += mb) {
+    const int b = nw - w0 < mb ? nw - w0 : mb;
+    int rc = launch_stft(plan, d_mix, n_samples, p->n_channels, d_wins + w0, b, d_spec, p->dtype, st);
+    if (rc) return rc;
+    rc = ac_unet_forward(net, d_spec, d_spec, b, p->dtype, d_uws, uws_bytes, st);
+    if (rc) return rc;
+    rc = launch_istft(plan, d_spec, p->dtype, d_wins + w0, b, 1, nullptr, d_mix, n_samples, p->n_channels,
+                      p->output_is_vocal, d_vocal, d_instr, d_weight, st);
+    if (rc) return rc;
+  }
+  finalize_stems_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, st>>>(d_vocal, d_instr, d_weight, n_samples);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}

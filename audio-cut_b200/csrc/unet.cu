@@ -1,0 +1,381 @@
+// TFC-TDF U-Net: parameter upload / repacking and the forward schedule.
+// Replaces self._session.run(...) at backends.py:358 (onnxruntime executing Kim_Vocal_1.onnx).
+#include <vector>
+
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+struct Affine {
+  const float* scale;
+  const float* shift;
+};
+struct ConvLayer {  // implicit-GEMM B operand [K][N] in both dtypes
+  const float* w32;
+  const __nv_bfloat16* w16;
+  Affine af;
+  int K, N;
+  TcConvWeights* tc = nullptr;  // tcgen05 packing (3x3 convs only)
+};
+struct TdfLayer {  // GEMM A operand [M][K] (PyTorch Linear weight as is)
+  const float* w32;
+  const __nv_bfloat16* w16;
+  Affine af;
+  int M, K;
+};
+struct Block {
+  int c, T, F;
+  ConvLayer conv[8];
+  TdfLayer tdf1, tdf2;
+};
+
+}  // namespace ac
+
+struct ac_unet {
+  ac_unet_geom g;
+  int n_blocks;
+  std::vector<ac::Block> blocks;  // enc0..enc(n-1), bottleneck, dec0..dec(n-1)
+  std::vector<ac::ConvLayer> ds, us;
+  const float* first_w;
+  ac::Affine first_af;
+  const float* final_w;
+  const float* final_b;
+  float* d_f32 = nullptr;           // arena: all fp32 params (repacked)
+  __nv_bfloat16* d_bf16 = nullptr;  // arena: bf16 copies, same offsets
+  size_t arena_floats = 0;
+  int force_simt = 0;
+};
+
+namespace ac {
+
+static size_t block_floats(const ac_unet_geom& g, int c, int f) {
+  size_t s = 0;
+  for (int j = 0; j < g.l; ++j) s += (size_t)c * c * 9 + 2 * c;
+  s += (size_t)(f / g.bn) * f + 2 * c;
+  s += (size_t)f * (f / g.bn) + 2 * c;
+  return s;
+}
+
+static size_t param_floats(const ac_unet_geom& g) {
+  size_t s = (size_t)g.g * g.dim_c + 2 * g.g;
+  for (int i = 0; i < g.n; ++i) {
+    int c = g.g * (i + 1), f = g.dim_f >> i;
+    s += block_floats(g, c, f);
+    s += (size_t)(c + g.g) * c * 4 + 2 * (c + g.g);
+  }
+  s += block_floats(g, g.g * (g.n + 1), g.dim_f >> g.n);
+  for (int i = 0; i < g.n; ++i) {
+    int lvl = g.n - 1 - i;
+    int c = g.g * (lvl + 1), f = g.dim_f >> lvl;
+    s += (size_t)(c + g.g) * c * 4 + 2 * c;
+    s += block_floats(g, c, f);
+  }
+  s += (size_t)g.dim_c * g.g + g.dim_c;
+  return s;
+}
+
+static bool geom_ok(const ac_unet_geom& g) {
+  return g.dim_c == 4 && g.g > 0 && g.g % 16 == 0 && g.n >= 1 && g.n <= 6 && g.l >= 1 && g.l <= 8 && g.bn >= 1 &&
+         g.dim_f % (g.bn << g.n) == 0 && g.dim_t % (1 << g.n) == 0 && g.dim_f > 0 && g.dim_t > 0;
+}
+
+}  // namespace ac
+
+extern "C" size_t ac_unet_param_floats(const ac_unet_geom* g) { return (g && ac::geom_ok(*g)) ? ac::param_floats(*g) : 0; }
+
+extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_t n_floats, ac_unet** out) {
+  using namespace ac;
+  AC_REQUIRE(gp && h_blob && out, "null pointer");
+  AC_REQUIRE(geom_ok(*gp), "unsupported U-Net geometry");
+  const ac_unet_geom g = *gp;
+  AC_REQUIRE(n_floats == param_floats(g), "parameter blob has the wrong size");
+
+  // Repack on the host into the device arena layout (same total size): conv weights become the
+  // implicit-GEMM B operand [K][N]; everything else is copied through.
+  std::vector<float> arena(n_floats);
+  ac_unet* net = new ac_unet();
+  net->g = g;
+  net->arena_floats = n_floats;
+  size_t rd = 0, wr = 0;
+  struct Fix {  // pointer fix-ups recorded as arena offsets
+    size_t off;
+  };
+  auto take = [&](size_t n) {
+    size_t o = wr;
+    std::copy(h_blob + rd, h_blob + rd + n, arena.begin() + wr);
+    rd += n;
+    wr += n;
+    return o;
+  };
+  // returns arena offset of the repacked [K][N] matrix
+  auto conv3 = [&](int cin, int cout, int kh, int kw) {  // src W[cout][cin][kh][kw] -> [(tap*cin+ci)][cout]
+    size_t o = wr;
+    const float* src = h_blob + rd;
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < kh * kw; ++t)
+          arena[o + ((size_t)t * cin + ci) * cout + co] = src[((size_t)co * cin + ci) * kh * kw + t];
+    rd += (size_t)cout * cin * kh * kw;
+    wr += (size_t)cout * cin * kh * kw;
+    return o;
+  };
+  auto convT = [&](int cin, int cout) {  // src W[cin][cout][2][2] -> [ci][(tap*cout+co)]
+    size_t o = wr;
+    const float* src = h_blob + rd;
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co)
+        for (int t = 0; t < 4; ++t) arena[o + (size_t)ci * 4 * cout + (size_t)t * cout + co] = src[((size_t)ci * cout + co) * 4 + t];
+    rd += (size_t)cin * cout * 4;
+    wr += (size_t)cin * cout * 4;
+    return o;
+  };
+  struct ConvOff { size_t w, sc, sh; int K, N; const float* raw; int cin, cout; };
+  struct TdfOff { size_t w, sc, sh; int M, K; };
+  struct BlockOff { int c, T, F; std::vector<ConvOff> conv; TdfOff t1, t2; };
+  std::vector<BlockOff> boffs;
+  std::vector<ConvOff> dsoffs, usoffs;
+
+  auto read_block = [&](int c, int T, int F) {
+    BlockOff b;
+    b.c = c; b.T = T; b.F = F;
+    for (int j = 0; j < g.l; ++j) {
+      ConvOff co;
+      co.raw = h_blob + rd;
+      co.cin = co.cout = c;
+      co.w = conv3(c, c, 3, 3);
+      co.sc = take(c);
+      co.sh = take(c);
+      co.K = 9 * c; co.N = c;
+      b.conv.push_back(co);
+    }
+    b.t1.w = take((size_t)(F / g.bn) * F); b.t1.sc = take(c); b.t1.sh = take(c); b.t1.M = F / g.bn; b.t1.K = F;
+    b.t2.w = take((size_t)F * (F / g.bn)); b.t2.sc = take(c); b.t2.sh = take(c); b.t2.M = F; b.t2.K = F / g.bn;
+    boffs.push_back(b);
+  };
+
+  size_t first_w = take((size_t)g.g * g.dim_c), first_sc = take(g.g), first_sh = take(g.g);
+  for (int i = 0; i < g.n; ++i) {
+    int c = g.g * (i + 1), T = g.dim_t >> i, F = g.dim_f >> i;
+    read_block(c, T, F);
+    ConvOff d;
+    d.raw = nullptr; d.cin = c; d.cout = c + g.g;
+    d.w = conv3(c, c + g.g, 2, 2); d.sc = take(c + g.g); d.sh = take(c + g.g); d.K = 4 * c; d.N = c + g.g;
+    dsoffs.push_back(d);
+  }
+  read_block(g.g * (g.n + 1), g.dim_t >> g.n, g.dim_f >> g.n);
+  for (int i = 0; i < g.n; ++i) {
+    int lvl = g.n - 1 - i;
+    int c = g.g * (lvl + 1), T = g.dim_t >> lvl, F = g.dim_f >> lvl;
+    ConvOff u;
+    u.raw = nullptr; u.cin = c + g.g; u.cout = c;
+    u.w = convT(c + g.g, c); u.sc = take(c); u.sh = take(c); u.K = c + g.g; u.N = 4 * c;
+    usoffs.push_back(u);
+    read_block(c, T, F);
+  }
+  size_t final_w = take((size_t)g.dim_c * g.g), final_b = take(g.dim_c);
+  if (rd != n_floats || wr != n_floats) {
+    delete net;
+    set_error("internal: blob walk mismatch");
+    return AC_E_INVALID;
+  }
+
+  std::vector<__nv_bfloat16> arena16(n_floats);
+  for (size_t i = 0; i < n_floats; ++i) arena16[i] = __float2bfloat16_rn(arena[i]);
+  if (cudaMalloc(&net->d_f32, n_floats * 4) != cudaSuccess || cudaMalloc(&net->d_bf16, n_floats * 2) != cudaSuccess ||
+      cudaMemcpy(net->d_f32, arena.data(), n_floats * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(net->d_bf16, arena16.data(), n_floats * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error(std::string("unet parameter upload: ") + cudaGetErrorString(cudaGetLastError()));
+    ac_unet_destroy(net);
+    return AC_E_CUDA;
+  }
+  auto mk_conv = [&](const ConvOff& o) {
+    ConvLayer L;
+    L.w32 = net->d_f32 + o.w; L.w16 = net->d_bf16 + o.w;
+    L.af = Affine{net->d_f32 + o.sc, net->d_f32 + o.sh};
+    L.K = o.K; L.N = o.N;
+    return L;
+  };
+  auto mk_tdf = [&](const TdfOff& o) {
+    TdfLayer L;
+    L.w32 = net->d_f32 + o.w; L.w16 = net->d_bf16 + o.w;
+    L.af = Affine{net->d_f32 + o.sc, net->d_f32 + o.sh};
+    L.M = o.M; L.K = o.K;
+    return L;
+  };
+  for (auto& bo : boffs) {
+    Block b;
+    b.c = bo.c; b.T = bo.T; b.F = bo.F;
+    for (int j = 0; j < g.l; ++j) {
+      b.conv[j] = mk_conv(bo.conv[j]);
+      if (tc_conv3x3_supported(bo.T, bo.F, bo.c) == AC_OK) {
+        if (tc_conv3x3_pack(bo.conv[j].raw, bo.c, &b.conv[j].tc) != AC_OK) {
+          ac_unet_destroy(net);
+          return AC_E_CUDA;
+        }
+      }
+    }
+    b.tdf1 = mk_tdf(bo.t1);
+    b.tdf2 = mk_tdf(bo.t2);
+    net->blocks.push_back(b);
+  }
+  for (auto& o : dsoffs) net->ds.push_back(mk_conv(o));
+  for (auto& o : usoffs) net->us.push_back(mk_conv(o));
+  net->first_w = net->d_f32 + first_w;
+  net->first_af = Affine{net->d_f32 + first_sc, net->d_f32 + first_sh};
+  net->final_w = net->d_f32 + final_w;
+  net->final_b = net->d_f32 + final_b;
+  net->n_blocks = (int)net->blocks.size();
+  *out = net;
+  return AC_OK;
+}
+
+extern "C" void ac_unet_destroy(ac_unet* net) {
+  if (!net) return;
+  for (auto& b : net->blocks)
+    for (int j = 0; j < net->g.l; ++j)
+      if (b.conv[j].tc) ac::tc_conv3x3_free(b.conv[j].tc);
+  if (net->d_f32) cudaFree(net->d_f32);
+  if (net->d_bf16) cudaFree(net->d_bf16);
+  delete net;
+}
+
+extern "C" int ac_unet_set_debug(ac_unet* net, int force_simt) {
+  AC_REQUIRE(net, "null");
+  net->force_simt = force_simt;
+  return AC_OK;
+}
+
+namespace ac {
+struct WsPlan {
+  size_t level0;       // elements of one level-0 activation tensor
+  size_t skip_off[8];  // element offsets of the skip tensors
+  size_t P, Q, H, total;
+};
+static WsPlan plan_ws(const ac_unet_geom& g, int B) {
+  WsPlan w;
+  w.level0 = (size_t)B * g.dim_t * g.dim_f * g.g;
+  size_t off = 0;
+  auto bump = [&](size_t n) {
+    size_t o = off;
+    off += (n + 127) / 128 * 128;
+    return o;
+  };
+  w.P = bump(w.level0);
+  w.Q = bump(w.level0);
+  w.H = bump(w.level0 / g.bn);
+  for (int i = 0; i < g.n; ++i) w.skip_off[i] = bump(((size_t)B * (g.dim_t >> i) * (g.dim_f >> i)) * g.g * (i + 1));
+  w.total = off;
+  return w;
+}
+}  // namespace ac
+
+extern "C" size_t ac_unet_workspace_bytes(const ac_unet* net, int B, int dtype) {
+  if (!net || B <= 0) return 0;
+  return ac::plan_ws(net->g, B).total * (dtype == AC_F32 ? 4 : 2) + 256;
+}
+
+extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int B, int dtype, void* d_ws,
+                               size_t ws_bytes, void* stream) {
+  using namespace ac;
+  AC_REQUIRE(net && d_in && d_out && d_ws, "null pointer");
+  AC_REQUIRE(B > 0, "batch must be positive");
+  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16, "dtype");
+  if (ws_bytes < ac_unet_workspace_bytes(net, B, dtype)) {
+    set_error("unet workspace too small");
+    return AC_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const ac_unet_geom& g = net->g;
+  const size_t es = dtype == AC_F32 ? 4 : 2;
+  const WsPlan wp = plan_ws(g, B);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~uintptr_t(255));
+  auto ptr = [&](size_t off) { return (void*)(base + off * es); };
+  void* P = ptr(wp.P);
+  void* Q = ptr(wp.Q);
+  void* H = ptr(wp.H);
+  auto wsel = [&](const float* w32, const __nv_bfloat16* w16) { return dtype == AC_F32 ? (const void*)w32 : (const void*)w16; };
+  int rc;
+
+  auto conv3x3 = [&](const ConvLayer& L, const void* x, void* y, int T, int F, int C) -> int {
+    if (dtype == AC_BF16 && L.tc && !net->force_simt) {
+      TcConvArgs ta{(const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, F, C, L.tc, L.af.scale, L.af.shift};
+      return launch_tc_conv3x3(ta, st);
+    }
+    GemmArgs a{};
+    a.M = B * T * F; a.N = L.N; a.K = L.K; a.batch = 1;
+    a.a_mode = A_CONV3; a.A = x; a.T = T; a.F = F; a.C = C;
+    a.Bm = wsel(L.w32, L.w16);
+    a.epi = EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = L.N; a.out = y;
+    return launch_gemm_simt(a, dtype, st);
+  };
+  // X is clobbered, Y is scratch, result lands in Z (Z != Y)
+  auto run_block = [&](const Block& b, void* X, void* Y, void* Z) -> int {
+    void* src = X;
+    void* dst = Y;
+    for (int j = 0; j < g.l; ++j) {
+      if ((rc = conv3x3(b.conv[j], src, dst, b.T, b.F, b.c))) return rc;
+      void* t = src; src = dst; dst = t;
+    }
+    // src now holds the TFC output; dst is free.  If Z aliases src the residual would be clobbered.
+    void* tfc = src;
+    if (Z == tfc) return (set_error("internal: block output aliases TFC output"), AC_E_INVALID);
+    GemmArgs a{};
+    a.M = b.tdf1.M; a.N = b.c; a.K = b.tdf1.K; a.batch = B * b.T;
+    a.a_mode = A_PLAIN; a.A = wsel(b.tdf1.w32, b.tdf1.w16); a.a_batch_stride = 0;
+    a.Bm = tfc; a.b_batch_stride = (long long)b.F * b.c;
+    a.epi = EPI_AFFINE_RELU; a.scale = b.tdf1.af.scale; a.shift = b.tdf1.af.shift; a.cmod = b.c;
+    a.out = H; a.c_batch_stride = (long long)b.tdf1.M * b.c;
+    if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
+    GemmArgs c{};
+    c.M = b.tdf2.M; c.N = b.c; c.K = b.tdf2.K; c.batch = B * b.T;
+    c.a_mode = A_PLAIN; c.A = wsel(b.tdf2.w32, b.tdf2.w16); c.a_batch_stride = 0;
+    c.Bm = H; c.b_batch_stride = (long long)b.tdf2.K * b.c;
+    c.epi = EPI_RESIDUAL; c.scale = b.tdf2.af.scale; c.shift = b.tdf2.af.shift; c.cmod = b.c;
+    c.out = Z; c.c_batch_stride = (long long)b.F * b.c; c.extra = tfc;
+    return launch_gemm_simt(c, dtype, st);
+  };
+
+  const long long P0 = (long long)B * g.dim_t * g.dim_f;
+  if ((rc = launch_first_conv(d_in, P, P0, g.g, net->first_w, net->first_af.scale, net->first_af.shift, dtype, st)))
+    return rc;
+  void* cur = P;
+  void* oth = Q;
+  for (int i = 0; i < g.n; ++i) {
+    const Block& b = net->blocks[i];
+    void* skip = ptr(wp.skip_off[i]);
+    // l convs ping-pong cur/oth; with odd l the TFC output is in oth, with even l in cur: either way != skip
+    if ((rc = run_block(b, cur, oth, skip))) return rc;
+    const ConvLayer& d = net->ds[i];
+    GemmArgs a{};
+    a.M = B * (b.T / 2) * (b.F / 2); a.N = d.N; a.K = d.K; a.batch = 1;
+    a.a_mode = A_DOWN2; a.A = skip; a.T = b.T / 2; a.F = b.F / 2; a.C = b.c;
+    a.Bm = wsel(d.w32, d.w16);
+    a.epi = EPI_AFFINE_RELU; a.scale = d.af.scale; a.shift = d.af.shift; a.cmod = d.N; a.out = cur;
+    if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
+  }
+  {
+    const Block& b = net->blocks[g.n];
+    // result must not alias the TFC output: TFC output is in (l odd ? oth : cur); write to the other one
+    void* Z = (g.l & 1) ? cur : oth;
+    if ((rc = run_block(b, cur, oth, Z))) return rc;
+    if (Z != cur) { void* t = cur; cur = oth; oth = t; }
+  }
+  for (int i = 0; i < g.n; ++i) {
+    const int lvl = g.n - 1 - i;
+    const Block& b = net->blocks[g.n + 1 + i];
+    const ConvLayer& u = net->us[i];
+    void* skip = ptr(wp.skip_off[lvl]);
+    GemmArgs a{};
+    a.M = B * (b.T / 2) * (b.F / 2); a.N = u.N; a.K = u.K; a.batch = 1;
+    a.a_mode = A_PLAIN; a.A = cur; a.a_batch_stride = 0;
+    a.Bm = wsel(u.w32, u.w16);
+    a.epi = EPI_UP_SKIP; a.scale = u.af.scale; a.shift = u.af.shift; a.cmod = b.c; a.out = oth; a.extra = skip;
+    a.up_T = b.T / 2; a.up_F = b.F / 2;
+    if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
+    { void* t = cur; cur = oth; oth = t; }
+    void* Z = (g.l & 1) ? cur : oth;
+    if ((rc = run_block(b, cur, oth, Z))) return rc;
+    if (Z != cur) { void* t = cur; cur = oth; oth = t; }
+  }
+  return launch_final_conv(cur, d_out, P0, g.g, net->final_w, net->final_b, dtype, st);
+}

@@ -1,0 +1,58 @@
+// Internal interface between the U-Net orchestration (unet.cu) and its kernels.
+// Activations are channels-last: [B][T][F][C] (C innermost), in float or bf16.
+#pragma once
+#include "common.cuh"
+
+namespace ac {
+
+enum AMode { A_CONV3 = 0, A_DOWN2 = 1, A_PLAIN = 2 };
+enum EpiMode { EPI_AFFINE_RELU = 0, EPI_UP_SKIP = 1, EPI_RESIDUAL = 2 };
+
+// C[batch][M][N] = A[M][K] * B[batch][K][N]  (+ epilogue), fp32 accumulate.
+struct GemmArgs {
+  int M, N, K;
+  int batch;               // blockIdx.z
+  // ---- A operand
+  int a_mode;
+  const void* A;           // A_PLAIN: [M][K] row-major (+ batch*a_batch_stride); else input activations
+  long long a_batch_stride;
+  int T, F, C;             // A_CONV3 / A_DOWN2: OUTPUT grid (T x F) and input channels; M = nB*T*F
+  // ---- B operand: [K][N] row-major
+  const void* Bm;
+  long long b_batch_stride;
+  // ---- epilogue: y = relu(acc*scale[n % cmod] + shift[n % cmod])
+  int epi;
+  const float* scale;
+  const float* shift;
+  int cmod;
+  void* out;               // EPI_AFFINE_RELU / EPI_RESIDUAL: [batch][M][N]
+  long long c_batch_stride;
+  const void* extra;       // EPI_UP_SKIP: skip tensor (same layout as out); EPI_RESIDUAL: residual [batch][M][N]
+  int up_T, up_F;          // EPI_UP_SKIP: INPUT grid; out is [nB][2*up_T][2*up_F][N/4]
+};
+
+int launch_gemm_simt(const GemmArgs& a, int dtype, cudaStream_t st);
+
+// first 1x1 conv: [P][4] -> [P][g] with affine+relu;  final 1x1 conv: [P][g] -> [P][4] + bias
+int launch_first_conv(const void* in, void* out, long long P, int g, const float* w /*[g][4]*/, const float* scale,
+                      const float* shift, int dtype, cudaStream_t st);
+int launch_final_conv(const void* in, void* out, long long P, int g, const float* w /*[4][g]*/, const float* bias,
+                      int dtype, cudaStream_t st);
+
+// ---- tcgen05 path (bf16) -------------------------------------------------------------------
+struct TcConvWeights;  // opaque: packed smem images for one 3x3 conv layer
+struct TcConvArgs {
+  const __nv_bfloat16* in;  // [nB][T][F][C]
+  __nv_bfloat16* out;       // [nB][T][F][C]
+  int nB, T, F, C;
+  const TcConvWeights* w;
+  const float* scale;
+  const float* shift;
+};
+// returns AC_OK, or AC_E_INVALID when the shape is not supported by the tensor-core kernel
+int tc_conv3x3_supported(int T, int F, int C);
+int tc_conv3x3_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWeights** out);
+void tc_conv3x3_free(TcConvWeights* w);
+int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
+
+}  // namespace ac

@@ -1,0 +1,176 @@
+"""Thin torch-tensor wrappers over the C ABI (device memory and streams are torch's; the math is ours)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AC_BF16, AC_F32, ChunkDesc, FeatSegment, MdxGeom, TrackParams, UNetGeom, check, ptr, stream_ptr
+from .unet_weights import UNetGeometry, pack_blob
+
+
+def _dev_index(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise _lib.AudioCutError("audio_cut_b200 ops need CUDA tensors (there is no CPU fallback)")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _torch_dtype(dtype: int):
+    return torch.float32 if dtype == AC_F32 else torch.bfloat16
+
+
+def frame_count(n: int, frame: int, hop: int, center: bool = True) -> int:
+    return int(_lib.load().ac_frame_count(int(n), int(frame), int(hop), int(bool(center))))
+
+
+def frame_rms(x: torch.Tensor, frame_length: int, hop_length: int, center: bool = True) -> torch.Tensor:
+    """librosa.feature.rms(y, frame_length, hop_length)[0] on the GPU."""
+    lib = _lib.init(_dev_index(x))
+    x = x.contiguous().float()
+    n = x.numel()
+    out = torch.empty(frame_count(n, frame_length, hop_length, center), dtype=torch.float32, device=x.device)
+    if out.numel():
+        check(lib.ac_frame_rms(ptr(x), n, frame_length, hop_length, int(center), ptr(out), stream_ptr()), "ac_frame_rms")
+    return out
+
+
+def zero_crossing_rate(x: torch.Tensor, frame_length: int = 2048, hop_length: int = 512) -> torch.Tensor:
+    lib = _lib.init(_dev_index(x))
+    x = x.contiguous().float()
+    n = x.numel()
+    out = torch.empty(frame_count(n, frame_length, hop_length, True), dtype=torch.float32, device=x.device)
+    if out.numel():
+        check(lib.ac_zero_crossing_rate(ptr(x), n, frame_length, hop_length, ptr(out), stream_ptr()), "ac_zero_crossing_rate")
+    return out
+
+
+def mdx_geom(n_fft=7680, hop=1024, dim_f=3072, dim_t=256) -> MdxGeom:
+    return MdxGeom(int(n_fft), int(hop), int(dim_f), int(dim_t))
+
+
+def stft_mdx(wave: torch.Tensor, geom: MdxGeom, dtype: int = AC_F32) -> torch.Tensor:
+    """wave [B,2,W] f32 -> spec [B,dim_t,dim_f,4] ("TFC" layout, see include/audiocut_b200.h)."""
+    lib = _lib.init(_dev_index(wave))
+    W = geom.hop * (geom.dim_t - 1)
+    assert wave.dim() == 3 and wave.shape[1] == 2 and wave.shape[2] == W, wave.shape
+    wave = wave.contiguous().float()
+    B = wave.shape[0]
+    spec = torch.empty((B, geom.dim_t, geom.dim_f, 4), dtype=_torch_dtype(dtype), device=wave.device)
+    check(lib.ac_stft_mdx(ptr(wave), ptr(spec), B, C.byref(geom), dtype, stream_ptr()), "ac_stft_mdx")
+    return spec
+
+
+def istft_mdx(spec: torch.Tensor, geom: MdxGeom) -> torch.Tensor:
+    lib = _lib.init(_dev_index(spec))
+    dtype = AC_F32 if spec.dtype == torch.float32 else AC_BF16
+    spec = spec.contiguous()
+    B = spec.shape[0]
+    assert tuple(spec.shape[1:]) == (geom.dim_t, geom.dim_f, 4), spec.shape
+    W = geom.hop * (geom.dim_t - 1)
+    wave = torch.empty((B, 2, W), dtype=torch.float32, device=spec.device)
+    check(lib.ac_istft_mdx(ptr(spec), ptr(wave), B, C.byref(geom), dtype, stream_ptr()), "ac_istft_mdx")
+    return wave
+
+
+def onnx_to_tfc(x: torch.Tensor) -> torch.Tensor:
+    """[B,4,F,T] (ONNX tensor of backends.py:356) -> [B,T,F,4]."""
+    return x.permute(0, 3, 2, 1).contiguous()
+
+
+def tfc_to_onnx(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(0, 3, 2, 1).contiguous()
+
+
+class UNet:
+    """Device-resident TFC-TDF U-Net (replaces the onnxruntime session of backends.py:216-253, 358)."""
+
+    def __init__(self, state: Dict[str, np.ndarray], geo: UNetGeometry = UNetGeometry(), device: int = 0):
+        self.geo = geo
+        self.device = torch.device("cuda", device)
+        self._lib = _lib.init(device)
+        g = UNetGeom(geo.dim_f, geo.dim_t, geo.dim_c, geo.g, geo.n, geo.l, geo.bn)
+        self._g = g
+        blob = pack_blob(state, geo)
+        want = int(self._lib.ac_unet_param_floats(C.byref(g)))
+        if blob.size != want:
+            raise _lib.AudioCutError(f"parameter blob has {blob.size} floats, geometry needs {want}")
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.ac_unet_create(C.byref(g), blob.ctypes.data_as(C.c_void_p), blob.size, C.byref(h)), "ac_unet_create")
+        self.handle = h
+        self._ws: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self._lib.ac_unet_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def set_debug(self, force_simt: bool) -> None:
+        check(self._lib.ac_unet_set_debug(self.handle, int(force_simt)))
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, spec: torch.Tensor) -> torch.Tensor:
+        """spec [B,dim_t,dim_f,4] float32 or bfloat16 (TFC layout) -> same shape/dtype."""
+        dtype = AC_F32 if spec.dtype == torch.float32 else AC_BF16
+        spec = spec.contiguous()
+        B = spec.shape[0]
+        assert tuple(spec.shape[1:]) == (self.geo.dim_t, self.geo.dim_f, 4), spec.shape
+        out = torch.empty_like(spec)
+        nbytes = int(self._lib.ac_unet_workspace_bytes(self.handle, B, dtype))
+        ws = self.workspace(nbytes)
+        check(self._lib.ac_unet_forward(self.handle, ptr(spec), ptr(out), B, dtype, ptr(ws), ws.numel(), stream_ptr()), "ac_unet_forward")
+        return out
+
+
+def make_chunk_descs(bounds: Sequence[Tuple[int, int, int, int]]):
+    """bounds: (chunk_start, chunk_end, eff_start, eff_end) per chunk, in samples."""
+    arr = (ChunkDesc * max(1, len(bounds)))()
+    for i, (cs, ce, es, ee) in enumerate(bounds):
+        arr[i] = ChunkDesc(int(cs), int(es), int(ee), int(ce - cs), 0)
+    return arr
+
+
+def separate_track(net: UNet, mix: torch.Tensor, bounds: Sequence[Tuple[int, int, int, int]], geom: MdxGeom, *,
+                   align_hop: int = 4096, output_is_vocal: bool = True, dtype: int = AC_F32, max_batch: int = 0):
+    """mix [n_ch, N] f32 on the GPU -> (vocal [N], instrumental [N], weight [N])."""
+    assert mix.dim() == 2 and mix.shape[0] in (1, 2)
+    mix = mix.contiguous().float()
+    n = mix.shape[1]
+    descs = make_chunk_descs(bounds)
+    tp = TrackParams(geom, int(align_hop), int(mix.shape[0]), int(bool(output_is_vocal)), int(dtype), int(max_batch), 0)
+    lib = net._lib
+    nbytes = int(lib.ac_track_workspace_bytes(net.handle, descs, len(bounds), C.byref(tp)))
+    ws = net.workspace(nbytes)
+    vocal = torch.empty(n, dtype=torch.float32, device=mix.device)
+    instr = torch.empty_like(vocal)
+    weight = torch.empty_like(vocal)
+    check(lib.ac_separate_track(net.handle, ptr(mix), n, descs, len(bounds), C.byref(tp), ptr(vocal), ptr(instr), ptr(weight),
+                                ptr(ws), ws.numel(), stream_ptr()), "ac_separate_track")
+    return vocal, instr, weight
+
+
+def stft_features(x: torch.Tensor, segments: Sequence[Tuple[int, int, int]], hop: int, sr: int, *, total_frames: int,
+                  want=("flatness", "onset_mean")) -> Dict[str, torch.Tensor]:
+    """segments: (start, len, frame_off).  Returns the requested series, each ``total_frames`` long."""
+    lib = _lib.init(_dev_index(x))
+    x = x.contiguous().float()
+    segs = (FeatSegment * len(segments))(*[FeatSegment(int(s), int(l), int(o)) for s, l, o in segments])
+    names = ("flatness", "onset_mean", "onset_median", "centroid", "low_ratio")
+    out = {k: torch.zeros(total_frames, dtype=torch.float32, device=x.device) for k in names if k in want}
+    nbytes = int(lib.ac_stft_features_workspace_bytes(segs, len(segments), hop))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib.ac_stft_features(ptr(x), segs, len(segments), hop, sr, *[ptr(out.get(k)) for k in names], ptr(ws), nbytes,
+                               stream_ptr()), "ac_stft_features")
+    return out

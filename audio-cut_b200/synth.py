@@ -55,6 +55,10 @@ def synth_track(seconds: float, *, sr: int = SR, seed: int = 0, stereo: bool = T
 
     mix = 0.6 * voc / (np.max(np.abs(voc)) + 1e-12) + 0.25 * noise + 0.35 * clicks
     mix *= 0.5 / (np.max(np.abs(mix)) + 1e-12)
+    # -70 dB white floor (as any real recording has): keeps every STFT bin well above the float32
+    # FFT rounding floor, so log-domain features (flatness, mel dB) are well conditioned
+    mix = mix + 3e-4 * rng.standard_normal(n)
+    mix *= 0.5 / (np.max(np.abs(mix)) + 1e-12)
     left = mix
     if not stereo:
         return left.astype(np.float32)

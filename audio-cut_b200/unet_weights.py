@@ -172,3 +172,33 @@ def save_npz(path: str, st: Dict[str, np.ndarray]) -> None:
 def load_npz(path: str) -> Dict[str, np.ndarray]:
     with np.load(path) as z:
         return {k: z[k] for k in z.files}
+
+
+def pack_blob(st: Dict[str, np.ndarray], geo: UNetGeometry = UNetGeometry()) -> np.ndarray:
+    """Flatten a state dict into the float32 blob ``ac_unet_create`` takes (include/audiocut_b200.h):
+    execution order, BatchNorm folded to (scale, shift), conv bias folded into shift."""
+    parts: List[np.ndarray] = []
+
+    def put(*arrs):
+        for a in arrs:
+            parts.append(np.ascontiguousarray(a, dtype=np.float32).reshape(-1))
+
+    def conv_bn(conv: str, bn: str):
+        put(st[conv + ".weight"], *fold_bn(st, bn, st.get(conv + ".bias")))
+
+    def block(p: str):
+        for j in range(geo.l):
+            conv_bn(f"{p}.tfc.H.{j}.0", f"{p}.tfc.H.{j}.1")
+        put(st[f"{p}.tdf.0.weight"], *fold_bn(st, f"{p}.tdf.1"))
+        put(st[f"{p}.tdf.3.weight"], *fold_bn(st, f"{p}.tdf.4"))
+
+    conv_bn("first_conv.0", "first_conv.1")
+    for i in range(geo.n):
+        block(f"encoding_blocks.{i}")
+        conv_bn(f"ds.{i}.0", f"ds.{i}.1")
+    block("bottleneck_block")
+    for i in range(geo.n):
+        conv_bn(f"us.{i}.0", f"us.{i}.1")
+        block(f"decoding_blocks.{i}")
+    put(st["final_conv.0.weight"], st["final_conv.0.bias"])
+    return np.concatenate(parts)

@@ -1,0 +1,168 @@
+/*
+ * audiocut_b200.h - C ABI of libaudiocut_b200.so, the B200 (sm_100a) implementation of the
+ * separation-and-feature hot path of BDMstudio/audio-cut.
+ *
+ * The reference is pure Python and has no FFI of its own for this path; the
+ * entry points below are what a ctypes binding inside the reference's files would bind.  Each
+ * one names the reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (torch tensors in the
+ *     Python host); h_* is a HOST pointer; nothing is allocated inside a hot-path call, the
+ *     caller passes a workspace sized by the matching *_workspace_bytes().
+ *   - stream is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - return value: 0 = ok, negative = error (AC_E_*); ac_last_error() gives the text
+ *     (thread-local).  There is NO CPU fallback: without a usable sm_100 device every call fails.
+ *   - spectrogram layout ("TFC"): [window][t = 0..dim_t)[f = 0..dim_f)[4] with the 4 innermost
+ *     values {L_re, L_im, R_re, R_im}.  It is a permutation of the ONNX tensor
+ *     [B,4,dim_f,dim_t] (backends.py:355-358): onnx[b][c][f][t] == tfc[b][t][f][c].
+ */
+#ifndef AUDIOCUT_B200_H
+#define AUDIOCUT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AC_API __attribute__((visibility("default")))
+#else
+#define AC_API
+#endif
+
+#define AC_OK 0
+#define AC_E_INVALID (-1)   /* bad argument */
+#define AC_E_CUDA (-2)      /* CUDA runtime/driver error */
+#define AC_E_NODEVICE (-3)  /* no sm_100 device */
+#define AC_E_WORKSPACE (-4) /* workspace too small */
+
+#define AC_F32 0  /* fp32 storage, fp32 FFMA math (the >=60 dB parity path) */
+#define AC_BF16 1 /* bf16 storage, tcgen05 tensor-core math with fp32 accumulation */
+
+/* Library / device bring-up.  Replaces torch.cuda device selection in gpu_pipeline.py:87-130. */
+AC_API int ac_init(int device);
+AC_API const char* ac_last_error(void);
+AC_API int ac_abi_version(void);
+/* Number of kernels this library has launched since load (for bench.py "gpu_launches"). */
+AC_API long long ac_launch_count(void);
+
+/* ---- framewise RMS ------------------------------------------------------------------------
+ * librosa.feature.rms(y, frame_length, hop_length, center=True, pad_mode="constant") as called at
+ * features_cache.py:182, pure_vocal_pause_detector.py:1111-1113 and :1397, seamless_splitter.py:1714
+ * and :1848, vocal_separator.py:483.  d_out has ac_frame_count(n, frame, hop, center) floats. */
+AC_API long long ac_frame_count(long long n, int frame, int hop, int center);
+AC_API int ac_frame_rms(const float* d_x, long long n, int frame, int hop, int center, float* d_out, void* stream);
+
+/* ---- MDX23 STFT / iSTFT ---------------------------------------------------------------------
+ * Conv_TDF_net_trim_model.stft / .istft of the external MVSEP-MDX23 inference.py, called at
+ * backends.py:355 and :376 (torch.stft / torch.istft, hann periodic, center, reflect pad). */
+typedef struct ac_mdx_geom {
+  int n_fft; /* 6144 (backends.py:264) or 7680 (Kim_Vocal geometry); any 2^a 3^b 5^c multiple of 2*hop.. */
+  int hop;   /* 1024 */
+  int dim_f; /* 3072 bins kept (<= n_fft/2) */
+  int dim_t; /* 256 frames; window length W = hop*(dim_t-1) */
+} ac_mdx_geom;
+
+/* d_wave [B][2][W] f32 -> d_spec [B][dim_t][dim_f][4] (dtype AC_F32 or AC_BF16). */
+AC_API int ac_stft_mdx(const float* d_wave, void* d_spec, int B, const ac_mdx_geom* g, int dtype, void* stream);
+/* d_spec [B][dim_t][dim_f][4] -> d_wave [B][2][W] f32 (full torch.istft output, no trim). */
+AC_API int ac_istft_mdx(const void* d_spec, float* d_wave, int B, const ac_mdx_geom* g, int dtype, void* stream);
+
+/* ---- TFC-TDF U-Net ---------------------------------------------------------------------------
+ * Replaces self._session.run(None, {input: stft}) at backends.py:358 (onnxruntime).  */
+typedef struct ac_unet_geom {
+  int dim_f, dim_t; /* 3072, 256 */
+  int dim_c;        /* 4 */
+  int g;            /* growth, 48 */
+  int n;            /* down/up levels, 5 (L = 11) */
+  int l;            /* convs per TFC, 3 */
+  int bn;           /* TDF bottleneck factor, 8 */
+} ac_unet_geom;
+typedef struct ac_unet ac_unet;
+
+/* h_blob: all parameters as float32 with BatchNorm folded to (scale, shift), in execution order:
+ *   first_conv:  W[g][dim_c], scale[g], shift[g]
+ *   for i in 0..n-1:  block(c_i, f_i);  ds_i: W[c+g][c][2][2], scale[c+g], shift[c+g]
+ *   block(c_n, f_n)                                                   (bottleneck)
+ *   for i in 0..n-1:  us_i: W[c_in][c_out][2][2], scale[c_out], shift[c_out];  block(c_out, f)
+ *   final_conv:  W[dim_c][g], bias[dim_c]
+ * block(c, f) = 3 x { W[c][c][3][3], scale[c], shift[c] },
+ *               tdf1 W[f/bn][f], scale[c], shift[c],  tdf2 W[f][f/bn], scale[c], shift[c]
+ * (audio-cut_b200/unet_weights.py:pack_blob builds it).  Uploads and repacks for both dtypes. */
+AC_API int ac_unet_create(const ac_unet_geom* g, const float* h_blob, size_t n_floats, ac_unet** out);
+AC_API void ac_unet_destroy(ac_unet* net);
+AC_API size_t ac_unet_param_floats(const ac_unet_geom* g);
+AC_API size_t ac_unet_workspace_bytes(const ac_unet* net, int B, int dtype);
+/* d_in, d_out: [B][dim_t][dim_f][4] in `dtype`.  d_out may alias d_in. */
+AC_API int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int B, int dtype, void* d_ws, size_t ws_bytes,
+                    void* stream);
+/* Test hook: 0 = let the library choose, 1 = force the CUDA-core kernels for every layer (bf16
+ * storage kept), so the tcgen05 kernels can be checked layer by layer. */
+AC_API int ac_unet_set_debug(ac_unet* net, int force_simt);
+
+/* ---- chunked separation of a whole track -------------------------------------------------------
+ * Replaces the chunk loop of EnhancedVocalSeparator._separate_with_pipeline
+ * (enhanced_vocal_separator.py:366-458) together with MDX23OnnxBackend.infer_chunk
+ * (backends.py:299-406): window build, STFT, network, iSTFT, trim/concat, crop, stem
+ * subtraction, mono mean, halo trim, accumulate, uniform average. */
+typedef struct ac_chunk_desc {
+  long long chunk_start; /* first track sample of the chunk: round(start_s*sr)                   */
+  long long eff_start;   /* effective region [eff_start, eff_end) in track samples (halo removed) */
+  long long eff_end;
+  int chunk_len;         /* samples in the chunk before align_hop padding                         */
+  int reserved;
+} ac_chunk_desc;
+
+typedef struct ac_track_params {
+  ac_mdx_geom mdx;
+  int align_hop;        /* 4096 (gpu_pipeline.align_hop / MDX23_ALIGN_HOP, backends.py:113)  */
+  int n_channels;       /* 1: mono duplicated to both network channels (backends.py:269-270); 2: stereo */
+  int output_is_vocal;  /* 1: network output is the vocal stem, other = mix - out (backends.py:395-401) */
+  int dtype;            /* AC_F32 / AC_BF16 */
+  int max_batch;        /* windows per network launch (0 = library default) */
+  int reserved;
+} ac_track_params;
+
+AC_API int ac_track_window_count(const ac_chunk_desc* h_chunks, int n_chunks, const ac_track_params* p);
+AC_API size_t ac_track_workspace_bytes(const ac_unet* net, const ac_chunk_desc* h_chunks, int n_chunks,
+                                const ac_track_params* p);
+/* d_mix [n_channels][n_samples]; d_vocal/d_instr/d_weight [n_samples] (overwritten).  On return
+ * (stream order) d_vocal and d_instr hold accum/max(weight,1) and d_weight the overlap counts. */
+AC_API int ac_separate_track(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
+                      int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr, float* d_weight,
+                      void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- STFT-2048 framewise features ----------------------------------------------------------------
+ * One pass over the signal per call; n_fft = 2048, periodic hann, center=True, zero padding
+ * (librosa.stft defaults).  Segments reproduce the per-call (= per-chunk) scope of
+ * power_to_db(top_db=80) in librosa.onset.onset_strength (features_cache.py:184): the clip
+ * reference is the maximum over the segment's own frames.
+ *   flatness   librosa.feature.spectral_flatness   features_cache.py:183, pure_vocal_pause_detector.py:1117
+ *   onset      librosa.onset.onset_strength (mean / median over 128 slaney mels)
+ *              features_cache.py:184, adaptive_vad_enhancer.py:61-67,143-148
+ *   centroid   librosa.feature.spectral_centroid    pure_vocal_pause_detector.py:434
+ *   low_ratio  _calculate_harmonic_ratio_direct     pure_vocal_pause_detector.py:937-959
+ * Any output pointer may be NULL.  Segment s covers samples [seg_start[s], seg_start[s]+seg_len[s])
+ * of d_x and writes n_s = 1 + seg_len/hop frames at frame offset seg_frame_off[s] of every output. */
+typedef struct ac_feat_segment {
+  long long start;     /* first sample                     */
+  long long len;       /* samples                          */
+  long long frame_off; /* first output frame of the segment */
+} ac_feat_segment;
+AC_API size_t ac_stft_features_workspace_bytes(const ac_feat_segment* h_segs, int n_segs, int hop);
+AC_API int ac_stft_features(const float* d_x, const ac_feat_segment* h_segs, int n_segs, int hop, int sr, float* d_flatness,
+                     float* d_onset_mean, float* d_onset_median, float* d_centroid, float* d_low_ratio, void* d_ws,
+                     size_t ws_bytes, void* stream);
+
+/* librosa.feature.zero_crossing_rate(y, frame_length, hop_length, center=True) (edge padding,
+ * |y| <= 1e-10 -> 0): pure_vocal_pause_detector.py:444. */
+AC_API int ac_zero_crossing_rate(const float* d_x, long long n, int frame, int hop, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOCUT_B200_H */

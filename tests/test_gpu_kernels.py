@@ -1,0 +1,215 @@
+"""Parity of every CUDA kernel against the CPU oracle, through the C ABI (run with -m gpu on a B200)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, sdr_db
+
+pytestmark = pytest.mark.gpu
+
+SR = 44100
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from audio_cut_b200 import ops as _ops
+
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def audio():
+    from audio_cut_b200 import synth
+
+    return synth.synth_track(21.0, seed=3)
+
+
+# --------------------------------------------------------------------------- framewise RMS / ZCR
+@pytest.mark.parametrize("frame,hop", [(4410, 2205), (1102, 441), (2048, 441), (2205, 882), (2048, 512), (100, 50)])
+def test_frame_rms_matches_oracle(ops, audio, frame, hop):
+    from oracle import features as OF
+
+    y = audio[0]
+    got = ops.frame_rms(torch.from_numpy(y).cuda(), frame, hop).cpu().numpy()
+    ref = OF.rms(y, frame, hop)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-7)  # north_star: features within 1e-4 relative
+
+
+def test_frame_rms_edge_cases(ops):
+    from oracle import features as OF
+
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 441, 2047, 2048, 2049, 5000):
+        y = rng.standard_normal(n).astype(np.float32)
+        # unaligned device pointer (slice of a larger tensor)
+        buf = torch.zeros(n + 3, device="cuda")
+        buf[3:] = torch.from_numpy(y).cuda()
+        got = ops.frame_rms(buf[3:], 2048, 441).cpu().numpy()
+        np.testing.assert_allclose(got, OF.rms(y, 2048, 441), rtol=1e-4, atol=1e-7)
+
+
+def test_zero_crossing_rate(ops, audio):
+    from oracle import features as OF
+
+    y = audio[0][: 5 * SR].copy()
+    y[1000:3000] = 0.0
+    got = ops.zero_crossing_rate(torch.from_numpy(y).cuda(), 2048, 441).cpu().numpy()
+    np.testing.assert_allclose(got, OF.zero_crossing_rate(y, 2048, 441), rtol=0, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- MDX STFT / iSTFT
+GEOMS = [(512, 128, 224, 32), (1280, 256, 512, 64), (640, 128, 256, 32), (6144, 1024, 3072, 256), (7680, 1024, 3072, 256)]
+
+
+@pytest.mark.parametrize("n_fft,hop,dim_f,dim_t", GEOMS)
+def test_stft_mdx_matches_torch(ops, n_fft, hop, dim_f, dim_t):
+    from oracle import mdx
+
+    g = mdx.MdxGeometry(n_fft, hop, dim_f, dim_t)
+    B = 2
+    x = torch.randn(B, 2, g.chunk_size, generator=torch.Generator().manual_seed(1)) * 0.3
+    ref = mdx.stft(x, g)  # [B,4,F,T]
+    got = ops.stft_mdx(x.cuda(), ops.mdx_geom(n_fft, hop, dim_f, dim_t))
+    got = ops.tfc_to_onnx(got).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(ref.numpy(), got.numpy()) < 2e-6
+    assert sdr_db(ref.numpy(), got.numpy()) > 110
+
+
+@pytest.mark.parametrize("n_fft,hop,dim_f,dim_t", GEOMS)
+def test_istft_mdx_matches_torch(ops, n_fft, hop, dim_f, dim_t):
+    from oracle import mdx
+
+    g = mdx.MdxGeometry(n_fft, hop, dim_f, dim_t)
+    B = 2
+    spec = torch.randn(B, 4, dim_f, dim_t, generator=torch.Generator().manual_seed(2))
+    ref = mdx.istft(spec, g)
+    got = ops.istft_mdx(ops.onnx_to_tfc(spec.cuda()), ops.mdx_geom(n_fft, hop, dim_f, dim_t)).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(ref.numpy(), got.numpy()) < 5e-6
+    assert sdr_db(ref.numpy(), got.numpy()) > 100
+
+
+def test_stft_bf16_output(ops):
+    from oracle import mdx
+
+    g = mdx.MdxGeometry(1280, 256, 512, 64)
+    x = torch.randn(1, 2, g.chunk_size, generator=torch.Generator().manual_seed(1)) * 0.3
+    ref = mdx.stft(x, g)
+    got = ops.tfc_to_onnx(ops.stft_mdx(x.cuda(), ops.mdx_geom(1280, 256, 512, 64), dtype=1)).float().cpu()
+    assert sdr_db(ref.numpy(), got.numpy()) > 45  # bf16 rounding of the output only
+
+
+# --------------------------------------------------------------------------- U-Net
+def _unet_case(ops, dim_f, dim_t, g, B, seed=0):
+    from audio_cut_b200 import unet_weights as uw
+    from oracle import unet as ounet
+
+    geo = uw.UNetGeometry(dim_f=dim_f, dim_t=dim_t, g=g)
+    st = uw.random_state(geo, seed=1234)
+    net = ops.UNet(st, geo)
+    ref_net = ounet.build_net(st, dim_f, dim_t, g)
+    x = torch.randn(B, 4, dim_f, dim_t, generator=torch.Generator().manual_seed(seed)) * 3.0
+    with torch.no_grad():
+        ref = ref_net(x)
+    return net, x, ref
+
+
+@pytest.mark.parametrize("dim_f,dim_t,g,B", [(256, 32, 16, 2), (512, 64, 32, 1), (256, 32, 48, 3)])
+def test_unet_fp32_matches_oracle(ops, dim_f, dim_t, g, B):
+    net, x, ref = _unet_case(ops, dim_f, dim_t, g, B)
+    got = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()))).cpu()
+    assert got.shape == ref.shape
+    s = sdr_db(ref.numpy(), got.numpy())
+    assert s > 80, s  # north_star asks >= 60 dB on stems for the fp32 path
+
+
+@pytest.mark.parametrize("dim_f,dim_t,g,B", [(256, 32, 16, 2), (512, 64, 48, 1)])
+def test_unet_bf16_simt_close_to_oracle(ops, dim_f, dim_t, g, B):
+    net, x, ref = _unet_case(ops, dim_f, dim_t, g, B)
+    net.set_debug(True)
+    got = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()).bfloat16())).float().cpu()
+    s = sdr_db(ref.numpy(), got.numpy())
+    assert s > 30, s
+
+
+def test_unet_full_geometry_fp32(ops):
+    net, x, ref = _unet_case(ops, 3072, 256, 48, 1)
+    got = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()))).cpu()
+    s = sdr_db(ref.numpy(), got.numpy())
+    assert s > 80, s
+
+
+# --------------------------------------------------------------------------- whole-track separation
+def _track_case(ops, n_fft, hop, dim_f, dim_t, g, seconds, stereo, sr, chunk_s, overlap_s, halo_s, align_hop, dtype=0,
+                output_is_vocal=True):
+    from audio_cut_b200 import synth, unet_weights as uw
+    from oracle import mdx, pipeline, planner
+    from oracle import unet as ounet
+
+    geo = uw.UNetGeometry(dim_f=dim_f, dim_t=dim_t, g=g)
+    st = uw.random_state(geo, seed=1234)
+    net = ops.UNet(st, geo)
+    ref_net = ounet.build_net(st, dim_f, dim_t, g)
+    mg = mdx.MdxGeometry(n_fft, hop, dim_f, dim_t)
+    audio = synth.synth_track(seconds, sr=sr, seed=5, stereo=stereo)
+    total = audio.shape[-1]
+    plans = planner.chunk_schedule(total / float(sr), chunk_s, overlap_s, halo_s)
+    bounds = [planner.sample_bounds(p, sr, total) for p in plans]
+    otype = "vocal" if output_is_vocal else "instrumental"
+    ref_v, ref_i = pipeline.separate_track(
+        audio, lambda ch: mdx.infer_chunk(ch, ref_net, mg, align_hop=align_hop, output_type=otype), sr=sr, plans=plans)
+    mix = torch.from_numpy(audio if stereo else audio[None, :]).cuda()
+    v, i, w = ops.separate_track(net, mix, bounds, ops.mdx_geom(n_fft, hop, dim_f, dim_t), align_hop=align_hop,
+                                 output_is_vocal=output_is_vocal, dtype=dtype)
+    return ref_v, ref_i, v.cpu().numpy(), i.cpu().numpy(), w.cpu().numpy(), bounds
+
+
+@pytest.mark.parametrize("stereo,output_is_vocal", [(True, True), (False, True), (True, False)])
+def test_separate_track_small_geometry(ops, stereo, output_is_vocal):
+    # 8 kHz, 2 s chunks: 11 chunks with ragged tail, seams of weight 2
+    ref_v, ref_i, v, i, w, bounds = _track_case(ops, 640, 128, 256, 32, 16, 17.3, stereo, 8000, 2.0, 0.5, 0.1, 256,
+                                               output_is_vocal=output_is_vocal)
+    assert sdr_db(ref_v, v) > 60 and sdr_db(ref_i, i) > 60, (sdr_db(ref_v, v), sdr_db(ref_i, i))
+    wref = np.zeros_like(w)
+    for cs, ce, es, ee in bounds:
+        wref[es:ee] += 1
+    np.testing.assert_array_equal(w, wref)
+    assert w.max() == 2 and w.min() == 1
+
+
+def test_separate_track_full_geometry_30s_stereo(ops):
+    """BASELINE config 1: 30 s stereo, Kim_Vocal geometry (n_fft 7680), 4 chunks / 8 windows."""
+    ref_v, ref_i, v, i, w, bounds = _track_case(ops, 7680, 1024, 3072, 256, 48, 30.0, True, 44100, 10.0, 2.5, 0.5, 4096)
+    assert len(bounds) == 4
+    sv, si = sdr_db(ref_v, v), sdr_db(ref_i, i)
+    assert sv > 60 and si > 60, (sv, si)
+
+
+# --------------------------------------------------------------------------- STFT-2048 features
+@pytest.mark.parametrize("hop", [2205, 441, 512])
+def test_stft_features_match_oracle(ops, audio, hop):
+    from oracle import features as OF
+
+    y = audio[0]
+    # two independent segments (chunks): the top_db clip reference is per segment
+    segs = [(0, 10 * SR), (7 * SR + 11, 9 * SR + 5)]
+    offs, total = [], 0
+    for s, l in segs:
+        offs.append(total)
+        total += 1 + l // hop
+    out = ops.stft_features(torch.from_numpy(y).cuda(), [(s, l, o) for (s, l), o in zip(segs, offs)], hop, SR,
+                            total_frames=total, want=("flatness", "onset_mean", "onset_median", "centroid", "low_ratio"))
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for (s, l), o in zip(segs, offs):
+        seg = y[s : s + l]
+        n = 1 + l // hop
+        sl = slice(o, o + n)
+        np.testing.assert_allclose(out["flatness"][sl], OF.spectral_flatness(seg, 2048, hop), rtol=1e-4, atol=1e-9)
+        ref_mean = OF.onset_strength(seg, SR, hop, aggregate=np.mean)
+        ref_med = OF.onset_strength(seg, SR, hop, aggregate=np.median)
+        np.testing.assert_allclose(out["onset_mean"][sl], ref_mean, rtol=1e-4, atol=1e-4 * ref_mean.max())
+        np.testing.assert_allclose(out["onset_median"][sl], ref_med, rtol=1e-4, atol=1e-4 * max(ref_med.max(), 1e-3))
+        np.testing.assert_allclose(out["centroid"][sl], OF.spectral_centroid(seg, SR, 2048, hop), rtol=1e-4)
+        np.testing.assert_allclose(out["low_ratio"][sl], OF.low_band_ratio(seg, 2048, hop), rtol=1e-4, atol=1e-7)
