@@ -19,7 +19,7 @@ EXPORTS = [
     "ac_stft_mdx", "ac_istft_mdx", "ac_unet_create", "ac_unet_destroy", "ac_unet_param_floats",
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
     "ac_track_workspace_bytes", "ac_separate_track", "ac_stft_features_workspace_bytes", "ac_stft_features",
-    "ac_zero_crossing_rate",
+    "ac_zero_crossing_rate", "ac_debug_tc_aborted",
 ]
 
 
@@ -78,6 +78,7 @@ def load() -> C.CDLL:
     lib.ac_unet_workspace_bytes.argtypes, lib.ac_unet_workspace_bytes.restype = [vp, i, i], sz
     lib.ac_unet_forward.argtypes, lib.ac_unet_forward.restype = [vp, vp, vp, i, i, vp, sz, vp], i
     lib.ac_unet_set_debug.argtypes, lib.ac_unet_set_debug.restype = [vp, i], i
+    lib.ac_debug_tc_aborted.argtypes, lib.ac_debug_tc_aborted.restype = [], i
     lib.ac_track_window_count.argtypes = [C.POINTER(ChunkDesc), i, C.POINTER(TrackParams)]
     lib.ac_track_window_count.restype = i
     lib.ac_track_workspace_bytes.argtypes = [vp, C.POINTER(ChunkDesc), i, C.POINTER(TrackParams)]

@@ -239,6 +239,9 @@ extern "C" void ac_unet_destroy(ac_unet* net) {
   delete net;
 }
 
+namespace ac { int tc_check_abort(); }
+extern "C" int ac_debug_tc_aborted(void) { return ac::tc_check_abort(); }
+
 extern "C" int ac_unet_set_debug(ac_unet* net, int force_simt) {
   AC_REQUIRE(net, "null");
   net->force_simt = force_simt;

@@ -1,8 +1,459 @@
-// tcgen05 (sm_100a tensor core) kernels of the U-Net - placeholder until the kernel lands.
+// tcgen05 / TMEM / TMA implementation of the 3x3 convolutions of the TFC blocks (75 % of the
+// network's FLOPs), bf16 operands, fp32 accumulation in tensor memory.
+//
+// Implicit GEMM, output stationary:  D[128 positions][NT out-channels] += A_tap[128][16] * W_tap[16][NT]
+//   * activations are channels-last [B][T][F][C]; an A operand tile is staged by TMA as
+//     [C/8 channel groups][130 positions][8 channels] = the canonical no-swizzle K-major UMMA
+//     layout with 16-byte rows packed back to back (SBO = 128 B), so the three horizontal taps are
+//     the SAME smem tile addressed with the descriptor start advanced by 16 B per position, and
+//     conv zero padding is TMA out-of-bounds fill (f = -1, F and t = -1, T);
+//   * weights are pre-packed on the host into the exact smem image ([K/8][NT][8], K-major) and
+//     fetched with one 1-D bulk copy per pipeline stage;
+//   * one CTA per SM, persistent over work units (n-tile, b, t, group of MT 128-position tiles);
+//     MT accumulators live in TMEM so every weight tile fetched from L2 is reused MT times;
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 =
+//     epilogue (tcgen05.ld -> scale/shift/ReLU -> bf16 -> global); smem ring and (when the
+//     accumulators fit twice) a double-buffered TMEM hand-off, all through mbarriers.
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+
 #include "unet_kernels.cuh"
+
 namespace ac {
-int tc_conv3x3_supported(int, int, int) { return AC_E_INVALID; }
-int tc_conv3x3_pack(const float*, int, TcConvWeights** out) { *out = nullptr; return AC_OK; }
-void tc_conv3x3_free(TcConvWeights*) {}
-int launch_tc_conv3x3(const TcConvArgs&, cudaStream_t) { set_error("tc conv not built"); return AC_E_INVALID; }
+
+// ------------------------------------------------------------------------------------------------
+// device helpers (inline PTX)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a wrong descriptor or byte count must not hang the GPU.  On timeout the flag is
+// raised and every role drains out of its loops.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((it & 1023u) == 1023u && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  return false;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//   [0,14) start>>4  [16,30) LBO>>4 (byte distance between the two 8-element K halves)
+//   [32,46) SBO>>4 (byte distance between 8-row groups)  [46,48) version = 1  [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 192;  // 6 warps
+constexpr int kTileM = 128;
+constexpr int kRowPos = kTileM + 2;  // positions per staged A tile (1-position halo each side)
+constexpr int kRowStride = 136;      // rows reserved per channel group: 136*16 B keeps every TMA destination 128-B aligned
+
+struct TcCfg {
+  int C, NT, nsplit, MT, KC, nkc, stages, nbuf;
+  int a_tile_bytes;   // one M tile of one stage: (KC/8) * 136 * 16 (130 rows written)
+  int b_stage_bytes;  // 3 * KC * NT * 2
+  int stage_bytes;    // MT * a_tile_bytes + b_stage_bytes, rounded up to 128
+  int smem_bytes;
+};
+
+struct TcParams {
+  TcCfg cfg;
+  int nB, T, F;
+  int n_fg;       // groups of MT tiles per row
+  int n_units;    // nsplit * nB * T * n_fg
+  const __nv_bfloat16* wpack;
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out;
+  int* abort_flag;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcCfg& c = p.cfg;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [stages]
+  uint64_t* empty = full + 8;                           // [stages]
+  uint64_t* tfull = full + 16;                          // [nbuf]
+  uint64_t* tempty = full + 20;                         // [nbuf]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
+  uint8_t* stage0 = smem + 1024;
+  volatile int* abort_flag = p.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < c.nbuf; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int steps = 3 * c.nkc;  // pipeline stages consumed per work unit (dt x channel chunk)
+
+  auto decode = [&](int u, int& nt, int& b, int& t, int& f0) {
+    const int fg = u % p.n_fg;
+    int q = u / p.n_fg;
+    t = q % p.T;
+    q /= p.T;
+    b = q % p.nB;
+    nt = q / p.nB;
+    f0 = fg * c.MT * kTileM;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
+        int nt, b, t, f0;
+        decode(u, nt, b, t, f0);
+        for (int dt = 0; dt < 3 && alive; ++dt) {
+          for (int kc = 0; kc < c.nkc; ++kc) {
+            if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+            uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
+            mbar_expect_tx(&full[s], (uint32_t)(c.MT * (c.KC / 8) * (kRowPos * 16) + c.b_stage_bytes));
+            for (int mt = 0; mt < c.MT; ++mt) {
+              for (int kg = 0; kg < c.KC / 8; ++kg) {
+                tma_load_4d(st + mt * c.a_tile_bytes + kg * (kRowStride * 16), &in_map, &full[s], kc * c.KC + kg * 8,
+                            f0 + mt * kTileM - 1, t + dt - 1, b);
+              }
+            }
+            const __nv_bfloat16* wsrc =
+                p.wpack + ((size_t)((nt * 3 + dt) * c.nkc + kc)) * (size_t)(3 * c.KC * c.NT);
+            bulk_load_1d(st + c.MT * c.a_tile_bytes, wsrc, (uint32_t)c.b_stage_bytes, &full[s]);
+            if (++s == c.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(c.NT);
+      const uint32_t a_lbo = kRowStride * 16, b_lbo = (uint32_t)c.NT * 16;
+      int s = 0;
+      uint32_t ph = 0;
+      int buf = 0;
+      uint32_t tph = 0;
+      bool alive = true;
+      for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
+        if (!mbar_wait(&tempty[buf], tph ^ 1, abort_flag)) break;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * c.MT * c.NT);
+        for (int step = 0; step < steps; ++step) {
+          if (!mbar_wait(&full[s], ph, abort_flag)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)(c.MT * c.a_tile_bytes);
+          for (int df = 0; df < 3; ++df) {
+            for (int mt = 0; mt < c.MT; ++mt) {
+              for (int k = 0; k < c.KC / 16; ++k) {
+                const uint64_t ad = make_desc(sa + mt * c.a_tile_bytes + df * 16 + k * 2 * a_lbo, a_lbo, 128);
+                const uint64_t bd = make_desc(sb + df * (c.KC * c.NT * 2) + k * 2 * b_lbo, b_lbo, 128);
+                umma_f16(acc0 + (uint32_t)(mt * c.NT), ad, bd, idesc, (step | df | k) != 0);
+              }
+            }
+          }
+          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          if (++s == c.stages) { s = 0; ph ^= 1; }
+        }
+        if (!alive) break;
+        umma_commit(&tfull[buf]);  // accumulators complete
+        if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    int buf = 0;
+    uint32_t tph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int nt, b, t, f0;
+      decode(u, nt, b, t, f0);
+      if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
+      tc_fence_after();
+      const int n0 = nt * c.NT;
+      for (int mt = 0; mt < c.MT; ++mt) {
+        const int f = f0 + mt * kTileM + quad * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
+        __nv_bfloat16* dst = p.out + (((size_t)b * p.T + t) * p.F + f) * c.C + n0;
+        for (int j = 0; j < c.NT; j += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j, r);
+          tmem_ld_wait();
+          if (f < p.F) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = n0 + j + 2 * e;
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), __ldg(p.scale + ch), __ldg(p.shift + ch)), 0.f);
+              const float v1 =
+                  fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), __ldg(p.scale + ch + 1), __ldg(p.shift + ch + 1)), 0.f);
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + j + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcConvWeights {
+  int C;
+  TcCfg cfg;
+  __nv_bfloat16* d_pack;
+};
+
+static bool make_cfg(int C, int F, TcCfg& c) {
+  if (C % 16 || C < 16 || C > 512) return false;
+  c.C = C;
+  c.nsplit = 1;
+  if (C > 160) {
+    c.nsplit = 0;
+    for (int s = 2; s <= 8; ++s)
+      if (C % (16 * s) == 0 && C / s <= 160) { c.nsplit = s; break; }
+    if (!c.nsplit) return false;
+  }
+  c.NT = C / c.nsplit;
+  const int mt2 = 256 / c.NT, mt1 = 512 / c.NT;
+  if (mt2 >= 2) { c.MT = mt2 > 4 ? 4 : mt2; c.nbuf = 2; }
+  else { c.MT = mt1 > 4 ? 4 : mt1; c.nbuf = 1; }
+  const int tiles_per_row = (F + kTileM - 1) / kTileM;
+  if (c.MT > tiles_per_row) c.MT = tiles_per_row;
+  c.KC = 16;
+  for (int k = 48; k >= 16; k -= 16)
+    if (C % k == 0) { c.KC = k; break; }
+  c.nkc = C / c.KC;
+  c.a_tile_bytes = (c.KC / 8) * kRowStride * 16;
+  c.b_stage_bytes = 3 * c.KC * c.NT * 2;
+  c.stage_bytes = (int)align_up((size_t)c.MT * c.a_tile_bytes + c.b_stage_bytes, 128);
+  const int budget = 220 * 1024 - 1024;
+  c.stages = budget / c.stage_bytes;
+  if (c.stages > 8) c.stages = 8;
+  if (c.stages < 2) return false;
+  c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+  return true;
+}
+
+int tc_conv3x3_supported(int T, int F, int C) {
+  TcCfg c;
+  (void)T;
+  return make_cfg(C, F, c) ? AC_OK : AC_E_INVALID;
+}
+
+int tc_conv3x3_pack(const float* h_w, int C, TcConvWeights** out) {
+  *out = nullptr;
+  TcCfg c;
+  if (!make_cfg(C, 1 << 20, c)) return AC_OK;  // unsupported shape: caller keeps the CUDA-core kernel
+  // [nt][dt][kc][df][KC/8][NT][8]  <-  W[co][ci][kh=dt][kw=df]
+  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  size_t o = 0;
+  for (int nt = 0; nt < c.nsplit; ++nt)
+    for (int dt = 0; dt < 3; ++dt)
+      for (int kc = 0; kc < c.nkc; ++kc)
+        for (int df = 0; df < 3; ++df)
+          for (int kg = 0; kg < c.KC / 8; ++kg)
+            for (int n = 0; n < c.NT; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int co = nt * c.NT + n, ci = kc * c.KC + kg * 8 + e;
+                pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df]);
+              }
+  TcConvWeights* w = new TcConvWeights();
+  w->C = C;
+  w->d_pack = nullptr;
+  if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
+      cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tc weight upload failed");
+    delete w;
+    return AC_E_CUDA;
+  }
+  *out = w;
+  return AC_OK;
+}
+
+void tc_conv3x3_free(TcConvWeights* w) {
+  if (!w) return;
+  if (w->d_pack) cudaFree(w->d_pack);
+  delete w;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int* g_abort_flag = nullptr;  // device
+static int* g_abort_host = nullptr;  // pinned mirror
+
+int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
+  AC_REQUIRE(a.w && a.w->C == a.C, "tc conv: weights do not match the layer");
+  TcCfg c;
+  AC_REQUIRE(make_cfg(a.C, a.F, c), "tc conv: unsupported shape");
+  // the packing depends only on (C): NT, KC, nkc, nsplit are functions of C alone
+  EncodeTiledFn enc = get_encode();
+  AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
+  if (!g_abort_flag) {
+    AC_CHECK_CUDA(cudaMalloc(&g_abort_flag, sizeof(int)));
+    AC_CHECK_CUDA(cudaMemset(g_abort_flag, 0, sizeof(int)));
+    AC_CHECK_CUDA(cudaMallocHost(&g_abort_host, sizeof(int)));
+    *g_abort_host = 0;
+  }
+  CUtensorMap map;
+  const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.F, (cuuint64_t)a.T, (cuuint64_t)a.nB};
+  const cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
+  const cuuint32_t box[4] = {8, (cuuint32_t)kRowPos, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return AC_E_CUDA;
+  }
+  TcParams p;
+  p.cfg = c;
+  p.nB = a.nB; p.T = a.T; p.F = a.F;
+  p.n_fg = ((a.F + kTileM - 1) / kTileM + c.MT - 1) / c.MT;
+  p.n_units = c.nsplit * a.nB * a.T * p.n_fg;
+  p.wpack = a.w->d_pack;
+  p.scale = a.scale; p.shift = a.shift;
+  p.out = a.out;
+  p.abort_flag = g_abort_flag;
+  static int max_smem_set = 0;
+  if (max_smem_set < c.smem_bytes) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    max_smem_set = 227 * 1024;
+  }
+  int grid = device_sm_count();
+  if (grid > p.n_units) grid = p.n_units;
+  tc_conv3x3_kernel<<<grid, kTcThreads, c.smem_bytes, st>>>(map, p);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+// returns 1 if any tensor-core kernel hit its wait watchdog since the last call (synchronises)
+int tc_check_abort() {
+  if (!g_abort_flag) return 0;
+  int v = 0;
+  if (cudaMemcpy(&v, g_abort_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (v) cudaMemset(g_abort_flag, 0, sizeof(int));
+  return v;
+}
+
 }  // namespace ac

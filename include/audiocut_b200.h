@@ -103,6 +103,9 @@ AC_API int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int B, i
 /* Test hook: 0 = let the library choose, 1 = force the CUDA-core kernels for every layer (bf16
  * storage kept), so the tcgen05 kernels can be checked layer by layer. */
 AC_API int ac_unet_set_debug(ac_unet* net, int force_simt);
+/* Test hook: synchronises and returns 1 when a tensor-core kernel gave up on an mbarrier wait
+ * (a pipeline bug; the watchdog keeps such a bug from hanging the GPU), 0 otherwise. */
+AC_API int ac_debug_tc_aborted(void);
 
 /* ---- chunked separation of a whole track -------------------------------------------------------
  * Replaces the chunk loop of EnhancedVocalSeparator._separate_with_pipeline

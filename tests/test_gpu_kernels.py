@@ -213,3 +213,34 @@ def test_stft_features_match_oracle(ops, audio, hop):
         np.testing.assert_allclose(out["onset_median"][sl], ref_med, rtol=1e-4, atol=1e-4 * max(ref_med.max(), 1e-3))
         np.testing.assert_allclose(out["centroid"][sl], OF.spectral_centroid(seg, SR, 2048, hop), rtol=1e-4)
         np.testing.assert_allclose(out["low_ratio"][sl], OF.low_band_ratio(seg, 2048, hop), rtol=1e-4, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- tcgen05 kernels
+def _tc_aborted():
+    from audio_cut_b200 import _lib
+
+    return _lib.load().ac_debug_tc_aborted()
+
+
+@pytest.mark.parametrize("dim_f,dim_t,g,B", [(256, 32, 16, 2), (512, 64, 48, 1), (512, 32, 32, 2)])
+def test_unet_tcgen05_matches_simt(ops, dim_f, dim_t, g, B):
+    """Same bf16 storage, same fp32 accumulation: tensor-core layers vs the CUDA-core kernels."""
+    net, x, ref = _unet_case(ops, dim_f, dim_t, g, B)
+    xin = ops.onnx_to_tfc(x.cuda()).bfloat16()
+    net.set_debug(True)
+    simt = net.forward(xin).float().cpu().numpy()
+    net.set_debug(False)
+    tc = net.forward(xin).float().cpu().numpy()
+    assert _tc_aborted() == 0, "a tcgen05 kernel hit its mbarrier watchdog"
+    s = sdr_db(simt, tc)
+    assert s > 40, s
+    s_ref = sdr_db(ops.onnx_to_tfc(ref).numpy(), tc)
+    assert s_ref > 30, s_ref
+
+
+def test_unet_tcgen05_full_geometry(ops):
+    net, x, ref = _unet_case(ops, 3072, 256, 48, 1)
+    tc = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()).bfloat16())).float().cpu()
+    assert _tc_aborted() == 0
+    s = sdr_db(ref.numpy(), tc.numpy())
+    assert s > 30, s
