@@ -26,12 +26,15 @@ def frame_count(n: int, frame: int, hop: int, center: bool = True) -> int:
     return int(_lib.load().ac_frame_count(int(n), int(frame), int(hop), int(bool(center))))
 
 
-def frame_rms(x: torch.Tensor, frame_length: int, hop_length: int, center: bool = True) -> torch.Tensor:
-    """librosa.feature.rms(y, frame_length, hop_length)[0] on the GPU."""
+def frame_rms(x: torch.Tensor, frame_length: int, hop_length: int, center: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """librosa.feature.rms(y, frame_length, hop_length)[0] on the GPU (``out``: preallocated float32 slice)."""
     lib = _lib.init(_dev_index(x))
     x = x.contiguous().float()
     n = x.numel()
-    out = torch.empty(frame_count(n, frame_length, hop_length, center), dtype=torch.float32, device=x.device)
+    nf = frame_count(n, frame_length, hop_length, center)
+    if out is None:
+        out = torch.empty(nf, dtype=torch.float32, device=x.device)
+    assert out.numel() == nf and out.is_contiguous() and out.dtype == torch.float32
     if out.numel():
         check(lib.ac_frame_rms(ptr(x), n, frame_length, hop_length, int(center), ptr(out), stream_ptr()), "ac_frame_rms")
     return out

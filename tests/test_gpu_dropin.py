@@ -1,0 +1,107 @@
+"""The reference-facing drop-ins (separator / backend / feature builder) end to end on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import sdr_db
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_backend(precision="fp32", stereo_sr=8000):
+    from audio_cut_b200 import unet_weights as uw
+    from audio_cut_b200.backends import B200Mdx23Backend
+
+    geo = uw.UNetGeometry(dim_f=256, dim_t=32, g=16)
+    st = uw.random_state(geo)
+    be = B200Mdx23Backend(weights=st, geometry=geo, n_fft=640, hop=128, align_hop=256, precision=precision, output_type="vocal")
+    be.load_model()
+    return be, st, geo
+
+
+def test_backend_infer_chunk_matches_oracle():
+    from audio_cut_b200 import synth
+    from oracle import mdx
+    from oracle import unet as ounet
+
+    be, st, geo = _small_backend()
+    ref_net = ounet.build_net(st, geo.dim_f, geo.dim_t, geo.g)
+    mg = mdx.MdxGeometry(640, 128, 256, 32)
+    audio = synth.synth_track(2.5, sr=8000, seed=2)
+    for chunk in (audio, audio[0], audio[0][:777]):
+        out = be.infer_chunk(chunk)
+        rv, ri = mdx.infer_chunk(chunk, ref_net, mg, align_hop=256, output_type="vocal")
+        assert out.vocal.shape == rv.shape and out.vocal.dtype == np.float32
+        assert sdr_db(rv, out.vocal) > 60 and sdr_db(ri, out.instrumental) > 60
+    m = be.get_performance_metrics(reset=True)
+    assert m["chunks"] == 3 and m["compute_ms"] > 0
+    assert be.describe_input() == {"name": "input", "shape": [1, 4, 256, 32]}
+    with pytest.raises(Exception):
+        be.fallback_to_cpu()
+
+
+def test_separator_dropin_matches_oracle_pipeline():
+    from audio_cut_b200 import synth
+    from audio_cut_b200.gpu_pipeline import PipelineConfig
+    from audio_cut_b200.separator import B200VocalSeparator, SeparationResult
+    from oracle import mdx, pipeline, planner
+    from oracle import unet as ounet
+
+    sr = 8000
+    be, st, geo = _small_backend()
+    cfg = PipelineConfig(chunk_s=4.0, overlap_s=1.0, halo_s=0.25, align_hop=256)
+    sep = B200VocalSeparator(sr, backend=be, pipeline_config=cfg)
+    audio = synth.synth_track(17.3, sr=sr, seed=4, stereo=False)  # the pipeline is mono-in
+    res = sep.separate_for_detection(audio)
+    assert isinstance(res, SeparationResult) and res.backend_used == "B200Mdx23Backend"
+    assert res.vocal_track.shape == audio.shape and res.vocal_track.dtype == np.float32
+
+    ref_net = ounet.build_net(st, geo.dim_f, geo.dim_t, geo.g)
+    mg = mdx.MdxGeometry(640, 128, 256, 32)
+    plans = planner.chunk_schedule(len(audio) / float(sr), 4.0, 1.0, 0.25)
+    rv, ri = pipeline.separate_track(audio, lambda ch: mdx.infer_chunk(ch, ref_net, mg, align_hop=256), sr=sr, plans=plans)
+    assert sdr_db(rv, res.vocal_track) > 60 and sdr_db(ri, res.instrumental_track) > 60
+
+    # feature cache vs the oracle's restatement of ChunkFeatureBuilder
+    cf = pipeline.ChunkFeatures(sr)
+    for p in plans:
+        cs, ce, _, _ = planner.sample_bounds(p, sr, len(audio))
+        cf.add_chunk(p, audio[cs:ce])
+    ref = cf.finalize()
+    fc = res.feature_cache
+    assert fc.hop_length == cf.hop_length and fc.rms_series.shape == ref["rms_series"].shape
+    np.testing.assert_allclose(fc.rms_series, ref["rms_series"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(fc.spectral_flatness, ref["spectral_flatness"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(fc.onset_envelope, ref["onset_envelope"], rtol=1e-4, atol=1e-4 * ref["onset_envelope"].max())
+    np.testing.assert_array_equal(fc.onset_frames, ref["onset_frames"])
+    np.testing.assert_allclose(fc.mdd_series, ref["mdd_series"], rtol=2e-4, atol=1e-6)
+    assert abs(fc.global_mdd - ref["global_mdd"]) < 1e-4
+    assert fc.bpm_features is not None and fc.tempo_curve.shape == fc.rms_series.shape
+
+    meta = res.gpu_meta
+    for k in ("gpu_pipeline_enabled", "gpu_pipeline_used", "gpu_pipeline_device", "gpu_pipeline_chunks",
+              "gpu_pipeline_processed_chunks", "gpu_pipeline_h2d_ms", "gpu_pipeline_dtoh_ms", "gpu_pipeline_compute_ms",
+              "gpu_pipeline_peak_mem_bytes", "gpu_pipeline_chunk_invocations", "mdx23_output_type", "silero_vad_segments",
+              "gpu_pipeline_mdx23_input", "gpu_pipeline_device_name", "gpu_pipeline_config"):
+        assert k in meta, k
+    assert meta["gpu_pipeline_used"] is True and meta["gpu_pipeline_processed_chunks"] == len(plans)
+    assert set(res.quality_metrics) == {"vocal_presence_cut_points_sec", "vocal_presence_cut_points_samples",
+                                        "vocal_presence_segments", "pure_music_segments"}
+
+
+def test_vad_hook_is_called_per_chunk():
+    from audio_cut_b200 import synth
+    from audio_cut_b200.gpu_pipeline import PipelineConfig
+    from audio_cut_b200.separator import B200VocalSeparator
+
+    be, _, _ = _small_backend()
+    seen = []
+
+    def vad(plan, vocal_chunk, sr):
+        seen.append((plan.index, len(vocal_chunk)))
+        return [{"start": plan.start_s, "end": plan.end_s}]
+
+    sep = B200VocalSeparator(8000, backend=be, pipeline_config=PipelineConfig(chunk_s=4.0, overlap_s=1.0, halo_s=0.25, align_hop=256), vad_fn=vad)
+    res = sep.separate_for_detection(synth.synth_track(9.0, sr=8000, stereo=False))
+    assert [i for i, _ in seen] == list(range(len(seen))) and len(res.vad_segments) == len(seen)
+    assert res.gpu_meta["silero_vad_segments"] == len(seen)

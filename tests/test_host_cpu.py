@@ -1,0 +1,142 @@
+"""CPU-only checks: host logic of the drop-in, C-ABI surface, oracle cross-checks."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import features as OF
+from oracle import planner
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_chunk_schedule_host_mirror_matches_reference_golden(golden_dir):
+    from audio_cut_b200.gpu_pipeline import chunk_schedule
+
+    for case in json.load(open(os.path.join(golden_dir, "chunk_schedule.json"))):
+        t, c, o, h = case["args"]
+        plans = chunk_schedule(t, chunk_s=c, overlap_s=o, halo_s=h)
+        got = [[p.index, repr(p.start_s), repr(p.end_s), repr(p.halo_left_s), repr(p.halo_right_s)] for p in plans]
+        assert got == case["plans"]
+
+
+def test_sample_bounds_match_oracle():
+    from audio_cut_b200.gpu_pipeline import chunk_schedule
+
+    for total in (1_323_000, 10_584_000, 441_001, 330_750):
+        a = chunk_schedule(total / 44100.0)
+        b = planner.chunk_schedule(total / 44100.0)
+        assert [p.sample_bounds(44100, total) for p in a] == [planner.sample_bounds(p, 44100, total) for p in b]
+
+
+def test_pipeline_config_mapping_and_meta_keys():
+    from audio_cut_b200.gpu_pipeline import (InflightLimiter, PinnedBufferPool, PipelineConfig, PipelineContext, Streams,
+                                             chunk_schedule)
+
+    cfg = PipelineConfig.from_mapping({"chunk_seconds": 8, "overlap_seconds": 2, "halo_seconds": 0.25, "align_hop": 2048,
+                                       "strict_mode": True, "ort": {"graph_optimization_level": "basic"}})
+    assert (cfg.chunk_s, cfg.overlap_s, cfg.halo_s, cfg.align_hop) == (8.0, 2.0, 0.25, 2048)
+    ctx = PipelineContext(device="cuda:0", streams=Streams(), plans=chunk_schedule(30.0), pinned_pool=None,
+                          limiter=InflightLimiter(2), config=cfg, use_streams=True)
+    ctx.mark_failure("separation", "boom")
+    meta = ctx.to_meta()
+    for k in ("gpu_pipeline_enabled", "gpu_pipeline_used", "gpu_pipeline_device", "gpu_pipeline_chunks", "gpu_pipeline_streams",
+              "gpu_pipeline_inflight_limit", "gpu_pipeline_prefetch", "gpu_pipeline_align_hop", "gpu_pipeline_config",
+              "gpu_pipeline_failures"):
+        assert k in meta, k
+    assert meta["gpu_pipeline_chunks"] == 4 and meta["gpu_pipeline_used"] is False  # no s_sep stream -> not enabled
+    with ctx.acquire_inflight():
+        pass
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from audio_cut_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "audiocut_b200.h")).read()
+    declared = set(re.findall(r"AC_API [^;(]*?\b(ac_\w+)\(", hdr))
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS)
+    assert lib.ac_abi_version() == 1
+    assert lib.ac_frame_count(10000, 2048, 441, 1) == 1 + 10000 // 441
+
+
+def test_ops_fail_loudly_without_cuda():
+    import torch
+
+    from audio_cut_b200 import _lib, ops
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.AudioCutError):
+        ops.frame_rms(torch.zeros(1000), 2048, 441)
+
+
+def test_peak_pick_vectorised_matches_loop_oracle():
+    from audio_cut_b200 import host_dsp
+
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 201, 1000):
+        env = np.abs(rng.standard_normal(n)).astype(np.float32)
+        env[rng.random(n) < 0.2] = 0
+        for sr, hop in ((44100, 2205), (44100, 512), (44100, 441)):
+            np.testing.assert_array_equal(host_dsp.onset_detect(env, sr, hop), OF.onset_detect(env, sr, hop))
+    assert host_dsp.onset_detect(np.zeros(10, np.float32), 44100, 512).size == 0
+
+
+def test_tempo_and_beats_on_click_envelope():
+    from audio_cut_b200 import host_dsp
+
+    sr, hop = 44100, 512
+    n = int(60 * sr / hop)
+    env = np.zeros(n, np.float32)
+    period = 60.0 / 100.0 * sr / hop  # 100 BPM
+    for k in range(int(n / period)):
+        env[int(round(k * period))] = 1.0
+    env += 0.01 * np.abs(np.random.default_rng(1).standard_normal(n)).astype(np.float32)
+    bpm, beats = host_dsp.beat_track(env, sr, hop)
+    assert abs(bpm - 100.0) < 3.0
+    iv = np.diff(beats)
+    assert len(beats) > 80 and abs(np.median(iv) - period) <= 1.0
+    curve = host_dsp.tempo(env, sr, hop, aggregate=None)
+    assert curve.shape == (n,) and abs(np.median(curve) - 100.0) < 3.0
+
+
+def test_unet_blob_layout_sizes():
+    import ctypes as C
+
+    from audio_cut_b200 import _lib, unet_weights as uw
+
+    lib = _lib.load()
+    for geo in (uw.UNetGeometry(), uw.UNetGeometry(256, 32, 4, 16), uw.UNetGeometry(512, 64, 4, 32)):
+        g = _lib.UNetGeom(geo.dim_f, geo.dim_t, geo.dim_c, geo.g, geo.n, geo.l, geo.bn)
+        want = lib.ac_unet_param_floats(C.byref(g))
+        shapes = uw.param_shapes(geo)
+        # blob = all weights + 2 floats (scale, shift) per BatchNorm channel + final bias; conv biases fold away
+        n_w = sum(int(np.prod(s)) for k, s in shapes.items() if len(s) > 1)
+        n_bn = sum(s[0] for k, s in shapes.items() if k.endswith("running_mean"))
+        assert want == n_w + 2 * n_bn + geo.dim_c
+    assert lib.ac_unet_param_floats(C.byref(_lib.UNetGeom(100, 32, 4, 16, 5, 3, 8))) == 0  # invalid geometry
+
+
+def test_oracle_net_matches_folded_numpy_first_layer():
+    """fold_bn used by the packer agrees with torch BatchNorm in eval mode."""
+    import torch
+
+    from audio_cut_b200 import unet_weights as uw
+    from oracle import unet as ounet
+
+    geo = uw.UNetGeometry(256, 32, 4, 16)
+    st = uw.random_state(geo)
+    net = ounet.build_net(st, 256, 32, 16)
+    x = torch.randn(1, 4, 256, 32)
+    with torch.no_grad():
+        ref = net.first_conv(x).numpy()
+    scale, shift = uw.fold_bn(st, "first_conv.1", st["first_conv.0.bias"])
+    y = np.einsum("oc,bcft->boft", st["first_conv.0.weight"][:, :, 0, 0], x.numpy())
+    y = np.maximum(y * scale[None, :, None, None] + shift[None, :, None, None], 0)
+    np.testing.assert_allclose(y, ref, rtol=1e-4, atol=1e-5)
