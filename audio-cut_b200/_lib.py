@@ -19,7 +19,7 @@ EXPORTS = [
     "ac_stft_mdx", "ac_istft_mdx", "ac_unet_create", "ac_unet_destroy", "ac_unet_param_floats",
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
     "ac_track_workspace_bytes", "ac_separate_track", "ac_stft_features_workspace_bytes", "ac_stft_features",
-    "ac_zero_crossing_rate", "ac_debug_tc_aborted",
+    "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
 ]
 
 
@@ -40,6 +40,11 @@ class ChunkDesc(C.Structure):
 class TrackParams(C.Structure):
     _fields_ = [("mdx", MdxGeom), ("align_hop", C.c_int), ("n_channels", C.c_int), ("output_is_vocal", C.c_int),
                 ("dtype", C.c_int), ("max_batch", C.c_int), ("reserved", C.c_int)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_longlong), ("total_ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
 
 
 class FeatSegment(C.Structure):
@@ -89,6 +94,8 @@ def load() -> C.CDLL:
     lib.ac_stft_features_workspace_bytes.restype = sz
     lib.ac_stft_features.argtypes = [vp, C.POINTER(FeatSegment), i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ac_stft_features.restype = i
+    lib.ac_profile_begin.argtypes, lib.ac_profile_begin.restype = [], i
+    lib.ac_profile_collect.argtypes, lib.ac_profile_collect.restype = [C.POINTER(KernelStat), i], i
     _lib = lib
     return lib
 
@@ -110,6 +117,23 @@ def init(device_index: int = 0) -> C.CDLL:
         check(lib.ac_init(int(device_index)), "ac_init")
         _inited_devices.add(device_index)
     return lib
+
+
+def profile_begin() -> None:
+    check(load().ac_profile_begin(), "ac_profile_begin")
+
+
+def profile_collect():
+    """[{name, launches, total_ms, flops, bytes}] for every kernel class that launched."""
+    arr = (KernelStat * 32)()
+    n = load().ac_profile_collect(arr, 32)
+    if n < 0:
+        check(n, "ac_profile_collect")
+    return [
+        {"name": arr[k].name.decode(), "launches": int(arr[k].launches), "total_ms": float(arr[k].total_ms),
+         "flops": float(arr[k].flops), "bytes": float(arr[k].bytes)}
+        for k in range(n) if arr[k].launches
+    ]
 
 
 def ptr(t) -> int:

@@ -15,6 +15,27 @@ static std::mutex g_plan_mu;
 static std::map<int, FftPlan*> g_plans;
 
 void set_error(const std::string& msg) { t_error = msg; }
+
+bool g_prof_on = false;
+struct ProfSpan { cudaEvent_t a, b; int cls; double flops, bytes; };
+static std::vector<ProfSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mu;
+static cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+int prof_start(int cls, double flops, double bytes, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfSpan s{prof_event(), prof_event(), cls, flops, bytes};
+  cudaEventRecord(s.a, st);
+  g_spans.push_back(s);
+  return (int)g_spans.size() - 1;
+}
+void prof_stop(int idx, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx >= 0 && idx < (int)g_spans.size()) cudaEventRecord(g_spans[idx].b, st);
+}
 int device_sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
 const FftPlan* get_fft_plan(int n) {
@@ -71,6 +92,42 @@ const FftPlan* get_fft_plan(int n) {
 }  // namespace ac
 
 extern "C" {
+
+int ac_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(ac::g_prof_mu);
+  for (auto& s : ac::g_spans) { ac::g_event_pool.push_back(s.a); ac::g_event_pool.push_back(s.b); }
+  ac::g_spans.clear();
+  ac::g_prof_on = true;
+  return AC_OK;
+}
+
+int ac_profile_collect(ac_kernel_stat* out, int max_classes) {
+  ac::g_prof_on = false;
+  AC_REQUIRE(out && max_classes >= ac::KC_COUNT, "ac_profile_collect needs room for every kernel class");
+  AC_CHECK_CUDA(cudaDeviceSynchronize());
+  static const char* names[ac::KC_COUNT] = {"stft_mdx", "istft_ola_stems", "conv3x3_tcgen05", "conv3x3_simt", "tdf_simt",
+                                            "resample_simt", "conv1x1", "frame_rms", "stft2048_features", "onset_flux",
+                                            "misc", "tdf_tcgen05", "resample_tcgen05"};
+  for (int c = 0; c < ac::KC_COUNT; ++c) {
+    out[c].name = names[c];
+    out[c].launches = 0;
+    out[c].total_ms = out[c].flops = out[c].bytes = 0.0;
+  }
+  std::lock_guard<std::mutex> lk(ac::g_prof_mu);
+  for (auto& s : ac::g_spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      out[s.cls].launches += 1;
+      out[s.cls].total_ms += ms;
+      out[s.cls].flops += s.flops;
+      out[s.cls].bytes += s.bytes;
+    }
+    ac::g_event_pool.push_back(s.a);
+    ac::g_event_pool.push_back(s.b);
+  }
+  ac::g_spans.clear();
+  return ac::KC_COUNT;
+}
 
 int ac_abi_version(void) { return 1; }
 const char* ac_last_error(void) { return ac::t_error.c_str(); }

@@ -42,6 +42,22 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- optional per-kernel-class timing (ac_profile_begin / ac_profile_collect) ---------------
+enum KernelClass {
+  KC_STFT = 0, KC_ISTFT, KC_CONV_TC, KC_CONV_SIMT, KC_TDF_SIMT, KC_RESAMPLE_SIMT, KC_CONV1X1, KC_RMS, KC_FEAT_STFT,
+  KC_FEAT_FLUX, KC_MISC, KC_TDF_TC, KC_RESAMPLE_TC, KC_COUNT
+};
+int prof_start(int cls, double flops, double bytes, cudaStream_t st);
+void prof_stop(int idx, cudaStream_t st);
+extern bool g_prof_on;
+struct ProfScope {  // brackets the launches issued during its lifetime with two events on `st`
+  int idx; cudaStream_t st;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t s) : idx(-1), st(s) {
+    if (g_prof_on) idx = prof_start(cls, flops, bytes, st);
+  }
+  ~ProfScope() { if (idx >= 0) prof_stop(idx, st); }
+};
+
 // storage type helpers: activations are float or __nv_bfloat16, math is always fp32
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }

@@ -364,13 +364,20 @@ extern "C" int ac_stft_features(const float* d_x, const ac_feat_segment* h_segs,
   const size_t smem = sizeof(float2) * 2 * fft_smem_floats2(kNfft) + sizeof(float) * 2 * (kBins + 3);
   AC_CHECK_CUDA(cudaFuncSetAttribute(stft_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AC_REQUIRE(pairs < 0x7fffffffLL, "too many frames");
-  stft_feat_kernel<<<(unsigned)pairs, kFeatThreads, smem, st>>>(fa);
-  AC_LAUNCH_CHECK();
+  {
+    double in_bytes = 0.0, n_fr = 0.0;
+    for (auto& sgm : segs) { in_bytes += 4.0 * (double)sgm.len; n_fr += sgm.n_frames; }
+    const int n_out = (d_flatness != nullptr) + (d_centroid != nullptr) + (d_low_ratio != nullptr);
+    ProfScope ps(KC_FEAT_STFT, 0.0, in_bytes + n_fr * (4.0 * n_out + (want_onset ? 512.0 : 0.0)), st);
+    stft_feat_kernel<<<(unsigned)pairs, kFeatThreads, smem, st>>>(fa);
+    AC_LAUNCH_CHECK();
+  }
   if (want_onset) {
     // the mel rows of a segment live at [frame_off, frame_off + n_frames): same slots as the outputs
     FluxArgs xa;
     xa.segs = d_segs; xa.n_segs = n_segs; xa.total_frames = frames; xa.mel_db = d_mel; xa.segmax = d_segmax;
     xa.shift = kNfft / (2 * hop); xa.onset_mean = d_onset_mean; xa.onset_median = d_onset_median;
+    ProfScope ps(KC_FEAT_FLUX, 0.0, (double)frames * (1024.0 + 8.0), st);
     onset_flux_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, st>>>(xa);
     AC_LAUNCH_CHECK();
   }

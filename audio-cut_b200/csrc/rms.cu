@@ -96,6 +96,7 @@ static int launch_frame_reduce(const float* d_x, long long n, int frame, int hop
     attr_done[MODE] = true;
   }
   const long long grid = (n_frames + fr - 1) / fr;
+  ProfScope ps(KC_RMS, 0.0, 4.0 * (double)n + 4.0 * (double)n_frames, st);
   frame_reduce_kernel<MODE><<<(unsigned)grid, kRmsThreads, smem, st>>>(d_x, n, frame, hop, center ? frame / 2 : 0, fr,
                                                                         n_frames, d_out);
   AC_LAUNCH_CHECK();

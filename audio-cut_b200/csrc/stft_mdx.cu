@@ -240,6 +240,8 @@ int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, in
   AC_REQUIRE(smem <= 227 * 1024, "n_fft too large for shared memory");
   FftDev fd = make_fft_dev(plan->fft);
   dim3 grid(g.dim_t, n_win);
+  const double es = dtype == AC_F32 ? 4.0 : 2.0;
+  ProfScope ps(KC_STFT, 0.0, n_win * (2.0 * plan->W * 4 + (double)g.dim_t * g.dim_f * 4 * es), st);
   if (dtype == AC_F32) {
     AC_CHECK_CUDA(cudaFuncSetAttribute(stft_mdx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stft_mdx_kernel<float><<<grid, kFftThreads, smem, st>>>(d_src, ch_stride, n_ch, d_wins, fd, plan->fft->d_hann,
@@ -295,6 +297,10 @@ int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDe
   const size_t smem = stft_smem_bytes(g.n_fft) + sizeof(float2) * (size_t)a.nb * g.hop;
   AC_REQUIRE(smem <= 227 * 1024, "n_fft too large for shared memory");
   dim3 grid(strips, n_win);
+  const double es = dtype == AC_F32 ? 4.0 : 2.0;
+  const double gen = plan->W - g.n_fft;
+  // read spec + (stems: read mix 2ch, read-modify-write 3 accumulators | raw: write 2ch wave)
+  ProfScope ps(KC_ISTFT, 0.0, n_win * ((double)g.dim_t * g.dim_f * 4 * es + (mode == 1 ? gen * (8 + 24) : plan->W * 8.0)), st);
   if (dtype == AC_F32) {
     AC_CHECK_CUDA(cudaFuncSetAttribute(istft_mdx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_mdx_kernel<float><<<grid, kFftThreads, smem, st>>>((const float*)d_spec, a);

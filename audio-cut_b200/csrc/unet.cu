@@ -309,6 +309,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.a_mode = A_CONV3; a.A = x; a.T = T; a.F = F; a.C = C;
     a.Bm = wsel(L.w32, L.w16);
     a.epi = EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = L.N; a.out = y;
+    a.kclass = KC_CONV_SIMT;
     return launch_gemm_simt(a, dtype, st);
   };
   // X is clobbered, Y is scratch, result lands in Z (Z != Y)
@@ -328,6 +329,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.Bm = tfc; a.b_batch_stride = (long long)b.F * b.c;
     a.epi = EPI_AFFINE_RELU; a.scale = b.tdf1.af.scale; a.shift = b.tdf1.af.shift; a.cmod = b.c;
     a.out = H; a.c_batch_stride = (long long)b.tdf1.M * b.c;
+    a.kclass = KC_TDF_SIMT;
     if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
     GemmArgs c{};
     c.M = b.tdf2.M; c.N = b.c; c.K = b.tdf2.K; c.batch = B * b.T;
@@ -335,6 +337,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     c.Bm = H; c.b_batch_stride = (long long)b.tdf2.K * b.c;
     c.epi = EPI_RESIDUAL; c.scale = b.tdf2.af.scale; c.shift = b.tdf2.af.shift; c.cmod = b.c;
     c.out = Z; c.c_batch_stride = (long long)b.F * b.c; c.extra = tfc;
+    c.kclass = KC_TDF_SIMT;
     return launch_gemm_simt(c, dtype, st);
   };
 
@@ -354,6 +357,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.a_mode = A_DOWN2; a.A = skip; a.T = b.T / 2; a.F = b.F / 2; a.C = b.c;
     a.Bm = wsel(d.w32, d.w16);
     a.epi = EPI_AFFINE_RELU; a.scale = d.af.scale; a.shift = d.af.shift; a.cmod = d.N; a.out = cur;
+    a.kclass = KC_RESAMPLE_SIMT;
     if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
   }
   {
@@ -374,6 +378,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.Bm = wsel(u.w32, u.w16);
     a.epi = EPI_UP_SKIP; a.scale = u.af.scale; a.shift = u.af.shift; a.cmod = b.c; a.out = oth; a.extra = skip;
     a.up_T = b.T / 2; a.up_F = b.F / 2;
+    a.kclass = KC_RESAMPLE_SIMT;
     if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
     { void* t = cur; cur = oth; oth = t; }
     void* Z = (g.l & 1) ? cur : oth;

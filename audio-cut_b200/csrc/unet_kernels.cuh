@@ -29,6 +29,7 @@ struct GemmArgs {
   long long c_batch_stride;
   const void* extra;       // EPI_UP_SKIP: skip tensor (same layout as out); EPI_RESIDUAL: residual [batch][M][N]
   int up_T, up_F;          // EPI_UP_SKIP: INPUT grid; out is [nB][2*up_T][2*up_F][N/4]
+  int kclass;              // profiler class (KC_*)
 };
 
 int launch_gemm_simt(const GemmArgs& a, int dtype, cudaStream_t st);

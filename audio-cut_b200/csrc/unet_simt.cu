@@ -162,6 +162,7 @@ static int launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
   int bn = (a.N % 48 == 0) ? 48 : (a.N % 32 == 0 ? 32 : 16);
   dim3 grid((a.M + 127) / 128, a.N / bn, a.batch);
   AC_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "gemm: grid too large");
+  ProfScope ps(a.kclass, 2.0 * a.M * (double)a.N * a.K * a.batch, 0.0, st);
   if (bn == 48) gemm_simt_kernel<T, 48><<<grid, 256, 0, st>>>(a);
   else if (bn == 32) gemm_simt_kernel<T, 32><<<grid, 256, 0, st>>>(a);
   else gemm_simt_kernel<T, 16><<<grid, 256, 0, st>>>(a);
@@ -232,6 +233,7 @@ int launch_first_conv(const void* in, void* out, long long P, int g, const float
                       const float* shift, int dtype, cudaStream_t st) {
   const long long total = P * (g / 8);
   const unsigned grid = (unsigned)((total + 255) / 256);
+  ProfScope ps(KC_CONV1X1, 2.0 * P * g * 4, (double)P * (4 + g) * (dtype == AC_F32 ? 4 : 2), st);
   if (dtype == AC_F32)
     first_conv_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, P, g, w, scale, shift);
   else
@@ -245,6 +247,7 @@ int launch_final_conv(const void* in, void* out, long long P, int g, const float
                       cudaStream_t st) {
   const unsigned grid = (unsigned)((P + 255) / 256);
   const size_t smem = sizeof(float) * (4 * g + 4);
+  ProfScope ps(KC_CONV1X1, 2.0 * P * g * 4, (double)P * (4 + g) * (dtype == AC_F32 ? 4 : 2), st);
   if (dtype == AC_F32)
     final_conv_kernel<float><<<grid, 256, smem, st>>>((const float*)in, (float*)out, P, g, w, bias);
   else

@@ -442,6 +442,7 @@ int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   }
   int grid = device_sm_count();
   if (grid > p.n_units) grid = p.n_units;
+  ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
   tc_conv3x3_kernel<<<grid, kTcThreads, c.smem_bytes, st>>>(map, p);
   AC_LAUNCH_CHECK();
   return AC_OK;

@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Headline benchmark: x-realtime separation+features of the audio-cut hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+
+A "step" is one pass of the hot path over one synthetic 4-minute 44.1 kHz stereo track per GPU
+(BASELINE.json configs[1]; at N > 1 configs[3]: tracks sharded across ranks, no data-path collective,
+weak scaling).  Prints ONE JSON line on rank 0 (see the task contract for the keys).
+
+  value  audio seconds / second with the track already resident in HBM: chunked separation
+         (STFT -> TFC-TDF U-Net -> fused iSTFT/OLA/stems) + every framewise series the v2.2_mdd path
+         consumes (TrackFeatureCache RMS/flatness/onset per chunk, BPM onset envelope, vocal RMS
+         1102/441, 2048/441, 2205/882, vocal flatness @441, mix RMS 2048/441).
+  e2e    the same metric through the reference-facing call B200VocalSeparator.separate_for_detection()
+         with HOST numpy buffers: pinned H2D of the mix, the kernels, D2H of both stems and all
+         series, and the host-side rhythm scans (tempogram / beat DP) of TrackFeatureCache.
+  --impl reference   times the CPU restatement of the reference path (oracle/: torch-CPU network +
+         numpy features; onnxruntime / librosa are not installable here) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 44100
+TRACK_SECONDS = 240.0
+METRIC = "x-realtime (audio s/s) separation+features"
+UNIT = "audio-s/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "bf16_burst": float(p["bf16_tflops"]), "bf16_sustained": float(p["bf16_tflops_sustained"]),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons sampled DURING the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as exc:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(exc).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle restatement of the reference's CPU path
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(sample_seconds: float, n_fft: int, threads: int, state=None):
+    """One bounded pass of the reference CPU path over `sample_seconds` of the workload: chunked
+    MDX23 separation (backends.py:299-406 + enhanced_vocal_separator.py:366-458 restated) with the
+    torch-CPU TFC-TDF net, ChunkFeatureBuilder features (features_cache.py:122-335 restated) and the
+    vocal RMS / flatness series of PureVocalPauseDetector.  Returns (audio_seconds, wall_seconds)."""
+    import torch
+
+    from audio_cut_b200 import synth, unet_weights as uw
+    from oracle import features as OF
+    from oracle import mdx, pipeline, planner
+    from oracle import unet as ounet
+
+    torch.set_num_threads(threads)
+    geo = uw.UNetGeometry()
+    st = state if state is not None else uw.random_state(geo)
+    net = ounet.build_net(st, geo.dim_f, geo.dim_t, geo.g)
+    mg = mdx.MdxGeometry(n_fft=n_fft)
+    audio = synth.synth_track(sample_seconds, seed=0, stereo=True)
+    n = audio.shape[-1]
+    plans = planner.chunk_schedule(n / float(SR))
+    t0 = time.perf_counter()
+    vocal, _ = pipeline.separate_track(audio, lambda ch: mdx.infer_chunk(ch, net, mg), sr=SR, plans=plans)
+    mono = audio.mean(axis=0)
+    cf = pipeline.ChunkFeatures(SR)
+    for p in plans:
+        cs, ce, _, _ = planner.sample_bounds(p, SR, n)
+        cf.add_chunk(p, mono[cs:ce])
+    out = cf.finalize()
+    OF.onset_strength(out["bpm_wave"], SR, 512, aggregate=np.median)
+    for fr, hop in ((1102, 441), (2048, 441), (2205, 882)):
+        OF.rms(vocal, fr, hop)
+    OF.spectral_flatness(vocal, 2048, 441)
+    OF.rms(mono, 2048, 441)
+    return n / float(SR), time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample_s = 10.0  # one pipeline chunk = 2 model windows per step
+    from audio_cut_b200 import unet_weights as uw
+
+    st = uw.random_state(uw.UNetGeometry())
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_pass(sample_s, args.n_fft, threads, st)
+    audio_s, wall = 0.0, 0.0
+    for _ in range(args.steps):
+        a, w = cpu_reference_pass(sample_s, args.n_fft, threads, st)
+        audio_s += a
+        wall += w
+    value = audio_s / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "v2.2_mdd hot path, 4-min 44.1 kHz stereo track (configs[1]); bounded sample per step",
+                   "n_fft": args.n_fft, "chunk_s": 10.0, "overlap_s": 2.5, "halo_s": 0.5},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample_s:.0f} s stereo (1 chunk, 2 MDX windows + its features) per step, {args.steps} steps; "
+                                   "oracle port: torch-CPU TFC-TDF net + numpy/scipy librosa restatement (onnxruntime/librosa absent)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def device_step(net_backend, mix_dev, plans, bounds, series_out):
+    """One hot-path pass with inputs resident in HBM; every series stays on the device."""
+    import torch
+
+    from audio_cut_b200 import ops
+    from audio_cut_b200.features_cache import B200ChunkFeatureBuilder
+
+    be = net_backend
+    vocal, instr, _ = ops.separate_track(be.net, mix_dev, bounds, be.geom, align_hop=be.align_hop,
+                                         output_is_vocal=True, dtype=be.dtype)
+    mono = mix_dev.mean(dim=0)
+    hop = 2205
+    segs, off = [], 0
+    for cs, ce, _, _ in bounds:
+        segs.append((cs, ce - cs, off))
+        off += 1 + (ce - cs) // hop
+    feats = ops.stft_features(mono, segs, hop, SR, total_frames=off, want=("flatness", "onset_mean"))
+    rms_c = [ops.frame_rms(mono[cs:ce], 4410, hop) for cs, ce, _, _ in bounds]
+    # BPM front end: onset envelope (median) at hop 512 over the effective-region concat
+    bpm_wave = torch.cat([mono[es:ee] for _, _, es, ee in bounds])
+    n_b = bpm_wave.numel()
+    bpm_env = ops.stft_features(bpm_wave, [(0, n_b, 0)], 512, SR, total_frames=1 + n_b // 512, want=("onset_median",))
+    # PureVocalPauseDetector / SeamlessSplitter series on the stems
+    v_rms = [ops.frame_rms(vocal, fr, hp) for fr, hp in ((1102, 441), (2048, 441), (2205, 882))]
+    v_flat = ops.stft_features(vocal, [(0, vocal.numel(), 0)], 441, SR, total_frames=1 + vocal.numel() // 441, want=("flatness",))
+    m_rms = ops.frame_rms(mono, 2048, 441)
+    series_out[:] = [vocal, instr, feats, rms_c, bpm_env, v_rms, v_flat, m_rms]
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from audio_cut_b200 import _lib, synth, unet_weights as uw
+    from audio_cut_b200.backends import B200Mdx23Backend
+    from audio_cut_b200.gpu_pipeline import PipelineConfig, chunk_schedule
+    from audio_cut_b200.separator import B200VocalSeparator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    geo = uw.UNetGeometry()
+    state = uw.random_state(geo)
+    be = B200Mdx23Backend(weights=state, device=f"cuda:{local}", precision=args.precision, n_fft=args.n_fft, output_type="vocal")
+    be.load_model()
+    # independent tracks per rank (track sharding): different seed per rank, same length
+    audio = synth.synth_track(TRACK_SECONDS, seed=rank, stereo=True)
+    n = audio.shape[-1]
+    plans = chunk_schedule(n / float(SR))
+    bounds = [p.sample_bounds(SR, n) for p in plans]
+    mix_dev = torch.from_numpy(audio).to(dev)
+    import ctypes
+
+    from audio_cut_b200 import ops
+    n_windows = int(_lib.load().ac_track_window_count(ops.make_chunk_descs(bounds), len(bounds),
+                                                      ctypes.byref(_lib.TrackParams(be.geom, be.align_hop, 2, 1, be.dtype, 0, 0))))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    keep = []
+    for _ in range(args.warmup):
+        device_step(be, mix_dev, plans, bounds, keep)
+    barrier()
+    lib = _lib.load()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.profile_begin()
+    launches0 = lib.ac_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        device_step(be, mix_dev, plans, bounds, keep)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = int(lib.ac_launch_count() - launches0)
+    kstats = _lib.profile_collect()
+    clocks = sampler.stop() if sampler else None
+
+    # ---- e2e through the reference-facing call, host buffers in / out
+    sep = B200VocalSeparator(SR, backend=be, pipeline_config=PipelineConfig())
+    for _ in range(min(args.warmup, 2)):
+        res = sep.separate_for_detection(audio)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = sep.separate_for_detection(audio)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    fc = res.feature_cache
+    d2h = res.vocal_track.nbytes + (res.instrumental_track.nbytes if res.instrumental_track is not None else 0) + \
+        4 * (fc.rms_series.size + fc.spectral_flatness.size + fc.onset_envelope.size) + 4 * (1 + (n + 1323000) // 512) + 4 * (1 + n // 882)
+
+    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = _peaks()
+        audio_total = TRACK_SECONDS * world * args.steps
+        value = audio_total / (dev_ms / 1000.0)
+        e2e_value = audio_total / (e2e_ms / 1000.0)
+        kstats.sort(key=lambda k: -k["total_ms"])
+        for k in kstats:
+            k["share"] = k["total_ms"] / max(1e-9, sum(x["total_ms"] for x in kstats))
+            k["avg_ms"] = k["total_ms"] / max(1, k["launches"])
+            k["tflops"] = k["flops"] / (k["total_ms"] * 1e9) if k["total_ms"] > 0 else 0.0
+            k["gbs"] = k["bytes"] / (k["total_ms"] * 1e6) if k["total_ms"] > 0 else 0.0
+        top = kstats[0]
+        tensor_bound = top["flops"] > 0
+        if tensor_bound:
+            roof = {"bound": "tensor", "kernel": top["name"], "achieved": top["tflops"], "peak": peaks["bf16_sustained"],
+                    "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"], "traffic": None,
+                    "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"]}
+        else:
+            roof = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": top["gbs"] / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                    "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"]}
+        cpu_threads = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            a, w = cpu_reference_pass(10.0, args.n_fft, cpu_threads, state)
+            cpu = {"value": a / w, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                   "sample": "10 s stereo (1 chunk, 2 MDX windows + its features), one pass; oracle port: torch-CPU TFC-TDF net + "
+                             "numpy/scipy librosa restatement (onnxruntime/librosa absent from the image)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "v2.2_mdd hot path, one 4-min 44.1 kHz stereo track per GPU per step (configs[1]; track-sharded at N>1 = configs[3])",
+                       "n_fft": args.n_fft, "hop": 1024, "dim_f": 3072, "dim_t": 256, "chunk_s": 10.0, "overlap_s": 2.5, "halo_s": 0.5,
+                       "chunks_per_track": len(plans), "windows_per_track": n_windows, "weights": "random-init TFC-TDF (Kim_Vocal geometry, seed 1234)",
+                       "l2": "working set per step (>4 GB of activations, 85 MB track) exceeds the 126 MB L2; no explicit flush",
+                       "parallelism": f"track-sharded x{world}, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(audio.nbytes), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps, "call": "B200VocalSeparator.separate_for_detection(host ndarray)"},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "kernels": [{k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in k.items()} for k in kstats],
+            "unet_tflops_overall": sum(k["flops"] for k in kstats) / (sum(k["total_ms"] for k in kstats if k["flops"] > 0) * 1e9 + 1e-9),
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--n-fft", dest="n_fft", type=int, default=7680)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -50,6 +50,19 @@ AC_API int ac_abi_version(void);
 /* Number of kernels this library has launched since load (for bench.py "gpu_launches"). */
 AC_API long long ac_launch_count(void);
 
+/* Per-kernel-class device timing with CUDA events on the launching stream (for bench.py's
+ * roofline line): begin, run the workload, collect (synchronises the device).  `flops` / `bytes`
+ * are the ALGORITHMIC counts of the launches, not hardware counters. */
+typedef struct ac_kernel_stat {
+  const char* name;
+  long long launches;
+  double total_ms;
+  double flops;
+  double bytes;
+} ac_kernel_stat;
+AC_API int ac_profile_begin(void);
+AC_API int ac_profile_collect(ac_kernel_stat* out, int max_classes); /* returns the number of classes filled */
+
 /* ---- framewise RMS ------------------------------------------------------------------------
  * librosa.feature.rms(y, frame_length, hop_length, center=True, pad_mode="constant") as called at
  * features_cache.py:182, pure_vocal_pause_detector.py:1111-1113 and :1397, seamless_splitter.py:1714
