@@ -22,6 +22,7 @@ struct TdfLayer {  // GEMM A operand [M][K] (PyTorch Linear weight as is)
   const __nv_bfloat16* w16;
   Affine af;
   int M, K;
+  TcTdfWeights* tc = nullptr;
 };
 struct Block {
   int c, T, F;
@@ -130,7 +131,7 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
     return o;
   };
   struct ConvOff { size_t w, sc, sh; int K, N; const float* raw; int cin, cout; };
-  struct TdfOff { size_t w, sc, sh; int M, K; };
+  struct TdfOff { size_t w, sc, sh; int M, K; const float* raw; };
   struct BlockOff { int c, T, F; std::vector<ConvOff> conv; TdfOff t1, t2; };
   std::vector<BlockOff> boffs;
   std::vector<ConvOff> dsoffs, usoffs;
@@ -148,7 +149,9 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
       co.K = 9 * c; co.N = c;
       b.conv.push_back(co);
     }
+    b.t1.raw = h_blob + rd;
     b.t1.w = take((size_t)(F / g.bn) * F); b.t1.sc = take(c); b.t1.sh = take(c); b.t1.M = F / g.bn; b.t1.K = F;
+    b.t2.raw = h_blob + rd;
     b.t2.w = take((size_t)F * (F / g.bn)); b.t2.sc = take(c); b.t2.sh = take(c); b.t2.M = F; b.t2.K = F / g.bn;
     boffs.push_back(b);
   };
@@ -216,6 +219,11 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
     }
     b.tdf1 = mk_tdf(bo.t1);
     b.tdf2 = mk_tdf(bo.t2);
+    if (tc_tdf_pack(bo.t1.raw, bo.t1.M, bo.t1.K, bo.c, bo.T, &b.tdf1.tc) != AC_OK ||
+        tc_tdf_pack(bo.t2.raw, bo.t2.M, bo.t2.K, bo.c, bo.T, &b.tdf2.tc) != AC_OK) {
+      ac_unet_destroy(net);
+      return AC_E_CUDA;
+    }
     net->blocks.push_back(b);
   }
   for (auto& o : dsoffs) net->ds.push_back(mk_conv(o));
@@ -231,9 +239,12 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
 
 extern "C" void ac_unet_destroy(ac_unet* net) {
   if (!net) return;
-  for (auto& b : net->blocks)
+  for (auto& b : net->blocks) {
     for (int j = 0; j < net->g.l; ++j)
       if (b.conv[j].tc) ac::tc_conv3x3_free(b.conv[j].tc);
+    ac::tc_tdf_free(b.tdf1.tc);
+    ac::tc_tdf_free(b.tdf2.tc);
+  }
   if (net->d_f32) cudaFree(net->d_f32);
   if (net->d_bf16) cudaFree(net->d_bf16);
   delete net;
@@ -323,6 +334,12 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     // src now holds the TFC output; dst is free.  If Z aliases src the residual would be clobbered.
     void* tfc = src;
     if (Z == tfc) return (set_error("internal: block output aliases TFC output"), AC_E_INVALID);
+    const bool use_tc = dtype == AC_BF16 && !net->force_simt;
+    if (use_tc && b.tdf1.tc) {
+      if ((rc = launch_tc_tdf(b.tdf1.tc, (const __nv_bfloat16*)tfc, nullptr, (__nv_bfloat16*)H, B, b.T, b.tdf1.af.scale,
+                              b.tdf1.af.shift, st)))
+        return rc;
+    } else {
     GemmArgs a{};
     a.M = b.tdf1.M; a.N = b.c; a.K = b.tdf1.K; a.batch = B * b.T;
     a.a_mode = A_PLAIN; a.A = wsel(b.tdf1.w32, b.tdf1.w16); a.a_batch_stride = 0;
@@ -331,6 +348,10 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.out = H; a.c_batch_stride = (long long)b.tdf1.M * b.c;
     a.kclass = KC_TDF_SIMT;
     if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
+    }
+    if (use_tc && b.tdf2.tc)
+      return launch_tc_tdf(b.tdf2.tc, (const __nv_bfloat16*)H, (const __nv_bfloat16*)tfc, (__nv_bfloat16*)Z, B, b.T,
+                           b.tdf2.af.scale, b.tdf2.af.shift, st);
     GemmArgs c{};
     c.M = b.tdf2.M; c.N = b.c; c.K = b.tdf2.K; c.batch = B * b.T;
     c.a_mode = A_PLAIN; c.A = wsel(b.tdf2.w32, b.tdf2.w16); c.a_batch_stride = 0;

@@ -56,4 +56,12 @@ int tc_conv3x3_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWeights** ou
 void tc_conv3x3_free(TcConvWeights* w);
 int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
 
+struct TcTdfWeights;  // opaque: packed smem images of one TDF linear layer
+// *out stays nullptr when the shape is left to the CUDA-core kernel (tiny deep-level layers)
+int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdfWeights** out);
+void tc_tdf_free(TcTdfWeights* w);
+// out[b][t][m][c] = relu(scale[c]*sum_k W[m][k]*in[b][t][k][c] + shift[c]) (+ residual[b][t][m][c])
+int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                  int nB, int T, const float* scale, const float* shift, cudaStream_t st);
+
 }  // namespace ac

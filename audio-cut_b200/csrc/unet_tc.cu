@@ -14,105 +14,13 @@
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 =
 //     epilogue (tcgen05.ld -> scale/shift/ReLU -> bf16 -> global); smem ring and (when the
 //     accumulators fit twice) a double-buffered TMEM hand-off, all through mbarriers.
-#include <cuda.h>
-
 #include <mutex>
 #include <vector>
 
+#include "tc_common.cuh"
 #include "unet_kernels.cuh"
 
 namespace ac {
-
-// ------------------------------------------------------------------------------------------------
-// device helpers (inline PTX)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a wrong descriptor or byte count must not hang the GPU.  On timeout the flag is
-// raised and every role drains out of its loops.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if ((it & 1023u) == 1023u && *abort_flag) return false;
-  }
-  *abort_flag = 1;
-  return false;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-//   [0,14) start>>4  [16,30) LBO>>4 (byte distance between the two 8-element K halves)
-//   [32,46) SBO>>4 (byte distance between 8-row groups)  [46,48) version = 1  [61,64) layout = 0
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // kernel
@@ -382,10 +290,7 @@ void tc_conv3x3_free(TcConvWeights* w) {
   delete w;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -399,21 +304,22 @@ static EncodeTiledFn get_encode() {
 }
 
 static int* g_abort_flag = nullptr;  // device
-static int* g_abort_host = nullptr;  // pinned mirror
+int* tc_abort_flag() {
+  if (!g_abort_flag) {
+    if (cudaMalloc(&g_abort_flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(g_abort_flag, 0, sizeof(int));
+  }
+  return g_abort_flag;
+}
 
 int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   AC_REQUIRE(a.w && a.w->C == a.C, "tc conv: weights do not match the layer");
   TcCfg c;
   AC_REQUIRE(make_cfg(a.C, a.F, c), "tc conv: unsupported shape");
   // the packing depends only on (C): NT, KC, nkc, nsplit are functions of C alone
-  EncodeTiledFn enc = get_encode();
+  EncodeTiledFn enc = get_tensor_map_encoder();
   AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
-  if (!g_abort_flag) {
-    AC_CHECK_CUDA(cudaMalloc(&g_abort_flag, sizeof(int)));
-    AC_CHECK_CUDA(cudaMemset(g_abort_flag, 0, sizeof(int)));
-    AC_CHECK_CUDA(cudaMallocHost(&g_abort_host, sizeof(int)));
-    *g_abort_host = 0;
-  }
+  AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
   CUtensorMap map;
   const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.F, (cuuint64_t)a.T, (cuuint64_t)a.nB};
   const cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};

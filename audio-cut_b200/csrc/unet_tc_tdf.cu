@@ -1,0 +1,312 @@
+// tcgen05 kernel for the TDF (time-distributed fully connected) layers: for every (b, t) row,
+//   Y[b][t][m][c] = relu(scale[c] * sum_k W[m][k] * X[b][t][k][c] + shift[c]) (+ R[b][t][m][c])
+// i.e. a GEMM over the frequency axis with channels riding along.  As UMMA:
+//   D[128 out-features][N = NTt*C] += A[128][16] (weights, K-major) * B[16][N] (activations)
+// The activations are channels-last, so B is MN-major: TMA stages [8 channels][Kt freqs] boxes
+// as [(t, c/8)][Kt][8] = the canonical no-swizzle MN-major layout (16-byte rows, 8-row core
+// matrices 128 B apart, SBO = Kt*16 between channel groups).  Weights are pre-packed smem images
+// fetched by 1-D bulk copies.  Pipeline / roles / TMEM hand-off as in unet_tc.cu.
+#include <vector>
+
+#include "tc_common.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+constexpr int kTdfThreads = 192;
+
+struct TdfCfg {
+  int C, M, K;
+  int NTt, N;            // time rows per unit, N = NTt*C
+  int n_mtiles, mt, n_mg;  // 128-row tiles of M, tiles per unit, groups
+  int Kt, nk;
+  int stages, nbuf;
+  int a_tile_bytes;   // 128*Kt*2
+  int b_stage_bytes;  // N*Kt*2
+  int stage_bytes;
+  int smem_bytes;
+};
+
+struct TdfParams {
+  TdfCfg cfg;
+  int nB, T;
+  int n_tg, n_units;
+  const __nv_bfloat16* wpack;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;  // nullable
+  __nv_bfloat16* out;             // [nB][T][M][C]
+  int* abort_flag;
+};
+
+__global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_constant__ CUtensorMap in_map, const TdfParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TdfCfg& c = p.cfg;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 8;
+  uint64_t* tfull = full + 16;
+  uint64_t* tempty = full + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
+  uint8_t* stage0 = smem + 1024;
+  volatile int* abort_flag = p.abort_flag;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < c.nbuf; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int cg = c.C / 8;  // channel groups per time row
+
+  auto decode = [&](int u, int& mg, int& b, int& t0) {
+    mg = u % c.n_mg;
+    int q = u / c.n_mg;
+    t0 = (q % p.n_tg) * c.NTt;
+    b = q / p.n_tg;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
+        int mg, b, t0;
+        decode(u, mg, b, t0);
+        for (int kc = 0; kc < c.nk; ++kc) {
+          if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+          uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
+          mbar_expect_tx(&full[s], (uint32_t)(c.mt * c.a_tile_bytes + c.b_stage_bytes));
+          const __nv_bfloat16* wsrc = p.wpack + ((size_t)mg * c.nk + kc) * (size_t)(c.mt * 128 * c.Kt);
+          bulk_load_1d(st, wsrc, (uint32_t)(c.mt * c.a_tile_bytes), &full[s]);
+          uint8_t* sb = st + c.mt * c.a_tile_bytes;
+          for (int tl = 0; tl < c.NTt; ++tl)
+            for (int g = 0; g < cg; ++g)
+              tma_load_4d(sb + (size_t)(tl * cg + g) * (c.Kt * 16), &in_map, &full[s], g * 8, kc * c.Kt, t0 + tl, b);
+          if (++s == c.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bmn(c.N);
+      int s = 0, buf = 0;
+      uint32_t ph = 0, tph = 0;
+      bool alive = true;
+      for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
+        if (!mbar_wait(&tempty[buf], tph ^ 1, abort_flag)) break;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * c.mt * c.N);
+        for (int kc = 0; kc < c.nk; ++kc) {
+          if (!mbar_wait(&full[s], ph, abort_flag)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)(c.mt * c.a_tile_bytes);
+          for (int mi = 0; mi < c.mt; ++mi) {
+            for (int k = 0; k < c.Kt / 16; ++k) {
+              const uint64_t ad = make_desc(sa + mi * c.a_tile_bytes + k * 2 * (128 * 16), 128 * 16, 128);
+              const uint64_t bd = make_desc_mn(sb + k * 256, 128, (uint32_t)c.Kt * 16);
+              umma_f16(acc0 + (uint32_t)(mi * c.N), ad, bd, idesc, (kc | k) != 0);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (++s == c.stages) { s = 0; ph ^= 1; }
+        }
+        if (!alive) break;
+        umma_commit(&tfull[buf]);
+        if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int buf = 0;
+    uint32_t tph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int mg, b, t0;
+      decode(u, mg, b, t0);
+      if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
+      tc_fence_after();
+      for (int mi = 0; mi < c.mt; ++mi) {
+        const int m = (mg * c.mt + mi) * 128 + quad * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.mt * c.N + mi * c.N);
+        for (int j = 0; j < c.N; j += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j, r);
+          tmem_ld_wait();
+          if (m < c.M) {
+            const int tl = j / c.C, ch0 = j - tl * c.C;
+            const size_t idx = (((size_t)b * p.T + t0 + tl) * c.M + m) * c.C + ch0;
+            float res[16];
+            if (p.residual) {
+              const uint4 q0 = *reinterpret_cast<const uint4*>(p.residual + idx);
+              const uint4 q1 = *reinterpret_cast<const uint4*>(p.residual + idx + 8);
+              const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                res[2 * e] = f.x;
+                res[2 * e + 1] = f.y;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) res[e] = 0.f;
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = ch0 + 2 * e;
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), __ldg(p.scale + ch), __ldg(p.shift + ch)), 0.f) + res[2 * e];
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), __ldg(p.scale + ch + 1), __ldg(p.shift + ch + 1)), 0.f) + res[2 * e + 1];
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(p.out + idx + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+struct TcTdfWeights {
+  TdfCfg cfg;
+  __nv_bfloat16* d_pack;
+};
+
+static bool make_tdf_cfg(int M, int K, int C, int T, TdfCfg& c) {
+  if (C % 16 || C > 256 || K % 16 || M < 64) return false;  // tiny layers stay on the CUDA-core kernel
+  c.C = C; c.M = M; c.K = K;
+  c.n_mtiles = (M + 127) / 128;
+  c.Kt = K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : 16);
+  c.nk = K / c.Kt;
+  auto pick_ntt = [&](int col_budget) {
+    int ntt = 1;
+    while (ntt * 2 <= 8 && (ntt * 2) * C <= 256 && (ntt * 2) * C <= col_budget && T % (ntt * 2) == 0) ntt *= 2;
+    return ntt;
+  };
+  if (c.n_mtiles <= 4 && c.n_mtiles * C <= 512) {
+    c.mt = c.n_mtiles;  // all of M in one unit: the activations are streamed exactly once
+    c.NTt = pick_ntt(512 / c.mt);
+    c.nbuf = (2 * c.mt * c.NTt * C <= 512) ? 2 : 1;
+  } else {
+    c.mt = 1;
+    c.NTt = pick_ntt(256);
+    c.nbuf = 2;
+  }
+  c.N = c.NTt * C;
+  if (c.N % 16 || c.N > 256 || c.mt * c.N * c.nbuf > 512) return false;
+  c.n_mg = (c.n_mtiles + c.mt - 1) / c.mt;
+  c.a_tile_bytes = 128 * c.Kt * 2;
+  c.b_stage_bytes = c.N * c.Kt * 2;
+  c.stage_bytes = (int)align_up((size_t)c.mt * c.a_tile_bytes + c.b_stage_bytes, 128);
+  c.stages = (220 * 1024 - 1024) / c.stage_bytes;
+  if (c.stages > 8) c.stages = 8;
+  if (c.stages < 2) return false;
+  c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+  return true;
+}
+
+int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdfWeights** out) {
+  *out = nullptr;
+  TdfCfg c;
+  if (!make_tdf_cfg(M, K, C, T, c)) return AC_OK;
+  // [m_group][k_chunk][mt][Kt/8][128][8]; rows >= M are zero
+  const size_t total = (size_t)c.n_mg * c.nk * c.mt * 128 * c.Kt;
+  std::vector<__nv_bfloat16> pack(total, __float2bfloat16_rn(0.f));
+  size_t o = 0;
+  for (int mg = 0; mg < c.n_mg; ++mg)
+    for (int kc = 0; kc < c.nk; ++kc)
+      for (int mi = 0; mi < c.mt; ++mi)
+        for (int kg = 0; kg < c.Kt / 8; ++kg)
+          for (int r = 0; r < 128; ++r)
+            for (int e = 0; e < 8; ++e, ++o) {
+              const int m = (mg * c.mt + mi) * 128 + r, k = kc * c.Kt + kg * 8 + e;
+              if (m < M) pack[o] = __float2bfloat16_rn(h_w[(size_t)m * K + k]);
+            }
+  TcTdfWeights* w = new TcTdfWeights();
+  w->cfg = c;
+  w->d_pack = nullptr;
+  if (cudaMalloc(&w->d_pack, total * 2) != cudaSuccess ||
+      cudaMemcpy(w->d_pack, pack.data(), total * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tdf weight upload failed");
+    delete w;
+    return AC_E_CUDA;
+  }
+  *out = w;
+  return AC_OK;
+}
+
+void tc_tdf_free(TcTdfWeights* w) {
+  if (!w) return;
+  if (w->d_pack) cudaFree(w->d_pack);
+  delete w;
+}
+
+int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                  int nB, int T, const float* scale, const float* shift, cudaStream_t st) {
+  AC_REQUIRE(w && in && out, "tc tdf: null");
+  const TdfCfg& c = w->cfg;
+  AC_REQUIRE(T % c.NTt == 0, "tc tdf: T not divisible by the time tile");
+  EncodeTiledFn enc = get_tensor_map_encoder();
+  AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
+  AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
+  CUtensorMap map;
+  const cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.K, (cuuint64_t)T, (cuuint64_t)nB};
+  const cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.K * c.C * 2, (cuuint64_t)T * c.K * c.C * 2};
+  const cuuint32_t box[4] = {8, (cuuint32_t)c.Kt, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (tdf) failed with code " + std::to_string((int)r));
+    return AC_E_CUDA;
+  }
+  TdfParams p;
+  p.cfg = c;
+  p.nB = nB; p.T = T;
+  p.n_tg = T / c.NTt;
+  p.n_units = c.n_mg * p.n_tg * nB;
+  p.wpack = w->d_pack;
+  p.scale = scale; p.shift = shift;
+  p.residual = residual;
+  p.out = out;
+  p.abort_flag = tc_abort_flag();
+  static bool attr = false;
+  if (!attr) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  int grid = device_sm_count();
+  if (grid > p.n_units) grid = p.n_units;
+  ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB, 2.0 * nB * (double)T * c.C * (c.K + c.M * (residual ? 2 : 1)), st);
+  tc_tdf_kernel<<<grid, kTdfThreads, c.smem_bytes, st>>>(map, p);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac
