@@ -16,6 +16,7 @@ struct ConvLayer {  // implicit-GEMM B operand [K][N] in both dtypes
   Affine af;
   int K, N;
   TcConvWeights* tc = nullptr;  // tcgen05 packing (3x3 convs only)
+  TcResampleWeights* rs = nullptr;  // tcgen05 packing (down / up convs only)
 };
 struct TdfLayer {  // GEMM A operand [M][K] (PyTorch Linear weight as is)
   const float* w32;
@@ -161,7 +162,7 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
     int c = g.g * (i + 1), T = g.dim_t >> i, F = g.dim_f >> i;
     read_block(c, T, F);
     ConvOff d;
-    d.raw = nullptr; d.cin = c; d.cout = c + g.g;
+    d.raw = h_blob + rd; d.cin = c; d.cout = c + g.g;
     d.w = conv3(c, c + g.g, 2, 2); d.sc = take(c + g.g); d.sh = take(c + g.g); d.K = 4 * c; d.N = c + g.g;
     dsoffs.push_back(d);
   }
@@ -170,7 +171,7 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
     int lvl = g.n - 1 - i;
     int c = g.g * (lvl + 1), T = g.dim_t >> lvl, F = g.dim_f >> lvl;
     ConvOff u;
-    u.raw = nullptr; u.cin = c + g.g; u.cout = c;
+    u.raw = h_blob + rd; u.cin = c + g.g; u.cout = c;
     u.w = convT(c + g.g, c); u.sc = take(c); u.sh = take(c); u.K = c + g.g; u.N = 4 * c;
     usoffs.push_back(u);
     read_block(c, T, F);
@@ -226,8 +227,16 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
     }
     net->blocks.push_back(b);
   }
-  for (auto& o : dsoffs) net->ds.push_back(mk_conv(o));
-  for (auto& o : usoffs) net->us.push_back(mk_conv(o));
+  for (auto& o : dsoffs) {
+    ConvLayer L = mk_conv(o);
+    if (tc_resample_pack(0, o.raw, o.cin, o.cout, &L.rs) != AC_OK) { ac_unet_destroy(net); return AC_E_CUDA; }
+    net->ds.push_back(L);
+  }
+  for (auto& o : usoffs) {
+    ConvLayer L = mk_conv(o);
+    if (tc_resample_pack(1, o.raw, o.cin, o.cout, &L.rs) != AC_OK) { ac_unet_destroy(net); return AC_E_CUDA; }
+    net->us.push_back(L);
+  }
   net->first_w = net->d_f32 + first_w;
   net->first_af = Affine{net->d_f32 + first_sc, net->d_f32 + first_sh};
   net->final_w = net->d_f32 + final_w;
@@ -245,6 +254,8 @@ extern "C" void ac_unet_destroy(ac_unet* net) {
     ac::tc_tdf_free(b.tdf1.tc);
     ac::tc_tdf_free(b.tdf2.tc);
   }
+  for (auto& L : net->ds) ac::tc_resample_free(L.rs);
+  for (auto& L : net->us) ac::tc_resample_free(L.rs);
   if (net->d_f32) cudaFree(net->d_f32);
   if (net->d_bf16) cudaFree(net->d_bf16);
   delete net;
@@ -373,6 +384,12 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     // l convs ping-pong cur/oth; with odd l the TFC output is in oth, with even l in cur: either way != skip
     if ((rc = run_block(b, cur, oth, skip))) return rc;
     const ConvLayer& d = net->ds[i];
+    if (dtype == AC_BF16 && d.rs && !net->force_simt) {
+      if ((rc = launch_tc_resample(d.rs, (const __nv_bfloat16*)skip, nullptr, (__nv_bfloat16*)cur, B, b.T / 2, b.F / 2,
+                                   d.af.scale, d.af.shift, st)))
+        return rc;
+      continue;
+    }
     GemmArgs a{};
     a.M = B * (b.T / 2) * (b.F / 2); a.N = d.N; a.K = d.K; a.batch = 1;
     a.a_mode = A_DOWN2; a.A = skip; a.T = b.T / 2; a.F = b.F / 2; a.C = b.c;
@@ -393,6 +410,11 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     const Block& b = net->blocks[g.n + 1 + i];
     const ConvLayer& u = net->us[i];
     void* skip = ptr(wp.skip_off[lvl]);
+    if (dtype == AC_BF16 && u.rs && !net->force_simt) {
+      if ((rc = launch_tc_resample(u.rs, (const __nv_bfloat16*)cur, (const __nv_bfloat16*)skip, (__nv_bfloat16*)oth, B, b.T / 2,
+                                   b.F / 2, u.af.scale, u.af.shift, st)))
+        return rc;
+    } else {
     GemmArgs a{};
     a.M = B * (b.T / 2) * (b.F / 2); a.N = u.N; a.K = u.K; a.batch = 1;
     a.a_mode = A_PLAIN; a.A = cur; a.a_batch_stride = 0;
@@ -401,6 +423,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.up_T = b.T / 2; a.up_F = b.F / 2;
     a.kclass = KC_RESAMPLE_SIMT;
     if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
+    }
     { void* t = cur; cur = oth; oth = t; }
     void* Z = (g.l & 1) ? cur : oth;
     if ((rc = run_block(b, cur, oth, Z))) return rc;

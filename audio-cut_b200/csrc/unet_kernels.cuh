@@ -56,6 +56,13 @@ int tc_conv3x3_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWeights** ou
 void tc_conv3x3_free(TcConvWeights* w);
 int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
 
+struct TcResampleWeights;  // opaque: packed smem images of a 2x2/s2 conv (down) or transposed conv (up)
+int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeights** out);
+void tc_resample_free(TcResampleWeights* w);
+// DOWN: in [nB][2T][2F][Cin] -> out [nB][T][F][Cout].  UP: in [nB][T][F][Cin]; skip, out [nB][2T][2F][Cout]
+int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* skip, __nv_bfloat16* out,
+                       int nB, int T, int F, const float* scale, const float* shift, cudaStream_t st);
+
 struct TcTdfWeights;  // opaque: packed smem images of one TDF linear layer
 // *out stays nullptr when the shape is left to the CUDA-core kernel (tiny deep-level layers)
 int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdfWeights** out);

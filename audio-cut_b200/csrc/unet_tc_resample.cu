@@ -1,0 +1,410 @@
+// tcgen05 kernels for the 2x2 / stride-2 down-sampling convs and the 2x2 / stride-2 transposed
+// convs (with the multiplicative skip fused into the epilogue) between U-Net levels.
+//
+// Both are implicit GEMMs over 128-position tiles of one output (down) / input (up) row:
+//   DOWN  D[128][NT] += X[b][2t+dt][2f+df][ci] * W[co][ci][dt][df]     K = 4*C_in, taps walk K
+//         the stride-2 gather is a 5-D tensor map (c, df, f, t, b): a box [8][1][128] lands as
+//         the K-major no-swizzle tile [128 positions][8 channels];
+//   UP    D_tap[128][C_out] += X[b][t][f][ci] * W[ci][co][dt][df]      K = C_in, taps walk N
+//         each tap has its own TMEM accumulator; the epilogue scatters tap (dt,df) of position
+//         (t,f) to out[b][2t+dt][2f+df][:] and multiplies by the encoder skip tensor.
+// These layers are HBM bound (<= 8 FLOP/B), so the design goal is streaming: one pass over the
+// input, one over the skip, one write - the MMA work hides under the memory time.
+#include <vector>
+
+#include "tc_common.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+constexpr int kRsThreads = 192;
+enum { RS_DOWN = 0, RS_UP = 1 };
+
+struct RsCfg {
+  int mode;
+  int Cin, Cout;
+  int NT, nsplit;   // DOWN: N tile of C_out.  UP: NT = C_out, nsplit = tap groups
+  int ntap;         // UP: taps per unit; DOWN: 2 (df taps per stage)
+  int MT, KC, nkc, stages, nbuf;
+  int a_tile_bytes;   // one [128 positions][KC] tile = (KC/8) * 2048
+  int b_stage_bytes;
+  int stage_bytes, smem_bytes;
+};
+
+struct RsParams {
+  RsCfg cfg;
+  int nB, T, F;  // DOWN: OUTPUT grid.  UP: INPUT grid
+  int n_fg, n_units;
+  const __nv_bfloat16* wpack;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* skip;  // UP only
+  __nv_bfloat16* out;
+  int* abort_flag;
+};
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid_constant__ CUtensorMap in_map, const RsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const RsCfg& c = p.cfg;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 8;
+  uint64_t* tfull = full + 16;
+  uint64_t* tempty = full + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
+  uint8_t* stage0 = smem + 1024;
+  volatile int* abort_flag = p.abort_flag;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < c.nbuf; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool down = c.mode == RS_DOWN;
+  const int ndt = down ? 2 : 1;             // K-walk over vertical taps (DOWN only)
+  const int steps = ndt * c.nkc;
+  const int a_per_stage = (down ? 2 : 1) * c.MT;  // A tiles per stage
+  const int acc_per_unit = down ? c.MT : c.MT * c.ntap;
+
+  auto decode = [&](int u, int& ns, int& b, int& t, int& f0) {
+    const int fg = u % p.n_fg;
+    int q = u / p.n_fg;
+    t = q % p.T;
+    q /= p.T;
+    b = q % p.nB;
+    ns = q / p.nB;
+    f0 = fg * c.MT * 128;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
+        int ns, b, t, f0;
+        decode(u, ns, b, t, f0);
+        for (int dt = 0; dt < ndt && alive; ++dt) {
+          for (int kc = 0; kc < c.nkc; ++kc) {
+            if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+            uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
+            mbar_expect_tx(&full[s], (uint32_t)(a_per_stage * c.a_tile_bytes + c.b_stage_bytes));
+            for (int mt = 0; mt < c.MT; ++mt) {
+              for (int kg = 0; kg < c.KC / 8; ++kg) {
+                if (down) {
+                  for (int df = 0; df < 2; ++df)
+                    tma_load_5d(st + (mt * 2 + df) * c.a_tile_bytes + kg * 2048, &in_map, &full[s], kc * c.KC + kg * 8, df,
+                                f0 + mt * 128, 2 * t + dt, b);
+                } else {
+                  tma_load_4d(st + mt * c.a_tile_bytes + kg * 2048, &in_map, &full[s], kc * c.KC + kg * 8, f0 + mt * 128, t, b);
+                }
+              }
+            }
+            const size_t blob = (size_t)c.ntap * c.KC * c.NT;
+            const __nv_bfloat16* wsrc = p.wpack + ((size_t)((ns * ndt + dt) * c.nkc + kc)) * blob;
+            bulk_load_1d(st + a_per_stage * c.a_tile_bytes, wsrc, (uint32_t)c.b_stage_bytes, &full[s]);
+            if (++s == c.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(c.NT);
+      const uint32_t b_lbo = (uint32_t)c.NT * 16;
+      int s = 0, buf = 0;
+      uint32_t ph = 0, tph = 0;
+      bool alive = true;
+      for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
+        if (!mbar_wait(&tempty[buf], tph ^ 1, abort_flag)) break;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * acc_per_unit * c.NT);
+        for (int step = 0; step < steps; ++step) {
+          if (!mbar_wait(&full[s], ph, abort_flag)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)(a_per_stage * c.a_tile_bytes);
+          for (int tp = 0; tp < c.ntap; ++tp) {
+            for (int mt = 0; mt < c.MT; ++mt) {
+              for (int k = 0; k < c.KC / 16; ++k) {
+                const uint32_t a_addr = sa + (down ? (mt * 2 + tp) : mt) * c.a_tile_bytes + k * 2 * 2048;
+                const uint64_t ad = make_desc(a_addr, 2048, 128);
+                const uint64_t bd = make_desc(sb + tp * (c.KC * c.NT * 2) + k * 2 * b_lbo, b_lbo, 128);
+                if (down)
+                  umma_f16(acc0 + (uint32_t)(mt * c.NT), ad, bd, idesc, (step | tp | k) != 0);
+                else
+                  umma_f16(acc0 + (uint32_t)((mt * c.ntap + tp) * c.NT), ad, bd, idesc, (step | k) != 0);
+              }
+            }
+          }
+          umma_commit(&empty[s]);
+          if (++s == c.stages) { s = 0; ph ^= 1; }
+        }
+        if (!alive) break;
+        umma_commit(&tfull[buf]);
+        if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int buf = 0;
+    uint32_t tph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      int ns, b, t, f0;
+      decode(u, ns, b, t, f0);
+      if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
+      tc_fence_after();
+      for (int a = 0; a < acc_per_unit; ++a) {
+        const int mt = down ? a : a / c.ntap;
+        const int tp = down ? 0 : a % c.ntap;
+        const int f = f0 + mt * 128 + quad * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * acc_per_unit + a) * c.NT);
+        size_t base;
+        int n0;
+        if (down) {
+          n0 = ns * c.NT;
+          base = (((size_t)b * p.T + t) * p.F + f) * c.Cout + n0;
+        } else {
+          const int tap = ns * c.ntap + tp;
+          n0 = 0;
+          base = (((size_t)b * (2 * p.T) + 2 * t + (tap >> 1)) * (size_t)(2 * p.F) + 2 * f + (tap & 1)) * c.Cout;
+        }
+        for (int j = 0; j < c.NT; j += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j, r);
+          tmem_ld_wait();
+          if (f < p.F) {
+            float mul[16];
+            if (!down) {
+              const uint4 q0 = *reinterpret_cast<const uint4*>(p.skip + base + j);
+              const uint4 q1 = *reinterpret_cast<const uint4*>(p.skip + base + j + 8);
+              const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                mul[2 * e] = fl.x;
+                mul[2 * e + 1] = fl.y;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) mul[e] = 1.f;
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = n0 + j + 2 * e;
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), __ldg(p.scale + ch), __ldg(p.shift + ch)), 0.f) * mul[2 * e];
+              const float v1 =
+                  fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), __ldg(p.scale + ch + 1), __ldg(p.shift + ch + 1)), 0.f) * mul[2 * e + 1];
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(p.out + base + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(p.out + base + j + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+struct TcResampleWeights {
+  RsCfg cfg;
+  __nv_bfloat16* d_pack;
+};
+
+static bool make_rs_cfg(int mode, int Cin, int Cout, RsCfg& c) {
+  if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16) return false;
+  c.mode = mode;
+  c.Cin = Cin;
+  c.Cout = Cout;
+  if (mode == RS_DOWN) {
+    c.nsplit = 1;
+    if (Cout > 256) {
+      c.nsplit = 0;
+      for (int s = 2; s <= 8; ++s)
+        if (Cout % (16 * s) == 0 && Cout / s <= 256) { c.nsplit = s; break; }
+      if (!c.nsplit) return false;
+    }
+    c.NT = Cout / c.nsplit;
+    c.ntap = 2;
+    c.MT = 256 / c.NT;
+    if (c.MT < 1) c.MT = 1;
+    if (c.MT > 2) c.MT = 2;
+    c.nbuf = (2 * c.MT * c.NT <= 512) ? 2 : 1;
+  } else {
+    if (Cout > 256) return false;
+    c.NT = Cout;
+    c.ntap = 4;
+    while (c.ntap > 1 && 2 * c.ntap * c.NT > 512) c.ntap /= 2;
+    c.nsplit = 4 / c.ntap;  // tap groups
+    c.MT = 1;
+    c.nbuf = (2 * c.ntap * c.NT <= 512) ? 2 : 1;
+  }
+  c.KC = 16;
+  for (int k = 48; k >= 16; k -= 16)
+    if (Cin % k == 0) { c.KC = k; break; }
+  c.nkc = Cin / c.KC;
+  c.a_tile_bytes = (c.KC / 8) * 2048;
+  c.b_stage_bytes = c.ntap * c.KC * c.NT * 2;
+  const int a_per_stage = (mode == RS_DOWN ? 2 : 1) * c.MT;
+  c.stage_bytes = (int)align_up((size_t)a_per_stage * c.a_tile_bytes + c.b_stage_bytes, 128);
+  c.stages = (220 * 1024 - 1024) / c.stage_bytes;
+  if (c.stages > 8) c.stages = 8;
+  if (c.stages < 2) return false;
+  c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+  return true;
+}
+
+// DOWN: h_w = Conv2d weight [Cout][Cin][2][2].  UP: h_w = ConvTranspose2d weight [Cin][Cout][2][2].
+int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeights** out) {
+  *out = nullptr;
+  RsCfg c;
+  if (!make_rs_cfg(up ? RS_UP : RS_DOWN, Cin, Cout, c)) return AC_OK;
+  std::vector<__nv_bfloat16> pack((size_t)4 * Cin * Cout);
+  size_t o = 0;
+  if (!up) {
+    // [ns][dt][kc][df][KC/8][NT][8]
+    for (int ns = 0; ns < c.nsplit; ++ns)
+      for (int dt = 0; dt < 2; ++dt)
+        for (int kc = 0; kc < c.nkc; ++kc)
+          for (int df = 0; df < 2; ++df)
+            for (int kg = 0; kg < c.KC / 8; ++kg)
+              for (int n = 0; n < c.NT; ++n)
+                for (int e = 0; e < 8; ++e) {
+                  const int co = ns * c.NT + n, ci = kc * c.KC + kg * 8 + e;
+                  pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * Cin + ci) * 2 + dt) * 2 + df]);
+                }
+  } else {
+    // [tap group][kc][tp][KC/8][NT][8]
+    for (int tg = 0; tg < c.nsplit; ++tg)
+      for (int kc = 0; kc < c.nkc; ++kc)
+        for (int tp = 0; tp < c.ntap; ++tp)
+          for (int kg = 0; kg < c.KC / 8; ++kg)
+            for (int n = 0; n < c.NT; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int tap = tg * c.ntap + tp, ci = kc * c.KC + kg * 8 + e;
+                pack[o++] = __float2bfloat16_rn(h_w[((size_t)ci * Cout + n) * 4 + tap]);
+              }
+  }
+  TcResampleWeights* w = new TcResampleWeights();
+  w->cfg = c;
+  w->d_pack = nullptr;
+  if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
+      cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("resample weight upload failed");
+    delete w;
+    return AC_E_CUDA;
+  }
+  *out = w;
+  return AC_OK;
+}
+
+void tc_resample_free(TcResampleWeights* w) {
+  if (!w) return;
+  if (w->d_pack) cudaFree(w->d_pack);
+  delete w;
+}
+
+// DOWN: in [nB][2T][2F][Cin] -> out [nB][T][F][Cout].   UP: in [nB][T][F][Cin], skip/out [nB][2T][2F][Cout].
+int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* skip, __nv_bfloat16* out,
+                       int nB, int T, int F, const float* scale, const float* shift, cudaStream_t st) {
+  AC_REQUIRE(w && in && out, "tc resample: null");
+  RsCfg c = w->cfg;
+  const bool down = c.mode == RS_DOWN;
+  AC_REQUIRE(down || skip, "tc resample: up needs the skip tensor");
+  const int tiles = (F + 127) / 128;
+  if (c.MT > tiles) {  // fewer tiles per unit: the packing does not depend on MT
+    c.MT = tiles;
+    const int a_per_stage = (down ? 2 : 1) * c.MT;
+    c.stage_bytes = (int)align_up((size_t)a_per_stage * c.a_tile_bytes + c.b_stage_bytes, 128);
+    c.stages = (220 * 1024 - 1024) / c.stage_bytes;
+    if (c.stages > 8) c.stages = 8;
+    c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+    c.nbuf = down ? ((2 * c.MT * c.NT <= 512) ? 2 : 1) : c.nbuf;
+  }
+  EncodeTiledFn enc = get_tensor_map_encoder();
+  AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
+  AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
+  CUtensorMap map;
+  CUresult r;
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (down) {
+    const cuuint64_t C2 = (cuuint64_t)c.Cin * 2;
+    const cuuint64_t dims[5] = {(cuuint64_t)c.Cin, 2, (cuuint64_t)F, (cuuint64_t)(2 * T), (cuuint64_t)nB};
+    const cuuint64_t strides[4] = {C2, 2 * C2, (cuuint64_t)(2 * F) * C2, (cuuint64_t)(2 * T) * (2 * F) * C2};
+    const cuuint32_t box[5] = {8, 1, 128, 1, 1};
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t C2 = (cuuint64_t)c.Cin * 2;
+    const cuuint64_t dims[4] = {(cuuint64_t)c.Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)nB};
+    const cuuint64_t strides[3] = {C2, (cuuint64_t)F * C2, (cuuint64_t)T * F * C2};
+    const cuuint32_t box[4] = {8, 128, 1, 1};
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (resample) failed with code " + std::to_string((int)r));
+    return AC_E_CUDA;
+  }
+  RsParams p;
+  p.cfg = c;
+  p.nB = nB; p.T = T; p.F = F;
+  p.n_fg = (tiles + c.MT - 1) / c.MT;
+  p.n_units = c.nsplit * nB * T * p.n_fg;
+  p.wpack = w->d_pack;
+  p.scale = scale; p.shift = shift;
+  p.skip = skip;
+  p.out = out;
+  p.abort_flag = tc_abort_flag();
+  static bool attr = false;
+  if (!attr) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  int grid = device_sm_count();
+  if (grid > p.n_units) grid = p.n_units;
+  const double pos = (double)nB * T * F;
+  const double bytes = down ? pos * 2.0 * (4.0 * c.Cin + c.Cout) : pos * 2.0 * (c.Cin + 8.0 * c.Cout);
+  ProfScope ps(KC_RESAMPLE_TC, 2.0 * pos * 4.0 * c.Cin * c.Cout, bytes, st);
+  tc_resample_kernel<<<grid, kRsThreads, c.smem_bytes, st>>>(map, p);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac
