@@ -13,7 +13,9 @@
 // over the whole call = one chunk) is folded in with an ordered-int atomicMax.
 // Pass 2 (one warp per frame): clip at max-80 dB, rectified difference to the previous frame,
 // mean and exact median (rank counting through shuffles) over the 128 bands.
+#include <algorithm>
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -380,6 +382,207 @@ extern "C" int ac_stft_features(const float* d_x, const ac_feat_segment* h_segs,
     ProfScope ps(KC_FEAT_FLUX, 0.0, (double)frames * (1024.0 + 8.0), st);
     onset_flux_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, st>>>(xa);
     AC_LAUNCH_CHECK();
+  }
+  return AC_OK;
+}
+
+// =================================================================================================
+// Autocorrelation tempogram statistics (librosa.feature.tempogram + rhythm.tempo front end):
+//   features_cache.py:283-288 (aggregate=None), adaptive_vad_enhancer.py:61-67 (beat_track -> mean
+//   aggregate), :151-156 (aggregate=None).  SURVEY.md section 8(f) row N2.
+// For every frame t: window = hann(win) * padded_env[t : t+win] (linear-ramp centring), autocorrelation
+// by FFT (two frames per complex transform, forward and inverse), max-normalised.  Emitted per frame:
+// argmax_lag(log1p(1e6*tg) + logprior); accumulated over frames: sum of the normalised tempogram.
+// =================================================================================================
+namespace ac {
+
+struct TgArgs {
+  const float* env;
+  long long n;
+  int win, half;
+  FftDev fft;
+  const float* window;    // hann(win), periodic
+  const float* logprior;  // [win], -inf where excluded
+  float* tg_sum;          // [win], pre-zeroed
+  int* best;              // [n]
+  int pairs_per_cta;
+};
+
+__device__ __forceinline__ float tg_padded(const TgArgs& a, long long p) {
+  // np.pad(env, half, mode="linear_ramp", end_values=0)
+  if (p < a.half) return a.env[0] * ((float)p / (float)a.half);
+  const long long q = p - a.half;
+  if (q < a.n) return a.env[q];
+  const long long i = q - a.n;  // 0 .. half-1
+  return a.env[a.n - 1] * (1.0f - (float)(i + 1) / (float)a.half);
+}
+
+__global__ void __launch_bounds__(256) tempogram_kernel(TgArgs a) {
+  extern __shared__ float2 smem_f2[];
+  const int N = a.fft.n;
+  float2* buf0 = smem_f2;
+  float2* buf1 = buf0 + fpad(N) + 1;
+  float* acc = reinterpret_cast<float*>(buf1 + fpad(N) + 1);  // [win]
+  __shared__ float s_max[2][8];
+  __shared__ float s_val[2][8];
+  __shared__ int s_idx[2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = threadIdx.x; j < a.win; j += 256) acc[j] = 0.f;
+  __syncthreads();
+  for (int pp = 0; pp < a.pairs_per_cta; ++pp) {
+    const long long t0 = 2 * ((long long)blockIdx.x * a.pairs_per_cta + pp);
+    if (t0 >= a.n) break;
+    const bool has_b = t0 + 1 < a.n;
+    for (int j = threadIdx.x; j < N; j += 256) {
+      float va = 0.f, vb = 0.f;
+      if (j < a.win) {
+        const float w = __ldg(a.window + j);
+        va = tg_padded(a, t0 + j) * w;
+        vb = has_b ? tg_padded(a, t0 + 1 + j) * w : 0.f;
+      }
+      buf0[fpad(j)] = make_float2(va, vb);
+    }
+    __syncthreads();
+    float2* Z = fft_smem<false>(buf0, buf1, a.fft);
+    float2* Q = (Z == buf0) ? buf1 : buf0;
+    for (int k = threadIdx.x; k < N; k += 256) {
+      const float2 u = Z[fpad(k)];
+      const float2 v = Z[fpad(k == 0 ? 0 : N - k)];
+      const float are = 0.5f * (u.x + v.x), aim = 0.5f * (u.y - v.y);
+      const float bre = 0.5f * (u.y + v.y), bim = -0.5f * (u.x - v.x);
+      Q[fpad(k)] = make_float2(are * are + aim * aim, bre * bre + bim * bim);
+    }
+    __syncthreads();
+    float2* R = fft_smem<true>(Q, Z, a.fft);  // R[j] = (autocorr_a[j], autocorr_b[j]) * N
+    // ---- per-frame max |ac| over the first `win` lags
+    float ma = 0.f, mb = 0.f;
+    for (int j = threadIdx.x; j < a.win; j += 256) {
+      const float2 r = R[fpad(j)];
+      ma = fmaxf(ma, fabsf(r.x));
+      mb = fmaxf(mb, fabsf(r.y));
+    }
+    ma = warp_max(ma);
+    mb = warp_max(mb);
+    if (lane == 0) { s_max[0][warp] = ma; s_max[1][warp] = mb; }
+    __syncthreads();
+    ma = mb = 0.f;
+    for (int w = 0; w < 8; ++w) { ma = fmaxf(ma, s_max[0][w]); mb = fmaxf(mb, s_max[1][w]); }
+    const float ia = ma < 1.17549435e-38f ? 1.f : 1.f / ma, ib = mb < 1.17549435e-38f ? 1.f : 1.f / mb;
+    // ---- normalise, accumulate, argmax of log1p(1e6*tg) + logprior (first maximum wins)
+    float best_a = -INFINITY, best_b = -INFINITY;
+    int idx_a = 0x7fffffff, idx_b = 0x7fffffff;
+    for (int j = threadIdx.x; j < a.win; j += 256) {
+      const float2 r = R[fpad(j)];
+      const float ta = r.x * ia, tb = r.y * ib;
+      acc[j] += ta + (has_b ? tb : 0.f);
+      const float lp = __ldg(a.logprior + j);
+      const float sa = log1pf(1e6f * ta) + lp, sb = log1pf(1e6f * tb) + lp;
+      if (sa > best_a) { best_a = sa; idx_a = j; }
+      if (sb > best_b) { best_b = sb; idx_b = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best_a, o);
+      int oi = __shfl_xor_sync(0xffffffffu, idx_a, o);
+      if (ov > best_a || (ov == best_a && oi < idx_a)) { best_a = ov; idx_a = oi; }
+      ov = __shfl_xor_sync(0xffffffffu, best_b, o);
+      oi = __shfl_xor_sync(0xffffffffu, idx_b, o);
+      if (ov > best_b || (ov == best_b && oi < idx_b)) { best_b = ov; idx_b = oi; }
+    }
+    if (lane == 0) { s_val[0][warp] = best_a; s_idx[0][warp] = idx_a; s_val[1][warp] = best_b; s_idx[1][warp] = idx_b; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int f = threadIdx.x;
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int w = 0; w < 8; ++w)
+        if (s_val[f][w] > bv || (s_val[f][w] == bv && s_idx[f][w] < bi)) { bv = s_val[f][w]; bi = s_idx[f][w]; }
+      if (bi == 0x7fffffff) bi = 0;  // every candidate was -inf / NaN: numpy's argmax returns 0
+      if (f == 0 || has_b) a.best[t0 + f] = bi;
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < a.win; j += 256) atomicAdd(a.tg_sum + j, acc[j]);
+}
+
+}  // namespace ac
+
+extern "C" int ac_tempogram_stats(const float* d_env, long long n, int win, const float* d_logprior, float* d_tg_sum,
+                                  int* d_best, void* stream) {
+  using namespace ac;
+  AC_REQUIRE(d_env && d_logprior && d_tg_sum && d_best, "null pointer");
+  AC_REQUIRE(n > 0 && win >= 2, "bad sizes");
+  int nfft = 16;
+  while (nfft < 2 * win - 1) nfft *= 2;
+  AC_REQUIRE(nfft <= 8192, "tempogram window too long");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FftPlan* fp = get_fft_plan(nfft);
+  if (!fp) return AC_E_CUDA;
+  // periodic hann(win): cached per win
+  static std::mutex mu;
+  static std::map<int, float*> cache;
+  float* d_win = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(win);
+    if (it == cache.end()) {
+      std::vector<float> h(win);
+      for (int i = 0; i < win; ++i) h[i] = (float)(0.5 - 0.5 * std::cos(6.283185307179586476925286766559 * i / win));
+      AC_CHECK_CUDA(cudaMalloc(&d_win, sizeof(float) * win));
+      AC_CHECK_CUDA(cudaMemcpy(d_win, h.data(), sizeof(float) * win, cudaMemcpyHostToDevice));
+      cache[win] = d_win;
+    } else {
+      d_win = it->second;
+    }
+  }
+  AC_CHECK_CUDA(cudaMemsetAsync(d_tg_sum, 0, sizeof(float) * win, st));
+  TgArgs a;
+  a.env = d_env; a.n = n; a.win = win; a.half = win / 2; a.fft = make_fft_dev(fp); a.window = d_win;
+  a.logprior = d_logprior; a.tg_sum = d_tg_sum; a.best = d_best;
+  const long long pairs = (n + 1) / 2;
+  a.pairs_per_cta = (int)std::max<long long>(1, std::min<long long>(16, pairs / (4LL * device_sm_count())));
+  const long long grid = (pairs + a.pairs_per_cta - 1) / a.pairs_per_cta;
+  const size_t smem = sizeof(float2) * 2 * fft_smem_floats2(nfft) + sizeof(float) * win;
+  AC_CHECK_CUDA(cudaFuncSetAttribute(tempogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(KC_MISC, 0.0, 4.0 * n * 3, st);
+  tempogram_kernel<<<(unsigned)grid, 256, smem, st>>>(a);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+// Ellis dynamic-programming beat tracker inner loop (librosa.beat.__beat_track_dp) - a strictly
+// sequential scan over frames, so it runs on the host; C++ instead of a Python loop.
+extern "C" int ac_host_beat_dp(const float* localscore, int n, int period, float tightness, long long* backlink,
+                               float* cumscore) {
+  AC_REQUIRE(localscore && backlink && cumscore && n >= 0 && period >= 1 && tightness > 0, "bad arguments");
+  const int w_lo = -2 * period, w_hi = -(int)std::nearbyint(period / 2.0);  // np.round: half to even  // window = arange(w_lo, w_hi + 1)
+  const int nw = w_hi - w_lo + 1;
+  if (nw <= 0) return AC_E_INVALID;
+  std::vector<double> txwt(nw);
+  for (int k = 0; k < nw; ++k) {
+    const double lg = std::log(-(double)(w_lo + k) / (double)period);
+    txwt[k] = -(double)tightness * lg * lg;
+  }
+  float mx = -INFINITY;
+  for (int i = 0; i < n; ++i) mx = std::max(mx, localscore[i]);
+  const double thresh = 0.01 * (double)mx;
+  bool first = true;
+  for (int i = 0; i < n; ++i) {
+    // candidates[k] = txwt[k] (+ cumscore[i + w_lo + k] when that index is >= 0); first maximum wins
+    double best = -INFINITY;
+    int loc = 0;
+    for (int k = 0; k < nw; ++k) {
+      const int j = i + w_lo + k;
+      const double c = txwt[k] + (j >= 0 ? (double)cumscore[j] : 0.0);
+      if (c > best) { best = c; loc = k; }
+    }
+    cumscore[i] = (float)((double)localscore[i] + best);
+    if (first && (double)localscore[i] < thresh) {
+      backlink[i] = -1;
+    } else {
+      backlink[i] = i + w_lo + loc;
+      first = false;
+    }
   }
   return AC_OK;
 }

@@ -108,17 +108,17 @@ def bpm_features_from_wave(wave_dev: torch.Tensor, sr: int) -> BPMFeatures:
     hop = 512
     n = wave_dev.numel()
     total = 1 + n // hop
-    env = ops.stft_features(wave_dev, [(0, n, 0)], hop, sr, total_frames=total, want=("onset_median",))["onset_median"].cpu().numpy()
+    env_d = ops.stft_features(wave_dev, [(0, n, 0)], hop, sr, total_frames=total, want=("onset_median",))["onset_median"]
+    curve, bpm, _ = ops.tempogram_stats(env_d, sr, hop, start_bpm=120.0)
+    env = env_d.cpu().numpy()
     if not env.any():
         return BPMFeatures(120.0, "medium", 0.5, 0.5, 0.1, {}, np.zeros(0, dtype=int))
-    tg = host_dsp.tempogram(env, int(np.floor(8.0 * sr / hop)))
-    bpm, beats = host_dsp.beat_track(env, sr, hop, start_bpm=120.0, tightness=100.0, tg=tg)
+    bpm, beats = host_dsp.beat_track(env, sr, hop, start_bpm=120.0, tightness=100.0, bpm=bpm, dp=ops.host_beat_dp)
     if len(beats) >= 3:
         iv = np.diff(beats)
         stability = float(np.clip(1.0 - np.std(iv) / np.mean(iv), 0.0, 1.0)) if np.mean(iv) > 0 else 0.5
     else:
         stability = 0.5
-    curve = host_dsp.tempo_from_tempogram(tg, sr, hop, aggregate=None)
     variance = float(np.clip(np.std(curve) / (np.mean(curve) + 1e-8), 0.0, 1.0)) if len(curve) > 1 else 0.1
     return BPMFeatures(float(bpm), classify_bpm(float(bpm)), stability, 0.8, variance, {}, beats)
 
@@ -233,9 +233,9 @@ class B200ChunkFeatureBuilder:
         onset_frames = np.array(sorted(i for i in uniq if i in oset), dtype=int)
         bpm_wave = torch.cat(self._segments) if self._segments else None
         bpm = bpm_features_from_wave(bpm_wave, self.sr) if bpm_wave is not None and bpm_wave.numel() else None
-        tg = host_dsp.tempogram(onset, int(np.floor(8.0 * self.sr / self.hop_length)))
-        tempo_curve = host_dsp.tempo_from_tempogram(tg, self.sr, self.hop_length, aggregate=None)
-        _, beat_frames = host_dsp.beat_track(onset, self.sr, self.hop_length, tg=tg)
+        onset_d = torch.from_numpy(onset).to(self.device)
+        tempo_curve, bpm_cache, _ = ops.tempogram_stats(onset_d, self.sr, self.hop_length)
+        _, beat_frames = host_dsp.beat_track(onset, self.sr, self.hop_length, bpm=bpm_cache, dp=ops.host_beat_dp)
         beat_times = beat_frames * self.hop_length / float(self.sr)
         mdd = compute_mdd_series(rms, flat, onset)
         n_total = full_mix_wave.shape[-1] if hasattr(full_mix_wave, "shape") else len(full_mix_wave)

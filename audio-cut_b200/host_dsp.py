@@ -147,7 +147,7 @@ def _localmax(x: np.ndarray) -> np.ndarray:
 
 
 def beat_track(onset_envelope: np.ndarray, sr: int, hop_length: int, start_bpm: float = 120.0, tightness: float = 100.0,
-               trim: bool = True, bpm: Optional[float] = None, tg: Optional[np.ndarray] = None) -> Tuple[float, np.ndarray]:
+               trim: bool = True, bpm: Optional[float] = None, tg: Optional[np.ndarray] = None, dp=None) -> Tuple[float, np.ndarray]:
     """Ellis dynamic-programming beat tracker: (tempo, beat frames)."""
     env = np.asarray(onset_envelope, dtype=np.float32)
     if env.size == 0 or not env.any():
@@ -162,7 +162,7 @@ def beat_track(onset_envelope: np.ndarray, sr: int, hop_length: int, start_bpm: 
     if period < 1:
         return bpm, np.zeros(0, dtype=int)
     localscore = _local_score(env, period)
-    backlink, cumscore = _beat_dp(localscore, period, tightness)
+    backlink, cumscore = (dp or _beat_dp)(localscore, period, tightness)
     maxes = _localmax(cumscore)
     if not maxes.any():
         return bpm, np.zeros(0, dtype=int)

@@ -177,3 +177,42 @@ def stft_features(x: torch.Tensor, segments: Sequence[Tuple[int, int, int]], hop
     check(lib.ac_stft_features(ptr(x), segs, len(segments), hop, sr, *[ptr(out.get(k)) for k in names], ptr(ws), nbytes,
                                stream_ptr()), "ac_stft_features")
     return out
+
+
+def tempo_prior(win: int, sr: int, hop: int, start_bpm: float = 120.0, std_bpm: float = 1.0, max_tempo: float = 320.0):
+    """(bpms[win], logprior[win]) of librosa.feature.rhythm.tempo (lag 0 -> inf bpm, excluded)."""
+    bpms = np.empty(win, dtype=np.float64)
+    bpms[0] = np.inf
+    bpms[1:] = 60.0 * sr / (hop * np.arange(1.0, win))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        logprior = -0.5 * ((np.log2(bpms) - np.log2(start_bpm)) / std_bpm) ** 2
+    logprior[: int(np.argmax(bpms < max_tempo))] = -np.inf
+    return bpms, logprior
+
+
+def tempogram_stats(env: torch.Tensor, sr: int, hop: int, start_bpm: float = 120.0):
+    """Device tempogram of an onset envelope -> (tempo per frame [n], global tempo, mean tempogram [win])."""
+    lib = _lib.init(_dev_index(env))
+    env = env.contiguous().float()
+    n = env.numel()
+    win = int(np.floor(8.0 * sr / hop))
+    bpms, logprior = tempo_prior(win, sr, hop, start_bpm)
+    lp = torch.from_numpy(logprior.astype(np.float32)).to(env.device)
+    tg_sum = torch.empty(win, dtype=torch.float32, device=env.device)
+    best = torch.empty(n, dtype=torch.int32, device=env.device)
+    check(lib.ac_tempogram_stats(ptr(env), n, win, ptr(lp), ptr(tg_sum), ptr(best), stream_ptr()), "ac_tempogram_stats")
+    tg_mean = (tg_sum / float(n)).cpu().numpy().astype(np.float64)
+    curve = bpms[best.cpu().numpy()]
+    glob = float(bpms[int(np.argmax(np.log1p(1e6 * tg_mean) + logprior))])
+    return curve, glob, tg_mean
+
+
+def host_beat_dp(localscore: np.ndarray, period: int, tightness: float):
+    """C++ scan of the beat-tracking DP (host)."""
+    lib = _lib.load()
+    ls = np.ascontiguousarray(localscore, dtype=np.float32)
+    n = ls.shape[0]
+    backlink = np.zeros(n, dtype=np.int64)
+    cumscore = np.zeros(n, dtype=np.float32)
+    check(lib.ac_host_beat_dp(ls.ctypes.data, n, int(period), float(tightness), backlink.ctypes.data, cumscore.ctypes.data), "ac_host_beat_dp")
+    return backlink, cumscore

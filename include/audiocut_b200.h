@@ -174,6 +174,19 @@ AC_API int ac_stft_features(const float* d_x, const ac_feat_segment* h_segs, int
                      float* d_onset_mean, float* d_onset_median, float* d_centroid, float* d_low_ratio, void* d_ws,
                      size_t ws_bytes, void* stream);
 
+/* ---- rhythm front end ------------------------------------------------
+ * Autocorrelation tempogram of an onset envelope (librosa.feature.tempogram: hann window of `win`
+ * frames, hop 1, centred with a linear ramp, autocorrelation max-normalised per frame) reduced on
+ * the device to what librosa.feature.rhythm.tempo needs (features_cache.py:283-288,
+ * adaptive_vad_enhancer.py:61-67, 151-156): d_best[t] = argmax_lag(log1p(1e6*tg[lag,t]) + logprior[lag])
+ * (aggregate=None) and d_tg_sum[lag] = sum_t tg[lag,t] (aggregate=mean is d_tg_sum / n). */
+AC_API int ac_tempogram_stats(const float* d_env, long long n, int win, const float* d_logprior, float* d_tg_sum,
+                              int* d_best, void* stream);
+/* HOST function: the sequential scan of librosa.beat.__beat_track_dp (Ellis DP).  h_cumscore must be
+ * zero-initialised; h_backlink[i] = previous beat frame or -1. */
+AC_API int ac_host_beat_dp(const float* h_localscore, int n, int period, float tightness, long long* h_backlink,
+                           float* h_cumscore);
+
 /* librosa.feature.zero_crossing_rate(y, frame_length, hop_length, center=True) (edge padding,
  * |y| <= 1e-10 -> 0): pure_vocal_pause_detector.py:444. */
 AC_API int ac_zero_crossing_rate(const float* d_x, long long n, int frame, int hop, float* d_out, void* stream);

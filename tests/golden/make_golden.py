@@ -177,8 +177,42 @@ def gen_pipeline():
     print("pipeline.npz", vocal.shape, cache.rms_series.shape, cache.onset_frames, ctx.gpu_meta)
 
 
-if __name__ == "__main__":
+def main():
     torch.set_num_threads(4)
-    gen_chunk_schedule()
-    gen_infer_chunk()
-    gen_pipeline()
+    if "--cuts" not in sys.argv:
+        gen_chunk_schedule()
+        gen_infer_chunk()
+        gen_pipeline()
+    gen_cuts()
+
+
+def gen_cuts():
+    """finalize_cut_points of the reference (refine.py, loaded standalone: its package __init__ pulls librosa)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_refine", os.path.join(REF, "src/audio_cut/cutting/refine.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_refine"] = mod
+    spec.loader.exec_module(mod)
+    cases = []
+    for seed in range(4):
+        rng = np.random.default_rng(100 + seed)
+        sr = 8000
+        n = int(24.0 * sr)
+        t = np.arange(n) / sr
+        gate = (np.sin(2 * np.pi * 0.23 * t + seed) > -0.3).astype(np.float64)
+        vocal = (0.3 * np.sin(2 * np.pi * 180 * t) * gate + 1e-4 * rng.standard_normal(n)).astype(np.float32)
+        mix = (vocal + 0.1 * np.sin(2 * np.pi * 55 * t) * (np.sin(2 * np.pi * 0.11 * t) > 0) + 1e-3 * rng.standard_normal(n)).astype(np.float32)
+        pts = [(float(x), float(s)) for x, s in zip(rng.uniform(0.2, 23.8, 14), rng.uniform(0, 1, 14))]
+        kw = dict(min_gap_s=1.0, guard_db=1.5, search_right_ms=450.0, guard_win_ms=80.0, floor_db=-45.0 + 5 * seed,
+                  zero_cross_win_ms=8.0, min_boundary_s=0.5, topk_per_10s=(None if seed % 2 else 4))
+        res = mod.finalize_cut_points(mod.CutContext(sr=sr, mix_wave=mix, vocal_wave=vocal), [mod.CutPoint(t=a, score=b) for a, b in pts], **kw)
+        cases.append({"seed": 100 + seed, "points": pts, "kwargs": kw, "sample_boundaries": [int(v) for v in res.sample_boundaries],
+                      "final_times": [repr(float(p.t)) for p in res.final_points]})
+    with open(os.path.join(HERE, "cuts.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+    print("cuts.json", [c["sample_boundaries"] for c in cases])
+
+
+if __name__ == "__main__":
+    main()

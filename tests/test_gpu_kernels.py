@@ -244,3 +244,23 @@ def test_unet_tcgen05_full_geometry(ops):
     assert _tc_aborted() == 0
     s = sdr_db(ref.numpy(), tc.numpy())
     assert s > 30, s
+
+
+def test_tempogram_stats_match_host_reference(ops):
+    """GPU tempogram (float32) vs the numpy restatement of librosa.feature.tempogram / rhythm.tempo."""
+    from audio_cut_b200 import host_dsp
+
+    for sr, hop, n, bpm_true in ((44100, 512, 5000, 100.0), (44100, 2205, 1203, 128.0)):
+        period = 60.0 / bpm_true * sr / hop
+        env = np.zeros(n, np.float32)
+        for k in range(int(n / period)):
+            env[int(round(k * period))] = 1.0
+        env += 0.05 * np.abs(np.random.default_rng(2).standard_normal(n)).astype(np.float32)
+        win = int(np.floor(8.0 * sr / hop))
+        tg = host_dsp.tempogram(env, win)
+        ref_curve = host_dsp.tempo_from_tempogram(tg, sr, hop, aggregate=None)
+        ref_glob = host_dsp.tempo_from_tempogram(tg, sr, hop, aggregate="mean")[0]
+        curve, glob, tg_mean = ops.tempogram_stats(torch.from_numpy(env).cuda(), sr, hop)
+        np.testing.assert_allclose(tg_mean, tg.mean(axis=1), rtol=0, atol=2e-5)
+        assert glob == ref_glob
+        assert np.mean(curve == ref_curve) > 0.995  # float32 vs float64 near-ties between adjacent lags

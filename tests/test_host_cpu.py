@@ -140,3 +140,16 @@ def test_oracle_net_matches_folded_numpy_first_layer():
     y = np.einsum("oc,bcft->boft", st["first_conv.0.weight"][:, :, 0, 0], x.numpy())
     y = np.maximum(y * scale[None, :, None, None] + shift[None, :, None, None], 0)
     np.testing.assert_allclose(y, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_cpp_beat_dp_matches_numpy_loop():
+    from audio_cut_b200 import host_dsp, ops
+
+    rng = np.random.default_rng(5)
+    for n, period in ((500, 43), (2000, 52), (300, 1), (64, 7)):
+        ls = np.abs(rng.standard_normal(n)).astype(np.float32)
+        ls[: n // 10] = 0
+        b0, c0 = host_dsp._beat_dp(ls, period, 100.0)
+        b1, c1 = ops.host_beat_dp(ls, period, 100.0)
+        np.testing.assert_array_equal(b0, b1)
+        np.testing.assert_allclose(c0, c1, rtol=1e-6, atol=1e-6)

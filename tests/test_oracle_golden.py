@@ -111,3 +111,25 @@ def test_mel_filterbank_matches_torchaudio_slaney():
     ta = __import__("pytest").importorskip("torchaudio")
     fb = ta.functional.melscale_fbanks(1025, 0.0, 22050.0, 128, 44100, norm="slaney", mel_scale="slaney").T.numpy()
     np.testing.assert_allclose(OF.mel_filterbank(44100, 2048, 128), fb, rtol=2e-5, atol=3e-7)
+
+
+def test_finalize_cut_points_matches_reference(golden_dir):
+    """oracle.cuts vs the reference's refine.py (run in the dev container -> tests/golden/cuts.json)."""
+    from oracle import cuts
+
+    cases = json.load(open(os.path.join(golden_dir, "cuts.json")))
+    assert len(cases) == 4
+    for case in cases:
+        seed = case["seed"]
+        rng = np.random.default_rng(seed)
+        sr = 8000
+        n = int(24.0 * sr)
+        t = np.arange(n) / sr
+        s = seed - 100
+        gate = (np.sin(2 * np.pi * 0.23 * t + s) > -0.3).astype(np.float64)
+        vocal = (0.3 * np.sin(2 * np.pi * 180 * t) * gate + 1e-4 * rng.standard_normal(n)).astype(np.float32)
+        mix = (vocal + 0.1 * np.sin(2 * np.pi * 55 * t) * (np.sin(2 * np.pi * 0.11 * t) > 0) + 1e-3 * rng.standard_normal(n)).astype(np.float32)
+        rng.uniform(0.2, 23.8, 14), rng.uniform(0, 1, 14)  # the generator drew the points from the same stream
+        bounds, times = cuts.finalize_cut_points(mix, vocal, sr, [tuple(p) for p in case["points"]], **case["kwargs"])
+        assert bounds == case["sample_boundaries"], seed
+        assert [repr(float(x)) for x in times] == case["final_times"], seed
