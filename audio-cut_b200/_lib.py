@@ -20,7 +20,7 @@ EXPORTS = [
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
     "ac_track_workspace_bytes", "ac_separate_track", "ac_stft_features_workspace_bytes", "ac_stft_features",
     "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
-    "ac_tempogram_stats", "ac_host_beat_dp",
+    "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats",
 ]
 
 
@@ -97,6 +97,8 @@ def load() -> C.CDLL:
     lib.ac_stft_features.restype = i
     lib.ac_tempogram_stats.argtypes, lib.ac_tempogram_stats.restype = [vp, ll, i, vp, vp, vp, vp], i
     lib.ac_host_beat_dp.argtypes, lib.ac_host_beat_dp.restype = [vp, i, i, C.c_float, vp, vp], i
+    lib.ac_downmix_mono.argtypes, lib.ac_downmix_mono.restype = [vp, i, ll, vp, vp], i
+    lib.ac_track_stats.argtypes, lib.ac_track_stats.restype = [vp, vp, vp, ll, vp, vp], i
     lib.ac_profile_begin.argtypes, lib.ac_profile_begin.restype = [], i
     lib.ac_profile_collect.argtypes, lib.ac_profile_collect.restype = [C.POINTER(KernelStat), i], i
     _lib = lib

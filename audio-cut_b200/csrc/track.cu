@@ -65,6 +65,74 @@ __global__ void finalize_stems_kernel(float* __restrict__ vocal, float* __restri
 
 static int default_batch(int dtype) { return dtype == AC_F32 ? 8 : 16; }
 
+// Pinned staging for the window descriptors, so that ac_separate_track never blocks the host:
+// a ring of slots, each guarded by the event recorded after its H2D copy was enqueued.
+struct WinStage {
+  static constexpr int kSlots = 4;
+  WinDesc* h[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0, 0};
+  cudaEvent_t ev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  int next = 0;
+  // returns a pinned buffer of >= n descriptors whose previous use has completed
+  WinDesc* acquire(size_t n, int& slot) {
+    slot = next;
+    next = (next + 1) % kSlots;
+    if (ev[slot]) cudaEventSynchronize(ev[slot]);
+    else if (cudaEventCreateWithFlags(&ev[slot], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cap[slot] < n) {
+      if (h[slot]) cudaFreeHost(h[slot]);
+      h[slot] = nullptr;
+      cap[slot] = 0;
+      const size_t want = n < 256 ? 256 : n * 2;
+      if (cudaMallocHost(reinterpret_cast<void**>(&h[slot]), want * sizeof(WinDesc)) != cudaSuccess) return nullptr;
+      cap[slot] = want;
+    }
+    return h[slot];
+  }
+};
+static thread_local WinStage g_win_stage;
+
+__global__ void downmix_kernel(const float* __restrict__ mix, int n_ch, long long n, float* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n && n_ch == 2) {
+    const float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(mix + i));
+    float4 b;
+    if ((n & 3) == 0) b = ldg_stream_f4(reinterpret_cast<const float4*>(mix + n + i));
+    else b = make_float4(mix[n + i], mix[n + i + 1], mix[n + i + 2], mix[n + i + 3]);
+    // numpy/torch mean over 2 channels: (a + b) / 2 in float32
+    *reinterpret_cast<float4*>(out + i) = make_float4((a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f, (a.w + b.w) * 0.5f);
+    return;
+  }
+  for (long long j = i; j < n && j < i + 4; ++j) out[j] = n_ch == 2 ? (mix[j] + mix[n + j]) * 0.5f : mix[j];
+}
+
+// sum of squares of up to three arrays + count of non-zero samples of the second one (fp64 accumulators)
+__global__ void track_stats_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                   long long n, double* __restrict__ out) {
+  double sa = 0, sb = 0, sc = 0, nz = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = a ? a[i] : 0.f, y = b ? b[i] : 0.f, z = c ? c[i] : 0.f;
+    sa += (double)x * x;
+    sb += (double)y * y;
+    sc += (double)z * z;
+    nz += y != 0.f ? 1.0 : 0.0;
+  }
+  __shared__ double sh[4][8];
+  double v[4] = {sa, sb, sc, nz};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+    atomicAdd(out + threadIdx.x, t);
+  }
+}
+
 }  // namespace ac
 
 extern "C" int ac_track_window_count(const ac_chunk_desc* h_chunks, int n_chunks, const ac_track_params* p) {
@@ -124,9 +192,16 @@ extern "C" int ac_separate_track(ac_unet* net, const float* d_mix, long long n_s
   AC_CHECK_CUDA(cudaMemsetAsync(d_instr, 0, sizeof(float) * n_samples, st));
   AC_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, sizeof(float) * n_samples, st));
   if (nw > 0) {
-    AC_CHECK_CUDA(cudaMemcpyAsync(d_wins, wins.data(), sizeof(WinDesc) * nw, cudaMemcpyHostToDevice, st));
-    // wins is a host temporary: the copy above must have consumed it before we return
-    AC_CHECK_CUDA(cudaStreamSynchronize(st));
+    // stage the descriptors in pinned memory: the copy is asynchronous and the host never waits here
+    int slot = 0;
+    WinDesc* h_pin = g_win_stage.acquire((size_t)nw, slot);
+    if (!h_pin) {
+      set_error("pinned staging for window descriptors failed");
+      return AC_E_CUDA;
+    }
+    std::copy(wins.begin(), wins.end(), h_pin);
+    AC_CHECK_CUDA(cudaMemcpyAsync(d_wins, h_pin, sizeof(WinDesc) * nw, cudaMemcpyHostToDevice, st));
+    AC_CHECK_CUDA(cudaEventRecord(g_win_stage.ev[slot], st));
   }
   for (int w0 = 0; w0 < nw; w0 += mb) {
     const int b = nw - w0 < mb ? nw - w0 : mb;
@@ -139,6 +214,31 @@ extern "C" int ac_separate_track(ac_unet* net, const float* d_mix, long long n_s
     if (rc) return rc;
   }
   finalize_stems_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, st>>>(d_vocal, d_instr, d_weight, n_samples);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_downmix_mono(const float* d_mix, int n_channels, long long n, float* d_out, void* stream) {
+  using namespace ac;
+  AC_REQUIRE(d_mix && d_out && n >= 0, "null pointer");
+  AC_REQUIRE(n_channels == 1 || n_channels == 2, "n_channels must be 1 or 2");
+  if (n == 0) return AC_OK;
+  const long long threads = (n + 3) / 4;
+  downmix_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_mix, n_channels, n, d_out);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_track_stats(const float* d_a, const float* d_b, const float* d_c, long long n, double* d_out4, void* stream) {
+  using namespace ac;
+  AC_REQUIRE(d_out4 && n >= 0, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  AC_CHECK_CUDA(cudaMemsetAsync(d_out4, 0, 4 * sizeof(double), st));
+  if (n == 0) return AC_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  track_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_a, d_b, d_c, n, d_out4);
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -288,7 +288,10 @@ class PipelineContext:
         try:
             import pynvml  # nvidia-ml-py
 
-            pynvml.nvmlInit()
+            global _NVML_READY
+            if not _NVML_READY:
+                pynvml.nvmlInit()
+                _NVML_READY = True
             h = pynvml.nvmlDeviceGetHandleByIndex(int(self.device_index or 0))
             util = pynvml.nvmlDeviceGetUtilizationRates(h)
             mem = pynvml.nvmlDeviceGetMemoryInfo(h)
@@ -302,6 +305,9 @@ class PipelineContext:
             )
         except Exception:
             pass
+
+
+_NVML_READY = False
 
 
 def build_pipeline_context(duration_s: float, cfg: PipelineConfig) -> PipelineContext:

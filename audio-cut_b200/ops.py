@@ -146,8 +146,8 @@ def make_chunk_descs(bounds: Sequence[Tuple[int, int, int, int]]):
 
 
 def separate_track(net: UNet, mix: torch.Tensor, bounds: Sequence[Tuple[int, int, int, int]], geom: MdxGeom, *,
-                   align_hop: int = 4096, output_is_vocal: bool = True, dtype: int = AC_F32, max_batch: int = 0):
-    """mix [n_ch, N] f32 on the GPU -> (vocal [N], instrumental [N], weight [N])."""
+                   align_hop: int = 4096, output_is_vocal: bool = True, dtype: int = AC_F32, max_batch: int = 0, out=None):
+    """mix [n_ch, N] f32 on the GPU -> (vocal [N], instrumental [N], weight [N]); ``out`` = preallocated triple."""
     assert mix.dim() == 2 and mix.shape[0] in (1, 2)
     mix = mix.contiguous().float()
     n = mix.shape[1]
@@ -156,9 +156,14 @@ def separate_track(net: UNet, mix: torch.Tensor, bounds: Sequence[Tuple[int, int
     lib = net._lib
     nbytes = int(lib.ac_track_workspace_bytes(net.handle, descs, len(bounds), C.byref(tp)))
     ws = net.workspace(nbytes)
-    vocal = torch.empty(n, dtype=torch.float32, device=mix.device)
-    instr = torch.empty_like(vocal)
-    weight = torch.empty_like(vocal)
+    if out is not None:
+        vocal, instr, weight = out
+        for t in out:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+    else:
+        vocal = torch.empty(n, dtype=torch.float32, device=mix.device)
+        instr = torch.empty_like(vocal)
+        weight = torch.empty_like(vocal)
     check(lib.ac_separate_track(net.handle, ptr(mix), n, descs, len(bounds), C.byref(tp), ptr(vocal), ptr(instr), ptr(weight),
                                 ptr(ws), ws.numel(), stream_ptr()), "ac_separate_track")
     return vocal, instr, weight

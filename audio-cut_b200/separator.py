@@ -12,6 +12,7 @@ re-raised (the reference's ``strict_gpu`` behaviour).
 from __future__ import annotations
 
 import time
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional
 
@@ -50,6 +51,17 @@ def vocal_presence_markers(vocal_dev: torch.Tensor, sr: int, threshold_db: float
     hop = max(1, int(0.02 * sr))
     frame = max(hop * 2, int(0.05 * sr))
     rms = ops.frame_rms(vocal_dev, frame, hop).cpu().numpy()
+    return vocal_presence_markers_from_rms(rms, n, sr, hop, threshold_db, pure_music_min)
+
+
+def vocal_presence_markers_from_rms(rms: np.ndarray, n: int, sr: int, hop: int, threshold_db: float = -50.0,
+                                    pure_music_min: float = 0.0) -> Dict:
+    """Host half of the markers: run-length segmentation of the 20 ms RMS mask and the marker cuts."""
+    empty = {"vocal_presence_cut_points_sec": [], "vocal_presence_cut_points_samples": [], "vocal_presence_segments": [],
+             "pure_music_segments": []}
+    if sr <= 0 or n == 0:
+        return empty
+    duration = n / float(sr)
     mask = 20.0 * np.log10(rms + 1e-12) > threshold_db
     if mask.size == 0:
         return empty
@@ -95,6 +107,95 @@ def estimate_confidence(vocal: np.ndarray, instrumental: Optional[np.ndarray], m
     return float(np.clip(conf, 0.0, 1.0))
 
 
+def confidence_from_energies(ve: float, ie: Optional[float], me: float) -> float:
+    """``estimate_confidence`` from mean-square energies computed on the device (``ac_track_stats``)."""
+    ratio = float(np.clip(ve / (me + 1e-8), 0.0, 1.0))
+    if ie is not None:
+        bal = ve / (ie + 1e-8)
+        conf = 0.5 * ratio + 0.5 * np.clip(bal / (1.0 + bal), 0.0, 1.0)
+    else:
+        conf = ratio
+    return float(np.clip(conf, 0.0, 1.0))
+
+
+_COPY_POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="ac-copy")
+
+
+def parallel_copy(dst: np.ndarray, src: np.ndarray, min_bytes: int = 8 << 20) -> None:
+    """dst[...] = src with the work split over a few threads (numpy releases the GIL while copying;
+    one core moves ~6 GB/s, which would otherwise cost more than the PCIe transfer itself)."""
+    if dst.shape != src.shape:
+        raise ValueError(f"shape mismatch {dst.shape} vs {src.shape}")
+    if dst.nbytes < min_bytes or dst.ndim == 0:
+        np.copyto(dst, src, casting="same_kind")
+        return
+    d2 = dst.reshape(-1, dst.shape[-1]) if dst.ndim > 1 else dst.reshape(1, -1)
+    s2 = src.reshape(-1, src.shape[-1]) if src.ndim > 1 else src.reshape(1, -1)
+    n = d2.shape[1]
+    parts = max(1, min(8, d2.nbytes // (4 << 20)))
+    step = -(-n // parts)
+    futs = []
+    for r in range(d2.shape[0]):
+        for a in range(0, n, step):
+            futs.append(_COPY_POOL.submit(np.copyto, d2[r, a : a + step], s2[r, a : a + step], "same_kind"))
+    for f in futs:
+        f.result()
+
+
+class _SmallBuf:
+    def __init__(self, n: int, dev: torch.device):
+        self.dev = torch.empty(n, dtype=torch.float32, device=dev)
+        self.pin = torch.empty(n, dtype=torch.float32, pin_memory=True)
+
+
+class _TrackViews:
+    pass
+
+
+class _TrackBuffers:
+    """Persistent staging of one separator on one device: pinned input/output, device mix / mono / stems,
+    two streams (separation; features at high priority) and the timing events.  Grown geometrically and
+    reused, so a steady stream of tracks makes no allocation at all (the reference re-allocates its
+    pinned staging per chunk, enhanced_vocal_separator.py:378-389)."""
+
+    def __init__(self, dev: torch.device):
+        self.dev = dev
+        self.cap = 0
+        self.s_sep = torch.cuda.Stream(device=dev)
+        self.s_feat = torch.cuda.Stream(device=dev, priority=-1)
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        self.stats_dev = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.stats_pin = torch.zeros(4, dtype=torch.float64, pin_memory=True)
+        self._small: Optional[_SmallBuf] = None
+
+    def small(self, n: int) -> _SmallBuf:
+        if self._small is None or self._small.dev.numel() < n:
+            self._small = _SmallBuf(max(n, 1) * 2, self.dev)
+        sb = _SmallBuf.__new__(_SmallBuf)
+        sb.dev, sb.pin = self._small.dev[:n], self._small.pin[:n]
+        return sb
+
+    def views(self, n_ch: int, n: int) -> _TrackViews:
+        if n > self.cap:
+            cap = int(n * 1.25) + 4096
+            self.pin_in = torch.empty(2 * cap, dtype=torch.float32, pin_memory=True)
+            self.pin_out = torch.empty(2 * cap, dtype=torch.float32, pin_memory=True)
+            self.mix = torch.empty(2 * cap, dtype=torch.float32, device=self.dev)
+            self.mono = torch.empty(cap, dtype=torch.float32, device=self.dev)
+            self.stems = torch.empty(3 * cap, dtype=torch.float32, device=self.dev)
+            self.cap = cap
+        v = _TrackViews()
+        v.pin_in = self.pin_in[: n_ch * n].view(n_ch, n)
+        v.pin_in_np = v.pin_in.numpy()
+        v.mix = self.mix[: n_ch * n].view(n_ch, n)
+        v.mono = self.mono[:n]
+        st = self.stems[: 3 * n].view(3, n)
+        v.vocal, v.instr, v.weight, v.stems2 = st[0], st[1], st[2], st[:2]
+        v.pin_out = self.pin_out[: 2 * n].view(2, n)
+        v.pin_out_np = v.pin_out.numpy()
+        return v
+
+
 class B200VocalSeparator:
     """``EnhancedVocalSeparator(sample_rate)`` drop-in; assign it to ``SeamlessSplitter.separator``."""
 
@@ -111,6 +212,9 @@ class B200VocalSeparator:
         self._marker_threshold_db = marker_threshold_db
         self.enable_fallback = False
         self.backend_pref = "mdx23"
+        self.capture_device_metrics = True  # NVML / nvidia-smi sample per call (gpu_pipeline.py:208-259)
+        self._bufs: Dict[torch.device, "_TrackBuffers"] = {}
+        self._energies = (0.0, None, 1e-8)
 
     # ---- context ---------------------------------------------------------------------------
     def _ensure_pipeline_context(self, n_samples: int, gpu_context: Optional[PipelineContext]) -> PipelineContext:
@@ -139,20 +243,23 @@ class B200VocalSeparator:
         except Exception as exc:
             ctx.mark_failure("separation", str(exc))
             raise
-        mono = audio if audio.ndim == 1 else audio.mean(axis=0)
         return SeparationResult(
             vocal_track=vocal, instrumental_track=instrumental,
-            separation_confidence=estimate_confidence(vocal, instrumental, mono),
+            separation_confidence=confidence_from_energies(*self._energies),
             backend_used=type(backend).__name__, processing_time=time.time() - t0, quality_metrics=markers,
             feature_cache=cache, vad_segments=vad_segments, gpu_meta=ctx.to_meta(), pipeline_used=ctx.enabled,
         )
 
     def _separate_with_pipeline(self, audio: np.ndarray, backend: B200Mdx23Backend, ctx: PipelineContext):
+        """One pinned H2D of the mix, all windows through STFT -> U-Net -> fused iSTFT/stitch, features on
+        a second (high-priority) stream while the network runs, one D2H of both stems.  Every buffer is
+        persistent (``_TrackBuffers``); the host blocks exactly twice: on the small feature series and on
+        the final D2H event."""
         sr = self.sample_rate
-        total = audio.shape[-1]
+        total = int(audio.shape[-1])
         dev = torch.device(ctx.device)
-        stream = ctx.streams.s_sep if ctx.use_streams and ctx.streams.s_sep is not None else torch.cuda.current_stream(dev)
-        feat_stream = ctx.streams.s_feat if ctx.use_streams and ctx.streams.s_feat is not None else stream
+        bufs = self._buffers(dev)
+        stream, feat_stream = bufs.s_sep, bufs.s_feat
         backend.reset_performance_metrics()
         torch.cuda.reset_peak_memory_stats(dev)
         ctx.gpu_meta.setdefault("gpu_pipeline_used", bool(ctx.enabled))
@@ -160,41 +267,62 @@ class B200VocalSeparator:
         plans = ctx.plans
         bounds = [p.sample_bounds(sr, total) for p in plans]
         live = [(p, b) for p, b in zip(plans, bounds) if b[1] > b[0]]
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        host = np.ascontiguousarray(audio if audio.ndim == 2 else audio[None, :], dtype=np.float32)
-        pinned = ctx.pinned_pool.acquire_view(host.shape) if ctx.pinned_pool is not None else None
+        n_ch = 1 if audio.ndim == 1 else int(audio.shape[0])
+        if n_ch not in (1, 2):
+            raise ValueError(f"expected mono (N,) or stereo (2,N) audio, got shape {audio.shape}")
+        v = bufs.views(n_ch, total)
+        ev = bufs.events
         vad_segments: List[Dict[str, float]] = []
-        with torch.cuda.device(dev):
-            with torch.cuda.stream(stream), ctx.acquire_inflight():
+        lib = backend.net._lib
+        with torch.cuda.device(dev), ctx.acquire_inflight():
+            parallel_copy(v.pin_in_np, audio.reshape(n_ch, total))  # pageable -> pinned staging
+            caller = torch.cuda.current_stream(dev)
+            stream.wait_stream(caller)
+            with torch.cuda.stream(stream):
                 ev[0].record()
-                if pinned is not None:
-                    pinned.copy_(torch.from_numpy(host))
-                    mix = pinned.to(dev, non_blocking=True)
-                else:
-                    mix = torch.from_numpy(host).to(dev)
+                v.mix.copy_(v.pin_in, non_blocking=True)
                 ev[1].record()
-                vocal_d, instr_d, _ = ops.separate_track(
-                    backend.net, mix, [b for _, b in live], backend.geom, align_hop=backend.align_hop,
-                    output_is_vocal=backend.get_output_type() == "vocal", dtype=backend.dtype)
-                ev[2].record()
-            # features read the mix, not the stems: they overlap the separation on their own stream
             feat_stream.wait_event(ev[1])
             with torch.cuda.stream(feat_stream):
-                mono = mix[0] if mix.shape[0] == 1 else mix.mean(dim=0)
-                builder = B200ChunkFeatureBuilder(sr, device=str(dev))
-                builder.add_track(mono, [p for p, _ in live])
-                cache = builder.finalize(audio)
+                ops.check(lib.ac_downmix_mono(ops.ptr(v.mix), n_ch, total, ops.ptr(v.mono), ops.stream_ptr()), "ac_downmix_mono")
+                ev[4].record()
             with torch.cuda.stream(stream):
-                markers = vocal_presence_markers(vocal_d, sr, self._marker_threshold_db)
-                any_instr = bool(torch.any(instr_d != 0).item())
-                stems = torch.stack([vocal_d, instr_d]).cpu()
+                ops.separate_track(backend.net, v.mix, [b for _, b in live], backend.geom, align_hop=backend.align_hop,
+                                   output_is_vocal=backend.get_output_type() == "vocal", dtype=backend.dtype,
+                                   out=(v.vocal, v.instr, v.weight))
+                ev[2].record()
+                # tail, all asynchronous: presence-marker RMS, energies, D2H of the stems and the scalars
+                hop = max(1, int(0.02 * sr))
+                frame = max(hop * 2, int(0.05 * sr))
+                n_mark = ops.frame_count(total, frame, hop)
+                mark = bufs.small(n_mark)
+                ops.frame_rms(v.vocal, frame, hop, out=mark.dev)
+                stream.wait_event(ev[4])
+                ops.check(lib.ac_track_stats(ops.ptr(v.vocal), ops.ptr(v.instr), ops.ptr(v.mono), total, ops.ptr(bufs.stats_dev),
+                                             ops.stream_ptr()), "ac_track_stats")
+                v.pin_out.copy_(v.stems2, non_blocking=True)
+                mark.pin.copy_(mark.dev, non_blocking=True)
+                bufs.stats_pin.copy_(bufs.stats_dev, non_blocking=True)
                 ev[3].record()
+            # features read the mix, not the stems: their kernels slip in between the network's on the
+            # high-priority stream, and the host DSP (peak pick, beat DP) overlaps the separation
+            with torch.cuda.stream(feat_stream):
+                builder = B200ChunkFeatureBuilder(sr, device=str(dev))
+                builder.add_track(v.mono, [p for p, _ in live])
+                cache = builder.finalize(audio)
             ev[3].synchronize()
-        if pinned is not None:
-            ctx.pinned_pool.release(pinned)
-        stems = stems.numpy()
-        vocal = stems[0].copy()
-        instrumental = stems[1].copy() if any_instr else None
+            caller.wait_stream(stream)
+            caller.wait_stream(feat_stream)
+        stats = bufs.stats_pin.numpy().copy()
+        vocal = np.empty(total, dtype=np.float32)
+        any_instr = stats[3] > 0
+        instrumental = np.empty(total, dtype=np.float32) if any_instr else None
+        parallel_copy(vocal, v.pin_out_np[0])
+        if instrumental is not None:
+            parallel_copy(instrumental, v.pin_out_np[1])
+        markers = vocal_presence_markers_from_rms(mark.pin.numpy()[:n_mark].copy(), total, sr, hop, self._marker_threshold_db)
+        self._energies = (float(stats[0]) / max(total, 1), float(stats[1]) / max(total, 1) if any_instr else None,
+                          float(stats[2]) / max(total, 1))
         if self._vad_fn is not None:  # hook kept from SileroChunkVAD (silero_chunk_vad.py:34, 56-116)
             for p, (cs, ce, _, _) in live:
                 vad_segments.extend(self._vad_fn(p, vocal[cs:ce], sr) or [])
@@ -215,8 +343,15 @@ class B200VocalSeparator:
             "gpu_pipeline_chunk_invocations": int(perf["chunks"]),
             "mdx23_output_type": backend.get_output_type(),
         })
-        ctx.capture_device_metrics()
-        return vocal.astype(np.float32), None if instrumental is None else instrumental.astype(np.float32), cache, vad_segments, markers
+        if self.capture_device_metrics:
+            ctx.capture_device_metrics()
+        return vocal, instrumental, cache, vad_segments, markers
+
+    def _buffers(self, dev: torch.device) -> "_TrackBuffers":
+        b = self._bufs.get(dev)
+        if b is None:
+            b = self._bufs[dev] = _TrackBuffers(dev)
+        return b
 
 
 EnhancedVocalSeparator = B200VocalSeparator

@@ -152,6 +152,14 @@ AC_API int ac_separate_track(ac_unet* net, const float* d_mix, long long n_sampl
                       int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr, float* d_weight,
                       void* d_ws, size_t ws_bytes, void* stream);
 
+/* Stereo -> mono mean (np.mean(mix, axis=0) at features_cache.py:137-139 / enhanced_vocal_separator.py
+ * mono handling); n_channels == 1 copies.  d_mix [n_channels][n] -> d_out [n]. */
+AC_API int ac_downmix_mono(const float* d_mix, int n_channels, long long n, float* d_out, void* stream);
+/* Energies for EnhancedVocalSeparator._estimate_separation_confidence (enhanced_vocal_separator.py:490-501)
+ * and the all-zero test of the instrumental accumulator (:456-458), without a host pass over the stems:
+ * d_out4 = { sum a^2, sum b^2, sum c^2, count(b != 0) } in fp64.  Any of d_a/d_b/d_c may be NULL. */
+AC_API int ac_track_stats(const float* d_a, const float* d_b, const float* d_c, long long n, double* d_out4, void* stream);
+
 /* ---- STFT-2048 framewise features ----------------------------------------------------------------
  * One pass over the signal per call; n_fft = 2048, periodic hann, center=True, zero padding
  * (librosa.stft defaults).  Segments reproduce the per-call (= per-chunk) scope of
