@@ -54,6 +54,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -107,6 +115,15 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_by
 }
 // kind::f16 idesc with B MN-major (bit 16)
 __device__ __forceinline__ uint32_t make_idesc_bmn(int n) { return make_idesc(n) | (1u << 16); }
+
+// Activation layout of the tensor-core path ("CG8", channel-group planar):
+//   X[b][t][c/8][f][c%8]   element index (((b*T + t)*(C/8) + c/8)*F + f)*8 + c%8
+// One (b, t, channel group) plane is F x 16 B of contiguous memory = exactly the canonical no-swizzle
+// UMMA core-matrix order (8 rows x 16 B), so TMA stages operand tiles with 128-byte (or longer)
+// contiguous rows instead of 16-byte gathers, and the smem image equals the global image.
+__host__ __device__ __forceinline__ size_t cg8_index(int b, int t, int cg, int f, int T, int C, int F) {
+  return ((((size_t)b * T + t) * (size_t)(C >> 3) + cg) * (size_t)F + f) * 8;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
