@@ -20,7 +20,7 @@ EXPORTS = [
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
     "ac_track_workspace_bytes", "ac_separate_track", "ac_stft_features_workspace_bytes", "ac_stft_features",
     "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
-    "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats",
+    "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3",
 ]
 
 
@@ -85,6 +85,8 @@ def load() -> C.CDLL:
     lib.ac_unet_forward.argtypes, lib.ac_unet_forward.restype = [vp, vp, vp, i, i, vp, sz, vp], i
     lib.ac_unet_set_debug.argtypes, lib.ac_unet_set_debug.restype = [vp, i], i
     lib.ac_debug_tc_aborted.argtypes, lib.ac_debug_tc_aborted.restype = [], i
+    lib.ac_debug_conv3x3.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, i, i, C.POINTER(C.c_float), vp]
+    lib.ac_debug_conv3x3.restype = i
     lib.ac_track_window_count.argtypes = [C.POINTER(ChunkDesc), i, C.POINTER(TrackParams)]
     lib.ac_track_window_count.restype = i
     lib.ac_track_workspace_bytes.argtypes = [vp, C.POINTER(ChunkDesc), i, C.POINTER(TrackParams)]

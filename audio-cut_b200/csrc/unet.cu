@@ -16,6 +16,7 @@ struct ConvLayer {  // implicit-GEMM B operand [K][N] in both dtypes
   Affine af;
   int K, N;
   TcConvWeights* tc = nullptr;  // tcgen05 packing (3x3 convs only)
+  TcConvWsWeights* ws = nullptr;  // weight-stationary tcgen05 packing (3x3 convs, C = 48 / 96)
   TcResampleWeights* rs = nullptr;  // tcgen05 packing (down / up convs only)
 };
 struct TdfLayer {  // GEMM A operand [M][K] (PyTorch Linear weight as is)
@@ -46,6 +47,7 @@ struct ac_unet {
   __nv_bfloat16* d_bf16 = nullptr;  // arena: bf16 copies, same offsets
   size_t arena_floats = 0;
   int force_simt = 0;
+  bool tc_ok = false;  // every layer has a CG8 / tcgen05 implementation: the bf16 path runs on tensor cores
 };
 
 namespace ac {
@@ -217,6 +219,12 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
           return AC_E_CUDA;
         }
       }
+      if (tc_conv3x3_ws_supported(bo.T, bo.F, bo.c) == AC_OK) {
+        if (tc_conv3x3_ws_pack(bo.conv[j].raw, bo.c, &b.conv[j].ws) != AC_OK) {
+          ac_unet_destroy(net);
+          return AC_E_CUDA;
+        }
+      }
     }
     b.tdf1 = mk_tdf(bo.t1);
     b.tdf2 = mk_tdf(bo.t2);
@@ -242,6 +250,11 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
   net->final_w = net->d_f32 + final_w;
   net->final_b = net->d_f32 + final_b;
   net->n_blocks = (int)net->blocks.size();
+  net->tc_ok = cg8_ends_supported(g.g) == AC_OK;
+  for (auto& b : net->blocks)
+    for (int j = 0; j < g.l; ++j) net->tc_ok = net->tc_ok && b.conv[j].tc != nullptr;
+  for (auto& L : net->ds) net->tc_ok = net->tc_ok && L.rs != nullptr;
+  for (auto& L : net->us) net->tc_ok = net->tc_ok && L.rs != nullptr;
   *out = net;
   return AC_OK;
 }
@@ -250,7 +263,10 @@ extern "C" void ac_unet_destroy(ac_unet* net) {
   if (!net) return;
   for (auto& b : net->blocks) {
     for (int j = 0; j < net->g.l; ++j)
+    {
       if (b.conv[j].tc) ac::tc_conv3x3_free(b.conv[j].tc);
+      if (b.conv[j].ws) ac::tc_conv3x3_ws_free(b.conv[j].ws);
+    }
     ac::tc_tdf_free(b.tdf1.tc);
     ac::tc_tdf_free(b.tdf2.tc);
   }
@@ -268,6 +284,71 @@ extern "C" int ac_unet_set_debug(ac_unet* net, int force_simt) {
   AC_REQUIRE(net, "null");
   net->force_simt = force_simt;
   return AC_OK;
+}
+
+// Test / profiling hook: one 3x3 conv layer (bf16, folded BN + ReLU) through a chosen implementation.
+extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int F, int C, const float* h_w,
+                                const float* d_scale, const float* d_shift, int impl, int iters, float* h_ms,
+                                void* stream) {
+  using namespace ac;
+  AC_REQUIRE(d_in && d_out && h_w && d_scale && d_shift && iters >= 1, "null pointer / iters");
+  cudaStream_t st = (cudaStream_t)stream;
+  TcConvArgs ta{(const __nv_bfloat16*)d_in, (__nv_bfloat16*)d_out, B, T, F, C, nullptr, d_scale, d_shift};
+  TcConvWeights* tc = nullptr;
+  TcConvWsWeights* ws = nullptr;
+  __nv_bfloat16* d_w16 = nullptr;
+  int rc = AC_OK;
+  if (impl == 1) {
+    AC_REQUIRE(tc_conv3x3_supported(T, F, C) == AC_OK, "streaming tc conv does not support this shape");
+    if ((rc = tc_conv3x3_pack(h_w, C, &tc))) return rc;
+    ta.w = tc;
+  } else if (impl == 2) {
+    AC_REQUIRE(tc_conv3x3_ws_supported(T, F, C) == AC_OK, "ws tc conv does not support this shape");
+    if ((rc = tc_conv3x3_ws_pack(h_w, C, &ws))) return rc;
+  } else {
+    std::vector<__nv_bfloat16> w16((size_t)9 * C * C);  // [(tap*C+ci)][co]
+    for (int co = 0; co < C; ++co)
+      for (int ci = 0; ci < C; ++ci)
+        for (int t = 0; t < 9; ++t) w16[((size_t)t * C + ci) * C + co] = __float2bfloat16_rn(h_w[((size_t)co * C + ci) * 9 + t]);
+    AC_CHECK_CUDA(cudaMalloc(&d_w16, w16.size() * 2));
+    AC_CHECK_CUDA(cudaMemcpy(d_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+  }
+  auto once = [&]() -> int {
+    if (impl == 1) return launch_tc_conv3x3(ta, st);
+    if (impl == 2) return launch_tc_conv3x3_ws(ws, ta, st);
+    GemmArgs a{};
+    a.M = B * T * F; a.N = C; a.K = 9 * C; a.batch = 1;
+    a.a_mode = A_CONV3; a.A = d_in; a.T = T; a.F = F; a.C = C;
+    a.Bm = d_w16;
+    a.epi = EPI_AFFINE_RELU; a.scale = d_scale; a.shift = d_shift; a.cmod = C; a.out = d_out;
+    a.kclass = KC_CONV_SIMT;
+    return launch_gemm_simt(a, AC_BF16, st);
+  };
+  rc = once();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (rc == AC_OK && iters > 1) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int i = 1; i < iters && rc == AC_OK; ++i) rc = once();
+    cudaEventRecord(e1, st);
+  }
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (e0) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (h_ms) *h_ms = ms / (iters - 1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  if (tc) tc_conv3x3_free(tc);
+  if (ws) tc_conv3x3_ws_free(ws);
+  if (d_w16) cudaFree(d_w16);
+  if (rc == AC_OK && ce != cudaSuccess) {
+    set_error(std::string("ac_debug_conv3x3: ") + cudaGetErrorString(ce));
+    return AC_E_CUDA;
+  }
+  return rc;
 }
 
 namespace ac {
@@ -321,9 +402,14 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
   auto wsel = [&](const float* w32, const __nv_bfloat16* w16) { return dtype == AC_F32 ? (const void*)w32 : (const void*)w16; };
   int rc;
 
+  // bf16 runs on the tensor-core path (all activations in the CG8 layout) unless the geometry has a layer
+  // without a tcgen05 kernel or the test hook forces the CUDA-core kernels (channels-last layout).
+  const bool use_tc = dtype == AC_BF16 && net->tc_ok && net->force_simt != 1;
+
   auto conv3x3 = [&](const ConvLayer& L, const void* x, void* y, int T, int F, int C) -> int {
-    if (dtype == AC_BF16 && L.tc && !net->force_simt) {
+    if (use_tc) {
       TcConvArgs ta{(const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, F, C, L.tc, L.af.scale, L.af.shift};
+      if (L.ws && net->force_simt != 2 && tc_conv3x3_ws_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_ws(L.ws, ta, st);
       return launch_tc_conv3x3(ta, st);
     }
     GemmArgs a{};
@@ -332,6 +418,24 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.Bm = wsel(L.w32, L.w16);
     a.epi = EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = L.N; a.out = y;
     a.kclass = KC_CONV_SIMT;
+    return launch_gemm_simt(a, dtype, st);
+  };
+  // out = relu(affine(W * in)) (+ residual)
+  auto tdf = [&](const TdfLayer& L, const Block& b, const void* in, const void* residual, void* out) -> int {
+    if (use_tc) {
+      if (L.tc)
+        return launch_tc_tdf(L.tc, (const __nv_bfloat16*)in, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, B, b.T,
+                             L.af.scale, L.af.shift, st);
+      return launch_tdf_small_cg8((const __nv_bfloat16*)in, L.w16, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, B, b.T,
+                                  b.c, L.M, L.K, L.af.scale, L.af.shift, st);
+    }
+    GemmArgs a{};
+    a.M = L.M; a.N = b.c; a.K = L.K; a.batch = B * b.T;
+    a.a_mode = A_PLAIN; a.A = wsel(L.w32, L.w16); a.a_batch_stride = 0;
+    a.Bm = in; a.b_batch_stride = (long long)L.K * b.c;
+    a.epi = residual ? EPI_RESIDUAL : EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = b.c;
+    a.out = out; a.c_batch_stride = (long long)L.M * b.c; a.extra = residual;
+    a.kclass = KC_TDF_SIMT;
     return launch_gemm_simt(a, dtype, st);
   };
   // X is clobbered, Y is scratch, result lands in Z (Z != Y)
@@ -345,37 +449,17 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     // src now holds the TFC output; dst is free.  If Z aliases src the residual would be clobbered.
     void* tfc = src;
     if (Z == tfc) return (set_error("internal: block output aliases TFC output"), AC_E_INVALID);
-    const bool use_tc = dtype == AC_BF16 && !net->force_simt;
-    if (use_tc && b.tdf1.tc) {
-      if ((rc = launch_tc_tdf(b.tdf1.tc, (const __nv_bfloat16*)tfc, nullptr, (__nv_bfloat16*)H, B, b.T, b.tdf1.af.scale,
-                              b.tdf1.af.shift, st)))
-        return rc;
-    } else {
-    GemmArgs a{};
-    a.M = b.tdf1.M; a.N = b.c; a.K = b.tdf1.K; a.batch = B * b.T;
-    a.a_mode = A_PLAIN; a.A = wsel(b.tdf1.w32, b.tdf1.w16); a.a_batch_stride = 0;
-    a.Bm = tfc; a.b_batch_stride = (long long)b.F * b.c;
-    a.epi = EPI_AFFINE_RELU; a.scale = b.tdf1.af.scale; a.shift = b.tdf1.af.shift; a.cmod = b.c;
-    a.out = H; a.c_batch_stride = (long long)b.tdf1.M * b.c;
-    a.kclass = KC_TDF_SIMT;
-    if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
-    }
-    if (use_tc && b.tdf2.tc)
-      return launch_tc_tdf(b.tdf2.tc, (const __nv_bfloat16*)H, (const __nv_bfloat16*)tfc, (__nv_bfloat16*)Z, B, b.T,
-                           b.tdf2.af.scale, b.tdf2.af.shift, st);
-    GemmArgs c{};
-    c.M = b.tdf2.M; c.N = b.c; c.K = b.tdf2.K; c.batch = B * b.T;
-    c.a_mode = A_PLAIN; c.A = wsel(b.tdf2.w32, b.tdf2.w16); c.a_batch_stride = 0;
-    c.Bm = H; c.b_batch_stride = (long long)b.tdf2.K * b.c;
-    c.epi = EPI_RESIDUAL; c.scale = b.tdf2.af.scale; c.shift = b.tdf2.af.shift; c.cmod = b.c;
-    c.out = Z; c.c_batch_stride = (long long)b.F * b.c; c.extra = tfc;
-    c.kclass = KC_TDF_SIMT;
-    return launch_gemm_simt(c, dtype, st);
+    if ((rc = tdf(b.tdf1, b, tfc, nullptr, H))) return rc;
+    return tdf(b.tdf2, b, H, tfc, Z);
   };
 
   const long long P0 = (long long)B * g.dim_t * g.dim_f;
-  if ((rc = launch_first_conv(d_in, P, P0, g.g, net->first_w, net->first_af.scale, net->first_af.shift, dtype, st)))
-    return rc;
+  if (use_tc)
+    rc = launch_first_conv_cg8(d_in, P, (long long)B * g.dim_t, g.dim_f, g.g, net->first_w, net->first_af.scale,
+                               net->first_af.shift, st);
+  else
+    rc = launch_first_conv(d_in, P, P0, g.g, net->first_w, net->first_af.scale, net->first_af.shift, dtype, st);
+  if (rc) return rc;
   void* cur = P;
   void* oth = Q;
   for (int i = 0; i < g.n; ++i) {
@@ -384,7 +468,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     // l convs ping-pong cur/oth; with odd l the TFC output is in oth, with even l in cur: either way != skip
     if ((rc = run_block(b, cur, oth, skip))) return rc;
     const ConvLayer& d = net->ds[i];
-    if (dtype == AC_BF16 && d.rs && !net->force_simt) {
+    if (use_tc) {
       if ((rc = launch_tc_resample(d.rs, (const __nv_bfloat16*)skip, nullptr, (__nv_bfloat16*)cur, B, b.T / 2, b.F / 2,
                                    d.af.scale, d.af.shift, st)))
         return rc;
@@ -410,7 +494,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     const Block& b = net->blocks[g.n + 1 + i];
     const ConvLayer& u = net->us[i];
     void* skip = ptr(wp.skip_off[lvl]);
-    if (dtype == AC_BF16 && u.rs && !net->force_simt) {
+    if (use_tc) {
       if ((rc = launch_tc_resample(u.rs, (const __nv_bfloat16*)cur, (const __nv_bfloat16*)skip, (__nv_bfloat16*)oth, B, b.T / 2,
                                    b.F / 2, u.af.scale, u.af.shift, st)))
         return rc;
@@ -429,5 +513,6 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     if ((rc = run_block(b, cur, oth, Z))) return rc;
     if (Z != cur) { void* t = cur; cur = oth; oth = t; }
   }
+  if (use_tc) return launch_final_conv_cg8(cur, d_out, (long long)B * g.dim_t, g.dim_f, g.g, net->final_w, net->final_b, st);
   return launch_final_conv(cur, d_out, P0, g.g, net->final_w, net->final_b, dtype, st);
 }

@@ -1,0 +1,207 @@
+// CUDA-core kernels of the bf16 tensor-core path that work on the CG8 activation layout
+// [B][T][C/8][F][8] (tc_common.cuh): the two 1x1 convolutions at the ends of the network (4 <-> g
+// channels; HBM-bound streaming) and the TDF layers of the deepest levels, whose GEMMs are too
+// small for a 128-row UMMA tile (M or K below 64).
+#include "tc_common.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+// ---- first 1x1 conv: spectrogram [P][4] bf16 -> CG8 [B][T][g/8][F][8], folded BN + ReLU ---------
+// One thread per position; lanes walk f, so every 16-byte store of a warp is 512 contiguous bytes.
+template <int G>
+__global__ void __launch_bounds__(256) first_conv_cg8_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                             long long rows /* B*T */, int F, const float* __restrict__ w,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift) {
+  __shared__ float sw[G * 4], ssc[G], ssh[G];
+  for (int i = threadIdx.x; i < G * 4; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < G; i += blockDim.x) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+  __syncthreads();
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= rows * F) return;
+  const long long row = pos / F;
+  const int f = (int)(pos - row * F);
+  const uint2 raw = *reinterpret_cast<const uint2*>(in + pos * 4);
+  const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  __nv_bfloat16* dst = out + ((size_t)row * (G / 8) * F + f) * 8;
+#pragma unroll
+  for (int cg = 0; cg < G / 8; ++cg) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = cg * 8 + 2 * e + h;
+        float s = sw[c * 4] * x01.x;
+        s = fmaf(sw[c * 4 + 1], x01.y, s);
+        s = fmaf(sw[c * 4 + 2], x23.x, s);
+        s = fmaf(sw[c * 4 + 3], x23.y, s);
+        v[h] = fmaxf(fmaf(s, ssc[c], ssh[c]), 0.f);
+      }
+      __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
+      pk[e] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)cg * F * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// ---- final 1x1 conv: CG8 [B][T][g/8][F][8] -> [P][4] bf16 (+ bias) -----------------------------
+template <int G>
+__global__ void __launch_bounds__(256) final_conv_cg8_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                             long long rows, int F, const float* __restrict__ w,
+                                                             const float* __restrict__ bias) {
+  __shared__ float sw[4 * G + 4];
+  for (int i = threadIdx.x; i < 4 * G + 4; i += blockDim.x) sw[i] = i < 4 * G ? w[i] : bias[i - 4 * G];
+  __syncthreads();
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= rows * F) return;
+  const long long row = pos / F;
+  const int f = (int)(pos - row * F);
+  const __nv_bfloat16* src = in + ((size_t)row * (G / 8) * F + f) * 8;
+  float s0 = sw[4 * G], s1 = sw[4 * G + 1], s2 = sw[4 * G + 2], s3 = sw[4 * G + 3];
+#pragma unroll
+  for (int cg = 0; cg < G / 8; ++cg) {
+    const uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)cg * F * 8);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+      const int c = cg * 8 + 2 * e;
+      s0 = fmaf(sw[c], v.x, s0); s0 = fmaf(sw[c + 1], v.y, s0);
+      s1 = fmaf(sw[G + c], v.x, s1); s1 = fmaf(sw[G + c + 1], v.y, s1);
+      s2 = fmaf(sw[2 * G + c], v.x, s2); s2 = fmaf(sw[2 * G + c + 1], v.y, s2);
+      s3 = fmaf(sw[3 * G + c], v.x, s3); s3 = fmaf(sw[3 * G + c + 1], v.y, s3);
+    }
+  }
+  __nv_bfloat162 a = __floats2bfloat162_rn(s0, s1), b = __floats2bfloat162_rn(s2, s3);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(out + pos * 4) = o;
+}
+
+template <int G>
+static void launch_ends(bool first, const void* in, void* out, long long rows, int F, const float* w, const float* a,
+                        const float* b, cudaStream_t st) {
+  const long long P = rows * F;
+  const unsigned grid = (unsigned)((P + 255) / 256);
+  if (first)
+    first_conv_cg8_kernel<G><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, F, w, a, b);
+  else
+    final_conv_cg8_kernel<G><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, F, w, a);
+}
+
+int cg8_ends_supported(int g) { return (g == 16 || g == 32 || g == 48 || g == 64) ? AC_OK : AC_E_INVALID; }
+
+static int launch_end_conv(bool first, const void* in, void* out, long long rows, int F, int g, const float* w,
+                           const float* a, const float* b, cudaStream_t st) {
+  AC_REQUIRE(cg8_ends_supported(g) == AC_OK, "cg8 1x1 conv: unsupported channel count");
+  ProfScope ps(KC_CONV1X1, 2.0 * rows * F * g * 4, (double)rows * F * (4 + g) * 2, st);
+  switch (g) {
+    case 16: launch_ends<16>(first, in, out, rows, F, w, a, b, st); break;
+    case 32: launch_ends<32>(first, in, out, rows, F, w, a, b, st); break;
+    case 48: launch_ends<48>(first, in, out, rows, F, w, a, b, st); break;
+    default: launch_ends<64>(first, in, out, rows, F, w, a, b, st); break;
+  }
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+int launch_first_conv_cg8(const void* in, void* out, long long rows, int F, int g, const float* w, const float* scale,
+                          const float* shift, cudaStream_t st) {
+  return launch_end_conv(true, in, out, rows, F, g, w, scale, shift, st);
+}
+int launch_final_conv_cg8(const void* in, void* out, long long rows, int F, int g, const float* w, const float* bias,
+                          cudaStream_t st) {
+  return launch_end_conv(false, in, out, rows, F, g, w, bias, nullptr, st);
+}
+
+// ---- small TDF layers on CUDA cores, CG8 in and out --------------------------------------------
+//   out[b][t][cg][m][e] = relu(scale[c] * sum_k W[m][k] * in[b][t][cg][k][e] + shift[c]) (+ res),  c = cg*8 + e
+// One CTA per group of PL (b, t, cg) planes: the planes ([K][8] bf16 each) are staged in shared
+// memory, every thread owns one output row m for all 8 channels of one plane, W rows come through L1.
+constexpr int kTdfSmallThreads = 128;
+__global__ void __launch_bounds__(kTdfSmallThreads) tdf_small_cg8_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                         const __nv_bfloat16* __restrict__ w /*[M][K]*/,
+                                                                         const __nv_bfloat16* __restrict__ residual,
+                                                                         __nv_bfloat16* __restrict__ out, long long n_planes,
+                                                                         int cgs, int M, int K, int PL,
+                                                                         const float* __restrict__ scale,
+                                                                         const float* __restrict__ shift) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* sx = reinterpret_cast<float*>(sm_raw);  // [PL][K][8] fp32
+  const long long plane0 = (long long)blockIdx.x * PL;
+  const int npl = (int)((n_planes - plane0) < PL ? (n_planes - plane0) : PL);
+  for (int i = threadIdx.x; i < npl * K; i += blockDim.x) {
+    const uint4 q = *reinterpret_cast<const uint4*>(in + ((size_t)plane0 * K + i) * 8);
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+      sx[(size_t)i * 8 + 2 * e] = v.x;
+      sx[(size_t)i * 8 + 2 * e + 1] = v.y;
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < npl * M; o += blockDim.x) {
+    const int pl = o / M, m = o - pl * M;
+    const float* x = sx + (size_t)pl * K * 8;
+    const __nv_bfloat16* wr = w + (size_t)m * K;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float wv = __bfloat162float(wr[k]);
+      const float4 a = *reinterpret_cast<const float4*>(x + (size_t)k * 8);
+      const float4 b = *reinterpret_cast<const float4*>(x + (size_t)k * 8 + 4);
+      acc[0] = fmaf(wv, a.x, acc[0]); acc[1] = fmaf(wv, a.y, acc[1]); acc[2] = fmaf(wv, a.z, acc[2]); acc[3] = fmaf(wv, a.w, acc[3]);
+      acc[4] = fmaf(wv, b.x, acc[4]); acc[5] = fmaf(wv, b.y, acc[5]); acc[6] = fmaf(wv, b.z, acc[6]); acc[7] = fmaf(wv, b.w, acc[7]);
+    }
+    const long long plane = plane0 + pl;
+    const int cg = (int)(plane % cgs);
+    const size_t oidx = ((size_t)plane * M + m) * 8;
+    float res[8];
+    if (residual) {
+      const uint4 q = *reinterpret_cast<const uint4*>(residual + oidx);
+      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+        res[2 * e] = v.x;
+        res[2 * e + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) res[e] = 0.f;
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = cg * 8 + 2 * e;
+      const float v0 = fmaxf(fmaf(acc[2 * e], __ldg(scale + c), __ldg(shift + c)), 0.f) + res[2 * e];
+      const float v1 = fmaxf(fmaf(acc[2 * e + 1], __ldg(scale + c + 1), __ldg(shift + c + 1)), 0.f) + res[2 * e + 1];
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      pk[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(out + oidx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// in CG8 [nB][T][C/8][K][8]; w bf16 [M][K]; residual/out CG8 [nB][T][C/8][M][8]
+int launch_tdf_small_cg8(const __nv_bfloat16* in, const __nv_bfloat16* w, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                         int nB, int T, int C, int M, int K, const float* scale, const float* shift, cudaStream_t st) {
+  AC_REQUIRE(C % 8 == 0 && M > 0 && K > 0, "tdf small: shape");
+  const long long n_planes = (long long)nB * T * (C / 8);
+  int PL = 1;
+  while (PL < 16 && (size_t)(2 * PL) * K * 32 <= 48 * 1024 && PL * M < 2 * kTdfSmallThreads) PL *= 2;
+  AC_REQUIRE((size_t)PL * K * 32 <= 48 * 1024, "tdf small: K too large for the CUDA-core kernel");
+  const size_t smem = (size_t)PL * K * 32;
+  const unsigned grid = (unsigned)((n_planes + PL - 1) / PL);
+  ProfScope ps(KC_TDF_SIMT, 2.0 * M * (double)K * C * T * nB, 2.0 * nB * (double)T * C * (K + M * (residual ? 2 : 1)), st);
+  tdf_small_cg8_kernel<<<grid, kTdfSmallThreads, smem, st>>>(in, w, residual, out, n_planes, C / 8, M, K, PL, scale, shift);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac

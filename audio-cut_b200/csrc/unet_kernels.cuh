@@ -1,5 +1,6 @@
 // Internal interface between the U-Net orchestration (unet.cu) and its kernels.
-// Activations are channels-last: [B][T][F][C] (C innermost), in float or bf16.
+// CUDA-core kernels (fp32 path, bf16 cross-check path): activations are channels-last [B][T][F][C].
+// tcgen05 kernels (bf16 production path): activations are "CG8" = [B][T][C/8][F][8], see tc_common.cuh.
 #pragma once
 #include "common.cuh"
 
@@ -43,8 +44,8 @@ int launch_final_conv(const void* in, void* out, long long P, int g, const float
 // ---- tcgen05 path (bf16) -------------------------------------------------------------------
 struct TcConvWeights;  // opaque: packed smem images for one 3x3 conv layer
 struct TcConvArgs {
-  const __nv_bfloat16* in;  // [nB][T][F][C]
-  __nv_bfloat16* out;       // [nB][T][F][C]
+  const __nv_bfloat16* in;  // CG8 [nB][T][C/8][F][8]
+  __nv_bfloat16* out;       // CG8 [nB][T][C/8][F][8]
   int nB, T, F, C;
   const TcConvWeights* w;
   const float* scale;
@@ -56,10 +57,28 @@ int tc_conv3x3_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWeights** ou
 void tc_conv3x3_free(TcConvWeights* w);
 int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
 
+// weight-stationary variant for C = 48 / 96 (unet_tc_conv_ws.cu); *out stays nullptr for other widths
+struct TcConvWsWeights;
+int tc_conv3x3_ws_supported(int T, int F, int C);
+int tc_conv3x3_ws_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWsWeights** out);
+void tc_conv3x3_ws_free(TcConvWsWeights* w);
+int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStream_t st);
+
+// CUDA-core pieces of the CG8 path (unet_cg8.cu)
+int cg8_ends_supported(int g);
+// spec [rows*F][4] bf16 -> CG8 [rows][g/8][F][8] (rows = nB*T);  and back with bias
+int launch_first_conv_cg8(const void* in, void* out, long long rows, int F, int g, const float* w /*[g][4]*/,
+                          const float* scale, const float* shift, cudaStream_t st);
+int launch_final_conv_cg8(const void* in, void* out, long long rows, int F, int g, const float* w /*[4][g]*/,
+                          const float* bias, cudaStream_t st);
+// TDF layer too small for a UMMA tile: in CG8 [nB][T][C/8][K][8], w bf16 [M][K], residual/out CG8 [nB][T][C/8][M][8]
+int launch_tdf_small_cg8(const __nv_bfloat16* in, const __nv_bfloat16* w, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                         int nB, int T, int C, int M, int K, const float* scale, const float* shift, cudaStream_t st);
+
 struct TcResampleWeights;  // opaque: packed smem images of a 2x2/s2 conv (down) or transposed conv (up)
 int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeights** out);
 void tc_resample_free(TcResampleWeights* w);
-// DOWN: in [nB][2T][2F][Cin] -> out [nB][T][F][Cout].  UP: in [nB][T][F][Cin]; skip, out [nB][2T][2F][Cout]
+// all tensors CG8.  DOWN: in (2T x 2F, Cin) -> out (T x F, Cout).  UP: in (T x F, Cin); skip, out (2T x 2F, Cout)
 int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* skip, __nv_bfloat16* out,
                        int nB, int T, int F, const float* scale, const float* shift, cudaStream_t st);
 
@@ -67,7 +86,7 @@ struct TcTdfWeights;  // opaque: packed smem images of one TDF linear layer
 // *out stays nullptr when the shape is left to the CUDA-core kernel (tiny deep-level layers)
 int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdfWeights** out);
 void tc_tdf_free(TcTdfWeights* w);
-// out[b][t][m][c] = relu(scale[c]*sum_k W[m][k]*in[b][t][k][c] + shift[c]) (+ residual[b][t][m][c])
+// out[b][t][m][c] = relu(scale[c]*sum_k W[m][k]*in[b][t][k][c] + shift[c]) (+ residual[b][t][m][c]); tensors CG8
 int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                   int nB, int T, const float* scale, const float* shift, cudaStream_t st);
 

@@ -2,11 +2,12 @@
 // network's FLOPs), bf16 operands, fp32 accumulation in tensor memory.
 //
 // Implicit GEMM, output stationary:  D[128 positions][NT out-channels] += A_tap[128][16] * W_tap[16][NT]
-//   * activations are channels-last [B][T][F][C]; an A operand tile is staged by TMA as
-//     [C/8 channel groups][130 positions][8 channels] = the canonical no-swizzle K-major UMMA
-//     layout with 16-byte rows packed back to back (SBO = 128 B), so the three horizontal taps are
-//     the SAME smem tile addressed with the descriptor start advanced by 16 B per position, and
-//     conv zero padding is TMA out-of-bounds fill (f = -1, F and t = -1, T);
+//   * activations use the channel-group planar layout [B][T][C/8][F][8] (tc_common.cuh): an A
+//     operand tile is ONE 3-D TMA box [KC/8 channel groups][130 positions][8 channels] whose rows
+//     are 2080 contiguous bytes in global memory and which lands as the canonical no-swizzle
+//     K-major UMMA layout (16-byte rows back to back, SBO = 128 B), so the three horizontal taps
+//     are the SAME smem tile addressed with the descriptor start advanced by 16 B per position,
+//     and conv zero padding is TMA out-of-bounds fill (f = -1, F and t = -1, T);
 //   * weights are pre-packed on the host into the exact smem image ([K/8][NT][8], K-major) and
 //     fetched with one 1-D bulk copy per pipeline stage;
 //   * one CTA per SM, persistent over work units (n-tile, b, t, group of MT 128-position tiles);
@@ -28,11 +29,11 @@ namespace ac {
 constexpr int kTcThreads = 192;  // 6 warps
 constexpr int kTileM = 128;
 constexpr int kRowPos = kTileM + 2;  // positions per staged A tile (1-position halo each side)
-constexpr int kRowStride = 136;      // rows reserved per channel group: 136*16 B keeps every TMA destination 128-B aligned
+constexpr int kRowStride = kRowPos;   // rows per channel group inside a staged tile (one dense 3-D box)
 
 struct TcCfg {
   int C, NT, nsplit, MT, KC, nkc, stages, nbuf;
-  int a_tile_bytes;   // one M tile of one stage: (KC/8) * 136 * 16 (130 rows written)
+  int a_tile_bytes;   // one M tile of one stage: (KC/8) * 130 * 16, rounded up to 128
   int b_stage_bytes;  // 3 * KC * NT * 2
   int stage_bytes;    // MT * a_tile_bytes + b_stage_bytes, rounded up to 128
   int smem_bytes;
@@ -109,12 +110,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
             if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
             uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
             mbar_expect_tx(&full[s], (uint32_t)(c.MT * (c.KC / 8) * (kRowPos * 16) + c.b_stage_bytes));
-            for (int mt = 0; mt < c.MT; ++mt) {
-              for (int kg = 0; kg < c.KC / 8; ++kg) {
-                tma_load_4d(st + mt * c.a_tile_bytes + kg * (kRowStride * 16), &in_map, &full[s], kc * c.KC + kg * 8,
-                            f0 + mt * kTileM - 1, t + dt - 1, b);
-              }
-            }
+            for (int mt = 0; mt < c.MT; ++mt)
+              tma_load_5d(st + mt * c.a_tile_bytes, &in_map, &full[s], 0, f0 + mt * kTileM - 1, kc * (c.KC / 8), t + dt - 1, b);
             const __nv_bfloat16* wsrc =
                 p.wpack + ((size_t)((nt * 3 + dt) * c.nkc + kc)) * (size_t)(3 * c.KC * c.NT);
             bulk_load_1d(st + c.MT * c.a_tile_bytes, wsrc, (uint32_t)c.b_stage_bytes, &full[s]);
@@ -125,37 +122,46 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
+    {
       const uint32_t idesc = make_idesc(c.NT);
       const uint32_t a_lbo = kRowStride * 16, b_lbo = (uint32_t)c.NT * 16;
+      const uint64_t a_proto = make_desc(0, a_lbo, 128), b_proto = make_desc(0, b_lbo, 128);
+      auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+        return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+      };
       int s = 0;
       uint32_t ph = 0;
       int buf = 0;
       uint32_t tph = 0;
       bool alive = true;
       for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
-        if (!mbar_wait(&tempty[buf], tph ^ 1, abort_flag)) break;
+        if (!wait_all(&tempty[buf], tph ^ 1)) break;
         tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * c.MT * c.NT);
         for (int step = 0; step < steps; ++step) {
-          if (!mbar_wait(&full[s], ph, abort_flag)) { alive = false; break; }
+          if (!wait_all(&full[s], ph)) { alive = false; break; }
           tc_fence_after();
           const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
           const uint32_t sb = sa + (uint32_t)(c.MT * c.a_tile_bytes);
-          for (int df = 0; df < 3; ++df) {
-            for (int mt = 0; mt < c.MT; ++mt) {
-              for (int k = 0; k < c.KC / 16; ++k) {
-                const uint64_t ad = make_desc(sa + mt * c.a_tile_bytes + df * 16 + k * 2 * a_lbo, a_lbo, 128);
-                const uint64_t bd = make_desc(sb + df * (c.KC * c.NT * 2) + k * 2 * b_lbo, b_lbo, 128);
-                umma_f16(acc0 + (uint32_t)(mt * c.NT), ad, bd, idesc, (step | df | k) != 0);
+          if (elect_one()) {
+            for (int df = 0; df < 3; ++df) {
+              for (int mt = 0; mt < c.MT; ++mt) {
+                const uint64_t ad0 = a_proto + ((sa + mt * c.a_tile_bytes + df * 16) >> 4);
+                const uint64_t bd0 = b_proto + ((sb + df * (c.KC * c.NT * 2)) >> 4);
+                for (int k = 0; k < c.KC / 16; ++k)
+                  umma_f16(acc0 + (uint32_t)(mt * c.NT), ad0 + (uint64_t)((k * 2 * a_lbo) >> 4), bd0 + (uint64_t)((k * 2 * b_lbo) >> 4),
+                           idesc, (step | df | k) != 0);
               }
             }
+            umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
           }
-          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++s == c.stages) { s = 0; ph ^= 1; }
         }
         if (!alive) break;
-        umma_commit(&tfull[buf]);  // accumulators complete
+        if (elect_one()) umma_commit(&tfull[buf]);  // accumulators complete
+        __syncwarp();
         if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
       }
     }
@@ -173,7 +179,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
       for (int mt = 0; mt < c.MT; ++mt) {
         const int f = f0 + mt * kTileM + quad * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
-        __nv_bfloat16* dst = p.out + (((size_t)b * p.T + t) * p.F + f) * c.C + n0;
+        __nv_bfloat16* dst = p.out + cg8_index(b, t, n0 >> 3, f, p.T, c.C, p.F);  // + (j/8) planes of F*8
         for (int j = 0; j < c.NT; j += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + j, r);
@@ -189,8 +195,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
               __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
               pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + j + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            *reinterpret_cast<uint4*>(dst + (size_t)j * p.F) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + (size_t)(j + 8) * p.F) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
@@ -237,7 +243,7 @@ static bool make_cfg(int C, int F, TcCfg& c) {
   for (int k = 48; k >= 16; k -= 16)
     if (C % k == 0) { c.KC = k; break; }
   c.nkc = C / c.KC;
-  c.a_tile_bytes = (c.KC / 8) * kRowStride * 16;
+  c.a_tile_bytes = (int)align_up((size_t)(c.KC / 8) * kRowStride * 16, 128);
   c.b_stage_bytes = 3 * c.KC * c.NT * 2;
   c.stage_bytes = (int)align_up((size_t)c.MT * c.a_tile_bytes + c.b_stage_bytes, 128);
   const int budget = 220 * 1024 - 1024;
@@ -321,11 +327,12 @@ int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
   AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
   CUtensorMap map;
-  const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.F, (cuuint64_t)a.T, (cuuint64_t)a.nB};
-  const cuuint64_t strides[3] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
-  const cuuint32_t box[4] = {8, (cuuint32_t)kRowPos, 1, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
+  // CG8 tensor [nB][T][C/8][F][8] as a 5-D map (c%8, f, c/8, t, b); one box = [KC/8][130 positions][8]
+  const cuuint64_t dims[5] = {8, (cuuint64_t)a.F, (cuuint64_t)(a.C / 8), (cuuint64_t)a.T, (cuuint64_t)a.nB};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)a.F * 16, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)kRowPos, (cuuint32_t)(c.KC / 8), 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

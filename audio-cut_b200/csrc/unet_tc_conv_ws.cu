@@ -1,0 +1,424 @@
+// Weight-stationary tcgen05 3x3 convolution for the two widest U-Net levels (C = 48 and C = 96,
+// 68 % of the conv FLOPs and the levels where the convolution sits at the HBM/tensor knee).
+//
+// The streaming kernel in unet_tc.cu re-fetches every input row three times (once per vertical tap)
+// and the whole weight tensor once per work unit; at C = 48 that makes it L2->smem bound (ncu: tensor
+// pipe 18 % active).  Here instead
+//   * the CTA's slice of the weights ([9 taps][C][NT] bf16, 41 KB at C = 48, 83 KB at C = 96/NT = 48)
+//     is loaded ONCE and stays in shared memory;
+//   * the CTA walks DOWN a strip of MT x 128 positions: a ring of R input rows lives in shared
+//     memory, each row is fetched from global memory exactly once (one 3-D TMA box per 128-position
+//     tile of the CG8 tensor, [C/8][130][8] = canonical no-swizzle K-major, 2080-byte contiguous
+//     global rows) and feeds the 9 taps of three output rows;
+//   * rows are handed out as one contiguous range per CTA of the linearised (batch, strip, t)
+//     space, so the load is balanced to +-1 row and only 2 halo rows per CTA are read twice;
+//   * accumulators (MT x NT columns) are double buffered in TMEM; 4 epilogue warps apply the folded
+//     BatchNorm + ReLU and store bf16 while the next row's MMAs run.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2..5 = epilogue.
+#include <vector>
+
+#include "tc_common.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+constexpr int kWsThreads = 192;
+constexpr int kWsTileM = 128;
+constexpr int kWsRowPos = kWsTileM + 2;
+constexpr int kWsMaxR = 8;
+
+struct WsCfg {
+  int C, NT, nsplit, MT, R;
+  int a_tile_bytes;  // (C/8) * 130 * 16, rounded up to 128
+  int a_lbo;         // 130 * 16
+  int slot_bytes;    // MT * a_tile_bytes
+  int w_bytes;       // 9 * C * NT * 2
+  int smem_bytes;
+};
+
+struct WsParams {
+  WsCfg cfg;
+  int nB, T, F;
+  int n_strips;          // strips of MT*128 positions per image row
+  long long total_rows;  // nB * n_strips * T
+  const __nv_bfloat16* wpack;
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out;
+  int* abort_flag;
+};
+
+struct WsSeg {
+  int b, f0, t0, t1;
+};
+
+// CTA -> contiguous range [lo, hi) of rows in the linearised (b, strip, t) space
+__device__ __forceinline__ void ws_range(const WsParams& p, int group_size, int j, long long& lo, long long& hi) {
+  lo = p.total_rows * j / group_size;
+  hi = p.total_rows * (j + 1) / group_size;
+}
+__device__ __forceinline__ WsSeg ws_segment(const WsParams& p, long long L, long long hi) {
+  WsSeg s;
+  const long long strip = L / p.T;
+  s.t0 = (int)(L - strip * p.T);
+  const long long left = hi - L;
+  s.t1 = (left < (long long)(p.T - s.t0)) ? s.t0 + (int)left : p.T;
+  s.b = (int)(strip / p.n_strips);
+  s.f0 = (int)(strip - (long long)s.b * p.n_strips) * p.cfg.MT * kWsTileM;
+  return s;
+}
+
+// descriptor helpers for the issue loop: the 64-bit smem descriptor only changes in its 14-bit start
+// field, so a tile's descriptor is (constant high word, low word + byte_offset/16)
+__device__ __forceinline__ uint64_t desc_at(uint32_t lo_base, uint32_t hi, uint32_t byte_off) {
+  return ((uint64_t)hi << 32) | (uint64_t)(lo_base + (byte_off >> 4));
+}
+template <bool kAcc>
+__device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if constexpr (kAcc)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc)
+        : "memory");
+}
+
+template <int C, int MT, int R>
+__global__ void __launch_bounds__(kWsThreads, 1)
+tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams p) {
+  constexpr int NT = 48;
+  constexpr int kALbo = kWsRowPos * 16;
+  constexpr int kATile = ((C / 8) * kALbo + 127) / 128 * 128;
+  constexpr int kSlot = MT * kATile;
+  constexpr int kTap = C * NT * 2;
+  constexpr int kWBytes = 9 * kTap;
+  constexpr int kBLbo = NT * 16;
+  constexpr int K16 = C / 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [R]
+  uint64_t* empty = full + kWsMaxR;                     // [R]
+  uint64_t* tfull = full + 2 * kWsMaxR;                 // [2]
+  uint64_t* tempty = tfull + 2;                         // [2]
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* s_scale = reinterpret_cast<float*>(smem + 256);  // [NT]
+  float* s_shift = s_scale + 96;
+  uint8_t* w_smem = smem + 1024;
+  uint8_t* ring = w_smem + kWBytes;
+  volatile int* abort_flag = p.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group_size = gridDim.x / (C / NT);
+  const int nt = blockIdx.x / group_size;
+  const int j_in_group = blockIdx.x - nt * group_size;
+  long long lo, hi;
+  ws_range(p, group_size, j_in_group, lo, hi);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < NT; i += blockDim.x) {
+    s_scale[i] = p.scale[nt * NT + i];
+    s_shift[i] = p.shift[nt * NT + i];
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)kWBytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)nt * kWBytes;
+      for (int tap = 0; tap < 9; ++tap) bulk_load_1d(w_smem + tap * kTap, wsrc + tap * kTap, kTap, wbar);
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (long long L = lo; L < hi && alive;) {
+        const WsSeg sg = ws_segment(p, L, hi);
+        for (int r = sg.t0 - 1; r <= sg.t1; ++r) {
+          if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+          uint8_t* dst = ring + (size_t)s * kSlot;
+          mbar_expect_tx(&full[s], (uint32_t)(MT * (C / 8) * kWsRowPos * 16));
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_5d(dst + mt * kATile, &in_map, &full[s], 0, sg.f0 + mt * kWsTileM - 1, 0, r, sg.b);
+          if (++s == R) { s = 0; ph ^= 1; }
+        }
+        L += sg.t1 - sg.t0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs the (uniform) loop and one elected lane issues, so descriptors and TMEM
+    // addresses stay in uniform registers instead of being broadcast (R2UR) before every MMA.
+    {
+      const uint32_t idesc = make_idesc(NT);
+      const uint64_t a_proto = make_desc(0, kALbo, 128), b_proto = make_desc(0, kBLbo, 128);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
+      const uint32_t b_lo0 = (uint32_t)b_proto + (smem_u32(w_smem) >> 4);
+      auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+        return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+      };
+      bool alive = wait_all(wbar, 0);
+      // ring bookkeeping without divisions: s0 = slot of the oldest row of the current output row
+      int s0 = 0;
+      uint32_t ph0 = 0;  // parity of slot s0's current fill
+      uint32_t orow = 0;
+      auto slot_after = [&](int s, int d, uint32_t ph, uint32_t& ph_out) {
+        int q = s + d;
+        ph_out = ph;
+        if (q >= R) { q -= R; ph_out ^= 1; }
+        return q;
+      };
+      for (long long L = lo; L < hi && alive;) {
+        const WsSeg sg = ws_segment(p, L, hi);
+        const int rows = sg.t1 - sg.t0;
+        {
+          uint32_t ph1;
+          const int s1 = slot_after(s0, 1, ph0, ph1);
+          if (!wait_all(&full[s0], ph0) || !wait_all(&full[s1], ph1)) { alive = false; break; }
+        }
+        for (int j = 0; j < rows; ++j, ++orow) {
+          const int buf = orow & 1;
+          uint32_t ph1, ph2;
+          const int s1 = slot_after(s0, 1, ph0, ph1);
+          const int s2 = slot_after(s0, 2, ph0, ph2);
+          if (!wait_all(&tempty[buf], ((orow >> 1) & 1) ^ 1)) { alive = false; break; }
+          if (!wait_all(&full[s2], ph2)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t acc0 = tmem_base + (uint32_t)(buf * MT * NT);
+          const int slots[3] = {s0, s1, s2};
+          if (elect_one()) {
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)slots[dt] * (kSlot >> 4);
+#pragma unroll
+              for (int df = 0; df < 3; ++df) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                  for (int k = 0; k < K16; ++k) {
+                    const uint64_t ad = desc_at(a_lo, a_hi, mt * kATile + df * 16 + k * 2 * kALbo);
+                    const uint64_t bd = desc_at(b_lo0, b_hi, (dt * 3 + df) * kTap + k * 2 * kBLbo);
+                    if (dt == 0 && df == 0 && k == 0)
+                      umma_f16_c<false>(acc0 + (uint32_t)(mt * NT), ad, bd, idesc);
+                    else
+                      umma_f16_c<true>(acc0 + (uint32_t)(mt * NT), ad, bd, idesc);
+                  }
+                }
+              }
+              if (dt == 0) umma_commit(&empty[s0]);  // oldest row is done: it is refilled during dt = 1, 2
+            }
+            if (j == rows - 1) {
+              umma_commit(&empty[s1]);
+              umma_commit(&empty[s2]);
+            }
+            umma_commit(&tfull[buf]);
+          }
+          __syncwarp();
+          s0 = s1;
+          ph0 = ph1;
+        }
+        // skip the two trailing rows of this segment
+        {
+          uint32_t ph;
+          s0 = slot_after(s0, 2, ph0, ph);
+          ph0 = ph;
+        }
+        L += rows;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;
+    uint32_t orow = 0;
+    bool alive = true;
+    for (long long L = lo; L < hi && alive;) {
+      const WsSeg sg = ws_segment(p, L, hi);
+      for (int t = sg.t0; t < sg.t1; ++t, ++orow) {
+        const int buf = orow & 1;
+        if (!mbar_wait(&tfull[buf], (orow >> 1) & 1, abort_flag)) { alive = false; break; }
+        tc_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int f = sg.f0 + mt * kWsTileM + quad * 32 + lane;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * MT * NT + mt * NT);
+          // CG8: plane (b, t, c/8) is [F][8], so the 32 lanes of a warp store 512 contiguous bytes
+          __nv_bfloat16* dst = p.out + cg8_index(sg.b, t, nt * (NT / 8), f, p.T, C, p.F);
+          uint32_t r[NT];
+#pragma unroll
+          for (int jn = 0; jn < NT; jn += 16) tmem_ld16(taddr + jn, r + jn);
+          tmem_ld_wait();
+          if (f < p.F) {
+#pragma unroll
+            for (int jn = 0; jn < NT; jn += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int ch = jn + 2 * e;
+                const float v0 = fmaxf(fmaf(__uint_as_float(r[ch]), s_scale[ch], s_shift[ch]), 0.f);
+                const float v1 = fmaxf(fmaf(__uint_as_float(r[ch + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
+                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(dst + (size_t)jn * p.F) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+      }
+      L += sg.t1 - sg.t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcConvWsWeights {
+  int C;
+  WsCfg cfg;
+  __nv_bfloat16* d_pack;
+};
+
+static bool ws_make_cfg(int C, int F, WsCfg& c) {
+  if (C != 48 && C != 96) return false;
+  c.C = C;
+  c.NT = 48;
+  c.nsplit = C / c.NT;
+  c.a_lbo = kWsRowPos * 16;
+  c.a_tile_bytes = (int)align_up((size_t)(C / 8) * c.a_lbo, 128);
+  c.w_bytes = 9 * C * c.NT * 2;
+  const int tiles = (F + kWsTileM - 1) / kWsTileM;
+  const int budget = 227 * 1024 - 1024 - c.w_bytes;
+  c.MT = 1;
+  for (int mt = 3; mt >= 1; --mt) {
+    if (mt > tiles) continue;
+    if (2 * mt * c.NT > 512) continue;
+    if (4 * mt * c.a_tile_bytes <= budget) { c.MT = mt; break; }
+  }
+  c.slot_bytes = c.MT * c.a_tile_bytes;
+  c.R = C == 48 ? (c.MT == 3 ? 5 : 6) : 5;  // must match the instantiations in launch_tc_conv3x3_ws
+  if (c.R * c.slot_bytes > budget) return false;
+  c.smem_bytes = 1024 + c.w_bytes + c.R * c.slot_bytes;
+  return true;
+}
+
+int tc_conv3x3_ws_supported(int T, int F, int C) {
+  WsCfg c;
+  (void)T;
+  return ws_make_cfg(C, F, c) ? AC_OK : AC_E_INVALID;
+}
+
+int tc_conv3x3_ws_pack(const float* h_w, int C, TcConvWsWeights** out) {
+  *out = nullptr;
+  WsCfg c;
+  if (!ws_make_cfg(C, 1 << 20, c)) return AC_OK;
+  // [nt][dt][df][C/8][NT][8]  <-  W[co][ci][kh=dt][kw=df]
+  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  size_t o = 0;
+  for (int nt = 0; nt < c.nsplit; ++nt)
+    for (int dt = 0; dt < 3; ++dt)
+      for (int df = 0; df < 3; ++df)
+        for (int kg = 0; kg < C / 8; ++kg)
+          for (int n = 0; n < c.NT; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int co = nt * c.NT + n, ci = kg * 8 + e;
+              pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df]);
+            }
+  TcConvWsWeights* w = new TcConvWsWeights();
+  w->C = C;
+  w->d_pack = nullptr;
+  if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
+      cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tc ws weight upload failed");
+    delete w;
+    return AC_E_CUDA;
+  }
+  *out = w;
+  return AC_OK;
+}
+
+void tc_conv3x3_ws_free(TcConvWsWeights* w) {
+  if (!w) return;
+  if (w->d_pack) cudaFree(w->d_pack);
+  delete w;
+}
+
+int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStream_t st) {
+  AC_REQUIRE(w && w->C == a.C, "tc ws conv: weights do not match the layer");
+  WsCfg c;
+  AC_REQUIRE(ws_make_cfg(a.C, a.F, c), "tc ws conv: unsupported shape");
+  EncodeTiledFn enc = get_tensor_map_encoder();
+  AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
+  AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
+  // 5-D view of the CG8 tensor [nB][T][C/8][F][8]: (c%8, f, c/8, t, b); one box = [C/8][130 positions][8 ch]
+  CUtensorMap map;
+  const cuuint64_t dims[5] = {8, (cuuint64_t)a.F, (cuuint64_t)(a.C / 8), (cuuint64_t)a.T, (cuuint64_t)a.nB};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)a.F * 16, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)kWsRowPos, (cuuint32_t)(a.C / 8), 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (ws conv) failed with code " + std::to_string((int)r));
+    return AC_E_CUDA;
+  }
+  WsParams p;
+  p.cfg = c;
+  p.nB = a.nB; p.T = a.T; p.F = a.F;
+  p.n_strips = ((a.F + kWsTileM - 1) / kWsTileM + c.MT - 1) / c.MT;
+  p.total_rows = (long long)a.nB * p.n_strips * a.T;
+  p.wpack = w->d_pack;
+  p.scale = a.scale; p.shift = a.shift;
+  p.out = a.out;
+  p.abort_flag = tc_abort_flag();
+  void (*kern)(const CUtensorMap, const WsParams) = nullptr;
+  if (c.C == 48 && c.MT == 3) kern = tc_conv3x3_ws_kernel<48, 3, 5>;
+  else if (c.C == 48 && c.MT == 2) kern = tc_conv3x3_ws_kernel<48, 2, 6>;
+  else if (c.C == 48 && c.MT == 1) kern = tc_conv3x3_ws_kernel<48, 1, 6>;
+  else if (c.C == 96 && c.MT == 1) kern = tc_conv3x3_ws_kernel<96, 1, 5>;
+  AC_REQUIRE(kern != nullptr, "tc ws conv: no instantiation for this shape");
+  AC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int group = device_sm_count() / c.nsplit;
+  if ((long long)group > p.total_rows) group = (int)p.total_rows;
+  const int grid = group * c.nsplit;
+  ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
+  kern<<<grid, kWsThreads, c.smem_bytes, st>>>(map, p);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac

@@ -3,8 +3,8 @@
 //
 // Both are implicit GEMMs over 128-position tiles of one output (down) / input (up) row:
 //   DOWN  D[128][NT] += X[b][2t+dt][2f+df][ci] * W[co][ci][dt][df]     K = 4*C_in, taps walk K
-//         the stride-2 gather is a 5-D tensor map (c, df, f, t, b): a box [8][1][128] lands as
-//         the K-major no-swizzle tile [128 positions][8 channels];
+//         the stride-2 gather is a 5-D tensor map over the CG8 tensor (c%8, df, f, c/8, row): a box
+//         [KC/8][128][1][8] lands as the K-major no-swizzle tile [KC/8][128 positions][8 channels];
 //   UP    D_tap[128][C_out] += X[b][t][f][ci] * W[ci][co][dt][df]      K = C_in, taps walk N
 //         each tap has its own TMEM accumulator; the epilogue scatters tap (dt,df) of position
 //         (t,f) to out[b][2t+dt][2f+df][:] and multiplies by the encoder skip tensor.
@@ -42,15 +42,6 @@ struct RsParams {
   __nv_bfloat16* out;
   int* abort_flag;
 };
-
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
-      "r"(c4)
-      : "memory");
-}
 
 __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid_constant__ CUtensorMap in_map, const RsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -112,14 +103,12 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
             uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
             mbar_expect_tx(&full[s], (uint32_t)(a_per_stage * c.a_tile_bytes + c.b_stage_bytes));
             for (int mt = 0; mt < c.MT; ++mt) {
-              for (int kg = 0; kg < c.KC / 8; ++kg) {
-                if (down) {
-                  for (int df = 0; df < 2; ++df)
-                    tma_load_5d(st + (mt * 2 + df) * c.a_tile_bytes + kg * 2048, &in_map, &full[s], kc * c.KC + kg * 8, df,
-                                f0 + mt * 128, 2 * t + dt, b);
-                } else {
-                  tma_load_4d(st + mt * c.a_tile_bytes + kg * 2048, &in_map, &full[s], kc * c.KC + kg * 8, f0 + mt * 128, t, b);
-                }
+              if (down) {
+                for (int df = 0; df < 2; ++df)
+                  tma_load_5d(st + (mt * 2 + df) * c.a_tile_bytes, &in_map, &full[s], 0, df, f0 + mt * 128, kc * (c.KC / 8),
+                              b * 2 * p.T + 2 * t + dt);
+              } else {
+                tma_load_5d(st + mt * c.a_tile_bytes, &in_map, &full[s], 0, f0 + mt * 128, kc * (c.KC / 8), t, b);
               }
             }
             const size_t blob = (size_t)c.ntap * c.KC * c.NT;
@@ -131,39 +120,45 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
+    {
       const uint32_t idesc = make_idesc(c.NT);
       const uint32_t b_lbo = (uint32_t)c.NT * 16;
+      const uint64_t a_proto = make_desc(0, 2048, 128), b_proto = make_desc(0, b_lbo, 128);
+      auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+        return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+      };
       int s = 0, buf = 0;
       uint32_t ph = 0, tph = 0;
       bool alive = true;
       for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
-        if (!mbar_wait(&tempty[buf], tph ^ 1, abort_flag)) break;
+        if (!wait_all(&tempty[buf], tph ^ 1)) break;
         tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * acc_per_unit * c.NT);
         for (int step = 0; step < steps; ++step) {
-          if (!mbar_wait(&full[s], ph, abort_flag)) { alive = false; break; }
+          if (!wait_all(&full[s], ph)) { alive = false; break; }
           tc_fence_after();
           const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
           const uint32_t sb = sa + (uint32_t)(a_per_stage * c.a_tile_bytes);
-          for (int tp = 0; tp < c.ntap; ++tp) {
-            for (int mt = 0; mt < c.MT; ++mt) {
-              for (int k = 0; k < c.KC / 16; ++k) {
-                const uint32_t a_addr = sa + (down ? (mt * 2 + tp) : mt) * c.a_tile_bytes + k * 2 * 2048;
-                const uint64_t ad = make_desc(a_addr, 2048, 128);
-                const uint64_t bd = make_desc(sb + tp * (c.KC * c.NT * 2) + k * 2 * b_lbo, b_lbo, 128);
-                if (down)
-                  umma_f16(acc0 + (uint32_t)(mt * c.NT), ad, bd, idesc, (step | tp | k) != 0);
-                else
-                  umma_f16(acc0 + (uint32_t)((mt * c.ntap + tp) * c.NT), ad, bd, idesc, (step | k) != 0);
+          if (elect_one()) {
+            for (int tp = 0; tp < c.ntap; ++tp) {
+              for (int mt = 0; mt < c.MT; ++mt) {
+                const uint64_t ad0 = a_proto + ((sa + (down ? (mt * 2 + tp) : mt) * c.a_tile_bytes) >> 4);
+                const uint64_t bd0 = b_proto + ((sb + tp * (c.KC * c.NT * 2)) >> 4);
+                const uint32_t acc = down ? acc0 + (uint32_t)(mt * c.NT) : acc0 + (uint32_t)((mt * c.ntap + tp) * c.NT);
+                for (int k = 0; k < c.KC / 16; ++k)
+                  umma_f16(acc, ad0 + (uint64_t)(k * 2 * 128), bd0 + (uint64_t)((k * 2 * b_lbo) >> 4), idesc,
+                           down ? (step | tp | k) != 0 : (step | k) != 0);
               }
             }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == c.stages) { s = 0; ph ^= 1; }
         }
         if (!alive) break;
-        umma_commit(&tfull[buf]);
+        if (elect_one()) umma_commit(&tfull[buf]);
+        __syncwarp();
         if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
       }
     }
@@ -181,15 +176,17 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
         const int tp = down ? 0 : a % c.ntap;
         const int f = f0 + mt * 128 + quad * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * acc_per_unit + a) * c.NT);
-        size_t base;
+        size_t base, plane;  // CG8 index of channel group n0/8 and the distance (elements) between channel groups
         int n0;
         if (down) {
           n0 = ns * c.NT;
-          base = (((size_t)b * p.T + t) * p.F + f) * c.Cout + n0;
+          base = cg8_index(b, t, n0 >> 3, f, p.T, c.Cout, p.F);
+          plane = (size_t)p.F * 8;
         } else {
           const int tap = ns * c.ntap + tp;
           n0 = 0;
-          base = (((size_t)b * (2 * p.T) + 2 * t + (tap >> 1)) * (size_t)(2 * p.F) + 2 * f + (tap & 1)) * c.Cout;
+          base = cg8_index(b, 2 * t + (tap >> 1), 0, 2 * f + (tap & 1), 2 * p.T, c.Cout, 2 * p.F);
+          plane = (size_t)(2 * p.F) * 8;
         }
         for (int j = 0; j < c.NT; j += 16) {
           uint32_t r[16];
@@ -198,8 +195,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
           if (f < p.F) {
             float mul[16];
             if (!down) {
-              const uint4 q0 = *reinterpret_cast<const uint4*>(p.skip + base + j);
-              const uint4 q1 = *reinterpret_cast<const uint4*>(p.skip + base + j + 8);
+              const uint4 q0 = *reinterpret_cast<const uint4*>(p.skip + base + (size_t)(j >> 3) * plane);
+              const uint4 q1 = *reinterpret_cast<const uint4*>(p.skip + base + (size_t)((j >> 3) + 1) * plane);
               const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -221,8 +218,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
               __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
               pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(p.out + base + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(p.out + base + j + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            *reinterpret_cast<uint4*>(p.out + base + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(p.out + base + (size_t)((j >> 3) + 1) * plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
@@ -338,7 +335,7 @@ void tc_resample_free(TcResampleWeights* w) {
   delete w;
 }
 
-// DOWN: in [nB][2T][2F][Cin] -> out [nB][T][F][Cout].   UP: in [nB][T][F][Cin], skip/out [nB][2T][2F][Cout].
+// All tensors CG8.  DOWN: in (2T x 2F, Cin) -> out (T x F, Cout).   UP: in (T x F, Cin); skip, out (2T x 2F, Cout).
 int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* skip, __nv_bfloat16* out,
                        int nB, int T, int F, const float* scale, const float* shift, cudaStream_t st) {
   AC_REQUIRE(w && in && out, "tc resample: null");
@@ -362,19 +359,19 @@ int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, cons
   CUresult r;
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (down) {
-    const cuuint64_t C2 = (cuuint64_t)c.Cin * 2;
-    const cuuint64_t dims[5] = {(cuuint64_t)c.Cin, 2, (cuuint64_t)F, (cuuint64_t)(2 * T), (cuuint64_t)nB};
-    const cuuint64_t strides[4] = {C2, 2 * C2, (cuuint64_t)(2 * F) * C2, (cuuint64_t)(2 * T) * (2 * F) * C2};
-    const cuuint32_t box[5] = {8, 1, 128, 1, 1};
+    // CG8 input [nB][2T][Cin/8][2F][8] as (c%8, df, f, c/8, row = b*2T + t'); box = [KC/8][128][1][8]
+    const cuuint64_t dims[5] = {8, 2, (cuuint64_t)F, (cuuint64_t)(c.Cin / 8), (cuuint64_t)nB * 2 * T};
+    const cuuint64_t strides[4] = {16, 32, (cuuint64_t)(2 * F) * 16, (cuuint64_t)(2 * F) * c.Cin * 2};
+    const cuuint32_t box[5] = {8, 1, 128, (cuuint32_t)(c.KC / 8), 1};
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    const cuuint64_t C2 = (cuuint64_t)c.Cin * 2;
-    const cuuint64_t dims[4] = {(cuuint64_t)c.Cin, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)nB};
-    const cuuint64_t strides[3] = {C2, (cuuint64_t)F * C2, (cuuint64_t)T * F * C2};
-    const cuuint32_t box[4] = {8, 128, 1, 1};
-    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+    // CG8 input [nB][T][Cin/8][F][8] as (c%8, f, c/8, t, b); box = [KC/8][128][8]
+    const cuuint64_t dims[5] = {8, (cuuint64_t)F, (cuuint64_t)(c.Cin / 8), (cuuint64_t)T, (cuuint64_t)nB};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)F * 16, (cuuint64_t)F * c.Cin * 2, (cuuint64_t)T * F * c.Cin * 2};
+    const cuuint32_t box[5] = {8, 128, (cuuint32_t)(c.KC / 8), 1, 1};
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }

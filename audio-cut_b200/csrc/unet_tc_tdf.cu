@@ -2,10 +2,12 @@
 //   Y[b][t][m][c] = relu(scale[c] * sum_k W[m][k] * X[b][t][k][c] + shift[c]) (+ R[b][t][m][c])
 // i.e. a GEMM over the frequency axis with channels riding along.  As UMMA:
 //   D[128 out-features][N = NTt*C] += A[128][16] (weights, K-major) * B[16][N] (activations)
-// The activations are channels-last, so B is MN-major: TMA stages [8 channels][Kt freqs] boxes
-// as [(t, c/8)][Kt][8] = the canonical no-swizzle MN-major layout (16-byte rows, 8-row core
-// matrices 128 B apart, SBO = Kt*16 between channel groups).  Weights are pre-packed smem images
-// fetched by 1-D bulk copies.  Pipeline / roles / TMEM hand-off as in unet_tc.cu.
+// Channels ride along N, so B is MN-major.  In the CG8 activation layout [B][T][C/8][F][8] a
+// (b, t, channel group) plane is [F][8] = Kt*16 contiguous bytes per K chunk, which IS the canonical
+// no-swizzle MN-major layout (16-byte rows, 8-row core matrices 128 B apart, SBO = Kt*16 between
+// channel groups): ONE 4-D TMA box [NTt][C/8][Kt][8] stages a whole pipeline step.  Weights are
+// pre-packed smem images fetched by 1-D bulk copies.  Pipeline / roles / TMEM hand-off as in
+// unet_tc.cu; outputs (and the residual) are CG8 too, so a warp stores 512 contiguous bytes.
 #include <vector>
 
 #include "tc_common.cuh"
@@ -35,7 +37,7 @@ struct TdfParams {
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;  // nullable
-  __nv_bfloat16* out;             // [nB][T][M][C]
+  __nv_bfloat16* out;             // CG8 [nB][T][C/8][M][8]
   int* abort_flag;
 };
 
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int cg = c.C / 8;  // channel groups per time row
+
 
   auto decode = [&](int u, int& mg, int& b, int& t0) {
     mg = u % c.n_mg;
@@ -93,40 +95,46 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
           const __nv_bfloat16* wsrc = p.wpack + ((size_t)mg * c.nk + kc) * (size_t)(c.mt * 128 * c.Kt);
           bulk_load_1d(st, wsrc, (uint32_t)(c.mt * c.a_tile_bytes), &full[s]);
           uint8_t* sb = st + c.mt * c.a_tile_bytes;
-          for (int tl = 0; tl < c.NTt; ++tl)
-            for (int g = 0; g < cg; ++g)
-              tma_load_4d(sb + (size_t)(tl * cg + g) * (c.Kt * 16), &in_map, &full[s], g * 8, kc * c.Kt, t0 + tl, b);
+          tma_load_5d(sb, &in_map, &full[s], 0, kc * c.Kt, 0, t0, b);  // [NTt][C/8][Kt][8]
           if (++s == c.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
+    {
       const uint32_t idesc = make_idesc_bmn(c.N);
+      const uint64_t a_proto = make_desc(0, 128 * 16, 128), b_proto = make_desc_mn(0, 128, (uint32_t)c.Kt * 16);
+      auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+        return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+      };
       int s = 0, buf = 0;
       uint32_t ph = 0, tph = 0;
       bool alive = true;
       for (int u = blockIdx.x; u < p.n_units && alive; u += gridDim.x) {
-        if (!mbar_wait(&tempty[buf], tph ^ 1, abort_flag)) break;
+        if (!wait_all(&tempty[buf], tph ^ 1)) break;
         tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * c.mt * c.N);
         for (int kc = 0; kc < c.nk; ++kc) {
-          if (!mbar_wait(&full[s], ph, abort_flag)) { alive = false; break; }
+          if (!wait_all(&full[s], ph)) { alive = false; break; }
           tc_fence_after();
           const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
           const uint32_t sb = sa + (uint32_t)(c.mt * c.a_tile_bytes);
-          for (int mi = 0; mi < c.mt; ++mi) {
-            for (int k = 0; k < c.Kt / 16; ++k) {
-              const uint64_t ad = make_desc(sa + mi * c.a_tile_bytes + k * 2 * (128 * 16), 128 * 16, 128);
-              const uint64_t bd = make_desc_mn(sb + k * 256, 128, (uint32_t)c.Kt * 16);
-              umma_f16(acc0 + (uint32_t)(mi * c.N), ad, bd, idesc, (kc | k) != 0);
+          if (elect_one()) {
+            for (int mi = 0; mi < c.mt; ++mi) {
+              const uint64_t ad0 = a_proto + ((sa + mi * c.a_tile_bytes) >> 4);
+              const uint64_t bd0 = b_proto + (sb >> 4);
+              for (int k = 0; k < c.Kt / 16; ++k)
+                umma_f16(acc0 + (uint32_t)(mi * c.N), ad0 + (uint64_t)(k * 2 * 128), bd0 + (uint64_t)(k * 16), idesc, (kc | k) != 0);
             }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == c.stages) { s = 0; ph ^= 1; }
         }
         if (!alive) break;
-        umma_commit(&tfull[buf]);
+        if (elect_one()) umma_commit(&tfull[buf]);
+        __syncwarp();
         if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
       }
     }
@@ -148,11 +156,12 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
           tmem_ld_wait();
           if (m < c.M) {
             const int tl = j / c.C, ch0 = j - tl * c.C;
-            const size_t idx = (((size_t)b * p.T + t0 + tl) * c.M + m) * c.C + ch0;
+            const size_t idx = cg8_index(b, t0 + tl, ch0 >> 3, m, p.T, c.C, c.M);  // channel groups ch0/8, ch0/8+1
+            const size_t idx1 = idx + (size_t)c.M * 8;
             float res[16];
             if (p.residual) {
               const uint4 q0 = *reinterpret_cast<const uint4*>(p.residual + idx);
-              const uint4 q1 = *reinterpret_cast<const uint4*>(p.residual + idx + 8);
+              const uint4 q1 = *reinterpret_cast<const uint4*>(p.residual + idx1);
               const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
               pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
             *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(p.out + idx + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            *reinterpret_cast<uint4*>(p.out + idx1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
@@ -198,7 +207,7 @@ struct TcTdfWeights {
 };
 
 static bool make_tdf_cfg(int M, int K, int C, int T, TdfCfg& c) {
-  if (C % 16 || C > 256 || K % 16 || M < 64) return false;  // tiny layers stay on the CUDA-core kernel
+  if (C % 16 || C > 256 || K % 16 || M < 32) return false;  // the tiniest layers stay on the CUDA-core kernel
   c.C = C; c.M = M; c.K = K;
   c.n_mtiles = (M + 127) / 128;
   c.Kt = K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : 16);
@@ -275,11 +284,12 @@ int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfl
   AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
   AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
   CUtensorMap map;
-  const cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.K, (cuuint64_t)T, (cuuint64_t)nB};
-  const cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.K * c.C * 2, (cuuint64_t)T * c.K * c.C * 2};
-  const cuuint32_t box[4] = {8, (cuuint32_t)c.Kt, 1, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+  // CG8 input [nB][T][C/8][K][8] as (c%8, k, c/8, t, b); one box = [NTt][C/8][Kt][8]
+  const cuuint64_t dims[5] = {8, (cuuint64_t)c.K, (cuuint64_t)(c.C / 8), (cuuint64_t)T, (cuuint64_t)nB};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)c.K * 16, (cuuint64_t)c.K * c.C * 2, (cuuint64_t)T * c.K * c.C * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)c.Kt, (cuuint32_t)(c.C / 8), (cuuint32_t)c.NTt, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

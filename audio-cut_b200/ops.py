@@ -137,6 +137,28 @@ class UNet:
         return out
 
 
+def debug_conv3x3(x: torch.Tensor, w: np.ndarray, scale: torch.Tensor, shift: torch.Tensor, impl: int, iters: int = 1):
+    """One bf16 3x3 conv layer (test hook): x [B,T,F,C] bf16, w [C,C,3,3] float32 -> (y, mean ms per launch).
+
+    impl 0 = CUDA cores, 1 = streaming tcgen05, 2 = weight-stationary tcgen05; the tensor-core kernels
+    work on the CG8 layout [B,T,C/8,F,8], the conversion to and from channels-last is done here."""
+    lib = _lib.init(_dev_index(x))
+    assert x.dtype == torch.bfloat16 and x.dim() == 4
+    B, T, F, Cc = x.shape
+    if impl != 0:
+        x = x.view(B, T, F, Cc // 8, 8).permute(0, 1, 3, 2, 4)
+    x = x.contiguous()
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    assert w.shape == (Cc, Cc, 3, 3)
+    y = torch.empty((B, T, F, Cc), dtype=torch.bfloat16, device=x.device)
+    ms = C.c_float(0.0)
+    check(lib.ac_debug_conv3x3(ptr(x), ptr(y), B, T, F, Cc, w.ctypes.data_as(C.c_void_p), ptr(scale.float().contiguous()),
+                               ptr(shift.float().contiguous()), impl, iters, C.byref(ms), stream_ptr()), "ac_debug_conv3x3")
+    if impl != 0:
+        y = y.view(B, T, Cc // 8, F, 8).permute(0, 1, 3, 2, 4).contiguous().view(B, T, F, Cc)
+    return y, float(ms.value)
+
+
 def make_chunk_descs(bounds: Sequence[Tuple[int, int, int, int]]):
     """bounds: (chunk_start, chunk_end, eff_start, eff_end) per chunk, in samples."""
     arr = (ChunkDesc * max(1, len(bounds)))()

@@ -114,8 +114,16 @@ AC_API size_t ac_unet_workspace_bytes(const ac_unet* net, int B, int dtype);
 AC_API int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int B, int dtype, void* d_ws, size_t ws_bytes,
                     void* stream);
 /* Test hook: 0 = let the library choose, 1 = force the CUDA-core kernels for every layer (bf16
- * storage kept), so the tcgen05 kernels can be checked layer by layer. */
+ * storage kept), so the tcgen05 kernels can be checked layer by layer, 2 = tcgen05 kernels but
+ * without the weight-stationary convolution (A/B timing). */
 AC_API int ac_unet_set_debug(ac_unet* net, int force_simt);
+/* Test / profiling hook: one bf16 3x3 convolution layer y = relu(scale * conv(x, W) + shift).
+ * impl: 0 = CUDA-core implicit GEMM on channels-last [B][T][F][C] tensors; 1 = streaming tcgen05
+ * kernel, 2 = weight-stationary tcgen05 kernel (C = 48 / 96), both on the tensor-core path's
+ * channel-group planar layout [B][T][C/8][F][8] for input and output.  h_w = W[C][C][3][3] float32 on the
+ * host.  Runs `iters` launches; *h_ms (optional) = mean ms of launches 2..iters.  Synchronises. */
+AC_API int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int F, int C, const float* h_w,
+                     const float* d_scale, const float* d_shift, int impl, int iters, float* h_ms, void* stream);
 /* Test hook: synchronises and returns 1 when a tensor-core kernel gave up on an mbarrier wait
  * (a pipeline bug; the watchdog keeps such a bug from hanging the GPU), 0 otherwise. */
 AC_API int ac_debug_tc_aborted(void);
