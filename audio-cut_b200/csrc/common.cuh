@@ -77,6 +77,13 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   return r;
 }
 
+// streaming 128-bit global load of raw bits (bf16 x 8)
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

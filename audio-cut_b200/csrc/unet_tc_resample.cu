@@ -17,7 +17,10 @@
 
 namespace ac {
 
-constexpr int kRsThreads = 192;
+constexpr int kRsEpiGroups = 3;  // epilogue warps per TMEM lane quadrant: group g owns the 16-channel chunks g, g+3, ...
+constexpr int kRsEpiWarps = 4 * kRsEpiGroups;
+constexpr int kRsThreads = (2 + kRsEpiWarps) * 32;
+constexpr int kRsHeader = 4096;   // barriers + scale/shift staged in shared memory
 enum { RS_DOWN = 0, RS_UP = 1 };
 
 struct RsCfg {
@@ -51,9 +54,15 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
   uint64_t* tfull = full + 16;
   uint64_t* tempty = full + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
-  uint8_t* stage0 = smem + 1024;
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [Cout] (<= 384)
+  float* s_shift = s_scale + 384;
+  uint8_t* stage0 = smem + kRsHeader;
   volatile int* abort_flag = p.abort_flag;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.cfg.Cout && i < 384; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -61,7 +70,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
     }
     for (int b = 0; b < c.nbuf; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);
+      mbar_init(&tempty[b], kRsEpiWarps);
     }
     fence_barrier_init();
   }
@@ -163,65 +172,94 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
       }
     }
   } else {
-    const int quad = warp & 3;
+    // ===================== epilogue (warps 2..13) =====================
+    // One warp per (TMEM lane quadrant, chunk group): group g owns the 16-channel chunks g, g+3, ... of
+    // every accumulator; three warps per scheduler hide each other's latencies.
+    const int quad = warp & 3;  // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
+    const int grp = (warp - 2) >> 2;
+    const int chunks_a = c.NT >> 4;
+    const int per_acc = chunks_a > grp ? (chunks_a - grp + kRsEpiGroups - 1) / kRsEpiGroups : 0;
+    const int n_my = acc_per_unit * per_acc;
+    constexpr int kMaxMy = 6;
+    int my_acc[kMaxMy], my_col[kMaxMy];
+#pragma unroll
+    for (int i = 0; i < kMaxMy; ++i) {
+      const int a = per_acc ? i / per_acc : 0, k = per_acc ? i - a * per_acc : 0;
+      my_acc[i] = a;
+      my_col[i] = (grp + kRsEpiGroups * k) * 16;
+    }
+    const bool fast = n_my <= kMaxMy;
+    const bool pre_ok = fast && !down;
+    const size_t plane = down ? (size_t)p.F * 8 : (size_t)(2 * p.F) * 8;  // elements between 8-channel groups of `out`
     int buf = 0;
     uint32_t tph = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int ns, b, t, f0;
       decode(u, ns, b, t, f0);
-      if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
-      tc_fence_after();
-      for (int a = 0; a < acc_per_unit; ++a) {
+      // CG8 index of channel 0 (of this unit's N slice) for accumulator a
+      auto locate = [&](int a, int& f, int& n0) -> size_t {
         const int mt = down ? a : a / c.ntap;
         const int tp = down ? 0 : a % c.ntap;
-        const int f = f0 + mt * 128 + quad * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * acc_per_unit + a) * c.NT);
-        size_t base, plane;  // CG8 index of channel group n0/8 and the distance (elements) between channel groups
-        int n0;
+        f = f0 + mt * 128 + quad * 32 + lane;
         if (down) {
           n0 = ns * c.NT;
-          base = cg8_index(b, t, n0 >> 3, f, p.T, c.Cout, p.F);
-          plane = (size_t)p.F * 8;
-        } else {
-          const int tap = ns * c.ntap + tp;
-          n0 = 0;
-          base = cg8_index(b, 2 * t + (tap >> 1), 0, 2 * f + (tap & 1), 2 * p.T, c.Cout, 2 * p.F);
-          plane = (size_t)(2 * p.F) * 8;
+          return cg8_index(b, t, n0 >> 3, f, p.T, c.Cout, p.F);
         }
-        for (int j = 0; j < c.NT; j += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + j, r);
-          tmem_ld_wait();
-          if (f < p.F) {
-            float mul[16];
-            if (!down) {
-              const uint4 q0 = *reinterpret_cast<const uint4*>(p.skip + base + (size_t)(j >> 3) * plane);
-              const uint4 q1 = *reinterpret_cast<const uint4*>(p.skip + base + (size_t)((j >> 3) + 1) * plane);
-              const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const int tap = ns * c.ntap + tp;
+        n0 = 0;
+        return cg8_index(b, 2 * t + (tap >> 1), 0, 2 * f + (tap & 1), 2 * p.T, c.Cout, 2 * p.F);
+      };
+      // UP: the skip values do not depend on the MMAs; request them before waiting for the accumulators
+      uint4 pre[2 * kMaxMy];
+      if (pre_ok) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                mul[2 * e] = fl.x;
-                mul[2 * e + 1] = fl.y;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) mul[e] = 1.f;
+        for (int i = 0; i < kMaxMy; ++i) {
+          if (i < n_my) {
+            int f, n0;
+            const size_t o0 = locate(my_acc[i], f, n0) + (size_t)(my_col[i] >> 3) * plane;
+            if (f < p.F) {
+              pre[2 * i] = ldg_stream_u4(p.skip + o0);
+              pre[2 * i + 1] = ldg_stream_u4(p.skip + o0 + plane);
             }
-            uint32_t pk[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int ch = n0 + j + 2 * e;
-              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), __ldg(p.scale + ch), __ldg(p.shift + ch)), 0.f) * mul[2 * e];
-              const float v1 =
-                  fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), __ldg(p.scale + ch + 1), __ldg(p.shift + ch + 1)), 0.f) * mul[2 * e + 1];
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(p.out + base + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(p.out + base + (size_t)((j >> 3) + 1) * plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
+      }
+      if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
+      tc_fence_after();
+      auto chunk16 = [&](int a, int j, bool have, uint4 q0, uint4 q1) {
+        int f, n0;
+        const size_t o0 = locate(a, f, n0) + (size_t)(j >> 3) * plane, o1 = o0 + plane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((buf * acc_per_unit + a) * c.NT);
+        uint32_t r[16];
+        tmem_ld16(taddr + j, r);
+        tmem_ld_wait();
+        if (f >= p.F) return;
+        if (!down && !have) {
+          q0 = *reinterpret_cast<const uint4*>(p.skip + o0);
+          q1 = *reinterpret_cast<const uint4*>(p.skip + o1);
+        }
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ch = n0 + j + 2 * e;
+          const float2 mul = down ? make_float2(1.f, 1.f) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+          const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f) * mul.x;
+          const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) * mul.y;
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p.out + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(p.out + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      };
+      if (fast) {
+#pragma unroll
+        for (int i = 0; i < kMaxMy; ++i)
+          if (i < n_my) chunk16(my_acc[i], my_col[i], pre_ok, pre[2 * i], pre[2 * i + 1]);
+      } else {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int a = 0; a < acc_per_unit; ++a)
+          for (int q = grp; q < chunks_a; q += kRsEpiGroups) chunk16(a, q * 16, false, z, z);
       }
       tc_fence_before();
       __syncwarp();
@@ -243,7 +281,7 @@ struct TcResampleWeights {
 };
 
 static bool make_rs_cfg(int mode, int Cin, int Cout, RsCfg& c) {
-  if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16) return false;
+  if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16 || Cout > 384) return false;
   c.mode = mode;
   c.Cin = Cin;
   c.Cout = Cout;
@@ -278,10 +316,10 @@ static bool make_rs_cfg(int mode, int Cin, int Cout, RsCfg& c) {
   c.b_stage_bytes = c.ntap * c.KC * c.NT * 2;
   const int a_per_stage = (mode == RS_DOWN ? 2 : 1) * c.MT;
   c.stage_bytes = (int)align_up((size_t)a_per_stage * c.a_tile_bytes + c.b_stage_bytes, 128);
-  c.stages = (220 * 1024 - 1024) / c.stage_bytes;
+  c.stages = (224 * 1024 - kRsHeader) / c.stage_bytes;
   if (c.stages > 8) c.stages = 8;
   if (c.stages < 2) return false;
-  c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+  c.smem_bytes = kRsHeader + c.stages * c.stage_bytes;
   return true;
 }
 
@@ -347,9 +385,9 @@ int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, cons
     c.MT = tiles;
     const int a_per_stage = (down ? 2 : 1) * c.MT;
     c.stage_bytes = (int)align_up((size_t)a_per_stage * c.a_tile_bytes + c.b_stage_bytes, 128);
-    c.stages = (220 * 1024 - 1024) / c.stage_bytes;
+    c.stages = (224 * 1024 - kRsHeader) / c.stage_bytes;
     if (c.stages > 8) c.stages = 8;
-    c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+    c.smem_bytes = kRsHeader + c.stages * c.stage_bytes;
     c.nbuf = down ? ((2 * c.MT * c.NT <= 512) ? 2 : 1) : c.nbuf;
   }
   EncodeTiledFn enc = get_tensor_map_encoder();

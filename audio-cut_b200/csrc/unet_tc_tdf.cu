@@ -15,7 +15,10 @@
 
 namespace ac {
 
-constexpr int kTdfThreads = 192;
+constexpr int kTdfEpiGroups = 3;  // epilogue warps per TMEM lane quadrant: group g owns the 16-channel chunks g, g+3, ...
+constexpr int kTdfEpiWarps = 4 * kTdfEpiGroups;
+constexpr int kTdfThreads = (2 + kTdfEpiWarps) * 32;
+constexpr int kTdfHeader = 4096;   // barriers + scale/shift staged in shared memory
 
 struct TdfCfg {
   int C, M, K;
@@ -49,9 +52,15 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
   uint64_t* tfull = full + 16;
   uint64_t* tempty = full + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
-  uint8_t* stage0 = smem + 1024;
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [C] (C <= 256)
+  float* s_shift = s_scale + 256;
+  uint8_t* stage0 = smem + kTdfHeader;
   volatile int* abort_flag = p.abort_flag;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < c.C; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -59,7 +68,7 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
     }
     for (int b = 0; b < c.nbuf; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);
+      mbar_init(&tempty[b], kTdfEpiWarps);
     }
     fence_barrier_init();
   }
@@ -139,52 +148,88 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
       }
     }
   } else {
-    const int quad = warp & 3;
+    // ===================== epilogue (warps 2..13) =====================
+    // One warp per (TMEM lane quadrant, chunk group): group g owns the 16-channel chunks g, g+3, ... of
+    // every time row, so all of a warp's column offsets are fixed for the whole kernel (no division or
+    // 64-bit multiply in the unit loop), and three warps per scheduler hide each other's latencies.
+    const int quad = warp & 3;        // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
+    const int grp = (warp - 2) >> 2;
+    const int chunks_c = c.C >> 4;                                        // 16-channel chunks per time row
+    const int per_row = chunks_c > grp ? (chunks_c - grp + kTdfEpiGroups - 1) / kTdfEpiGroups : 0;
+    const int n_my = c.NTt * per_row;                                     // chunks this warp owns per accumulator tile
+    constexpr int kMaxMy = 6;
+    const size_t plane = (size_t)c.M * 8;                                 // elements between 8-channel groups (CG8)
+    const size_t t_stride = (size_t)(c.C >> 3) * plane;                   // elements between time rows
+    int my_col[kMaxMy], my_ch[kMaxMy];
+    size_t my_off[kMaxMy];
+#pragma unroll
+    for (int i = 0; i < kMaxMy; ++i) {
+      const int tl = per_row ? i / per_row : 0, k = per_row ? i - tl * per_row : 0;
+      const int cq = grp + kTdfEpiGroups * k;
+      my_ch[i] = cq * 16;
+      my_col[i] = tl * c.C + cq * 16;
+      my_off[i] = (size_t)tl * t_stride + (size_t)(cq * 2) * plane;
+    }
+    const bool fast = n_my <= kMaxMy;
+    const bool pre_ok = fast && p.residual != nullptr && c.mt == 1;
     int buf = 0;
     uint32_t tph = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int mg, b, t0;
       decode(u, mg, b, t0);
+      const int m0 = mg * c.mt * 128 + quad * 32 + lane;
+      const size_t base0 = cg8_index(b, t0, 0, m0, p.T, c.C, c.M);
+      // The residual does not depend on the MMAs: request this warp's share of it before waiting for the
+      // accumulators so the latency hides behind the MMA time.
+      uint4 pre[2 * kMaxMy];
+      if (pre_ok && m0 < c.M) {
+#pragma unroll
+        for (int i = 0; i < kMaxMy; ++i) {
+          if (i < n_my) {
+            pre[2 * i] = ldg_stream_u4(p.residual + base0 + my_off[i]);
+            pre[2 * i + 1] = ldg_stream_u4(p.residual + base0 + my_off[i] + plane);
+          }
+        }
+      }
       if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
       tc_fence_after();
+      // one 16-column chunk: TMEM -> affine/ReLU (+ residual q0|q1) -> bf16 -> global (512 contiguous bytes per warp)
+      auto chunk16 = [&](uint32_t taddr, int col, int ch0, bool valid, size_t idx, bool have_res, uint4 q0, uint4 q1) {
+        uint32_t r[16];
+        tmem_ld16(taddr + col, r);
+        tmem_ld_wait();
+        if (!valid) return;
+        if (p.residual && !have_res) {
+          q0 = *reinterpret_cast<const uint4*>(p.residual + idx);
+          q1 = *reinterpret_cast<const uint4*>(p.residual + idx + plane);
+        }
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ch = ch0 + 2 * e;
+          const float2 res = p.residual ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e])) : make_float2(0.f, 0.f);
+          const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
+          const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(p.out + idx + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      };
       for (int mi = 0; mi < c.mt; ++mi) {
-        const int m = (mg * c.mt + mi) * 128 + quad * 32 + lane;
+        const bool valid = m0 + mi * 128 < c.M;
+        const size_t base = base0 + (size_t)mi * 128 * 8;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.mt * c.N + mi * c.N);
-        for (int j = 0; j < c.N; j += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + j, r);
-          tmem_ld_wait();
-          if (m < c.M) {
-            const int tl = j / c.C, ch0 = j - tl * c.C;
-            const size_t idx = cg8_index(b, t0 + tl, ch0 >> 3, m, p.T, c.C, c.M);  // channel groups ch0/8, ch0/8+1
-            const size_t idx1 = idx + (size_t)c.M * 8;
-            float res[16];
-            if (p.residual) {
-              const uint4 q0 = *reinterpret_cast<const uint4*>(p.residual + idx);
-              const uint4 q1 = *reinterpret_cast<const uint4*>(p.residual + idx1);
-              const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        if (fast) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                res[2 * e] = f.x;
-                res[2 * e + 1] = f.y;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) res[e] = 0.f;
-            }
-            uint32_t pk[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int ch = ch0 + 2 * e;
-              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), __ldg(p.scale + ch), __ldg(p.shift + ch)), 0.f) + res[2 * e];
-              const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), __ldg(p.scale + ch + 1), __ldg(p.shift + ch + 1)), 0.f) + res[2 * e + 1];
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(p.out + idx1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
+          for (int i = 0; i < kMaxMy; ++i)
+            if (i < n_my) chunk16(taddr, my_col[i], my_ch[i], valid, base + my_off[i], pre_ok, pre[2 * i], pre[2 * i + 1]);
+        } else {
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          for (int tl = 0; tl < c.NTt; ++tl)
+            for (int cq = grp; cq < chunks_c; cq += kTdfEpiGroups)
+              chunk16(taddr, tl * c.C + cq * 16, cq * 16, valid, base + (size_t)tl * t_stride + (size_t)(cq * 2) * plane, false, z, z);
         }
       }
       tc_fence_before();
@@ -232,10 +277,10 @@ static bool make_tdf_cfg(int M, int K, int C, int T, TdfCfg& c) {
   c.a_tile_bytes = 128 * c.Kt * 2;
   c.b_stage_bytes = c.N * c.Kt * 2;
   c.stage_bytes = (int)align_up((size_t)c.mt * c.a_tile_bytes + c.b_stage_bytes, 128);
-  c.stages = (220 * 1024 - 1024) / c.stage_bytes;
+  c.stages = (224 * 1024 - kTdfHeader) / c.stage_bytes;
   if (c.stages > 8) c.stages = 8;
   if (c.stages < 2) return false;
-  c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+  c.smem_bytes = kTdfHeader + c.stages * c.stage_bytes;
   return true;
 }
 
