@@ -302,7 +302,8 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
     AC_REQUIRE(tc_conv3x3_supported(T, F, C) == AC_OK, "streaming tc conv does not support this shape");
     if ((rc = tc_conv3x3_pack(h_w, C, &tc))) return rc;
     ta.w = tc;
-  } else if (impl == 2) {
+  } else if (impl == 2 || impl == 3) {
+    tc_conv3x3_ws_set_pair(impl == 3);
     AC_REQUIRE(tc_conv3x3_ws_supported(T, F, C) == AC_OK, "ws tc conv does not support this shape");
     if ((rc = tc_conv3x3_ws_pack(h_w, C, &ws))) return rc;
   } else {
@@ -315,7 +316,7 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
   }
   auto once = [&]() -> int {
     if (impl == 1) return launch_tc_conv3x3(ta, st);
-    if (impl == 2) return launch_tc_conv3x3_ws(ws, ta, st);
+    if (impl == 2 || impl == 3) return launch_tc_conv3x3_ws(ws, ta, st);
     GemmArgs a{};
     a.M = B * T * F; a.N = C; a.K = 9 * C; a.batch = 1;
     a.a_mode = A_CONV3; a.A = d_in; a.T = T; a.F = F; a.C = C;
@@ -341,6 +342,7 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
+  tc_conv3x3_ws_set_pair(1);
   if (tc) tc_conv3x3_free(tc);
   if (ws) tc_conv3x3_ws_free(ws);
   if (d_w16) cudaFree(d_w16);

@@ -12,7 +12,7 @@
 //     fetched with one 1-D bulk copy per pipeline stage;
 //   * one CTA per SM, persistent over work units (n-tile, b, t, group of MT 128-position tiles);
 //     MT accumulators live in TMEM so every weight tile fetched from L2 is reused MT times;
-//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 =
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..13 =
 //     epilogue (tcgen05.ld -> scale/shift/ReLU -> bf16 -> global); smem ring and (when the
 //     accumulators fit twice) a double-buffered TMEM hand-off, all through mbarriers.
 #include <mutex>
@@ -26,7 +26,10 @@ namespace ac {
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 192;  // 6 warps
+constexpr int kTcEpiGroups = 3;   // epilogue warps per TMEM lane quadrant: group g owns the 16-channel chunks g, g+3, ...
+constexpr int kTcEpiWarps = 4 * kTcEpiGroups;
+constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;
+constexpr int kTcHeader = 5120;   // barriers + this layer's scale/shift (<= 512 channels)
 constexpr int kTileM = 128;
 constexpr int kRowPos = kTileM + 2;  // positions per staged A tile (1-position halo each side)
 constexpr int kRowStride = kRowPos;   // rows per channel group inside a staged tile (one dense 3-D box)
@@ -60,10 +63,16 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
   uint64_t* tfull = full + 16;                          // [nbuf]
   uint64_t* tempty = full + 20;                         // [nbuf]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 24);
-  uint8_t* stage0 = smem + 1024;
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [C] (C <= 512)
+  float* s_shift = s_scale + 512;
+  uint8_t* stage0 = smem + kTcHeader;
   volatile int* abort_flag = p.abort_flag;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < c.C; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < c.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -71,7 +80,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
     }
     for (int b = 0; b < c.nbuf; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[b], kTcEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -166,37 +175,42 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    // ===================== epilogue (warps 2..13) =====================
+    // One warp per (TMEM lane quadrant, chunk group): three warps per scheduler hide each other's
+    // latencies (with one warp per scheduler the dependent ALU chains of the epilogue set the pace).
+    const int quad = warp & 3;  // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
+    const int grp = (warp - 2) >> 2;
+    const size_t plane = (size_t)p.F * 8;  // elements between 8-channel groups (CG8)
     int buf = 0;
     uint32_t tph = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       int nt, b, t, f0;
       decode(u, nt, b, t, f0);
+      const int n0 = nt * c.NT;
+      const int f_lane = f0 + quad * 32 + lane;
+      __nv_bfloat16* dst0 = p.out + cg8_index(b, t, n0 >> 3, f_lane, p.T, c.C, p.F);
       if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
       tc_fence_after();
-      const int n0 = nt * c.NT;
       for (int mt = 0; mt < c.MT; ++mt) {
-        const int f = f0 + mt * kTileM + quad * 32 + lane;
+        const bool valid = f_lane + mt * kTileM < p.F;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
-        __nv_bfloat16* dst = p.out + cg8_index(b, t, n0 >> 3, f, p.T, c.C, p.F);  // + (j/8) planes of F*8
-        for (int j = 0; j < c.NT; j += 16) {
+        __nv_bfloat16* dst = dst0 + (size_t)mt * kTileM * 8;
+        for (int j = grp * 16; j < c.NT; j += 16 * kTcEpiGroups) {
           uint32_t r[16];
           tmem_ld16(taddr + j, r);
           tmem_ld_wait();
-          if (f < p.F) {
+          if (valid) {
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int ch = n0 + j + 2 * e;
-              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), __ldg(p.scale + ch), __ldg(p.shift + ch)), 0.f);
-              const float v1 =
-                  fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), __ldg(p.scale + ch + 1), __ldg(p.shift + ch + 1)), 0.f);
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
               __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
               pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(dst + (size_t)j * p.F) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + (size_t)(j + 8) * p.F) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            *reinterpret_cast<uint4*>(dst + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + (size_t)((j >> 3) + 1) * plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
@@ -246,11 +260,11 @@ static bool make_cfg(int C, int F, TcCfg& c) {
   c.a_tile_bytes = (int)align_up((size_t)(c.KC / 8) * kRowStride * 16, 128);
   c.b_stage_bytes = 3 * c.KC * c.NT * 2;
   c.stage_bytes = (int)align_up((size_t)c.MT * c.a_tile_bytes + c.b_stage_bytes, 128);
-  const int budget = 220 * 1024 - 1024;
+  const int budget = 224 * 1024 - kTcHeader;
   c.stages = budget / c.stage_bytes;
   if (c.stages > 8) c.stages = 8;
   if (c.stages < 2) return false;
-  c.smem_bytes = 1024 + c.stages * c.stage_bytes;
+  c.smem_bytes = kTcHeader + c.stages * c.stage_bytes;
   return true;
 }
 

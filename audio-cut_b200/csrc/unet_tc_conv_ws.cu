@@ -318,6 +318,230 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for C = 96: the two CTAs of a cluster form one M = 256 tile (128
+// positions each) with the full N = 96.  Each CTA keeps its half of the weights resident (output
+// channels 48*rank .. +48 = the N/2 rows of B the pair MMA reads from this CTA) and loads only its own
+// 130-position input rows, so nothing is fetched twice; an N = 96 MMA is tensor-pipe bound (48 cycles)
+// where the single-CTA N = 48 shape is shared-memory bound (44 cycles for half the work).
+//   leader (rank 0): issues the MMAs; its full[] barriers collect the TMA bytes of BOTH CTAs;
+//   commits are multicast to the empty[] / tfull[] barriers of both CTAs; the peer's epilogue warps
+//   release the accumulators by arriving remotely on the leader's tempty[] barrier.
+// ------------------------------------------------------------------------------------------------
+template <int C, int R>
+__global__ void __launch_bounds__(kWsThreads, 1)
+tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams p) {
+  constexpr int NH = C / 2;               // output channels whose weights live in this CTA
+  constexpr int kGrpCh = C / kWsEpiGroups;  // channels per epilogue column group
+  static_assert(C % 32 == 0 && kGrpCh % 16 == 0, "shape");
+  constexpr int kALbo = kWsRowPos * 16;
+  constexpr int kATile = ((C / 8) * kALbo + 127) / 128 * 128;
+  constexpr int kSlot = kATile;
+  constexpr int kTap = C * NH * 2;
+  constexpr int kWBytes = 9 * kTap;
+  constexpr int kBLbo = NH * 16;
+  constexpr int K16 = C / 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [R]   (used in the leader)
+  uint64_t* empty = full + kWsMaxR;                     // [R]
+  uint64_t* tfull = full + 2 * kWsMaxR;                 // [2]
+  uint64_t* tempty = tfull + 2;                         // [2]   (used in the leader)
+  uint64_t* wbar = tempty + 2;                          // own weights landed
+  uint64_t* wbar_peer = wbar + 1;                       // leader: the peer's weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar_peer + 1);
+  float* s_scale = reinterpret_cast<float*>(smem + 256);  // [C]
+  float* s_shift = s_scale + 96;
+  uint8_t* w_smem = smem + 1024;
+  uint8_t* ring = w_smem + kWBytes;
+  volatile int* abort_flag = p.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_pairs = gridDim.x >> 1;
+  long long lo, hi;
+  ws_range(p, n_pairs, blockIdx.x >> 1, lo, hi);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 2 * kWsEpiWarps);
+    }
+    mbar_init(wbar, 1);
+    mbar_init(wbar_peer, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before anything can signal them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)kWBytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)rank * kWBytes;
+      for (int tap = 0; tap < 9; ++tap) bulk_load_1d(w_smem + tap * kTap, wsrc + tap * kTap, kTap, wbar);
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (long long L = lo; L < hi && alive;) {
+        const WsSeg sg = ws_segment(p, L, hi);
+        for (int r = sg.t0 - 1; r <= sg.t1; ++r) {
+          if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+          // the leader's barrier counts the bytes of both CTAs' tiles
+          if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)((C / 8) * kWsRowPos * 16));
+          tma_load_5d_2sm(ring + (size_t)s * kSlot, &in_map, mapa_u32(smem_u32(&full[s]), 0), 0,
+                          sg.f0 + (int)rank * kWsTileM - 1, 0, r, sg.b);
+          if (++s == R) { s = 0; ph ^= 1; }
+        }
+        L += sg.t1 - sg.t0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) ======
+    auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+      return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+    };
+    bool alive = wait_all(wbar, 0);
+    if (!leader) {
+      if (alive && lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(wbar_peer), 0));  // "my weights are in place"
+    } else {
+      alive = alive && wait_all(wbar_peer, 0);
+      const uint32_t idesc = make_idesc_2sm(C);
+      const uint64_t a_proto = make_desc(0, kALbo, 128), b_proto = make_desc(0, kBLbo, 128);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
+      const uint32_t b_lo0 = (uint32_t)b_proto + (smem_u32(w_smem) >> 4);
+      int s0 = 0;
+      uint32_t ph0 = 0;
+      uint32_t orow = 0;
+      auto slot_after = [&](int s, int d, uint32_t ph, uint32_t& ph_out) {
+        int q = s + d;
+        ph_out = ph;
+        if (q >= R) { q -= R; ph_out ^= 1; }
+        return q;
+      };
+      for (long long L = lo; L < hi && alive;) {
+        const WsSeg sg = ws_segment(p, L, hi);
+        const int rows = sg.t1 - sg.t0;
+        {
+          uint32_t ph1;
+          const int s1 = slot_after(s0, 1, ph0, ph1);
+          if (!wait_all(&full[s0], ph0) || !wait_all(&full[s1], ph1)) { alive = false; break; }
+        }
+        for (int j = 0; j < rows; ++j, ++orow) {
+          const int buf = orow & 1;
+          uint32_t ph1, ph2;
+          const int s1 = slot_after(s0, 1, ph0, ph1);
+          const int s2 = slot_after(s0, 2, ph0, ph2);
+          if (!wait_all(&tempty[buf], ((orow >> 1) & 1) ^ 1)) { alive = false; break; }
+          if (!wait_all(&full[s2], ph2)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t acc = tmem_base + (uint32_t)(buf * C);
+          const int slots[3] = {s0, s1, s2};
+          if (elect_one()) {
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)slots[dt] * (kSlot >> 4);
+#pragma unroll
+              for (int df = 0; df < 3; ++df) {
+#pragma unroll
+                for (int k = 0; k < K16; ++k) {
+                  const uint64_t ad = desc_at(a_lo, a_hi, df * 16 + k * 2 * kALbo);
+                  const uint64_t bd = desc_at(b_lo0, b_hi, (dt * 3 + df) * kTap + k * 2 * kBLbo);
+                  if (dt == 0 && df == 0 && k == 0)
+                    umma_f16_2sm<false>(acc, ad, bd, idesc);
+                  else
+                    umma_f16_2sm<true>(acc, ad, bd, idesc);
+                }
+              }
+              if (dt == 0) umma_commit_2sm(&empty[s0]);  // oldest row is done in both CTAs: refill during dt = 1, 2
+            }
+            if (j == rows - 1) {
+              umma_commit_2sm(&empty[s1]);
+              umma_commit_2sm(&empty[s2]);
+            }
+            umma_commit_2sm(&tfull[buf]);
+          }
+          __syncwarp();
+          s0 = s1;
+          ph0 = ph1;
+        }
+        {
+          uint32_t ph;
+          s0 = slot_after(s0, 2, ph0, ph);
+          ph0 = ph;
+        }
+        L += rows;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..13, both CTAs: own 128 positions x all C channels) =====
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;  // channels [kGrpCh*grp, +kGrpCh)
+    const size_t plane = (size_t)p.F * 8;
+    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
+    uint32_t orow = 0;
+    bool alive = true;
+    for (long long L = lo; L < hi && alive;) {
+      const WsSeg sg = ws_segment(p, L, hi);
+      const int f = sg.f0 + (int)rank * kWsTileM + quad * 32 + lane;
+      __nv_bfloat16* row0 = p.out + cg8_index(sg.b, sg.t0, grp * (kGrpCh / 8), f, p.T, C, p.F);
+      const size_t row_stride = (size_t)(C / 8) * plane;
+      for (int t = sg.t0; t < sg.t1; ++t, ++orow, row0 += row_stride) {
+        const int buf = orow & 1;
+        if (!mbar_wait(&tfull[buf], (orow >> 1) & 1, abort_flag)) { alive = false; break; }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * C + grp * kGrpCh);
+        uint32_t r[kGrpCh];
+#pragma unroll
+        for (int j = 0; j < kGrpCh; j += 16) tmem_ld16(taddr + j, r + j);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf * 8);  // accumulators are in registers
+        if (f < p.F) {
+#pragma unroll
+          for (int j = 0; j < kGrpCh; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int ch = grp * kGrpCh + j + 2 * e;
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[j + 2 * e]), s_scale[ch], s_shift[ch]), 0.f);
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[j + 2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(row0 + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      L += sg.t1 - sg.t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TcConvWsWeights {
@@ -390,6 +614,9 @@ void tc_conv3x3_ws_free(TcConvWsWeights* w) {
   delete w;
 }
 
+static bool g_ws_pair_enabled = true;
+void tc_conv3x3_ws_set_pair(int enabled) { g_ws_pair_enabled = enabled != 0; }
+
 int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStream_t st) {
   AC_REQUIRE(w && w->C == a.C, "tc ws conv: weights do not match the layer");
   WsCfg c;
@@ -410,15 +637,40 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
     set_error("cuTensorMapEncodeTiled (ws conv) failed with code " + std::to_string((int)r));
     return AC_E_CUDA;
   }
+  const bool pair = g_ws_pair_enabled && a.C == 96 && device_sm_count() >= 2;
   WsParams p;
   p.cfg = c;
+  if (pair) p.cfg.MT = 2;  // a strip = the pair's two 128-position tiles
   p.nB = a.nB; p.T = a.T; p.F = a.F;
-  p.n_strips = ((a.F + kWsTileM - 1) / kWsTileM + c.MT - 1) / c.MT;
+  p.n_strips = ((a.F + kWsTileM - 1) / kWsTileM + p.cfg.MT - 1) / p.cfg.MT;
   p.total_rows = (long long)a.nB * p.n_strips * a.T;
   p.wpack = w->d_pack;
   p.scale = a.scale; p.shift = a.shift;
   p.out = a.out;
   p.abort_flag = tc_abort_flag();
+  ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
+  if (pair) {
+    auto kern = tc_conv3x3_ws2_kernel<96, 5>;
+    const int smem = 1024 + 9 * 96 * 48 * 2 + 5 * c.a_tile_bytes;
+    AC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int pairs = device_sm_count() / 2;
+    if ((long long)pairs > p.total_rows) pairs = (int)p.total_rows;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kWsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map, p));
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+  }
   void (*kern)(const CUtensorMap, const WsParams) = nullptr;
   if (c.C == 48 && c.MT == 3) kern = tc_conv3x3_ws_kernel<48, 3, 5>;
   else if (c.C == 48 && c.MT == 2) kern = tc_conv3x3_ws_kernel<48, 2, 6>;
@@ -429,7 +681,6 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
   int group = device_sm_count() / c.nsplit;
   if ((long long)group > p.total_rows) group = (int)p.total_rows;
   const int grid = group * c.nsplit;
-  ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
   kern<<<grid, kWsThreads, c.smem_bytes, st>>>(map, p);
   AC_LAUNCH_CHECK();
   return AC_OK;
