@@ -91,4 +91,12 @@ void tc_tdf_free(TcTdfWeights* w);
 int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                   int nB, int T, const float* scale, const float* shift, cudaStream_t st);
 
+// CTA-pair (cta_group::2), activation-stationary kernel for the second TDF layer (with residual);
+// *out stays nullptr when the shape is not supported (M % 256, K % 32, N = NTt*C <= 256 ...)
+struct TcTdf2PairWeights;
+int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf2PairWeights** out);
+void tc_tdf2_pair_free(TcTdf2PairWeights* w);
+int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                        int nB, int T, const float* scale, const float* shift, cudaStream_t st);
+
 }  // namespace ac

@@ -216,7 +216,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) mbar_arrive_relaxed(&tempty[buf]);
       if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
     }
   }

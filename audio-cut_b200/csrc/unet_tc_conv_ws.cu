@@ -288,7 +288,7 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
         // the accumulators are in registers: hand the TMEM buffer back before the stores
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (lane == 0) mbar_arrive_relaxed(&tempty[buf]);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           if (sg.f0 + mt * kWsTileM + quad * 32 + lane < p.F) {
@@ -512,7 +512,7 @@ tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)buf * 8);  // accumulators are in registers
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);  // accumulators are in registers
         if (f < p.F) {
 #pragma unroll
           for (int j = 0; j < kGrpCh; j += 8) {

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) mbar_arrive_relaxed(&tempty[buf]);
       if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
     }
   }

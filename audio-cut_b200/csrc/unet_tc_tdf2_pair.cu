@@ -1,0 +1,439 @@
+// CTA-pair (cta_group::2) tcgen05 kernel for the second TDF layer of a block (F/8 -> F features, plus
+// the residual):   Y[b][t][m][c] = relu(scale[c] * sum_k W[m][k] * H[b][t][k][c] + shift[c]) + X[b][t][m][c]
+//
+// The single-CTA kernel (unet_tc_tdf.cu) re-fetches the activation tile H for every 128-row slice
+// of the wide output and was L2 -> shared-memory ingest bound (ncu: half of all stall samples are the
+// epilogue waiting for accumulators).  Here the activations are stationary and the weights stream:
+//   * a work unit is one (b, NTt time rows) tile = N = NTt*C <= 256 columns; each CTA of the pair keeps
+//     ITS half of the columns of H resident ([N/2/8 groups][K][8], MN-major B operand, double buffered
+//     across units) and the pair walks all M/256 output row pairs of the layer over it;
+//   * per row pair every CTA streams only its own 128 rows of W (pre-packed K-major smem images,
+//     [Kt/8][128][8] per stage) through a ring; M = 256, N <= 256 MMAs are issued by the leader CTA;
+//   * so per 128 x N output tile a CTA ingests 128*K*2 B of weights + 1/(M/256) of a half H tile,
+//     2.4x less than before, and the MMA shape is tensor-pipe bound instead of smem bound;
+//   * three producer warps take ring stages round-robin (a single issuing thread tops out near
+//     18 B/clk, scripts/microbench/tma_box.cu), a fourth loads H, warp 4 issues MMAs, 12 epilogue
+//     warps (TMEM lane quadrant x channel-chunk group) prefetch the residual, apply BN/ReLU, add, store.
+#include <vector>
+
+#include "tc_common.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+constexpr int kT2AProducers = 1;
+constexpr int kT2EpiGroups = 3;
+constexpr int kT2EpiWarps = 4 * kT2EpiGroups;
+constexpr int kT2FirstEpiWarp = kT2AProducers + 2;  // warps: 0 weight producer, 1 H producer, 2 MMA, 3..14 epilogue
+constexpr int kT2Threads = (kT2FirstEpiWarp + kT2EpiWarps) * 32;
+constexpr int kT2Header = 4096;
+constexpr int kT2MaxStages = 12;
+
+struct T2Cfg {
+  int C, M, K;
+  int NTt, N;       // time rows per unit, N = NTt * C columns (pair); each CTA holds N/2
+  int split_t;      // 1: the CTAs split the unit by time rows (NTt even); 0: by channel halves (NTt == 1)
+  int Kt, nk;       // K chunk per ring stage
+  int Kb, nkb;      // K extent of one H box (<= 256) and boxes per H tile
+  int n_mp;         // M / 256
+  int stages;
+  int n_hbuf;         // H buffers (2 when they leave room for a deep enough weight ring)
+  int a_stage_bytes;  // 128 * Kt * 2
+  int h_bytes;        // (N/2) * K * 2
+  int smem_bytes;
+};
+
+struct T2Params {
+  T2Cfg cfg;
+  int nB, T;
+  int n_tg, n_units;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  int* abort_flag;
+};
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kT2Threads, 1)
+tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_constant__ CUtensorMap w_map, const T2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const T2Cfg& c = p.cfg;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem);  // [stages]  leader: both CTAs' A stage landed
+  uint64_t* aempty = afull + kT2MaxStages;              // [stages]
+  uint64_t* hfull = aempty + kT2MaxStages;              // [2]       leader: both CTAs' H half landed
+  uint64_t* hempty = hfull + 2;                         // [2]
+  uint64_t* tfull = hempty + 2;                         // [2]
+  uint64_t* tempty = tfull + 2;                         // [2]       leader: both CTAs' epilogues drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [C] (<= 256)
+  float* s_shift = s_scale + 256;
+  uint8_t* h_smem = smem + kT2Header;                   // 2 x h_bytes
+  uint8_t* ring = h_smem + c.n_hbuf * c.h_bytes;
+  volatile int* abort_flag = p.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int n_my = pair < p.n_units ? (p.n_units - pair + n_pairs - 1) / n_pairs : 0;  // units of this pair
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.stages; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&aempty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&hfull[b], 1);
+      mbar_init(&hempty[b], 1);
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 2 * kT2EpiWarps);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < c.C; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  if (warp == kT2AProducers + 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int stages_per_unit = c.n_mp * c.nk;
+
+  if (warp < kT2AProducers) {
+    // ===================== weight producer (one 48-KB stage per mbarrier phase) =====================
+    if (lane == 0) {
+      const long long total = (long long)n_my * stages_per_unit;
+      for (long long i = warp; i < total; i += kT2AProducers) {
+        const int s = (int)(i % c.stages);
+        const uint32_t ph = (uint32_t)((i / c.stages) & 1);
+        if (!mbar_wait(&aempty[s], ph ^ 1, abort_flag)) break;
+        const int within = (int)(i % stages_per_unit);  // (mp, kc) - the weight stream repeats for every unit
+        const int mp = within / c.nk, kc = within - mp * c.nk;
+        if (leader) mbar_expect_tx(&afull[s], 2u * (uint32_t)c.a_stage_bytes);
+        // packed weights: blob index ((mp*2 + rank)*nk + kc), each blob = a_stage_bytes = rows of 512 B
+        const int blob = (mp * 2 + (int)rank) * c.nk + kc;
+        tma_load_2d_2sm(ring + (size_t)s * c.a_stage_bytes, &w_map, mapa_u32(smem_u32(&afull[s]), 0), 0,
+                        blob * (c.a_stage_bytes / 512));
+      }
+    }
+  } else if (warp == kT2AProducers) {
+    // ===================== activation producer: this CTA's half of the unit's H tile =====================
+    if (lane == 0) {
+      for (int lu = 0; lu < n_my; ++lu) {
+        const int hb = c.n_hbuf == 2 ? (lu & 1) : 0;
+        const uint32_t use = c.n_hbuf == 2 ? (uint32_t)(lu >> 1) : (uint32_t)lu;  // how often this buffer was filled before
+        if (!mbar_wait(&hempty[hb], (use & 1) ^ 1, abort_flag)) break;
+        const int u = pair + lu * n_pairs;
+        const int b = u / p.n_tg, t0 = (u - b * p.n_tg) * c.NTt;
+        if (leader) mbar_expect_tx(&hfull[hb], 2u * (uint32_t)c.h_bytes);
+        const uint32_t bar = mapa_u32(smem_u32(&hfull[hb]), 0);
+        uint8_t* dst = h_smem + (size_t)hb * c.h_bytes;
+        const int box_bytes = c.h_bytes / c.nkb;
+        for (int kb = 0; kb < c.nkb; ++kb) {
+          if (c.split_t)
+            tma_load_5d_2sm(dst + (size_t)kb * box_bytes, &h_map, bar, 0, kb * c.Kb, 0, t0 + (int)rank * (c.NTt / 2), b);
+          else
+            tma_load_5d_2sm(dst + (size_t)kb * box_bytes, &h_map, bar, 0, kb * c.Kb, (int)rank * (c.C / 16), t0, b);
+        }
+      }
+    }
+  } else if (warp == kT2AProducers + 1) {
+    // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) ======
+    if (leader) {
+      auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+        return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+      };
+      const uint32_t idesc = make_idesc_2sm(c.N) | (1u << 16);  // B is MN-major
+      const uint64_t a_proto = make_desc(0, 128 * 16, 128);
+      const uint64_t b_proto = make_desc_mn(0, 128, (uint32_t)c.Kb * 16);
+      const uint32_t hbox_bytes = (uint32_t)(c.h_bytes / c.nkb);
+      long long i = 0;   // ring stage counter
+      uint32_t acc_n = 0;  // accumulator tiles issued
+      bool alive = true;
+      for (int lu = 0; lu < n_my && alive; ++lu) {
+        const int hb = c.n_hbuf == 2 ? (lu & 1) : 0;
+        const uint32_t use = c.n_hbuf == 2 ? (uint32_t)(lu >> 1) : (uint32_t)lu;
+        if (!wait_all(&hfull[hb], use & 1)) break;
+        const uint32_t h_addr = smem_u32(h_smem + (size_t)hb * c.h_bytes);
+        for (int mp = 0; mp < c.n_mp && alive; ++mp, ++acc_n) {
+          const int buf = acc_n & 1;
+          if (!wait_all(&tempty[buf], ((acc_n >> 1) & 1) ^ 1)) { alive = false; break; }
+          const uint32_t acc = tmem_base + (uint32_t)(buf * c.N);
+          for (int kc = 0; kc < c.nk; ++kc, ++i) {
+            const int s = (int)(i % c.stages);
+            if (!wait_all(&afull[s], (uint32_t)((i / c.stages) & 1))) { alive = false; break; }
+            tc_fence_after();
+            const uint32_t sa = smem_u32(ring + (size_t)s * c.a_stage_bytes);
+            if (elect_one()) {
+              for (int k = 0; k < c.Kt / 16; ++k) {
+                const int kk = kc * c.Kt + k * 16;  // K offset inside the H tile
+                const int kb = kk / c.Kb, kin = kk - kb * c.Kb;
+                const uint64_t ad = a_proto + (uint64_t)((sa + (uint32_t)k * 2 * 128 * 16) >> 4);
+                const uint64_t bd = b_proto + (uint64_t)((h_addr + (uint32_t)kb * hbox_bytes + (uint32_t)kin * 16) >> 4);
+                if (kc == 0 && k == 0)
+                  umma_f16_2sm<false>(acc, ad, bd, idesc);
+                else
+                  umma_f16_2sm<true>(acc, ad, bd, idesc);
+              }
+              umma_commit_2sm(&aempty[s]);
+              if (kc == c.nk - 1) {
+                umma_commit_2sm(&tfull[buf]);
+                if (mp == c.n_mp - 1) umma_commit_2sm(&hempty[hb]);  // the unit's H halves are free in both CTAs
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (12 warps per CTA: own 128 rows x all N columns) =====================
+    const int quad = warp & 3;  // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
+    const int grp = (warp - kT2FirstEpiWarp) >> 2;
+    const int chunks_c = c.C >> 4;
+    const int per_row = chunks_c > grp ? (chunks_c - grp + kT2EpiGroups - 1) / kT2EpiGroups : 0;
+    const int n_mine = c.NTt * per_row;  // 16-column chunks this warp owns per accumulator tile
+    constexpr int kMaxMy = 4;
+    const size_t plane = (size_t)c.M * 8;
+    const size_t t_stride = (size_t)(c.C >> 3) * plane;
+    int my_col[kMaxMy], my_ch[kMaxMy];
+    size_t my_off[kMaxMy];
+#pragma unroll
+    for (int i = 0; i < kMaxMy; ++i) {
+      const int tl = per_row ? i / per_row : 0, k = per_row ? i - tl * per_row : 0;
+      const int cq = grp + kT2EpiGroups * k;
+      my_ch[i] = cq * 16;
+      my_col[i] = tl * c.C + cq * 16;
+      my_off[i] = (size_t)tl * t_stride + (size_t)(cq * 2) * plane;
+    }
+    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
+    uint32_t acc_n = 0;
+    bool alive = true;
+    for (int lu = 0; lu < n_my && alive; ++lu) {
+      const int u = pair + lu * n_pairs;
+      const int b = u / p.n_tg, t0 = (u - b * p.n_tg) * c.NTt;
+      for (int mp = 0; mp < c.n_mp; ++mp, ++acc_n) {
+        const int buf = acc_n & 1;
+        const int m = mp * 256 + (int)rank * 128 + quad * 32 + lane;
+        const size_t base = cg8_index(b, t0, 0, m, p.T, c.C, c.M);
+        if (!mbar_wait(&tfull[buf], (acc_n >> 1) & 1, abort_flag)) { alive = false; break; }
+        tc_fence_after();
+        // 1. all of this warp's accumulator columns -> registers, then hand the TMEM buffer straight back
+        //    (relaxed arrive: it must not wait for the global stores of the previous tile)
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.N);
+        uint32_t r[kMaxMy][16];
+#pragma unroll
+        for (int i = 0; i < kMaxMy; ++i)
+          if (i < n_mine) tmem_ld16(taddr + my_col[i], r[i]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
+        // 2. residual (all loads in flight together), BN/ReLU, add, store: off the MMA's critical path
+        uint4 q[2 * kMaxMy];
+#pragma unroll
+        for (int i = 0; i < kMaxMy; ++i) {
+          if (i < n_mine) {
+            q[2 * i] = ldg_stream_u4(p.residual + base + my_off[i]);
+            q[2 * i + 1] = ldg_stream_u4(p.residual + base + my_off[i] + plane);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxMy; ++i) {
+          if (i < n_mine) {
+            const uint32_t w[8] = {q[2 * i].x, q[2 * i].y, q[2 * i].z, q[2 * i].w, q[2 * i + 1].x, q[2 * i + 1].y, q[2 * i + 1].z, q[2 * i + 1].w};
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = my_ch[i] + 2 * e;
+              const float2 res = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[i][2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[i][2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const size_t idx = base + my_off[i];
+            *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(p.out + idx + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == kT2AProducers + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcTdf2PairWeights {
+  T2Cfg cfg;
+  __nv_bfloat16* d_pack;
+  size_t pack_elems;
+};
+
+static bool make_t2_cfg(int M, int K, int C, int T, T2Cfg& c) {
+  if (C % 16 || C > 256 || M % 256 || K % 32 || K > 512) return false;
+  c.C = C; c.M = M; c.K = K;
+  // columns per unit: as many time rows as fit in N <= 256; the pair splits an even NTt by time rows,
+  // NTt == 1 by channel halves (then C/2 must be a multiple of 8)
+  int ntt = 1;
+  while ((ntt * 2) * C <= 256 && T % (ntt * 2) == 0 && ntt * 2 <= 8) ntt *= 2;
+  c.NTt = ntt;
+  c.split_t = ntt >= 2;
+  if (!c.split_t && C % 32) return false;
+  c.N = ntt * C;
+  if (c.N % 32 || c.N > 256) return false;
+  // the 12 epilogue warps own at most 4 chunks of 16 columns each (registers: 4 x 16 accumulators + residual)
+  if (((C / 16 + kT2EpiGroups - 1) / kT2EpiGroups) * ntt > 4) return false;
+  c.Kb = K <= 256 ? K : K / 2;
+  if (c.Kb > 256 || c.Kb % 16) return false;
+  c.nkb = K / c.Kb;
+  // One ring stage = one H box worth of K (<= 48 KB of weights): every mbarrier hand-off costs the
+  // issuing thread several hundred cycles, so a stage has to carry >= ~1000 cycles of MMA work.
+  c.Kt = c.Kb;
+  while (128 * c.Kt * 2 > 48 * 1024 && c.Kt % 32 == 0) c.Kt /= 2;
+  if (128 * c.Kt * 2 > 48 * 1024 || c.Kb % c.Kt) return false;
+  c.nk = K / c.Kt;
+  c.n_mp = M / 256;
+  c.a_stage_bytes = 128 * c.Kt * 2;
+  c.h_bytes = (c.N / 2) * K * 2;
+  c.n_hbuf = 2;
+  int budget = 227 * 1024 - kT2Header - 2 * c.h_bytes;
+  if (budget / c.a_stage_bytes < 3) {  // a single H buffer (a short bubble per unit) buys a deeper weight ring
+    c.n_hbuf = 1;
+    budget = 227 * 1024 - kT2Header - c.h_bytes;
+  }
+  c.stages = budget / c.a_stage_bytes;
+  if (c.stages > kT2MaxStages) c.stages = kT2MaxStages;
+  if (c.stages < 3) return false;
+  c.smem_bytes = kT2Header + c.n_hbuf * c.h_bytes + c.stages * c.a_stage_bytes;
+  return true;
+}
+
+int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf2PairWeights** out) {
+  *out = nullptr;
+  T2Cfg c;
+  if (!make_t2_cfg(M, K, C, T, c)) return AC_OK;
+  // [mp][rank][kc][Kt/8][128][8]
+  const size_t total = (size_t)M * K;
+  std::vector<__nv_bfloat16> pack(total);
+  size_t o = 0;
+  for (int mp = 0; mp < c.n_mp; ++mp)
+    for (int r = 0; r < 2; ++r)
+      for (int kc = 0; kc < c.nk; ++kc)
+        for (int kg = 0; kg < c.Kt / 8; ++kg)
+          for (int row = 0; row < 128; ++row)
+            for (int e = 0; e < 8; ++e)
+              pack[o++] = __float2bfloat16_rn(h_w[(size_t)(mp * 256 + r * 128 + row) * K + kc * c.Kt + kg * 8 + e]);
+  TcTdf2PairWeights* w = new TcTdf2PairWeights();
+  w->cfg = c;
+  w->d_pack = nullptr;
+  w->pack_elems = total;
+  if (cudaMalloc(&w->d_pack, total * 2) != cudaSuccess ||
+      cudaMemcpy(w->d_pack, pack.data(), total * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tdf2 pair weight upload failed");
+    delete w;
+    return AC_E_CUDA;
+  }
+  *out = w;
+  return AC_OK;
+}
+
+void tc_tdf2_pair_free(TcTdf2PairWeights* w) {
+  if (!w) return;
+  if (w->d_pack) cudaFree(w->d_pack);
+  delete w;
+}
+
+int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                        int nB, int T, const float* scale, const float* shift, cudaStream_t st) {
+  AC_REQUIRE(w && in && residual && out, "tc tdf2 pair: null");
+  const T2Cfg& c = w->cfg;
+  AC_REQUIRE(T % c.NTt == 0, "tc tdf2 pair: T not divisible by the time tile");
+  EncodeTiledFn enc = get_tensor_map_encoder();
+  AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
+  AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // H: CG8 [nB][T][C/8][K][8] as (c%8, k, c/8, t, b); one box = this CTA's column half for one K box
+  CUtensorMap h_map, w_map;
+  {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)c.K, (cuuint64_t)(c.C / 8), (cuuint64_t)T, (cuuint64_t)nB};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)c.K * 16, (cuuint64_t)c.K * c.C * 2, (cuuint64_t)T * c.K * c.C * 2};
+    const cuuint32_t box[5] = {8, (cuuint32_t)c.Kb, (cuuint32_t)(c.split_t ? c.C / 8 : c.C / 16),
+                               (cuuint32_t)(c.split_t ? c.NTt / 2 : 1), 1};
+    CUresult r = enc(&h_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (tdf2 pair, H) failed with code " + std::to_string((int)r));
+      return AC_E_CUDA;
+    }
+  }
+  {
+    // packed weights as rows of 256 bf16 (512 B); one ring stage = a_stage_bytes/512 consecutive rows
+    const cuuint64_t dims[2] = {256, (cuuint64_t)(w->pack_elems / 256)};
+    const cuuint64_t strides[1] = {512};
+    const cuuint32_t box[2] = {256, (cuuint32_t)(c.a_stage_bytes / 512)};
+    CUresult r = enc(&w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w->d_pack, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (tdf2 pair, W) failed with code " + std::to_string((int)r));
+      return AC_E_CUDA;
+    }
+  }
+  T2Params p;
+  p.cfg = c;
+  p.nB = nB; p.T = T;
+  p.n_tg = T / c.NTt;
+  p.n_units = p.n_tg * nB;
+  p.scale = scale; p.shift = shift;
+  p.residual = residual;
+  p.out = out;
+  p.abort_flag = tc_abort_flag();
+  static bool attr_set = false;
+  if (!attr_set) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int pairs = device_sm_count() / 2;
+  if (pairs > p.n_units) pairs = p.n_units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kT2Threads);
+  cfg.dynamicSmemBytes = c.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB, 2.0 * nB * (double)T * c.C * (c.K + c.M * 2), st);
+  AC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_tdf2_pair_kernel, h_map, w_map, p));
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac

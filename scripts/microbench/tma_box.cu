@@ -12,8 +12,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ int g_arrive_mode = 0;  // 0: arrive.expect_tx (release), 1: arrive.expect_tx.relaxed.cta, 2: copy first, then arrive.expect_tx
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_relaxed(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ int g_wait_mode = 0;  // 0: try_wait (may suspend), 1: test_wait spin
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(256, 1) bulk_multi_kernel(const uint8_t* src, 
 
 // (a) pure issue + transfer: `n` bulk copies of chunk_bytes into a small smem ring, ONE barrier phase per `group` copies
 __global__ void __launch_bounds__(128, 1) bulk_group_kernel(const uint8_t* src, size_t span_bytes, int chunk_bytes, int group, int n_groups,
-                                                           int depth, long long* cycles) {
+                                                           int depth, long long* cycles, int amode) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint8_t* ring = smem + 1024;
@@ -188,7 +192,8 @@ __global__ void __launch_bounds__(128, 1) bulk_group_kernel(const uint8_t* src, 
     while (waited < n_groups) {
       while (issued < n_groups && issued - waited < depth) {
         const int s = issued % depth;
-        mbar_expect_tx(&bar[s], (uint32_t)(group * chunk_bytes));
+        if (amode == 0) mbar_expect_tx(&bar[s], (uint32_t)(group * chunk_bytes));
+        else if (amode == 1) mbar_expect_tx_relaxed(&bar[s], (uint32_t)(group * chunk_bytes));
         for (int g = 0; g < group; ++g) {
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                            smem_u32(ring + ((size_t)s * group + g) * chunk_bytes)),
@@ -196,6 +201,7 @@ __global__ void __launch_bounds__(128, 1) bulk_group_kernel(const uint8_t* src, 
                        : "memory");
           off += (uint32_t)chunk_bytes * 3;
         }
+        if (amode == 2) mbar_expect_tx(&bar[s], (uint32_t)(group * chunk_bytes));
         ++issued;
       }
       mbar_wait(&bar[waited % depth], ph);
@@ -272,19 +278,20 @@ int main(int argc, char** argv) {
     }
     cudaFuncSetAttribute(bulk_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(bulk_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    for (int chunk : {2048, 8192})
-      for (int group : {1, 4, 8})
-        for (int depth : {1, 2, 3}) {
+    for (int amode : {0, 1, 2})
+    for (int chunk : {8192})
+      for (int group : {1, 4})
+        for (int depth : {1, 3, 6}) {
           const int n_groups = 400;
           const int smem = 1024 + depth * group * chunk;
           if (smem > 227 * 1024) continue;
-          bulk_group_kernel<<<148, 128, smem>>>((const uint8_t*)d, bytes, chunk, group, n_groups, depth, d_cyc);
+          bulk_group_kernel<<<148, 128, smem>>>((const uint8_t*)d, bytes, chunk, group, n_groups, depth, d_cyc, amode);
           cudaError_t err = cudaDeviceSynchronize();
           long long cyc[148];
           cudaMemcpy(cyc, d_cyc, 148 * 8, cudaMemcpyDeviceToHost);
           long long mx = 0;
           for (int i = 0; i < 148; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
-          printf("bulk group: %5d B x %d per phase, depth %d: %7.1f cycles/phase  %6.1f B/clk/SM (%s)\n", chunk, group, depth,
+          printf("bulk group (arrive mode %d): %5d B x %d per phase, depth %d: %7.1f cycles/phase  %6.1f B/clk/SM (%s)\n", amode, chunk, group, depth,
                  (double)mx / n_groups, (double)chunk * group * n_groups / (double)mx, cudaGetErrorString(err));
         }
     for (int mode : {0}) {
