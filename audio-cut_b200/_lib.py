@@ -20,7 +20,8 @@ EXPORTS = [
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
     "ac_track_workspace_bytes", "ac_separate_track", "ac_stft_features_workspace_bytes", "ac_stft_features",
     "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
-    "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3",
+    "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3", "ac_pyin_frame_count", "ac_pyin_workspace_bytes", "ac_pyin",
+    "ac_lpc_frame_count", "ac_lpc_formants",
 ]
 
 
@@ -101,6 +102,11 @@ def load() -> C.CDLL:
     lib.ac_host_beat_dp.argtypes, lib.ac_host_beat_dp.restype = [vp, i, i, C.c_float, vp, vp], i
     lib.ac_downmix_mono.argtypes, lib.ac_downmix_mono.restype = [vp, i, ll, vp, vp], i
     lib.ac_track_stats.argtypes, lib.ac_track_stats.restype = [vp, vp, vp, ll, vp, vp], i
+    lib.ac_pyin_frame_count.argtypes, lib.ac_pyin_frame_count.restype = [ll, i], ll
+    lib.ac_pyin_workspace_bytes.argtypes, lib.ac_pyin_workspace_bytes.restype = [ll, i, i, C.c_float, C.c_float], sz
+    lib.ac_pyin.argtypes, lib.ac_pyin.restype = [vp, ll, i, i, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp], i
+    lib.ac_lpc_frame_count.argtypes, lib.ac_lpc_frame_count.restype = [ll, i, i], ll
+    lib.ac_lpc_formants.argtypes, lib.ac_lpc_formants.restype = [vp, ll, i, i, i, vp, vp, vp], i
     lib.ac_profile_begin.argtypes, lib.ac_profile_begin.restype = [], i
     lib.ac_profile_collect.argtypes, lib.ac_profile_collect.restype = [C.POINTER(KernelStat), i], i
     _lib = lib

@@ -1,0 +1,734 @@
+// F0 and formant features of the legacy pause-detector branch:
+//   ac_pyin          librosa.pyin(y, fmin=C2, fmax=C7, sr, hop_length=441)      pure_vocal_pause_detector.py:422-428
+//   ac_lpc_formants  _extract_formants (pre-emphasis, Burg LPC(12), |1/A| peaks) pure_vocal_pause_detector.py:961-1018
+// librosa is not part of the reference tree: the algorithms follow the published librosa 0.10
+// implementation (core/pitch.py, sequence.py, core/audio.py) as restated in oracle/features.py.
+//
+// pYIN runs as three kernels:
+//   1. yin_probs_kernel    one CTA per frame: difference function (direct form, fp32 products, the
+//                          reference's FFT autocorrelation evaluates the same sums), cumulative mean
+//                          normalisation, parabolic refinement, troughs, per-threshold Boltzmann prior x
+//                          beta weights  ->  a short (pitch bin, probability) candidate list per frame;
+//   2. pyin_viterbi_kernel one CTA per sequence, fp64: the 2 x 601-state HMM; the transition matrix is
+//                          kron(t_switch, 41-wide triangle band), every zero entry is log(tiny) exactly as
+//                          librosa's log(transition + tiny), so one block-wide max covers the out-of-band
+//                          predecessors; back pointers go to global memory;
+//   3. pyin_backtrack_kernel  pointer chase from the best final state.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace ac {
+
+constexpr int kYinFrame = 2048;
+constexpr int kYinWin = 1024;
+constexpr int kYinThreads = 128;
+constexpr int kYinMaxLags = 1024;   // max_period + 1 <= frame - win
+constexpr int kYinMaxCand = 328;    // a 655-point CMND curve has at most 328 troughs
+constexpr int kNThresholds = 100;
+constexpr double kLogTiny = -708.3964185322641;  // log(np.finfo(float64).tiny)
+
+struct YinParams {
+  const float* x;
+  long long n;
+  int hop, sr;
+  int min_period, max_period;  // 21, 675
+  int n_pitch_bins, bins_per_semitone;
+  float fmin;
+  float boltzmann, no_trough_prob;
+  const float* beta_probs;  // [100]
+  long long n_frames;
+  uint2* cand;              // [n_frames][kYinMaxCand] (bin, float bits of the probability)
+  int* n_cand;              // [n_frames]
+  float* voiced_prob;       // [n_frames]
+};
+
+__device__ __forceinline__ float block_sum_f(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(kYinThreads) yin_probs_kernel(const YinParams p) {
+  __shared__ float y[kYinFrame];
+  __shared__ float cs[kYinFrame + 1];     // cs[i] = sum_{j<i} y[j]^2
+  __shared__ float yin[kYinMaxLags];      // difference function, then CMND (indexed by tau - min_period)
+  __shared__ float probs[kYinMaxLags];    // per CMND index: probability mass (0 = not a candidate)
+  __shared__ int trough_list[kYinMaxCand];
+  __shared__ float red[8];
+  __shared__ float wsum[kYinThreads / 32 + 1];
+  __shared__ int n_troughs_s, gmin_idx_s;
+
+  const long long frame = blockIdx.x;
+  const int tid = threadIdx.x;
+  const long long start = frame * p.hop - kYinFrame / 2;  // centred, zero padded
+  for (int i = tid; i < kYinFrame; i += kYinThreads) {
+    const long long s = start + i;
+    y[i] = (s >= 0 && s < p.n) ? __ldg(p.x + s) : 0.f;
+  }
+  __syncthreads();
+  // ---- energy prefix sums (block scan of y^2; each thread owns 16 consecutive samples)
+  {
+    constexpr int PER = kYinFrame / kYinThreads;
+    float loc[PER];
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float v = y[tid * PER + i];
+      run += v * v;
+      loc[i] = run;
+    }
+    // exclusive scan of the per-thread totals
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += u;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    float base = 0.f;
+    for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
+    const float excl = base + incl - run;
+    if (tid == 0) cs[0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) cs[tid * PER + i + 1] = excl + loc[i];
+  }
+  __syncthreads();
+  // ---- difference function d[tau] = E[0] + E[tau] - 2 acf[tau], tau = 0..max_period
+  const int n_lags = p.max_period + 1;
+  const float e0_raw = cs[kYinWin] - cs[0];
+  const float e0 = fabsf(e0_raw) < 1e-6f ? 0.f : e0_raw;
+  for (int tau = tid; tau < n_lags; tau += kYinThreads) {
+    // acf for the reference's |.| < 1e-6 zeroing rules; the difference itself is summed directly as
+    // sum (y[j] - y[j+tau])^2, which is the same quantity without the cancellation of E0 + E - 2 acf
+    float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+    const float* ya = y + 1;
+    const float* yb = y + 1 + tau;
+#pragma unroll 4
+    for (int j = 0; j < kYinWin; j += 2) {
+      const float u0 = ya[j], v0 = yb[j], u1 = ya[j + 1], v1 = yb[j + 1];
+      a0 = fmaf(u0, v0, a0);
+      a1 = fmaf(u1, v1, a1);
+      const float q0 = u0 - v0, q1 = u1 - v1;
+      d0 = fmaf(q0, q0, d0);
+      d1 = fmaf(q1, q1, d1);
+    }
+    const float acf = a0 + a1;
+    const float e = cs[tau + kYinWin] - cs[tau];
+    const bool tiny_terms = fabsf(acf) < 1e-6f || fabsf(e) < 1e-6f || fabsf(e0_raw) < 1e-6f;
+    yin[tau] = tiny_terms ? e0 + (fabsf(e) < 1e-6f ? 0.f : e) - 2.f * (fabsf(acf) < 1e-6f ? 0.f : acf) : d0 + d1;
+  }
+  __syncthreads();
+  // ---- cumulative mean normalisation: cmnd[tau] = d[tau] / (mean_{1..tau} d + tiny); done by one warp
+  //      (sequential prefix over <= 675 values in 32-wide steps), result stored at index tau - min_period
+  if (tid < 32) {
+    float carry = 0.f;
+    for (int b = 1; b < n_lags; b += 32) {
+      const int tau = b + tid;
+      float v = tau < n_lags ? yin[tau] : 0.f;
+      float incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += u;
+      }
+      const float csum = carry + incl;
+      carry = __shfl_sync(0xffffffffu, csum, 31);
+      if (tau < n_lags) probs[tau] = v / (csum / (float)tau + 1.17549435e-38f);  // staging: CMND by tau
+    }
+  }
+  __syncthreads();
+  const int n_c = p.max_period - p.min_period + 1;
+  for (int i = tid; i < n_c; i += kYinThreads) yin[i] = probs[i + p.min_period];
+  __syncthreads();
+  for (int i = tid; i < kYinMaxLags; i += kYinThreads) probs[i] = 0.f;
+  if (tid == 0) { n_troughs_s = 0; gmin_idx_s = 0; }
+  __syncthreads();
+  // ---- troughs (util.localmin + the first-sample rule), compacted in index order by one warp
+  if (tid < 32) {
+    int count = 0;
+    for (int b = 0; b < n_c; b += 32) {
+      const int i = b + tid;
+      bool tr = false;
+      if (i < n_c) {
+        const float v = yin[i];
+        if (i == 0) tr = v < yin[1];
+        else if (i == n_c - 1) tr = v < yin[i - 1];
+        else tr = (v < yin[i - 1]) && (v <= yin[i + 1]);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, tr);
+      if (tr) {
+        const int pos = count + __popc(m & ((1u << tid) - 1u));
+        if (pos < kYinMaxCand) trough_list[pos] = i;
+      }
+      count += __popc(m);
+    }
+    if (tid == 0) n_troughs_s = count < kYinMaxCand ? count : kYinMaxCand;
+  }
+  __syncthreads();
+  const int nt = n_troughs_s;
+  float voiced = 0.f;
+  int n_out = 0;
+  if (nt > 0) {
+    // global minimum among the troughs (first one on ties, as np.argmin)
+    if (tid < 32) {
+      float best = INFINITY;
+      int bi = 0x7fffffff;
+      for (int k = tid; k < nt; k += 32) {
+        const float h = yin[trough_list[k]];
+        if (h < best || (h == best && k < bi)) { best = h; bi = k; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (tid == 0) gmin_idx_s = bi;
+    }
+    __syncthreads();
+    // Per trough k (in index order): first threshold index it is below, k0 = #{thr[1..100] <= h}.
+    // For threshold t (1-based, thr = t/100) the troughs below it are those with k0 < t; trough k's rank among
+    // them is pos_t(k) = #{k' < k : k0(k') < t}.  One thread per trough walks the thresholds with a running
+    // count of earlier troughs that have entered (entry times are read from shared memory).
+    int* k0s = reinterpret_cast<int*>(cs);  // reuse: [kYinMaxCand]
+    for (int k = tid; k < nt; k += kYinThreads) {
+      const float h = yin[trough_list[k]];
+      // thresholds are np.linspace(0,1,101)[1:], compared as float64 against the float32 h promoted exactly
+      int c = 0;
+      for (int t = 1; t <= kNThresholds; ++t)
+        if (!((double)h < (double)t / 100.0)) c = t;
+      k0s[k] = c;  // below thresholds t > c
+    }
+    __syncthreads();
+    // n_troughs(t) = #{k : k0 < t}: histogram of entry times, prefix summed (100 entries, one thread)
+    int* cnt_t = reinterpret_cast<int*>(cs) + kYinMaxCand;  // [101]
+    if (tid == 0) {
+      for (int t = 0; t <= kNThresholds; ++t) cnt_t[t] = 0;
+      for (int k = 0; k < nt; ++k)
+        if (k0s[k] < kNThresholds) cnt_t[k0s[k] + 1] += 1;  // enters at threshold k0+1
+      for (int t = 1; t <= kNThresholds; ++t) cnt_t[t] += cnt_t[t - 1];
+    }
+    __syncthreads();
+    const float lam = p.boltzmann;
+    const float one_m = 1.f - expf(-lam);
+    for (int k = tid; k < nt; k += kYinThreads) {
+      const int myk0 = k0s[k];
+      float acc = 0.f;
+      if (myk0 < kNThresholds) {
+        // entries of earlier troughs, as a per-threshold running rank
+        int rank_at[kNThresholds + 1];
+#pragma unroll 1
+        for (int t = 0; t <= kNThresholds; ++t) rank_at[t] = 0;
+        for (int k2 = 0; k2 < k; ++k2) {
+          const int e = k0s[k2] + 1;
+          if (e <= kNThresholds) rank_at[e] += 1;
+        }
+        int run = 0;
+        for (int t = 1; t <= kNThresholds; ++t) {
+          run += rank_at[t];
+          if (t > myk0) {
+            const int n_t = cnt_t[t];
+            const float prior = one_m * expf(-lam * (float)run) / (1.f - expf(-lam * (float)n_t));
+            acc = fmaf(prior, __ldg(p.beta_probs + t - 1), acc);
+          }
+        }
+      }
+      if (k == gmin_idx_s) {
+        // thresholds the global minimum is NOT below: t <= k0  ->  no-trough mass goes to it
+        float s = 0.f;
+        for (int t = 0; t < myk0; ++t) s += __ldg(p.beta_probs + t);
+        acc = fmaf(p.no_trough_prob, s, acc);
+      }
+      probs[trough_list[k]] = acc;
+    }
+    __syncthreads();
+    // ---- candidates: refine the period, map to a pitch bin, emit in increasing-period order (one warp)
+    if (tid < 32) {
+      uint2* out = p.cand + frame * (long long)kYinMaxCand;
+      int count = 0;
+      for (int b = 0; b < nt; b += 32) {
+        const int k = b + tid;
+        bool on = false;
+        int bin = 0;
+        float pr = 0.f;
+        if (k < nt) {
+          const int i = trough_list[k];
+          pr = probs[i];
+          on = pr != 0.f;
+          if (on) {
+            float shift = 0.f;
+            if (i > 0 && i < n_c - 1) {
+              const float a = yin[i + 1] + yin[i - 1] - 2.f * yin[i];
+              const float bb = (yin[i + 1] - yin[i - 1]) * 0.5f;
+              shift = fabsf(bb) >= fabsf(a) ? 0.f : -bb / a;
+            }
+            const float period = (float)(p.min_period + i) + shift;
+            const double bidx = 12.0 * p.bins_per_semitone * log2(((double)p.sr / (double)period) / (double)p.fmin);
+            double rb = rint(bidx);
+            if (rb < 0.0) rb = 0.0;
+            if (rb > (double)p.n_pitch_bins) rb = (double)p.n_pitch_bins;
+            bin = (int)rb;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) out[count + __popc(m & ((1u << tid) - 1u))] = make_uint2((unsigned)bin, __float_as_uint(pr));
+        count += __popc(m);
+      }
+      n_out = count;
+      // voiced probability = sum over DISTINCT bins < n_pitch_bins of the LAST candidate written to the bin
+      // (bins decrease with the period, so equal bins are adjacent: the last of a run wins)
+      __syncwarp();
+      float s = 0.f;
+      for (int c = tid; c < count; c += 32) {
+        const uint2 me = out[c];
+        const bool last = (c == count - 1) || (out[c + 1].x != me.x);
+        if (last && (int)me.x < p.n_pitch_bins) s += __uint_as_float(me.y);
+      }
+      s = warp_sum(s);
+      voiced = fminf(fmaxf(s, 0.f), 1.f);
+    }
+  }
+  if (tid == 0) {
+    p.n_cand[frame] = n_out;
+    p.voiced_prob[frame] = voiced;
+  }
+  (void)red;
+  (void)block_sum_f;
+}
+
+// ---- Viterbi ---------------------------------------------------------------------------------------
+constexpr int kVitThreads = 640;
+struct VitParams {
+  const uint2* cand;
+  const int* n_cand;
+  const float* voiced_prob;
+  long long n_steps;
+  int nb;              // pitch bins (601)
+  int half;            // band half width (20)
+  const double* logL;  // [nb][2*half+1]: log(local[k][k+d] + 0) for source k, d = -half..half (-inf -> handled as log tiny)
+  double log_stay, log_switch, log_init;
+  unsigned short* ptr;  // [n_steps][2*nb]
+  int* final_state;
+};
+
+__global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitParams p) {
+  extern __shared__ double vsm[];
+  const int nb = p.nb, S = 2 * nb;
+  double* val0 = vsm;            // [S]
+  double* val1 = vsm + S;        // [S]
+  double* obs = vsm + 2 * S;     // [nb] log observation of the voiced states for this step
+  double* redv = obs + nb;       // [32]
+  int* redi = reinterpret_cast<int*>(redv + 32);  // [32]
+  __shared__ double gmax_s;
+  __shared__ int gidx_s;
+  const int tid = threadIdx.x;
+  const int W = 2 * p.half + 1;
+
+  auto load_obs = [&](long long t, double& lu) {
+    for (int j = tid; j < nb; j += kVitThreads) obs[j] = kLogTiny;
+    __syncthreads();
+    const int nc = p.n_cand[t];
+    const uint2* c = p.cand + t * (long long)kYinMaxCand;
+    for (int i = tid; i < nc; i += kVitThreads) {
+      const uint2 me = c[i];
+      const bool last = (i == nc - 1) || (c[i + 1].x != me.x);
+      if (last && (int)me.x < nb) obs[me.x] = log((double)__uint_as_float(me.y) + 2.2250738585072014e-308);
+    }
+    const double vp = (double)p.voiced_prob[t];
+    lu = log((1.0 - vp) / (double)nb + 2.2250738585072014e-308);
+    __syncthreads();
+  };
+
+  double lu;
+  load_obs(0, lu);
+  for (int s = tid; s < S; s += kVitThreads) val0[s] = (s < nb ? obs[s] : lu) + p.log_init;
+  __syncthreads();
+  double* cur = val0;
+  double* nxt = val1;
+  for (long long t = 1; t < p.n_steps; ++t) {
+    // block-wide (max, first argmax) of the previous values: the best out-of-band predecessor
+    {
+      double bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int s = tid; s < S; s += kVitThreads) {
+        const double v = cur[s];
+        if (v > bv || (v == bv && s < bi)) { bv = v; bi = s; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if ((tid & 31) == 0) { redv[tid >> 5] = bv; redi[tid >> 5] = bi; }
+      __syncthreads();
+      if (tid < 32) {
+        bv = tid < (kVitThreads >> 5) ? redv[tid] : -INFINITY;
+        bi = tid < (kVitThreads >> 5) ? redi[tid] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (tid == 0) { gmax_s = bv; gidx_s = bi; }
+      }
+    }
+    load_obs(t, lu);  // contains the __syncthreads() that publishes gmax_s / gidx_s
+    const double oob = gmax_s + kLogTiny;
+    const int oob_idx = gidx_s;
+    if (tid < nb) {
+      const int j = tid;
+      // in-band predecessors k = j-half .. j+half (both voicings); value + log(t_switch * local[k][j])
+      double best_v = -INFINITY, best_u = -INFINITY;  // into voiced j / into unvoiced j
+      int arg_v = 0, arg_u = 0;
+      const int k_lo = j - p.half < 0 ? 0 : j - p.half;
+      const int k_hi = j + p.half > nb - 1 ? nb - 1 : j + p.half;
+      // candidates are visited in increasing state index (voiced k ascending, then unvoiced k ascending) and
+      // replaced only on strict improvement: np.argmax's first-maximum rule
+      for (int k = k_lo; k <= k_hi; ++k) {
+        const double l = __ldg(p.logL + (size_t)k * W + (j - k + p.half));
+        const double a = cur[k] + l;
+        const double cv = a + p.log_stay, cu = a + p.log_switch;
+        if (cv > best_v) { best_v = cv; arg_v = k; }
+        if (cu > best_u) { best_u = cu; arg_u = k; }
+      }
+      for (int k = k_lo; k <= k_hi; ++k) {
+        const double l = __ldg(p.logL + (size_t)k * W + (j - k + p.half));
+        const double a = cur[nb + k] + l;
+        const double cv = a + p.log_switch, cu = a + p.log_stay;
+        if (cv > best_v) { best_v = cv; arg_v = nb + k; }
+        if (cu > best_u) { best_u = cu; arg_u = nb + k; }
+      }
+      // the out-of-band maximum wins only if strictly larger, or equal with a smaller state index
+      if (oob > best_v || (oob == best_v && oob_idx < arg_v)) { best_v = oob; arg_v = oob_idx; }
+      if (oob > best_u || (oob == best_u && oob_idx < arg_u)) { best_u = oob; arg_u = oob_idx; }
+      nxt[j] = obs[j] + best_v;
+      nxt[nb + j] = lu + best_u;
+      unsigned short* pr = p.ptr + t * (long long)S;
+      pr[j] = (unsigned short)arg_v;
+      pr[nb + j] = (unsigned short)arg_u;
+    }
+    __syncthreads();
+    double* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  // final state = first argmax
+  if (tid < 32) {
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int s = tid; s < S; s += 32) {
+      const double v = cur[s];
+      if (v > bv || (v == bv && s < bi)) { bv = v; bi = s; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (tid == 0) *p.final_state = bi;
+  }
+}
+
+__global__ void pyin_backtrack_kernel(const unsigned short* __restrict__ ptr, const int* __restrict__ final_state, long long n_steps,
+                                      int nb, float fmin, int bins_per_semitone, float* __restrict__ f0,
+                                      unsigned char* __restrict__ voiced_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int S = 2 * nb;
+  int s = *final_state;
+  for (long long t = n_steps - 1; t >= 0; --t) {
+    const bool v = s < nb;
+    const int k = v ? s : s - nb;
+    if (f0) f0[t] = v ? fmin * exp2f((float)k / (12.f * (float)bins_per_semitone)) : __int_as_float(0x7fc00000);
+    if (voiced_flag) voiced_flag[t] = v ? 1 : 0;
+    if (t > 0) s = ptr[t * (long long)S + s];
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static double beta_cdf_int(double x, int a, int b) {  // regularised incomplete beta for integer a, b
+  const int n = a + b - 1;
+  double s = 0.0;
+  for (int j = a; j <= n; ++j) {
+    double c = 1.0;
+    for (int i = 0; i < j; ++i) c = c * (double)(n - i) / (double)(i + 1);
+    s += c * pow(x, j) * pow(1.0 - x, n - j);
+  }
+  return s;
+}
+
+struct PyinGeom {
+  int win, min_period, max_period, bps, nb, half;
+};
+static PyinGeom pyin_geom(int sr, double fmin, double fmax, int frame_length, int hop) {
+  PyinGeom g;
+  g.win = frame_length / 2;
+  g.min_period = (int)floor((double)sr / fmax);
+  g.max_period = (int)ceil((double)sr / fmin);
+  if (g.max_period > frame_length - g.win - 1) g.max_period = frame_length - g.win - 1;
+  g.bps = 10;
+  g.nb = (int)floor(12.0 * g.bps * log2(fmax / fmin)) + 1;
+  const int semis = (int)llround(35.92 * 12.0 * hop / sr);
+  g.half = (semis * g.bps + 1) / 2;
+  return g;
+}
+
+}  // namespace ac
+
+extern "C" long long ac_pyin_frame_count(long long n, int hop) { return (n < 0 || hop <= 0) ? 0 : 1 + n / hop; }
+
+extern "C" size_t ac_pyin_workspace_bytes(long long n, int hop, int sr, float fmin, float fmax) {
+  using namespace ac;
+  if (n <= 0 || hop <= 0) return 0;
+  const long long nf = 1 + n / hop;
+  const PyinGeom g = pyin_geom(sr, fmin, fmax, kYinFrame, hop);
+  size_t b = 0;
+  b += align_up((size_t)nf * kYinMaxCand * sizeof(uint2), 256);
+  b += align_up((size_t)nf * sizeof(int), 256);
+  b += align_up((size_t)nf * 2 * g.nb * sizeof(unsigned short), 256);
+  b += align_up((size_t)g.nb * (2 * g.half + 1) * sizeof(double), 256);
+  b += align_up((size_t)kNThresholds * sizeof(float), 256);
+  b += 256;
+  return b;
+}
+
+extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmin, float fmax, float* d_f0,
+                       unsigned char* d_voiced_flag, float* d_voiced_prob, void* d_ws, size_t ws_bytes, void* stream) {
+  using namespace ac;
+  AC_REQUIRE(d_x && d_voiced_prob && d_ws && n > 0 && hop > 0 && sr > 0 && fmin > 0 && fmax > fmin, "ac_pyin: arguments");
+  AC_REQUIRE(ws_bytes >= ac_pyin_workspace_bytes(n, hop, sr, fmin, fmax), "ac_pyin: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const PyinGeom g = pyin_geom(sr, fmin, fmax, kYinFrame, hop);
+  AC_REQUIRE(g.max_period + 1 <= kYinMaxLags && g.min_period >= 1 && g.max_period > g.min_period + 2, "ac_pyin: period range");
+  AC_REQUIRE((g.max_period - g.min_period + 2) / 2 <= kYinMaxCand, "ac_pyin: candidate capacity");
+  AC_REQUIRE(2 * g.nb < 65536 && g.nb <= 1024, "ac_pyin: too many pitch bins");
+  const long long nf = 1 + n / hop;
+  char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~uintptr_t(255));
+  uint2* cand = reinterpret_cast<uint2*>(w); w += align_up((size_t)nf * kYinMaxCand * sizeof(uint2), 256);
+  int* n_cand = reinterpret_cast<int*>(w); w += align_up((size_t)nf * sizeof(int), 256);
+  unsigned short* ptr = reinterpret_cast<unsigned short*>(w); w += align_up((size_t)nf * 2 * g.nb * sizeof(unsigned short), 256);
+  double* logL = reinterpret_cast<double*>(w); w += align_up((size_t)g.nb * (2 * g.half + 1) * sizeof(double), 256);
+  float* beta = reinterpret_cast<float*>(w); w += align_up((size_t)kNThresholds * sizeof(float), 256);
+  int* final_state = reinterpret_cast<int*>(w);
+
+  // beta(2, 18) weights of the 100 thresholds and the banded log transition (row-normalised triangle)
+  {
+    std::vector<float> hb(kNThresholds);
+    double prev = 0.0;
+    for (int t = 1; t <= kNThresholds; ++t) {
+      const double c = beta_cdf_int((double)t / kNThresholds, 2, 18);
+      hb[t - 1] = (float)(c - prev);
+      prev = c;
+    }
+    const int W = 2 * g.half + 1;
+    std::vector<double> hl((size_t)g.nb * W);
+    for (int k = 0; k < g.nb; ++k) {
+      double sum = 0.0;
+      std::vector<double> row(W, 0.0);
+      for (int d = -g.half; d <= g.half; ++d) {
+        const int j = k + d;
+        if (j < 0 || j >= g.nb) continue;
+        // scipy.signal.windows.triang(W) (odd, symmetric): 1 - |d| / ((W + 1) / 2)
+        row[d + g.half] = 1.0 - fabs((double)d) / ((W + 1) / 2.0);
+        sum += row[d + g.half];
+      }
+      for (int d = 0; d < W; ++d) hl[(size_t)k * W + d] = row[d] > 0.0 ? log(row[d] / sum) : kLogTiny;
+    }
+    AC_CHECK_CUDA(cudaMemcpyAsync(beta, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    AC_CHECK_CUDA(cudaMemcpyAsync(logL, hl.data(), hl.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    AC_CHECK_CUDA(cudaStreamSynchronize(st));  // the host vectors die at the end of this scope
+  }
+  YinParams yp;
+  yp.x = d_x; yp.n = n; yp.hop = hop; yp.sr = sr;
+  yp.min_period = g.min_period; yp.max_period = g.max_period;
+  yp.n_pitch_bins = g.nb; yp.bins_per_semitone = g.bps;
+  yp.fmin = fmin; yp.boltzmann = 2.f; yp.no_trough_prob = 0.01f;
+  yp.beta_probs = beta;
+  yp.n_frames = nf;
+  yp.cand = cand; yp.n_cand = n_cand; yp.voiced_prob = d_voiced_prob;
+  {
+    ProfScope ps(KC_MISC, 2.0 * nf * (double)(g.max_period + 1) * kYinWin, 4.0 * n, st);
+    yin_probs_kernel<<<(unsigned)nf, kYinThreads, 0, st>>>(yp);
+    AC_LAUNCH_CHECK();
+  }
+  if (d_f0 || d_voiced_flag) {
+    VitParams vp;
+    vp.cand = cand; vp.n_cand = n_cand; vp.voiced_prob = d_voiced_prob;
+    vp.n_steps = nf; vp.nb = g.nb; vp.half = g.half; vp.logL = logL;
+    vp.log_stay = log(0.99); vp.log_switch = log(0.01);
+    vp.log_init = log(1.0 / (2.0 * g.nb) + 2.2250738585072014e-308);
+    vp.ptr = ptr; vp.final_state = final_state;
+    const size_t smem = (size_t)(5 * g.nb + 32) * sizeof(double) + 32 * sizeof(int);
+    AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(KC_MISC, 0.0, (double)nf * 2 * g.nb * 2, st);
+    pyin_viterbi_kernel<<<1, kVitThreads, smem, st>>>(vp);
+    AC_LAUNCH_CHECK();
+    pyin_backtrack_kernel<<<1, 32, 0, st>>>(ptr, final_state, nf, g.nb, fmin, g.bps, d_f0, d_voiced_flag);
+    AC_LAUNCH_CHECK();
+  }
+  return AC_OK;
+}
+
+// ---- LPC formants ----------------------------------------------------------------------------------
+namespace ac {
+constexpr int kLpcThreads = 128;
+constexpr int kLpcMaxFrame = 2048;
+constexpr int kLpcMaxOrder = 16;
+constexpr int kLpcFreq = 512;
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+// one CTA per frame: pre-emphasis, Burg recursion in fp64 (librosa.lpc), |1/A(e^jw)| on 512 points of
+// [0, pi), peaks (strict local maxima, flat tops at their midpoint as scipy.signal.find_peaks) above
+// 0.1 * max, magnitudes of the first three
+__global__ void __launch_bounds__(kLpcThreads) lpc_formant_kernel(const float* __restrict__ x, long long n, int frame, int hop,
+                                                                  int order, long long n_frames, float* __restrict__ mags,
+                                                                  int* __restrict__ counts) {
+  __shared__ double fwd[kLpcMaxFrame], bwd[kLpcMaxFrame];
+  __shared__ double ar[kLpcMaxOrder + 1], ar_prev[kLpcMaxOrder + 1];
+  __shared__ double red[8];
+  __shared__ float mag[kLpcFreq];
+  __shared__ int peak_idx[4];
+  __shared__ int n_peaks_s;
+  const long long fr = blockIdx.x;
+  const int tid = threadIdx.x;
+  const long long s0 = fr * hop;
+  // pre-emphasised frame p[0] = x[0], p[i] = x[i] - 0.95 x[i-1]  (float32 arithmetic as np.append on float32)
+  bool any = false;
+  for (int i = tid; i < frame; i += kLpcThreads) {
+    const float cur = x[s0 + i];
+    const float pe = i == 0 ? cur : cur - 0.95f * x[s0 + i - 1];
+    any = any || (pe != 0.f);
+    if (i >= 1) fwd[i - 1] = (double)pe;        // fwd = p[1:]
+    if (i < frame - 1) bwd[i] = (double)pe;     // bwd = p[:-1]
+  }
+  const int any_all = __syncthreads_or(any ? 1 : 0);
+  if (tid <= order) { ar[tid] = tid == 0 ? 1.0 : 0.0; ar_prev[tid] = ar[tid]; }
+  __syncthreads();
+  bool ok = any_all != 0;
+  int len = frame - 1;
+  double den = 0.0;
+  {
+    double part = 0.0;
+    for (int i = tid; i < len; i += kLpcThreads) part += fwd[i] * fwd[i] + bwd[i] * bwd[i];
+    den = block_sum_d(part, red);
+  }
+  double* a_cur = ar;
+  double* a_old = ar_prev;
+  for (int it = 0; it < order && ok; ++it) {
+    double part = 0.0;
+    for (int i = tid; i < len; i += kLpcThreads) part += bwd[i] * fwd[i];
+    const double dot = block_sum_d(part, red);
+    const double rc = -2.0 * dot / (den + 2.2250738585072014e-308);
+    // ar_prev, ar = ar, ar_prev ; ar[j] = ar_prev[j] + rc * ar_prev[i - j + 1]
+    double* t = a_old; a_old = a_cur; a_cur = t;
+    __syncthreads();
+    if (tid >= 1 && tid <= it + 1) a_cur[tid] = a_old[tid] + rc * a_old[it - tid + 1];
+    if (tid == 0) a_cur[0] = 1.0;
+    // fwd' = fwd + rc*bwd ; bwd' = bwd + rc*fwd   (both from the old values), then drop fwd'[0] and bwd'[-1]
+    const double b_last_new = bwd[len - 1] + rc * fwd[len - 1];
+    const double f_first_new = fwd[0] + rc * bwd[0];
+    __syncthreads();
+    // new fwd[i] = old fwd[i+1] + rc*old bwd[i+1] (shifted by one), new bwd[i] = old bwd[i] + rc*old fwd[i]
+    double nf_[ (kLpcMaxFrame + kLpcThreads - 1) / kLpcThreads ], nb_[ (kLpcMaxFrame + kLpcThreads - 1) / kLpcThreads ];
+    int c = 0;
+    for (int i = tid; i < len - 1; i += kLpcThreads, ++c) {
+      nf_[c] = fwd[i + 1] + rc * bwd[i + 1];
+      nb_[c] = bwd[i] + rc * fwd[i];
+    }
+    __syncthreads();
+    c = 0;
+    for (int i = tid; i < len - 1; i += kLpcThreads, ++c) {
+      fwd[i] = nf_[c];
+      bwd[i] = nb_[c];
+    }
+    const double q = 1.0 - rc * rc;
+    den = q * den - b_last_new * b_last_new - f_first_new * f_first_new;
+    len -= 1;
+    if (!isfinite(rc)) ok = false;
+    __syncthreads();
+  }
+  // |1 / A(e^{jw})|, w_k = pi * k / 512
+  float local_max = 0.f;
+  for (int k = tid; k < kLpcFreq; k += kLpcThreads) {
+    const double w = 3.14159265358979323846 * (double)k / (double)kLpcFreq;
+    double re = 0.0, im = 0.0;
+    for (int m = 0; m <= order; ++m) {
+      double s, c;
+      sincos(w * m, &s, &c);
+      re += a_cur[m] * c;
+      im -= a_cur[m] * s;
+    }
+    const float v = (float)(1.0 / sqrt(re * re + im * im));
+    mag[k] = v;
+    local_max = fmaxf(local_max, v);
+  }
+  local_max = warp_max(local_max);
+  __shared__ float mx_s[8];
+  if ((tid & 31) == 0) mx_s[tid >> 5] = local_max;
+  __syncthreads();
+  float mx = 0.f;
+  for (int i = 0; i < kLpcThreads / 32; ++i) mx = fmaxf(mx, mx_s[i]);
+  if (tid == 0) {
+    int np = 0;
+    if (ok && isfinite(mx)) {
+      const float height = mx * 0.1f;
+      int i = 1;
+      while (i < kLpcFreq - 1 && np < 3) {
+        if (mag[i - 1] < mag[i]) {
+          int ahead = i + 1;
+          while (ahead < kLpcFreq - 1 && mag[ahead] == mag[i]) ++ahead;  // flat top
+          if (mag[ahead] < mag[i]) {
+            const int mid = (i + ahead - 1) / 2;
+            if (mag[mid] >= height) peak_idx[np++] = mid;
+            i = ahead;
+            continue;
+          }
+        }
+        ++i;
+      }
+    }
+    n_peaks_s = np;
+  }
+  __syncthreads();
+  if (tid < 3) mags[fr * 3 + tid] = tid < n_peaks_s ? mag[peak_idx[tid]] : 0.f;
+  if (tid == 0) counts[fr] = n_peaks_s;
+}
+}  // namespace ac
+
+extern "C" long long ac_lpc_frame_count(long long n, int frame, int hop) {
+  if (n - frame <= 0 || hop <= 0) return 0;
+  return (n - frame + hop - 1) / hop;  // len(range(0, n - frame, hop))
+}
+
+extern "C" int ac_lpc_formants(const float* d_x, long long n, int frame, int hop, int order, float* d_mags, int* d_counts,
+                               void* stream) {
+  using namespace ac;
+  AC_REQUIRE(d_x && d_mags && d_counts, "ac_lpc_formants: null pointer");
+  AC_REQUIRE(frame >= order + 2 && frame <= kLpcMaxFrame && order >= 1 && order <= kLpcMaxOrder && hop > 0, "ac_lpc_formants: geometry");
+  const long long nf = ac_lpc_frame_count(n, frame, hop);
+  if (nf == 0) return AC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(KC_MISC, 8.0 * nf * order * frame, 4.0 * n, st);
+  lpc_formant_kernel<<<(unsigned)nf, kLpcThreads, 0, st>>>(d_x, n, frame, hop, order, nf, d_mags, d_counts);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}

@@ -243,3 +243,51 @@ def host_beat_dp(localscore: np.ndarray, period: int, tightness: float):
     cumscore = np.zeros(n, dtype=np.float32)
     check(lib.ac_host_beat_dp(ls.ctypes.data, n, int(period), float(tightness), backlink.ctypes.data, cumscore.ctypes.data), "ac_host_beat_dp")
     return backlink, cumscore
+
+
+# ---- F0 / formants of the legacy pause-detector branch (pure_vocal_pause_detector.py:410-459, 961-1018)
+C2_HZ = 65.40639132514966   # librosa.note_to_hz("C2")
+C7_HZ = 2093.004522404789   # librosa.note_to_hz("C7")
+
+
+def pyin(x: torch.Tensor, sr: int = 44100, hop_length: int = 441, fmin: float = C2_HZ, fmax: float = C7_HZ, *,
+         decode: bool = True):
+    """librosa.pyin(y, fmin=C2, fmax=C7, sr=sr, hop_length=hop) on the GPU.
+
+    Returns (f0 [n_frames] with NaN where unvoiced, voiced_flag bool, voiced_prob); with ``decode=False`` only
+    the YIN/candidate stage runs and f0 / voiced_flag are None."""
+    lib = _lib.init(_dev_index(x))
+    x = x.contiguous().float()
+    n = x.numel()
+    nf = int(lib.ac_pyin_frame_count(n, hop_length))
+    ws = torch.empty(int(lib.ac_pyin_workspace_bytes(n, hop_length, sr, fmin, fmax)), dtype=torch.uint8, device=x.device)
+    vp = torch.empty(nf, dtype=torch.float32, device=x.device)
+    f0 = torch.empty(nf, dtype=torch.float32, device=x.device) if decode else None
+    flag = torch.empty(nf, dtype=torch.uint8, device=x.device) if decode else None
+    check(lib.ac_pyin(ptr(x), n, sr, hop_length, fmin, fmax, ptr(f0), ptr(flag), ptr(vp), ptr(ws), ws.numel(), stream_ptr()), "ac_pyin")
+    return f0, (flag.bool() if decode else None), vp
+
+
+def lpc_formants(x: torch.Tensor, sr: int = 44100, hop_length: int = 441, order: int = 12):
+    """Dense form of _extract_formants: (mags [n_frames, 3], counts [n_frames]); frame = int(0.025 * sr)."""
+    lib = _lib.init(_dev_index(x))
+    x = x.contiguous().float()
+    n = x.numel()
+    frame = int(0.025 * sr)
+    nf = int(lib.ac_lpc_frame_count(n, frame, hop_length))
+    mags = torch.zeros((nf, 3), dtype=torch.float32, device=x.device)
+    counts = torch.zeros(nf, dtype=torch.int32, device=x.device)
+    check(lib.ac_lpc_formants(ptr(x), n, frame, hop_length, order, ptr(mags), ptr(counts), stream_ptr()), "ac_lpc_formants")
+    return mags, counts
+
+
+def formant_tracks(mags: np.ndarray, counts: np.ndarray):
+    """The reference's three ragged lists (pure_vocal_pause_detector.py:1000-1016): a frame with k >= 1 peaks
+    appends to the first k tracks only; a frame with no peak (or a failed LPC) appends 0.0 to all three."""
+    mags = np.asarray(mags)
+    counts = np.asarray(counts)
+    tracks = []
+    for j in range(3):
+        keep = (counts > j) | (counts == 0)
+        tracks.append(np.where(counts[keep] == 0, 0.0, mags[keep, j]).astype(mags.dtype))
+    return tracks

@@ -191,6 +191,30 @@ AC_API int ac_stft_features(const float* d_x, const ac_feat_segment* h_segs, int
                      float* d_onset_mean, float* d_onset_median, float* d_centroid, float* d_low_ratio, void* d_ws,
                      size_t ws_bytes, void* stream);
 
+/* ---- F0 and formants of the legacy pause-detector branch --------
+ * ac_pyin == librosa.pyin(y, fmin, fmax, sr, frame_length=2048, hop_length=hop) with librosa's defaults
+ * (win_length 1024, 100 thresholds, beta(2,18), Boltzmann 2, 0.1-semitone bins, max_transition_rate
+ * 35.92, switch_prob 0.01, no_trough_prob 0.01, center=True zero padding), as called at
+ * pure_vocal_pause_detector.py:422-428.  n_frames = ac_pyin_frame_count = 1 + n/hop.
+ *   d_f0           [n_frames] Hz, NaN where unvoiced (may be NULL: skips the Viterbi pass)
+ *   d_voiced_flag  [n_frames] 0/1                    (may be NULL)
+ *   d_voiced_prob  [n_frames]
+ * The YIN/candidate stage is one CTA per frame; the HMM decode (1202 states, fp64) is sequential in
+ * time and runs as one CTA. */
+AC_API long long ac_pyin_frame_count(long long n, int hop);
+AC_API size_t ac_pyin_workspace_bytes(long long n, int hop, int sr, float fmin, float fmax);
+AC_API int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmin, float fmax, float* d_f0,
+                   unsigned char* d_voiced_flag, float* d_voiced_prob, void* d_ws, size_t ws_bytes, void* stream);
+/* ac_lpc_formants == the per-frame body of PureVocalPauseDetector._extract_formants
+ * (pure_vocal_pause_detector.py:961-1018): frames start at i = 0, hop, ... < n - frame (no centring),
+ * pre-emphasis 0.95, librosa.lpc (Burg, `order`), |freqz(1, a, worN=512)|, scipy find_peaks above
+ * 0.1 * max; d_mags[f][j] = magnitude of the j-th peak by frequency (0 beyond d_counts[f]).  The host
+ * rebuilds the reference's ragged F1/F2/F3 lists: count k >= 1 appends to the first k tracks, k == 0
+ * appends 0.0 to all three.  n_frames = ac_lpc_frame_count = len(range(0, n - frame, hop)). */
+AC_API long long ac_lpc_frame_count(long long n, int frame, int hop);
+AC_API int ac_lpc_formants(const float* d_x, long long n, int frame, int hop, int order, float* d_mags /*[n_frames][3]*/,
+                           int* d_counts, void* stream);
+
 /* ---- rhythm front end ------------------------------------------------
  * Autocorrelation tempogram of an onset envelope (librosa.feature.tempogram: hann window of `win`
  * frames, hop 1, centred with a linear ramp, autocorrelation max-normalised per frame) reduced on

@@ -264,3 +264,67 @@ def test_tempogram_stats_match_host_reference(ops):
         np.testing.assert_allclose(tg_mean, tg.mean(axis=1), rtol=0, atol=2e-5)
         assert glob == ref_glob
         assert np.mean(curve == ref_curve) > 0.995  # float32 vs float64 near-ties between adjacent lags
+
+
+# --------------------------------------------------------------------------- pYIN / LPC formants (A17, A18)
+def _voiced_test_signal(seconds=3.0, seed=5):
+    """Vibrato harmonic tone with pauses + noise floor + an unvoiced noise burst."""
+    rng = np.random.default_rng(seed)
+    n = int(seconds * SR)
+    t = np.arange(n) / SR
+    f0 = 180.0 * 2 ** (0.5 * np.sin(2 * np.pi * 0.7 * t)) * (1 + 0.01 * np.sin(2 * np.pi * 5.5 * t))
+    ph = 2 * np.pi * np.cumsum(f0) / SR
+    y = sum(a * np.sin(k * ph) for k, a in ((1, 0.5), (2, 0.3), (3, 0.15), (4, 0.08)))
+    gate = (np.sin(2 * np.pi * 0.9 * t) > -0.3).astype(np.float64)
+    y = y * gate + 2e-3 * rng.standard_normal(n)
+    a, b = int(0.72 * n), int(0.82 * n)
+    y[a:b] = 0.2 * rng.standard_normal(b - a)
+    return y.astype(np.float32)
+
+
+def test_pyin_matches_oracle(ops):
+    from oracle import features as OF
+
+    y = _voiced_test_signal()
+    f0, flag, vp = ops.pyin(torch.from_numpy(y).cuda(), SR, 441)
+    f0, flag, vp = f0.cpu().numpy(), flag.cpu().numpy(), vp.cpu().numpy()
+    r_f0, r_flag, r_vp = OF.pyin(y, SR, hop_length=441)
+    assert f0.shape == r_f0.shape == (1 + len(y) // 441,)
+    # voiced probability is a sum of beta-weighted masses: fp32 CMND vs the fp64 oracle can move a trough
+    # across one of the 100 thresholds, which shifts at most one beta weight (<= 0.07) in a frame
+    assert np.mean(np.abs(vp - r_vp) < 1e-3) > 0.97, np.mean(np.abs(vp - r_vp) < 1e-3)
+    assert np.max(np.abs(vp - r_vp)) < 0.15
+    agree = flag == r_flag
+    assert agree.mean() > 0.99, agree.mean()
+    both = flag & r_flag
+    assert both.sum() > 50
+    same = np.isclose(f0[both], r_f0[both], rtol=1e-5)
+    assert same.mean() > 0.99, same.mean()
+    # never more than one 0.1-semitone bin apart
+    assert np.max(np.abs(np.log2(f0[both] / r_f0[both]))) * 120 < 1.01
+
+
+def test_pyin_candidate_stage_only(ops):
+    y = _voiced_test_signal(1.0)
+    f0, flag, vp = ops.pyin(torch.from_numpy(y).cuda(), SR, 441, decode=False)
+    assert f0 is None and flag is None and vp.shape == (1 + len(y) // 441,)
+    assert float(vp.max()) <= 1.0 and float(vp.min()) >= 0.0
+
+
+def test_lpc_formants_match_oracle(ops):
+    from oracle import features as OF
+
+    y = _voiced_test_signal(2.0)
+    y[5000:9000] = 0.0  # all-zero frames: the reference's "no peaks" branch
+    mags, counts = ops.lpc_formants(torch.from_numpy(y).cuda(), SR, 441, 12)
+    mags, counts = mags.cpu().numpy(), counts.cpu().numpy()
+    r_mags, r_counts = OF.lpc_formant_frames(y, SR, int(0.025 * SR), 441, 12)
+    assert mags.shape == r_mags.shape == (len(range(0, len(y) - int(0.025 * SR), 441)), 3)
+    same = counts == r_counts
+    assert same.mean() > 0.98, same.mean()
+    # Burg in fp64 on both sides; the 512-point response is fp32 on the GPU
+    np.testing.assert_allclose(mags[same], r_mags[same], rtol=2e-3, atol=1e-5)
+    # ragged track reconstruction follows the reference's append rule
+    tr = ops.formant_tracks(mags, counts)
+    assert len(tr[0]) >= len(tr[1]) >= len(tr[2])
+    assert len(tr[0]) == int(np.sum((counts > 0) | (counts == 0)))

@@ -153,3 +153,39 @@ def test_cpp_beat_dp_matches_numpy_loop():
         b1, c1 = ops.host_beat_dp(ls, period, 100.0)
         np.testing.assert_array_equal(b0, b1)
         np.testing.assert_allclose(c0, c1, rtol=1e-6, atol=1e-6)
+
+
+def test_pyin_oracle_recovers_a_harmonic_tone():
+    """The librosa.pyin restatement (oracle/features.py): a 220 Hz harmonic tone decodes to the 220 Hz pitch bin."""
+    from oracle import features as OF
+
+    sr = 44100
+    t = np.arange(int(1.0 * sr)) / sr
+    y = (0.5 * np.sin(2 * np.pi * 220 * t) + 0.25 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    y[: int(0.25 * sr)] = 0.0
+    y += (1e-3 * np.random.default_rng(0).standard_normal(len(y))).astype(np.float32)
+    f0, flag, vp = OF.pyin(y, sr, hop_length=441)
+    assert f0.shape == (1 + len(y) // 441,)
+    assert not flag[:15].any() and flag[40:90].all()
+    assert np.allclose(f0[40:90], 220.0, rtol=0.006)  # one 0.1-semitone bin
+    W, pmin, pmax, bps, nb = OF.pyin_geometry(sr)
+    assert (W, pmin, pmax, bps, nb) == (1024, 21, 675, 10, 601)  # SURVEY.md Appendix A.4
+    T = OF.transition_local_triangle(nb, 41)
+    assert np.allclose(T.sum(axis=1), 1.0) and T[300, 279] == 0 and T[300, 280] > 0 and T[0, 21] == 0
+
+
+def test_lpc_burg_recovers_an_ar2_process_and_ragged_tracks():
+    from audio_cut_b200 import ops
+    from oracle import features as OF
+
+    rng = np.random.default_rng(1)
+    e = rng.standard_normal(20000)
+    y = np.zeros_like(e)
+    for i in range(2, len(e)):
+        y[i] = 1.3 * y[i - 1] - 0.6 * y[i - 2] + e[i]
+    a = OF.lpc_burg(y, 2)
+    assert np.allclose(a, [1.0, -1.3, 0.6], atol=0.03)
+    mags = np.array([[3.0, 2.0, 1.0], [5.0, 0.0, 0.0], [0.0, 0.0, 0.0], [7.0, 6.0, 0.0]], dtype=np.float32)
+    counts = np.array([3, 1, 0, 2])
+    t1, t2, t3 = ops.formant_tracks(mags, counts)
+    assert t1.tolist() == [3.0, 5.0, 0.0, 7.0] and t2.tolist() == [2.0, 0.0, 6.0] and t3.tolist() == [1.0, 0.0]
