@@ -105,3 +105,24 @@ def test_vad_hook_is_called_per_chunk():
     res = sep.separate_for_detection(synth.synth_track(9.0, sr=8000, stereo=False))
     assert [i for i, _ in seen] == list(range(len(seen))) and len(res.vad_segments) == len(seen)
     assert res.gpu_meta["silero_vad_segments"] == len(seen)
+
+
+def test_vocal_features_dropin_matches_oracle():
+    """PureVocalPauseDetector._extract_vocal_features (pure_vocal_pause_detector.py:410-459) on the GPU."""
+    from audio_cut_b200 import synth
+    from audio_cut_b200.vocal_features import extract_vocal_features
+    from oracle import features as OF
+
+    y = synth.synth_track(3.0, seed=11)[0].astype(np.float32)
+    vf = extract_vocal_features(y, 44100, 441)
+    n_frames = 1 + len(y) // 441
+    for a in (vf.f0_contour, vf.f0_confidence, vf.spectral_centroid, vf.harmonic_ratio, vf.zero_crossing_rate, vf.rms_energy):
+        assert a.shape == (n_frames,)
+    assert len(vf.formant_energies) == 3
+    np.testing.assert_allclose(vf.rms_energy, OF.rms(y, 2048, 441), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(vf.zero_crossing_rate, OF.zero_crossing_rate(y, 2048, 441), atol=1e-7)
+    np.testing.assert_allclose(vf.spectral_centroid, OF.spectral_centroid(y, 44100, 2048, 441), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(vf.harmonic_ratio, OF.low_band_ratio(y, 2048, 441), rtol=1e-4, atol=1e-7)
+    r_f0, r_flag, r_vp = OF.pyin(y, 44100, hop_length=441)
+    assert np.mean(np.isnan(vf.f0_contour) == np.isnan(r_f0)) > 0.99
+    assert np.mean(np.abs(vf.f0_confidence - r_vp) < 1e-3) > 0.95
