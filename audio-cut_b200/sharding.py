@@ -65,3 +65,28 @@ def merge_chunk_shards(total_samples: int, shards: Sequence[Dict[str, np.ndarray
         wacc[lo:hi] += w
     wacc[wacc == 0.0] = 1.0
     return vacc / wacc, iacc / wacc
+
+
+def separate_chunk_shard(net, geom, mix: np.ndarray, bounds: Sequence[Tuple[int, int, int, int]], rank: int, world: int, *,
+                         device: int = 0, **separate_kwargs) -> Dict[str, np.ndarray]:
+    """What ONE rank does for a chunk-sharded track (BASELINE configs[4]): take its contiguous block of
+    pipeline chunks, upload only the samples they touch, separate them on this rank's GPU with the same
+    ``ac_separate_track`` entry point, and hand back the shard ``merge_chunk_shards`` expects.
+
+    mix: host array [n_ch, N]; bounds: per-chunk (chunk_start, chunk_end, eff_start, eff_end) in samples for
+    the WHOLE track (``ChunkPlan.sample_bounds``).  No collective: the caller gathers the dicts on the host.
+    """
+    import torch
+
+    from . import ops
+
+    lo_c, hi_c = shard_chunks(len(bounds), world)[rank]
+    mine = list(bounds[lo_c:hi_c])
+    lo, hi = shard_sample_range(mine)
+    if hi <= lo:
+        z = np.zeros(0, np.float32)
+        return {"lo": 0, "vocal": z, "instr": z, "weight": z}
+    local = torch.from_numpy(np.ascontiguousarray(mix[:, lo:hi], dtype=np.float32)).cuda(device)
+    vocal, instr, weight = ops.separate_track(net, local, localize_bounds(mine, lo), geom, **separate_kwargs)
+    torch.cuda.synchronize(local.device)
+    return {"lo": lo, "vocal": vocal.cpu().numpy(), "instr": instr.cpu().numpy(), "weight": weight.cpu().numpy()}

@@ -187,6 +187,32 @@ def test_separate_track_full_geometry_30s_stereo(ops):
     assert sv > 60 and si > 60, (sv, si)
 
 
+@pytest.mark.parametrize("world,dtype_name", [(2, "f32"), (3, "bf16")])
+def test_chunk_sharded_track_equals_single_gpu_stitch(ops, world, dtype_name):
+    """BASELINE configs[4]: every rank separates a contiguous block of chunks of ONE track (halo recomputed
+    locally, only its own samples uploaded); the host merge of the shards is sample-identical to the
+    single-GPU result.  The ranks are emulated one after the other on this GPU."""
+    from audio_cut_b200 import sharding, synth, unet_weights as uw
+    from audio_cut_b200._lib import AC_BF16, AC_F32
+    from oracle import planner
+
+    sr, n_fft, hop, dim_f, dim_t, g = 8000, 640, 128, 256, 32, 16
+    geo = uw.UNetGeometry(dim_f=dim_f, dim_t=dim_t, g=g)
+    net = ops.UNet(uw.random_state(geo, seed=1234), geo)
+    geom = ops.mdx_geom(n_fft, hop, dim_f, dim_t)
+    audio = synth.synth_track(23.7, sr=sr, seed=9, stereo=True)
+    total = audio.shape[-1]
+    plans = planner.chunk_schedule(total / float(sr), 2.0, 0.5, 0.1)
+    bounds = [planner.sample_bounds(p, sr, total) for p in plans]
+    dtype = AC_F32 if dtype_name == "f32" else AC_BF16
+    v, i, w = ops.separate_track(net, torch.from_numpy(audio).cuda(), bounds, geom, align_hop=256, dtype=dtype)
+    shards = [sharding.separate_chunk_shard(net, geom, audio, bounds, r, world, align_hop=256, dtype=dtype) for r in range(world)]
+    assert sum(len(s["weight"]) for s in shards) > total  # neighbouring ranks overlap at the seams
+    mv, mi = sharding.merge_chunk_shards(total, shards)
+    np.testing.assert_array_equal(mv, v.cpu().numpy())
+    np.testing.assert_array_equal(mi, i.cpu().numpy())
+
+
 # --------------------------------------------------------------------------- STFT-2048 features
 @pytest.mark.parametrize("hop", [2205, 441, 512])
 def test_stft_features_match_oracle(ops, audio, hop):
