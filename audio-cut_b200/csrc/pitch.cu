@@ -306,15 +306,23 @@ __global__ void __launch_bounds__(kYinThreads) yin_probs_kernel(const YinParams 
 }
 
 // ---- Viterbi ---------------------------------------------------------------------------------------
+// log T[(v,k) -> (v',j)] = log t_switch[v][v'] + log tri[j-k] - log rowsum[k]  inside the band |j-k| <= half,
+// log(tiny) outside (librosa: log(transition + tiny)).  Per step a thread owns pitch bin j (both voicings):
+//   m_v = max_k (val_v[k] - lognorm[k]) + logtri[j-k],   m_u likewise over the unvoiced states,
+//   into voiced j:   max(m_v + log stay, m_u + log switch, gmax + log tiny)   (first maximum on ties)
+// Two block barriers per step; the next step's observations are prefetched and scattered while this
+// step's maxima are being taken.
 constexpr int kVitThreads = 640;
+constexpr int kVitMaxHalf = 32;
 struct VitParams {
   const uint2* cand;
   const int* n_cand;
   const float* voiced_prob;
   long long n_steps;
-  int nb;              // pitch bins (601)
-  int half;            // band half width (20)
-  const double* logL;  // [nb][2*half+1]: log(local[k][k+d] + 0) for source k, d = -half..half (-inf -> handled as log tiny)
+  int nb;    // pitch bins (601)
+  int half;  // band half width (20)
+  const double* logtri;   // [2*half+1] log of the un-normalised triangle
+  const double* lognorm;  // [nb] log of the row sums (rows are truncated at the edges)
   double log_stay, log_switch, log_init;
   unsigned short* ptr;  // [n_steps][2*nb]
   int* final_state;
@@ -322,45 +330,82 @@ struct VitParams {
 
 __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitParams p) {
   extern __shared__ double vsm[];
-  const int nb = p.nb, S = 2 * nb;
-  double* val0 = vsm;            // [S]
-  double* val1 = vsm + S;        // [S]
-  double* obs = vsm + 2 * S;     // [nb] log observation of the voiced states for this step
-  double* redv = obs + nb;       // [32]
+  const int nb = p.nb, S = 2 * nb, half = p.half;
+  double* val = vsm;                 // [2][S] raw values (double buffered)
+  double* adj = val + 2 * S;         // [2][S] value - lognorm[k]
+  double* obs = adj + 2 * S;         // [2][nb] log observation of the voiced states (double buffered)
+  double* tri = obs + 2 * nb;        // [2*half+1]
+  double* lnorm = tri + (2 * kVitMaxHalf + 1);  // [nb]
+  double* redv = lnorm + nb;         // [32]
   int* redi = reinterpret_cast<int*>(redv + 32);  // [32]
-  __shared__ double gmax_s;
-  __shared__ int gidx_s;
-  const int tid = threadIdx.x;
-  const int W = 2 * p.half + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kVitThreads / 32;
+  const double tiny = 2.2250738585072014e-308;
 
-  auto load_obs = [&](long long t, double& lu) {
-    for (int j = tid; j < nb; j += kVitThreads) obs[j] = kLogTiny;
-    __syncthreads();
-    const int nc = p.n_cand[t];
-    const uint2* c = p.cand + t * (long long)kYinMaxCand;
-    for (int i = tid; i < nc; i += kVitThreads) {
-      const uint2 me = c[i];
-      const bool last = (i == nc - 1) || (c[i + 1].x != me.x);
-      if (last && (int)me.x < nb) obs[me.x] = log((double)__uint_as_float(me.y) + 2.2250738585072014e-308);
-    }
-    const double vp = (double)p.voiced_prob[t];
-    lu = log((1.0 - vp) / (double)nb + 2.2250738585072014e-308);
-    __syncthreads();
-  };
-
-  double lu;
-  load_obs(0, lu);
-  for (int s = tid; s < S; s += kVitThreads) val0[s] = (s < nb ? obs[s] : lu) + p.log_init;
+  for (int i = tid; i < 2 * half + 1; i += kVitThreads) tri[i] = p.logtri[i];
+  for (int i = tid; i < nb; i += kVitThreads) { lnorm[i] = p.lognorm[i]; obs[i] = kLogTiny; obs[nb + i] = kLogTiny; }
   __syncthreads();
-  double* cur = val0;
-  double* nxt = val1;
+  // Observation inputs are software-pipelined through registers two steps ahead, so no global-memory
+  // latency sits on the per-step critical path: thread i owns candidate i of a frame (n_cand <= 328 < 640).
+  struct ObsIn {
+    int nc;
+    float vp;
+    uint2 me, nxt;
+  };
+  auto fetch = [&](long long t) {
+    ObsIn o;
+    o.nc = 0; o.vp = 0.f; o.me = make_uint2(0, 0); o.nxt = make_uint2(0, 0);
+    if (t < p.n_steps) {
+      o.nc = p.n_cand[t];
+      o.vp = p.voiced_prob[t];
+      if (tid < kYinMaxCand) {
+        const uint2* c = p.cand + t * (long long)kYinMaxCand;
+        o.me = c[tid];
+        o.nxt = tid + 1 < kYinMaxCand ? c[tid + 1] : make_uint2(0xffffffffu, 0);
+      }
+    }
+    return o;
+  };
+  // returns the bin this thread wrote (or -1): last candidate of a run of equal bins wins
+  auto scatter = [&](const ObsIn& o, int ob) -> int {
+    if (tid < o.nc) {
+      const bool last = (tid == o.nc - 1) || (o.nxt.x != o.me.x);
+      if (last && (int)o.me.x < nb) {
+        obs[ob * nb + o.me.x] = log((double)__uint_as_float(o.me.y) + tiny);
+        return (int)o.me.x;
+      }
+    }
+    return -1;
+  };
+  ObsIn in0 = fetch(0), in1 = fetch(1), in2 = fetch(2);
+  int wrote_cur = scatter(in0, 0);
+  __syncthreads();
+  {
+    const double lu0 = log((1.0 - (double)in0.vp) / (double)nb + tiny);
+    for (int s = tid; s < S; s += kVitThreads) {
+      const int k = s < nb ? s : s - nb;
+      const double v = (s < nb ? obs[s] : lu0) + p.log_init;
+      val[s] = v;
+      adj[s] = v - lnorm[k];
+    }
+  }
+  __syncthreads();
+  if (wrote_cur >= 0) obs[wrote_cur] = kLogTiny;
+  wrote_cur = scatter(in1, 1);  // observations of step 1 live in buffer 1
+  __syncthreads();
+  int cur = 0;
+  // in1 = inputs of step t (already scattered), in2 = inputs of step t+1
   for (long long t = 1; t < p.n_steps; ++t) {
-    // block-wide (max, first argmax) of the previous values: the best out-of-band predecessor
+    const int ob = (int)(t & 1);
+    const double* cv = val + cur * S;
+    const double* ca = adj + cur * S;
+    const ObsIn in3 = fetch(t + 2);  // issued now, consumed two steps later
+    // ---- P1: per-warp (max, first argmax) of the previous values + the in-band maxima
     {
       double bv = -INFINITY;
       int bi = 0x7fffffff;
       for (int s = tid; s < S; s += kVitThreads) {
-        const double v = cur[s];
+        const double v = cv[s];
         if (v > bv || (v == bv && s < bi)) { bv = v; bi = s; }
       }
 #pragma unroll
@@ -369,64 +414,75 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      if ((tid & 31) == 0) { redv[tid >> 5] = bv; redi[tid >> 5] = bi; }
-      __syncthreads();
-      if (tid < 32) {
-        bv = tid < (kVitThreads >> 5) ? redv[tid] : -INFINITY;
-        bi = tid < (kVitThreads >> 5) ? redi[tid] : 0x7fffffff;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (tid == 0) { gmax_s = bv; gidx_s = bi; }
-      }
+      if (lane == 0) { redv[warp] = bv; redi[warp] = bi; }
+      if (tid == kVitThreads - 1) redv[31] = log((1.0 - (double)in1.vp) / (double)nb + tiny);
     }
-    load_obs(t, lu);  // contains the __syncthreads() that publishes gmax_s / gidx_s
-    const double oob = gmax_s + kLogTiny;
-    const int oob_idx = gidx_s;
+    double mv = -INFINITY, mu = -INFINITY;
+    int av = 0, au = 0;
     if (tid < nb) {
       const int j = tid;
-      // in-band predecessors k = j-half .. j+half (both voicings); value + log(t_switch * local[k][j])
-      double best_v = -INFINITY, best_u = -INFINITY;  // into voiced j / into unvoiced j
-      int arg_v = 0, arg_u = 0;
-      const int k_lo = j - p.half < 0 ? 0 : j - p.half;
-      const int k_hi = j + p.half > nb - 1 ? nb - 1 : j + p.half;
-      // candidates are visited in increasing state index (voiced k ascending, then unvoiced k ascending) and
-      // replaced only on strict improvement: np.argmax's first-maximum rule
+      const int k_lo = j - half < 0 ? 0 : j - half;
+      const int k_hi = j + half > nb - 1 ? nb - 1 : j + half;
+      const double* tr = tri + (half - j);  // tr[k] = logtri[k - j + half]: the triangle is symmetric
       for (int k = k_lo; k <= k_hi; ++k) {
-        const double l = __ldg(p.logL + (size_t)k * W + (j - k + p.half));
-        const double a = cur[k] + l;
-        const double cv = a + p.log_stay, cu = a + p.log_switch;
-        if (cv > best_v) { best_v = cv; arg_v = k; }
-        if (cu > best_u) { best_u = cu; arg_u = k; }
+        const double l = tr[k];
+        const double a = ca[k] + l, b = ca[nb + k] + l;
+        if (a > mv) { mv = a; av = k; }
+        if (b > mu) { mu = b; au = k; }
       }
-      for (int k = k_lo; k <= k_hi; ++k) {
-        const double l = __ldg(p.logL + (size_t)k * W + (j - k + p.half));
-        const double a = cur[nb + k] + l;
-        const double cv = a + p.log_switch, cu = a + p.log_stay;
-        if (cv > best_v) { best_v = cv; arg_v = nb + k; }
-        if (cu > best_u) { best_u = cu; arg_u = nb + k; }
-      }
-      // the out-of-band maximum wins only if strictly larger, or equal with a smaller state index
-      if (oob > best_v || (oob == best_v && oob_idx < arg_v)) { best_v = oob; arg_v = oob_idx; }
-      if (oob > best_u || (oob == best_u && oob_idx < arg_u)) { best_u = oob; arg_u = oob_idx; }
-      nxt[j] = obs[j] + best_v;
-      nxt[nb + j] = lu + best_u;
-      unsigned short* pr = p.ptr + t * (long long)S;
-      pr[j] = (unsigned short)arg_v;
-      pr[nb + j] = (unsigned short)arg_u;
     }
-    __syncthreads();
-    double* tmp = cur; cur = nxt; nxt = tmp;
+    __syncthreads();  // S1: warp partials visible
+    // ---- P2: finish, write the new values, scatter the next step's observations into the other buffer
+    int wrote_next;
+    {
+      // block maximum from the warp partials: one partial per lane, shuffle tree (every warp does it for itself)
+      double gv = lane < kWarps ? redv[lane] : -INFINITY;
+      int gi = lane < kWarps ? redi[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, gv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+        if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
+      }
+      if (tid < nb) {
+        const int j = tid;
+        const double oob = gv + kLogTiny;
+        // candidates in increasing state index: voiced k, then unvoiced k; replace only on strict improvement
+        double best_v = mv + p.log_stay, best_u = mv + p.log_switch;
+        int arg_v = av, arg_u = av;
+        const double c2v = mu + p.log_switch, c2u = mu + p.log_stay;
+        if (c2v > best_v) { best_v = c2v; arg_v = nb + au; }
+        if (c2u > best_u) { best_u = c2u; arg_u = nb + au; }
+        if (oob > best_v || (oob == best_v && gi < arg_v)) { best_v = oob; arg_v = gi; }
+        if (oob > best_u || (oob == best_u && gi < arg_u)) { best_u = oob; arg_u = gi; }
+        const double lu = redv[31];  // log observation of the unvoiced states, published in P1
+        const double nv = obs[ob * nb + j] + best_v, nu = lu + best_u;
+        double* wv = val + (cur ^ 1) * S;
+        double* wa = adj + (cur ^ 1) * S;
+        const double ln = lnorm[j];
+        wv[j] = nv; wv[nb + j] = nu;
+        wa[j] = nv - ln; wa[nb + j] = nu - ln;
+        unsigned short* pr = p.ptr + t * (long long)S;
+        pr[j] = (unsigned short)arg_v;
+        pr[nb + j] = (unsigned short)arg_u;
+      }
+      wrote_next = scatter(in2, ob ^ 1);
+    }
+    __syncthreads();  // S2: new values visible, everyone is done reading obs[ob]
+    if (wrote_cur >= 0) obs[ob * nb + wrote_cur] = kLogTiny;  // un-scatter this step's observations
+    wrote_cur = wrote_next;
+    in1 = in2;
+    in2 = in3;
+    cur ^= 1;
   }
+  __syncthreads();
   // final state = first argmax
   if (tid < 32) {
+    const double* cv = val + cur * S;
     double bv = -INFINITY;
     int bi = 0x7fffffff;
     for (int s = tid; s < S; s += 32) {
-      const double v = cur[s];
+      const double v = cv[s];
       if (v > bv || (v == bv && s < bi)) { bv = v; bi = s; }
     }
 #pragma unroll
@@ -439,18 +495,43 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
   }
 }
 
-__global__ void pyin_backtrack_kernel(const unsigned short* __restrict__ ptr, const int* __restrict__ final_state, long long n_steps,
-                                      int nb, float fmin, int bins_per_semitone, float* __restrict__ f0,
-                                      unsigned char* __restrict__ voiced_flag) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Back pointers are consumed newest-first in blocks of kBtSteps steps staged through shared memory, so the
+// pointer chase itself runs out of smem and the global reads are coalesced.
+constexpr int kBtSteps = 64;
+__global__ void __launch_bounds__(256) pyin_backtrack_kernel(const unsigned short* __restrict__ ptr, const int* __restrict__ final_state,
+                                                             long long n_steps, int nb, float fmin, int bins_per_semitone,
+                                                             float* __restrict__ f0, unsigned char* __restrict__ voiced_flag) {
+  extern __shared__ unsigned short bsm[];  // [kBtSteps][2*nb]
+  __shared__ int states[kBtSteps];
+  __shared__ int carry;
   const int S = 2 * nb;
-  int s = *final_state;
-  for (long long t = n_steps - 1; t >= 0; --t) {
-    const bool v = s < nb;
-    const int k = v ? s : s - nb;
-    if (f0) f0[t] = v ? fmin * exp2f((float)k / (12.f * (float)bins_per_semitone)) : __int_as_float(0x7fc00000);
-    if (voiced_flag) voiced_flag[t] = v ? 1 : 0;
-    if (t > 0) s = ptr[t * (long long)S + s];
+  if (threadIdx.x == 0) carry = *final_state;
+  __syncthreads();
+  for (long long hi = n_steps - 1; hi >= 0; hi -= kBtSteps) {
+    const long long lo = hi - kBtSteps + 1 < 0 ? 0 : hi - kBtSteps + 1;  // steps lo..hi
+    const int cnt = (int)(hi - lo + 1);
+    // stage ptr[lo+1 .. hi] (ptr[t] maps the state at t to the state at t-1)
+    const long long words = (long long)cnt * S;
+    const unsigned short* src = ptr + lo * (long long)S;
+    for (long long i = threadIdx.x; i < words; i += blockDim.x) bsm[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = carry;
+      for (int r = cnt - 1; r >= 0; --r) {
+        states[r] = s;
+        if (lo + r > 0) s = bsm[(size_t)r * S + s];
+      }
+      carry = s;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+      const int s = states[r];
+      const bool v = s < nb;
+      const int k = v ? s : s - nb;
+      if (f0) f0[lo + r] = v ? fmin * exp2f((float)k / (12.f * (float)bins_per_semitone)) : __int_as_float(0x7fc00000);
+      if (voiced_flag) voiced_flag[lo + r] = v ? 1 : 0;
+    }
+    __syncthreads();
   }
 }
 
@@ -495,7 +576,7 @@ extern "C" size_t ac_pyin_workspace_bytes(long long n, int hop, int sr, float fm
   b += align_up((size_t)nf * kYinMaxCand * sizeof(uint2), 256);
   b += align_up((size_t)nf * sizeof(int), 256);
   b += align_up((size_t)nf * 2 * g.nb * sizeof(unsigned short), 256);
-  b += align_up((size_t)g.nb * (2 * g.half + 1) * sizeof(double), 256);
+  b += align_up((size_t)(g.nb + 2 * g.half + 1) * sizeof(double), 256);
   b += align_up((size_t)kNThresholds * sizeof(float), 256);
   b += 256;
   return b;
@@ -516,7 +597,7 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
   uint2* cand = reinterpret_cast<uint2*>(w); w += align_up((size_t)nf * kYinMaxCand * sizeof(uint2), 256);
   int* n_cand = reinterpret_cast<int*>(w); w += align_up((size_t)nf * sizeof(int), 256);
   unsigned short* ptr = reinterpret_cast<unsigned short*>(w); w += align_up((size_t)nf * 2 * g.nb * sizeof(unsigned short), 256);
-  double* logL = reinterpret_cast<double*>(w); w += align_up((size_t)g.nb * (2 * g.half + 1) * sizeof(double), 256);
+  double* logtab = reinterpret_cast<double*>(w); w += align_up((size_t)(g.nb + 2 * g.half + 1) * sizeof(double), 256);
   float* beta = reinterpret_cast<float*>(w); w += align_up((size_t)kNThresholds * sizeof(float), 256);
   int* final_state = reinterpret_cast<int*>(w);
 
@@ -530,21 +611,17 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
       prev = c;
     }
     const int W = 2 * g.half + 1;
-    std::vector<double> hl((size_t)g.nb * W);
+    // [0, W): log of scipy.signal.windows.triang(W) = 1 - |d| / ((W + 1) / 2);  [W, W + nb): log of the row sums
+    std::vector<double> hl((size_t)W + g.nb);
+    for (int d = -g.half; d <= g.half; ++d) hl[d + g.half] = log(1.0 - fabs((double)d) / ((W + 1) / 2.0));
     for (int k = 0; k < g.nb; ++k) {
       double sum = 0.0;
-      std::vector<double> row(W, 0.0);
-      for (int d = -g.half; d <= g.half; ++d) {
-        const int j = k + d;
-        if (j < 0 || j >= g.nb) continue;
-        // scipy.signal.windows.triang(W) (odd, symmetric): 1 - |d| / ((W + 1) / 2)
-        row[d + g.half] = 1.0 - fabs((double)d) / ((W + 1) / 2.0);
-        sum += row[d + g.half];
-      }
-      for (int d = 0; d < W; ++d) hl[(size_t)k * W + d] = row[d] > 0.0 ? log(row[d] / sum) : kLogTiny;
+      for (int d = -g.half; d <= g.half; ++d)
+        if (k + d >= 0 && k + d < g.nb) sum += 1.0 - fabs((double)d) / ((W + 1) / 2.0);
+      hl[W + k] = log(sum);
     }
     AC_CHECK_CUDA(cudaMemcpyAsync(beta, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    AC_CHECK_CUDA(cudaMemcpyAsync(logL, hl.data(), hl.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    AC_CHECK_CUDA(cudaMemcpyAsync(logtab, hl.data(), hl.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     AC_CHECK_CUDA(cudaStreamSynchronize(st));  // the host vectors die at the end of this scope
   }
   YinParams yp;
@@ -563,16 +640,19 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
   if (d_f0 || d_voiced_flag) {
     VitParams vp;
     vp.cand = cand; vp.n_cand = n_cand; vp.voiced_prob = d_voiced_prob;
-    vp.n_steps = nf; vp.nb = g.nb; vp.half = g.half; vp.logL = logL;
+    vp.n_steps = nf; vp.nb = g.nb; vp.half = g.half; vp.logtri = logtab; vp.lognorm = logtab + (2 * g.half + 1);
     vp.log_stay = log(0.99); vp.log_switch = log(0.01);
     vp.log_init = log(1.0 / (2.0 * g.nb) + 2.2250738585072014e-308);
     vp.ptr = ptr; vp.final_state = final_state;
-    const size_t smem = (size_t)(5 * g.nb + 32) * sizeof(double) + 32 * sizeof(int);
+    AC_REQUIRE(g.half <= kVitMaxHalf, "ac_pyin: transition band too wide");
+    const size_t smem = (size_t)(4 * 2 * g.nb + 2 * g.nb + (2 * kVitMaxHalf + 1) + g.nb + 32) * sizeof(double) + 32 * sizeof(int);
     AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(KC_MISC, 0.0, (double)nf * 2 * g.nb * 2, st);
     pyin_viterbi_kernel<<<1, kVitThreads, smem, st>>>(vp);
     AC_LAUNCH_CHECK();
-    pyin_backtrack_kernel<<<1, 32, 0, st>>>(ptr, final_state, nf, g.nb, fmin, g.bps, d_f0, d_voiced_flag);
+    const size_t bt_smem = (size_t)kBtSteps * 2 * g.nb * sizeof(unsigned short);
+    AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
+    pyin_backtrack_kernel<<<1, 256, bt_smem, st>>>(ptr, final_state, nf, g.nb, fmin, g.bps, d_f0, d_voiced_flag);
     AC_LAUNCH_CHECK();
   }
   return AC_OK;

@@ -284,14 +284,20 @@ def run_b200(args):
             k["gbs"] = k["bytes"] / (k["total_ms"] * 1e6) if k["total_ms"] > 0 else 0.0
         top = kstats[0]
         tensor_bound = top["flops"] > 0
+        traffic = None  # DRAM bytes per launch of the dominant kernel class, from the committed ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = float(json.load(f)[top["name"]]["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
         if tensor_bound:
             roof = {"bound": "tensor", "kernel": top["name"], "achieved": top["tflops"], "peak": peaks["bf16_sustained"],
-                    "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"], "traffic": traffic,
                     "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                     "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"]}
         else:
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": top["gbs"] / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                    "frac": top["gbs"] / peaks["hbm"], "traffic": traffic, "peak_source": peaks["src"],
                     "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"]}
         cpu_threads = os.cpu_count() or 1
         cpu = None
