@@ -26,6 +26,7 @@ struct TdfLayer {  // GEMM A operand [M][K] (PyTorch Linear weight as is)
   int M, K;
   TcTdfWeights* tc = nullptr;
   TcTdf2PairWeights* pair = nullptr;  // CTA-pair kernel (second TDF layer of a block only)
+  TcTdf1PairWeights* pair1 = nullptr;  // CTA-pair kernel (first TDF layer of a block only)
 };
 struct Block {
   int c, T, F;
@@ -231,7 +232,8 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
     b.tdf2 = mk_tdf(bo.t2);
     if (tc_tdf_pack(bo.t1.raw, bo.t1.M, bo.t1.K, bo.c, bo.T, &b.tdf1.tc) != AC_OK ||
         tc_tdf_pack(bo.t2.raw, bo.t2.M, bo.t2.K, bo.c, bo.T, &b.tdf2.tc) != AC_OK ||
-        tc_tdf2_pair_pack(bo.t2.raw, bo.t2.M, bo.t2.K, bo.c, bo.T, &b.tdf2.pair) != AC_OK) {
+        tc_tdf2_pair_pack(bo.t2.raw, bo.t2.M, bo.t2.K, bo.c, bo.T, &b.tdf2.pair) != AC_OK ||
+        tc_tdf1_pair_pack(bo.t1.raw, bo.t1.M, bo.t1.K, bo.c, bo.T, &b.tdf1.pair1) != AC_OK) {
       ac_unet_destroy(net);
       return AC_E_CUDA;
     }
@@ -272,6 +274,7 @@ extern "C" void ac_unet_destroy(ac_unet* net) {
     ac::tc_tdf_free(b.tdf1.tc);
     ac::tc_tdf_free(b.tdf2.tc);
     ac::tc_tdf2_pair_free(b.tdf2.pair);
+    ac::tc_tdf1_pair_free(b.tdf1.pair1);
   }
   for (auto& L : net->ds) ac::tc_resample_free(L.rs);
   for (auto& L : net->us) ac::tc_resample_free(L.rs);
@@ -431,6 +434,8 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
       if (L.pair && residual && net->force_simt != 2)
         return launch_tc_tdf2_pair(L.pair, (const __nv_bfloat16*)in, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, B, b.T,
                                    L.af.scale, L.af.shift, st);
+      if (L.pair1 && !residual && net->force_simt != 2)
+        return launch_tc_tdf1_pair(L.pair1, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, b.T, L.af.scale, L.af.shift, st);
       if (L.tc)
         return launch_tc_tdf(L.tc, (const __nv_bfloat16*)in, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, B, b.T,
                              L.af.scale, L.af.shift, st);

@@ -119,72 +119,84 @@ int launch_final_conv_cg8(const void* in, void* out, long long rows, int F, int 
 
 // ---- small TDF layers on CUDA cores, CG8 in and out --------------------------------------------
 //   out[b][t][cg][m][e] = relu(scale[c] * sum_k W[m][k] * in[b][t][cg][k][e] + shift[c]) (+ res),  c = cg*8 + e
-// One CTA per group of PL (b, t, cg) planes: the planes ([K][8] bf16 each) are staged in shared
-// memory, every thread owns one output row m for all 8 channels of one plane, W rows come through L1.
-constexpr int kTdfSmallThreads = 128;
+// The whole weight matrix (<= 36 KB as fp32, transposed to [K][M] so that lanes read consecutive m) and
+// PL (b, t, cg) planes ([K][8] each) are staged in shared memory; a thread owns one output row m of one
+// plane for all 8 channels: per k one conflict-free weight read + two broadcast 16-byte plane reads.
+constexpr int kTdfSmallThreads = 256;
 __global__ void __launch_bounds__(kTdfSmallThreads) tdf_small_cg8_kernel(const __nv_bfloat16* __restrict__ in,
                                                                          const __nv_bfloat16* __restrict__ w /*[M][K]*/,
                                                                          const __nv_bfloat16* __restrict__ residual,
                                                                          __nv_bfloat16* __restrict__ out, long long n_planes,
-                                                                         int cgs, int M, int K, int PL,
+                                                                         int cgs, int M, int K, int PL, int planes_per_cta,
                                                                          const float* __restrict__ scale,
                                                                          const float* __restrict__ shift) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  float* sx = reinterpret_cast<float*>(sm_raw);  // [PL][K][8] fp32
-  const long long plane0 = (long long)blockIdx.x * PL;
-  const int npl = (int)((n_planes - plane0) < PL ? (n_planes - plane0) : PL);
-  for (int i = threadIdx.x; i < npl * K; i += blockDim.x) {
-    const uint4 q = *reinterpret_cast<const uint4*>(in + ((size_t)plane0 * K + i) * 8);
-    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
-      sx[(size_t)i * 8 + 2 * e] = v.x;
-      sx[(size_t)i * 8 + 2 * e + 1] = v.y;
-    }
+  float* sw = reinterpret_cast<float*>(sm_raw);  // [K][M]
+  float* sx = sw + (size_t)K * M;                // [PL][K][8]
+  for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+    const int m = i / K, k = i - m * K;
+    sw[(size_t)k * M + m] = __bfloat162float(w[i]);
   }
-  __syncthreads();
-  for (int o = threadIdx.x; o < npl * M; o += blockDim.x) {
-    const int pl = o / M, m = o - pl * M;
-    const float* x = sx + (size_t)pl * K * 8;
-    const __nv_bfloat16* wr = w + (size_t)m * K;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float wv = __bfloat162float(wr[k]);
-      const float4 a = *reinterpret_cast<const float4*>(x + (size_t)k * 8);
-      const float4 b = *reinterpret_cast<const float4*>(x + (size_t)k * 8 + 4);
-      acc[0] = fmaf(wv, a.x, acc[0]); acc[1] = fmaf(wv, a.y, acc[1]); acc[2] = fmaf(wv, a.z, acc[2]); acc[3] = fmaf(wv, a.w, acc[3]);
-      acc[4] = fmaf(wv, b.x, acc[4]); acc[5] = fmaf(wv, b.y, acc[5]); acc[6] = fmaf(wv, b.z, acc[6]); acc[7] = fmaf(wv, b.w, acc[7]);
-    }
-    const long long plane = plane0 + pl;
-    const int cg = (int)(plane % cgs);
-    const size_t oidx = ((size_t)plane * M + m) * 8;
-    float res[8];
-    if (residual) {
-      const uint4 q = *reinterpret_cast<const uint4*>(residual + oidx);
+  const long long first = (long long)blockIdx.x * planes_per_cta;
+  for (long long plane0 = first; plane0 < first + planes_per_cta && plane0 < n_planes; plane0 += PL) {
+    const int npl = (int)((n_planes - plane0) < PL ? (n_planes - plane0) : PL);
+    __syncthreads();  // weights staged / previous group consumed
+    for (int i = threadIdx.x; i < npl * K; i += blockDim.x) {
+      const uint4 q = *reinterpret_cast<const uint4*>(in + ((size_t)plane0 * K + i) * 8);
       const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+      float4 lo, hi;
+      float2 v;
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[0])); lo.x = v.x; lo.y = v.y;
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[1])); lo.z = v.x; lo.w = v.y;
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[2])); hi.x = v.x; hi.y = v.y;
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[3])); hi.z = v.x; hi.w = v.y;
+      *reinterpret_cast<float4*>(sx + (size_t)i * 8) = lo;
+      *reinterpret_cast<float4*>(sx + (size_t)i * 8 + 4) = hi;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < npl * M; o += blockDim.x) {
+      const int pl = o / M, m = o - pl * M;
+      const float* x = sx + (size_t)pl * K * 8;
+      const float* wc = sw + m;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        const float wv = wc[(size_t)k * M];
+        const float4 a = *reinterpret_cast<const float4*>(x + (size_t)k * 8);
+        const float4 b = *reinterpret_cast<const float4*>(x + (size_t)k * 8 + 4);
+        acc[0] = fmaf(wv, a.x, acc[0]); acc[1] = fmaf(wv, a.y, acc[1]); acc[2] = fmaf(wv, a.z, acc[2]); acc[3] = fmaf(wv, a.w, acc[3]);
+        acc[4] = fmaf(wv, b.x, acc[4]); acc[5] = fmaf(wv, b.y, acc[5]); acc[6] = fmaf(wv, b.z, acc[6]); acc[7] = fmaf(wv, b.w, acc[7]);
+      }
+      const long long plane = plane0 + pl;
+      const int cg = (int)(plane % cgs);
+      const size_t oidx = ((size_t)plane * M + m) * 8;
+      float res[8];
+      if (residual) {
+        const uint4 q = *reinterpret_cast<const uint4*>(residual + oidx);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+          res[2 * e] = v.x;
+          res[2 * e + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) res[e] = 0.f;
+      }
+      uint32_t pk[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
-        res[2 * e] = v.x;
-        res[2 * e + 1] = v.y;
+        const int c = cg * 8 + 2 * e;
+        const float v0 = fmaxf(fmaf(acc[2 * e], __ldg(scale + c), __ldg(shift + c)), 0.f) + res[2 * e];
+        const float v1 = fmaxf(fmaf(acc[2 * e + 1], __ldg(scale + c + 1), __ldg(shift + c + 1)), 0.f) + res[2 * e + 1];
+        __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        pk[e] = *reinterpret_cast<uint32_t*>(&h);
       }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) res[e] = 0.f;
+      *reinterpret_cast<uint4*>(out + oidx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    uint32_t pk[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = cg * 8 + 2 * e;
-      const float v0 = fmaxf(fmaf(acc[2 * e], __ldg(scale + c), __ldg(shift + c)), 0.f) + res[2 * e];
-      const float v1 = fmaxf(fmaf(acc[2 * e + 1], __ldg(scale + c + 1), __ldg(shift + c + 1)), 0.f) + res[2 * e + 1];
-      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-      pk[e] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(out + oidx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -193,13 +205,27 @@ int launch_tdf_small_cg8(const __nv_bfloat16* in, const __nv_bfloat16* w, const 
                          int nB, int T, int C, int M, int K, const float* scale, const float* shift, cudaStream_t st) {
   AC_REQUIRE(C % 8 == 0 && M > 0 && K > 0, "tdf small: shape");
   const long long n_planes = (long long)nB * T * (C / 8);
+  const size_t w_bytes = (size_t)M * K * 4;
+  AC_REQUIRE(w_bytes <= 64 * 1024, "tdf small: weight matrix too large for the CUDA-core kernel");
+  // planes per group: enough outputs for every thread, within ~96 KB of shared memory
   int PL = 1;
-  while (PL < 16 && (size_t)(2 * PL) * K * 32 <= 48 * 1024 && PL * M < 2 * kTdfSmallThreads) PL *= 2;
-  AC_REQUIRE((size_t)PL * K * 32 <= 48 * 1024, "tdf small: K too large for the CUDA-core kernel");
-  const size_t smem = (size_t)PL * K * 32;
-  const unsigned grid = (unsigned)((n_planes + PL - 1) / PL);
+  while (PL < 32 && w_bytes + (size_t)(2 * PL) * K * 32 <= 96 * 1024 && PL * M < 2 * kTdfSmallThreads) PL *= 2;
+  const size_t smem = w_bytes + (size_t)PL * K * 32;
+  AC_REQUIRE(smem <= 160 * 1024, "tdf small: K too large for the CUDA-core kernel");
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tdf_small_cg8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = 160 * 1024;
+  }
+  // each CTA stages the weights once and walks several plane groups: ~4 CTAs per SM in total
+  const long long groups = (n_planes + PL - 1) / PL;
+  long long ctas = 4LL * device_sm_count();
+  if (ctas > groups) ctas = groups;
+  const int planes_per_cta = (int)(((groups + ctas - 1) / ctas) * PL);
+  const unsigned grid = (unsigned)((n_planes + planes_per_cta - 1) / planes_per_cta);
   ProfScope ps(KC_TDF_SIMT, 2.0 * M * (double)K * C * T * nB, 2.0 * nB * (double)T * C * (K + M * (residual ? 2 : 1)), st);
-  tdf_small_cg8_kernel<<<grid, kTdfSmallThreads, smem, st>>>(in, w, residual, out, n_planes, C / 8, M, K, PL, scale, shift);
+  tdf_small_cg8_kernel<<<grid, kTdfSmallThreads, smem, st>>>(in, w, residual, out, n_planes, C / 8, M, K, PL, planes_per_cta, scale,
+                                                             shift);
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -99,4 +99,11 @@ void tc_tdf2_pair_free(TcTdf2PairWeights* w);
 int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                         int nB, int T, const float* scale, const float* shift, cudaStream_t st);
 
+// CTA-pair kernel for the first TDF layer (no residual); *out stays nullptr for unsupported shapes
+struct TcTdf1PairWeights;
+int tc_tdf1_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf1PairWeights** out);
+void tc_tdf1_pair_free(TcTdf1PairWeights* w);
+int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const __nv_bfloat16* in, __nv_bfloat16* out, int nB, int T, const float* scale,
+                        const float* shift, cudaStream_t st);
+
 }  // namespace ac
