@@ -17,6 +17,7 @@ struct ConvLayer {  // implicit-GEMM B operand [K][N] in both dtypes
   int K, N;
   TcConvWeights* tc = nullptr;  // tcgen05 packing (3x3 convs only)
   TcConvWsWeights* ws = nullptr;  // weight-stationary tcgen05 packing (3x3 convs, C = 48 / 96)
+  TcConvPairWeights* cp = nullptr;  // CTA-pair streaming packing (3x3 convs, C >= 144)
   TcResampleWeights* rs = nullptr;  // tcgen05 packing (down / up convs only)
 };
 struct TdfLayer {  // GEMM A operand [M][K] (PyTorch Linear weight as is)
@@ -221,6 +222,12 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
           return AC_E_CUDA;
         }
       }
+      if (tc_conv3x3_pair_supported(bo.T, bo.F, bo.c) == AC_OK) {
+        if (tc_conv3x3_pair_pack(bo.conv[j].raw, bo.c, &b.conv[j].cp) != AC_OK) {
+          ac_unet_destroy(net);
+          return AC_E_CUDA;
+        }
+      }
       if (tc_conv3x3_ws_supported(bo.T, bo.F, bo.c) == AC_OK) {
         if (tc_conv3x3_ws_pack(bo.conv[j].raw, bo.c, &b.conv[j].ws) != AC_OK) {
           ac_unet_destroy(net);
@@ -270,6 +277,7 @@ extern "C" void ac_unet_destroy(ac_unet* net) {
     {
       if (b.conv[j].tc) ac::tc_conv3x3_free(b.conv[j].tc);
       if (b.conv[j].ws) ac::tc_conv3x3_ws_free(b.conv[j].ws);
+      if (b.conv[j].cp) ac::tc_conv3x3_pair_free(b.conv[j].cp);
     }
     ac::tc_tdf_free(b.tdf1.tc);
     ac::tc_tdf_free(b.tdf2.tc);
@@ -302,12 +310,16 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
   TcConvArgs ta{(const __nv_bfloat16*)d_in, (__nv_bfloat16*)d_out, B, T, F, C, nullptr, d_scale, d_shift};
   TcConvWeights* tc = nullptr;
   TcConvWsWeights* ws = nullptr;
+  TcConvPairWeights* cp = nullptr;
   __nv_bfloat16* d_w16 = nullptr;
   int rc = AC_OK;
   if (impl == 1) {
     AC_REQUIRE(tc_conv3x3_supported(T, F, C) == AC_OK, "streaming tc conv does not support this shape");
     if ((rc = tc_conv3x3_pack(h_w, C, &tc))) return rc;
     ta.w = tc;
+  } else if (impl == 4) {
+    AC_REQUIRE(tc_conv3x3_pair_supported(T, F, C) == AC_OK, "pair streaming tc conv does not support this shape");
+    if ((rc = tc_conv3x3_pair_pack(h_w, C, &cp))) return rc;
   } else if (impl == 2 || impl == 3) {
     tc_conv3x3_ws_set_pair(impl == 3);
     AC_REQUIRE(tc_conv3x3_ws_supported(T, F, C) == AC_OK, "ws tc conv does not support this shape");
@@ -323,6 +335,7 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
   auto once = [&]() -> int {
     if (impl == 1) return launch_tc_conv3x3(ta, st);
     if (impl == 2 || impl == 3) return launch_tc_conv3x3_ws(ws, ta, st);
+    if (impl == 4) return launch_tc_conv3x3_pair(cp, ta, st);
     GemmArgs a{};
     a.M = B * T * F; a.N = C; a.K = 9 * C; a.batch = 1;
     a.a_mode = A_CONV3; a.A = d_in; a.T = T; a.F = F; a.C = C;
@@ -351,6 +364,7 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
   tc_conv3x3_ws_set_pair(1);
   if (tc) tc_conv3x3_free(tc);
   if (ws) tc_conv3x3_ws_free(ws);
+  if (cp) tc_conv3x3_pair_free(cp);
   if (d_w16) cudaFree(d_w16);
   if (rc == AC_OK && ce != cudaSuccess) {
     set_error(std::string("ac_debug_conv3x3: ") + cudaGetErrorString(ce));
@@ -418,6 +432,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     if (use_tc) {
       TcConvArgs ta{(const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, F, C, L.tc, L.af.scale, L.af.shift};
       if (L.ws && net->force_simt != 2 && tc_conv3x3_ws_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_ws(L.ws, ta, st);
+      if (L.cp && net->force_simt != 2 && tc_conv3x3_pair_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_pair(L.cp, ta, st);
       return launch_tc_conv3x3(ta, st);
     }
     GemmArgs a{};

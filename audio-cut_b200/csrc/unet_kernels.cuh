@@ -76,6 +76,13 @@ int launch_final_conv_cg8(const void* in, void* out, long long rows, int F, int 
 int launch_tdf_small_cg8(const __nv_bfloat16* in, const __nv_bfloat16* w, const __nv_bfloat16* residual, __nv_bfloat16* out,
                          int nB, int T, int C, int M, int K, const float* scale, const float* shift, cudaStream_t st);
 
+// CTA-pair streaming variant for C >= 144 (unet_tc_conv_pair.cu); *out stays nullptr for other widths
+struct TcConvPairWeights;
+int tc_conv3x3_pair_supported(int T, int F, int C);
+int tc_conv3x3_pair_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvPairWeights** out);
+void tc_conv3x3_pair_free(TcConvPairWeights* w);
+int launch_tc_conv3x3_pair(const TcConvPairWeights* w, const TcConvArgs& a, cudaStream_t st);
+
 struct TcResampleWeights;  // opaque: packed smem images of a 2x2/s2 conv (down) or transposed conv (up)
 int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeights** out);
 void tc_resample_free(TcResampleWeights* w);

@@ -1,0 +1,392 @@
+// CTA-pair (cta_group::2) streaming 3x3 convolution for the deep U-Net levels (C = 144 ... 288), whose
+// weight tensors (373 KB ... 1.5 MB) cannot stay in shared memory.
+//
+// The single-CTA streaming kernel (unet_tc.cu) is L2 -> shared-memory ingest bound there: per pipeline
+// step a CTA fetches MT input tiles AND the complete [3 taps][KC][N] weight slab (79 KB per 1944 MMA
+// cycles at C = 144; ncu: tensor pipe 52 % active).  As a CTA pair (M = 256 = one 128-position tile per
+// CTA, full N) each CTA fetches only the weights of ITS N/2 output channels - the half of B the pair
+// MMA reads from this CTA - so the weight stream per CTA halves while every MMA does twice the work.
+// Everything else follows unet_tc.cu (output-stationary implicit GEMM, [KC/8][130][8] TMA tiles whose
+// three horizontal taps are 16-byte descriptor shifts, MT accumulators per weight fetch) and the pair
+// protocol of unet_tc_conv_ws.cu (leader-side full barriers fed by both CTAs' TMA, multicast commits,
+// relaxed remote TMEM release).
+#include <vector>
+
+#include "tc_common.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+constexpr int kCpEpiGroups = 3;
+constexpr int kCpEpiWarps = 4 * kCpEpiGroups;
+constexpr int kCpThreads = (2 + kCpEpiWarps) * 32;
+constexpr int kCpHeader = 5120;
+constexpr int kCpTileM = 128;
+constexpr int kCpRowPos = kCpTileM + 2;
+constexpr int kCpMaxStages = 8;
+
+struct CpCfg {
+  int C, NT, nsplit, MT, KC, nkc, stages, nbuf;
+  int a_tile_bytes;   // (KC/8) * 130 * 16 rounded up to 128
+  int b_tap_bytes;    // KC * (NT/2) * 2: one horizontal tap of this CTA's half of the weights
+  int stage_bytes;    // MT * a_tile_bytes + 3 * b_tap_bytes
+  int smem_bytes;
+};
+
+struct CpParams {
+  CpCfg cfg;
+  int nB, T, F;
+  int n_fg;      // groups of 2*MT tiles per row (the pair's strip)
+  int n_units;   // nsplit * nB * T * n_fg
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out;
+  int* abort_flag;
+};
+
+__device__ __forceinline__ void cp_tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kCpThreads, 1)
+tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const CpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const CpCfg& c = p.cfg;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [stages]  leader: both CTAs' stage landed
+  uint64_t* empty = full + kCpMaxStages;                // [stages]
+  uint64_t* tfull = empty + kCpMaxStages;               // [2]
+  uint64_t* tempty = tfull + 2;                         // [2]       leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [C] (<= 512)
+  float* s_shift = s_scale + 512;
+  uint8_t* stage0 = smem + kCpHeader;
+  volatile int* abort_flag = p.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  for (int i = threadIdx.x; i < c.C; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < c.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 2 * kCpEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int steps = 3 * c.nkc;  // (dt, channel chunk) pipeline steps per unit
+  const int b_rows = c.b_tap_bytes / 128;  // rows of the weight tensor map per tap
+
+  auto decode = [&](int u, int& nt, int& b, int& t, int& f0) {
+    const int fg = u % p.n_fg;
+    int q = u / p.n_fg;
+    t = q % p.T;
+    q /= p.T;
+    b = q % p.nB;
+    nt = q / p.nB;
+    f0 = fg * (2 * c.MT * kCpTileM);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own tiles + own half of the weights =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (int u = pair; u < p.n_units && alive; u += n_pairs) {
+        int nt, b, t, f0;
+        decode(u, nt, b, t, f0);
+        for (int dt = 0; dt < 3 && alive; ++dt) {
+          for (int kc = 0; kc < c.nkc; ++kc) {
+            if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+            if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)(c.MT * (c.KC / 8) * (kCpRowPos * 16) + 3 * c.b_tap_bytes));
+            const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+            uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
+            for (int mt = 0; mt < c.MT; ++mt)
+              tma_load_5d_2sm(st + mt * c.a_tile_bytes, &in_map, bar, 0, f0 + (2 * mt + (int)rank) * kCpTileM - 1, kc * (c.KC / 8),
+                              t + dt - 1, b);
+            // weights: slab (nt, rank, dt, kc) = 3 taps of b_rows rows each
+            const int slab = ((nt * 2 + (int)rank) * 3 + dt) * c.nkc + kc;
+            for (int df = 0; df < 3; ++df)
+              cp_tma_load_2d_2sm(st + c.MT * c.a_tile_bytes + df * c.b_tap_bytes, &w_map, bar, 0, (slab * 3 + df) * b_rows);
+            if (++s == c.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader; warp-uniform loop, one elected lane issues) =====================
+    if (leader) {
+      const uint32_t idesc = make_idesc_2sm(c.NT);
+      const uint32_t a_lbo = kCpRowPos * 16, b_lbo = (uint32_t)(c.NT / 2) * 16;
+      const uint64_t a_proto = make_desc(0, a_lbo, 128), b_proto = make_desc(0, b_lbo, 128);
+      auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+        return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+      };
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t n_acc = 0;
+      bool alive = true;
+      for (int u = pair; u < p.n_units && alive; u += n_pairs, ++n_acc) {
+        const int buf = c.nbuf == 2 ? (int)(n_acc & 1) : 0;
+        const uint32_t use = c.nbuf == 2 ? (n_acc >> 1) : n_acc;
+        if (!wait_all(&tempty[buf], (use & 1) ^ 1)) break;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * c.MT * c.NT);
+        for (int step = 0; step < steps; ++step) {
+          if (!wait_all(&full[s], ph)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
+          const uint32_t sb = sa + (uint32_t)(c.MT * c.a_tile_bytes);
+          if (elect_one()) {
+            for (int df = 0; df < 3; ++df) {
+              for (int mt = 0; mt < c.MT; ++mt) {
+                const uint64_t ad0 = a_proto + ((sa + mt * c.a_tile_bytes + df * 16) >> 4);
+                const uint64_t bd0 = b_proto + ((sb + df * c.b_tap_bytes) >> 4);
+                const uint32_t acc = acc0 + (uint32_t)(mt * c.NT);
+                for (int k = 0; k < c.KC / 16; ++k) {
+                  if ((step | df | k) == 0)
+                    umma_f16_2sm<false>(acc, ad0 + (uint64_t)((k * 2 * a_lbo) >> 4), bd0 + (uint64_t)((k * 2 * b_lbo) >> 4), idesc);
+                  else
+                    umma_f16_2sm<true>(acc, ad0 + (uint64_t)((k * 2 * a_lbo) >> 4), bd0 + (uint64_t)((k * 2 * b_lbo) >> 4), idesc);
+                }
+              }
+            }
+            umma_commit_2sm(&empty[s]);
+            if (step == steps - 1) umma_commit_2sm(&tfull[buf]);
+          }
+          __syncwarp();
+          if (++s == c.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (12 warps per CTA: own tiles, all NT channels) =====================
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const size_t plane = (size_t)p.F * 8;
+    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
+    uint32_t n_acc = 0;
+    for (int u = pair; u < p.n_units; u += n_pairs, ++n_acc) {
+      const int buf = c.nbuf == 2 ? (int)(n_acc & 1) : 0;
+      const uint32_t use = c.nbuf == 2 ? (n_acc >> 1) : n_acc;
+      int nt, b, t, f0;
+      decode(u, nt, b, t, f0);
+      const int n0 = nt * c.NT;
+      if (!mbar_wait(&tfull[buf], use & 1, abort_flag)) break;
+      tc_fence_after();
+      for (int mt = 0; mt < c.MT; ++mt) {
+        const int f = f0 + (2 * mt + (int)rank) * kCpTileM + quad * 32 + lane;
+        const bool valid = f < p.F;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
+        __nv_bfloat16* dst = p.out + cg8_index(b, t, n0 >> 3, valid ? f : 0, p.T, c.C, p.F);
+        for (int j = grp * 16; j < c.NT; j += 16 * kCpEpiGroups) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j, r);
+          tmem_ld_wait();
+          if (valid) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = n0 + j + 2 * e;
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + (size_t)((j >> 3) + 1) * plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcConvPairWeights {
+  int C;
+  CpCfg cfg;
+  __nv_bfloat16* d_pack;
+  size_t pack_elems;
+};
+
+static bool cp_make_cfg(int C, int F, CpCfg& c) {
+  if (C % 48 || C < 144 || C > 512) return false;  // C = 48 / 96 have the weight-stationary kernels
+  c.C = C;
+  c.nsplit = 0;
+  for (int s = 1; s <= 4; ++s)
+    if (C % (32 * s) == 0 && C / s <= 256) { c.nsplit = s; break; }  // N/2 must be a multiple of 8 (N % 16 for M = 256 -> % 32)
+  if (!c.nsplit) {
+    for (int s = 1; s <= 4; ++s)
+      if (C % (16 * s) == 0 && C / s <= 256) { c.nsplit = s; break; }
+  }
+  if (!c.nsplit) return false;
+  c.NT = C / c.nsplit;
+  if (c.NT % 16 || (c.NT / 2) % 8) return false;
+  c.MT = 512 / c.NT;
+  if (c.MT > 4) c.MT = 4;
+  const int tiles_per_row = (F + kCpTileM - 1) / kCpTileM;
+  if (tiles_per_row < 2) return false;  // a single 128-position tile per row would leave the peer CTA idle
+  const int pair_tiles = (tiles_per_row + 1) / 2;
+  if (c.MT > pair_tiles) c.MT = pair_tiles;
+  if (c.MT < 1) return false;
+  c.nbuf = (2 * c.MT * c.NT <= 512) ? 2 : 1;
+  c.KC = 48;
+  c.nkc = C / c.KC;
+  c.a_tile_bytes = (int)align_up((size_t)(c.KC / 8) * kCpRowPos * 16, 128);
+  c.b_tap_bytes = c.KC * (c.NT / 2) * 2;
+  if (c.b_tap_bytes % 128 || c.b_tap_bytes / 128 > 256) return false;
+  c.stage_bytes = c.MT * c.a_tile_bytes + 3 * c.b_tap_bytes;
+  c.stages = (226 * 1024 - kCpHeader) / c.stage_bytes;
+  if (c.stages > kCpMaxStages) c.stages = kCpMaxStages;
+  if (c.stages < 2) return false;
+  c.smem_bytes = kCpHeader + c.stages * c.stage_bytes;
+  return true;
+}
+
+int tc_conv3x3_pair_supported(int T, int F, int C) {
+  CpCfg c;
+  (void)T;
+  return cp_make_cfg(C, F, c) ? AC_OK : AC_E_INVALID;
+}
+
+int tc_conv3x3_pair_pack(const float* h_w, int C, TcConvPairWeights** out) {
+  *out = nullptr;
+  CpCfg c;
+  if (!cp_make_cfg(C, 1 << 20, c)) return AC_OK;
+  // [nt][rank][dt][kc][df][KC/8][NT/2][8]  <-  W[co][ci][kh=dt][kw=df]
+  const int NH = c.NT / 2;
+  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  size_t o = 0;
+  for (int nt = 0; nt < c.nsplit; ++nt)
+    for (int r = 0; r < 2; ++r)
+      for (int dt = 0; dt < 3; ++dt)
+        for (int kc = 0; kc < c.nkc; ++kc)
+          for (int df = 0; df < 3; ++df)
+            for (int kg = 0; kg < c.KC / 8; ++kg)
+              for (int n = 0; n < NH; ++n)
+                for (int e = 0; e < 8; ++e) {
+                  const int co = nt * c.NT + r * NH + n, ci = kc * c.KC + kg * 8 + e;
+                  pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df]);
+                }
+  TcConvPairWeights* w = new TcConvPairWeights();
+  w->C = C;
+  w->d_pack = nullptr;
+  w->pack_elems = pack.size();
+  if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
+      cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tc pair conv weight upload failed");
+    delete w;
+    return AC_E_CUDA;
+  }
+  *out = w;
+  return AC_OK;
+}
+
+void tc_conv3x3_pair_free(TcConvPairWeights* w) {
+  if (!w) return;
+  if (w->d_pack) cudaFree(w->d_pack);
+  delete w;
+}
+
+int launch_tc_conv3x3_pair(const TcConvPairWeights* w, const TcConvArgs& a, cudaStream_t st) {
+  AC_REQUIRE(w && w->C == a.C, "tc pair conv: weights do not match the layer");
+  CpCfg c;
+  AC_REQUIRE(cp_make_cfg(a.C, a.F, c), "tc pair conv: unsupported shape");
+  EncodeTiledFn enc = get_tensor_map_encoder();
+  AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
+  AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMap in_map, w_map;
+  {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)a.F, (cuuint64_t)(a.C / 8), (cuuint64_t)a.T, (cuuint64_t)a.nB};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)a.F * 16, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
+    const cuuint32_t box[5] = {8, (cuuint32_t)kCpRowPos, (cuuint32_t)(c.KC / 8), 1, 1};
+    CUresult r = enc(&in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (pair conv, input) failed with code " + std::to_string((int)r));
+      return AC_E_CUDA;
+    }
+  }
+  {
+    // packed weights as rows of 64 bf16 (128 B); one tap of one slab = b_tap_bytes / 128 consecutive rows
+    const cuuint64_t dims[2] = {64, (cuuint64_t)(w->pack_elems / 64)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(c.b_tap_bytes / 128)};
+    CUresult r = enc(&w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w->d_pack, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (pair conv, weights) failed with code " + std::to_string((int)r));
+      return AC_E_CUDA;
+    }
+  }
+  CpParams p;
+  p.cfg = c;
+  p.nB = a.nB; p.T = a.T; p.F = a.F;
+  const int tiles = (a.F + kCpTileM - 1) / kCpTileM;
+  p.n_fg = (tiles + 2 * c.MT - 1) / (2 * c.MT);
+  p.n_units = c.nsplit * a.nB * a.T * p.n_fg;
+  p.scale = a.scale; p.shift = a.shift;
+  p.out = a.out;
+  p.abort_flag = tc_abort_flag();
+  static bool attr_set = false;
+  if (!attr_set) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int pairs = device_sm_count() / 2;
+  if (pairs > p.n_units) pairs = p.n_units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kCpThreads);
+  cfg.dynamicSmemBytes = c.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
+  AC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv3x3_pair_kernel, in_map, w_map, p));
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac

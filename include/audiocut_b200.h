@@ -120,7 +120,8 @@ AC_API int ac_unet_set_debug(ac_unet* net, int force_simt);
 /* Test / profiling hook: one bf16 3x3 convolution layer y = relu(scale * conv(x, W) + shift).
  * impl: 0 = CUDA-core implicit GEMM on channels-last [B][T][F][C] tensors; 1 = streaming tcgen05
  * kernel, 2 = weight-stationary tcgen05 kernel (C = 48 / 96), 3 = the same with the CTA-pair
- * (cta_group::2) kernel where one exists (C = 96), all on the tensor-core path's
+ * (cta_group::2) kernel where one exists (C = 96), 4 = CTA-pair streaming kernel (C >= 144), all on the
+ * tensor-core path's
  * channel-group planar layout [B][T][C/8][F][8] for input and output.  h_w = W[C][C][3][3] float32 on the
  * host.  Runs `iters` launches; *h_ms (optional) = mean ms of launches 2..iters.  Synchronises. */
 AC_API int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int F, int C, const float* h_w,
