@@ -322,6 +322,7 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
     if ((rc = tc_conv3x3_pair_pack(h_w, C, &cp))) return rc;
   } else if (impl == 2 || impl == 3) {
     tc_conv3x3_ws_set_pair(impl == 3);
+    tc_conv3x3_ws_set_rs(impl == 3);
     AC_REQUIRE(tc_conv3x3_ws_supported(T, F, C) == AC_OK, "ws tc conv does not support this shape");
     if ((rc = tc_conv3x3_ws_pack(h_w, C, &ws))) return rc;
   } else {
@@ -362,6 +363,7 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
     cudaEventDestroy(e1);
   }
   tc_conv3x3_ws_set_pair(1);
+  tc_conv3x3_ws_set_rs(0);
   if (tc) tc_conv3x3_free(tc);
   if (ws) tc_conv3x3_ws_free(ws);
   if (cp) tc_conv3x3_pair_free(cp);

@@ -63,6 +63,7 @@ int tc_conv3x3_ws_supported(int T, int F, int C);
 int tc_conv3x3_ws_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWsWeights** out);
 void tc_conv3x3_ws_free(TcConvWsWeights* w);
 int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStream_t st);
+void tc_conv3x3_ws_set_rs(int enabled);    // test hook: 0 = never use the row-stacked (N = 144) kernel for C = 48
 void tc_conv3x3_ws_set_pair(int enabled);  // test hook: 0 = never use the CTA-pair (cta_group::2) kernel
 
 // CUDA-core pieces of the CG8 path (unet_cg8.cu)

@@ -542,12 +542,279 @@ tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-stacked variant for C = 48 ("rs"): the three VERTICAL taps are stacked along N.
+//
+// With N = 48 an SS-MMA spends 44 cycles reading its operands for 24 cycles of math (ncu: L1/smem 80 %
+// busy, tensor pipe 44 %).  Input row r contributes to output rows r+1, r, r-1 through the taps dt = 0, 1, 2
+// at the SAME position, so one MMA of N = 144 with the weight columns ordered (dt, co) computes all three
+// contributions of row r from one read of the A tile - provided the accumulators of the output rows
+// r+1, r, r-1 sit side by side in TMEM.  They do: every M tile owns a ring of kRsBlocks 48-column blocks,
+// output row x lives in block (-x mod kRsBlocks), so the three rows touched by step g are consecutive
+// blocks (a window that straddles the end of the ring is issued as two MMAs).  Blocks are handed back
+// ZEROED by the epilogue (tcgen05.st), so every MMA accumulates and no flag has to differ across N.
+// An input row is now used by exactly one step: the rolling row ring becomes a plain stream.
+//   per 128 positions: 9 MMAs x 72 cycles (tensor bound) instead of 27 x 44 (shared-memory bound).
+// Virtual step index g runs over (rows + 4) steps per segment: rows + 2 real input rows (with the two halo
+// rows) and two empty steps that flush the last two blocks; block x is complete after step x + 1.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRsBlocks = 5;
+constexpr int kRsMT = 2;
+constexpr int kRsSlots = 6;
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+tc_conv3x3_rs_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams p) {
+  constexpr int C = 48, NT = 48, MT = kRsMT, RB = kRsBlocks, RA = kRsSlots;
+  constexpr int kALbo = kWsRowPos * 16;
+  constexpr int kATile = ((C / 8) * kALbo + 127) / 128 * 128;
+  constexpr int kSlot = MT * kATile;
+  constexpr int kBLbo = 3 * NT * 16;              // rows of B = (dt, co): 144 rows of 16 B per channel group
+  constexpr int kDfBytes = (C / 8) * kBLbo;        // one horizontal tap: [C/8][144][8]
+  constexpr int kWBytes = 3 * kDfBytes;
+  constexpr int K16 = C / 16;
+  constexpr int kTileCols = RB * NT;               // TMEM columns of one M tile's block ring
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [RA]
+  uint64_t* empty = full + kWsMaxR;                     // [RA]
+  uint64_t* done = full + 2 * kWsMaxR;                  // [RB]  MMA -> epilogue: block complete
+  uint64_t* bfree = done + 8;                           // [RB]  epilogue -> MMA: block drained and zeroed
+  uint64_t* wbar = bfree + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* s_scale = reinterpret_cast<float*>(smem + 512);  // [NT]
+  float* s_shift = s_scale + 64;
+  uint8_t* w_smem = smem + 1024;
+  uint8_t* ring = w_smem + kWBytes;
+  volatile int* abort_flag = p.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long lo, hi;
+  ws_range(p, gridDim.x, blockIdx.x, lo, hi);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RA; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < RB; ++b) {
+      mbar_init(&done[b], 1);
+      mbar_init(&bfree[b], kWsEpiWarps);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < NT; i += blockDim.x) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weights once, then one slot per input row =====================
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)kWBytes);
+      for (int df = 0; df < 3; ++df)
+        bulk_load_1d(w_smem + df * kDfBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)df * kDfBytes, kDfBytes, wbar);
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (long long L = lo; L < hi && alive;) {
+        const WsSeg sg = ws_segment(p, L, hi);
+        for (int r = sg.t0 - 1; r <= sg.t1; ++r) {
+          if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+          uint8_t* dst = ring + (size_t)s * kSlot;
+          mbar_expect_tx(&full[s], (uint32_t)(MT * (C / 8) * kWsRowPos * 16));
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_5d(dst + mt * kATile, &in_map, &full[s], 0, sg.f0 + mt * kWsTileM - 1, 0, r, sg.b);
+          if (++s == RA) { s = 0; ph ^= 1; }
+        }
+        L += sg.t1 - sg.t0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc144 = make_idesc(144), idesc96 = make_idesc(96), idesc48 = make_idesc(48);
+    const uint64_t a_proto = make_desc(0, kALbo, 128), b_proto = make_desc(0, kBLbo, 128);
+    const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
+    const uint32_t b_lo0 = (uint32_t)b_proto + (smem_u32(w_smem) >> 4);
+    auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+      return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+    };
+    bool alive = wait_all(wbar, 0);
+    // the epilogue warps zero the block ring before the first MMA (named barrier 1: 12 epilogue warps + this warp)
+    asm volatile("bar.sync 1, %0;" ::"r"((kWsEpiWarps + 1) * 32) : "memory");
+    tc_fence_after();
+    int s = 0;
+    uint32_t ph = 0;
+    int gm = 0;         // g mod RB
+    uint32_t cyc = 0;   // g / RB
+    for (long long L = lo; L < hi && alive;) {
+      const WsSeg sg = ws_segment(p, L, hi);
+      const int rows = sg.t1 - sg.t0;
+      for (int v = 0; v < rows + 4 && alive; ++v) {
+        // virtual step g touches output indices g+1, g, g-1 = blocks sb, sb+1, sb+2 (mod RB), sb = (-(g+1)) mod RB
+        const int sb = RB - 1 - gm;
+        // Index g+1 enters block sb at this step (also at the two empty steps, so that every index is entered in
+        // order): its n earlier owners (indices g+1-RB, ...; the ring starts zeroed, owners start at index -1)
+        // must have been drained and zeroed: n = floor((g + 2) / RB).
+        {
+          const uint32_t n = (gm + 2 >= RB) ? cyc + 1 : cyc;
+          if (n > 0 && !wait_all(&bfree[sb], (n - 1) & 1)) { alive = false; break; }
+        }
+        if (v < rows + 2) {
+          if (!wait_all(&full[s], ph)) { alive = false; break; }
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * (kSlot >> 4);
+            const int n1 = (sb + 3 <= RB) ? 3 : RB - sb;  // blocks before the ring wraps
+#pragma unroll
+            for (int df = 0; df < 3; ++df) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t d0 = tmem_base + (uint32_t)(mt * kTileCols + sb * NT);
+                const uint32_t d1 = tmem_base + (uint32_t)(mt * kTileCols);
+#pragma unroll
+                for (int k = 0; k < K16; ++k) {
+                  const uint64_t ad = desc_at(a_lo, a_hi, mt * kATile + df * 16 + k * 2 * kALbo);
+                  const uint32_t boff = df * kDfBytes + k * 2 * kBLbo;
+                  if (n1 == 3) {
+                    umma_f16_c<true>(d0, ad, desc_at(b_lo0, b_hi, boff), idesc144);
+                  } else if (n1 == 2) {
+                    umma_f16_c<true>(d0, ad, desc_at(b_lo0, b_hi, boff), idesc96);
+                    umma_f16_c<true>(d1, ad, desc_at(b_lo0, b_hi, boff + 2 * NT * 16), idesc48);
+                  } else {
+                    umma_f16_c<true>(d0, ad, desc_at(b_lo0, b_hi, boff), idesc48);
+                    umma_f16_c<true>(d1, ad, desc_at(b_lo0, b_hi, boff + NT * 16), idesc96);
+                  }
+                }
+              }
+            }
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
+          if (++s == RA) { s = 0; ph ^= 1; }
+        }
+        // output index g-1 (block sb+2 mod RB) is complete after this step
+        if (elect_one()) umma_commit(&done[(sb + 2) % RB]);
+        __syncwarp();
+        if (++gm == RB) { gm = 0; ++cyc; }
+      }
+      L += rows;
+    }
+  } else {
+    // ===================== epilogue (warps 2..13): drain + zero one block per virtual step =====================
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;  // channels [16*grp, +16)
+    float sc[16], sh[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      sc[e] = s_scale[grp * 16 + e];
+      sh[e] = s_shift[grp * 16 + e];
+    }
+    const size_t plane = (size_t)p.F * 8;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 16);
+    // the ring starts zeroed: every warp clears its 16 columns of every block of both tiles
+    {
+      const uint32_t z = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < MT * kTileCols; c0 += NT)
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(lane_addr + c0),
+            "r"(z)
+            : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+    }
+    // every warp has zeroed its columns before the first MMA: named barrier 1 = 12 epilogue warps + the MMA warp
+    asm volatile("bar.sync 1, %0;" ::"r"((kWsEpiWarps + 1) * 32) : "memory");
+    uint32_t uses[RB];   // completions of each block seen so far (parity of its `done` barrier)
+#pragma unroll
+    for (int b = 0; b < RB; ++b) uses[b] = 0;
+    // virtual output index x runs in lockstep with the MMA warp: one drained block per virtual step, in order
+    int blk = 1 % RB;    // first drained index is x = g - 1 with g = 0  ->  x = -1  ->  block (1 mod RB)
+    bool alive = true;
+    for (long long L = lo; L < hi && alive;) {
+      const WsSeg sg = ws_segment(p, L, hi);
+      const int rows = sg.t1 - sg.t0;
+      for (int v = 0; v < rows + 4; ++v) {
+        // step v completes output row t = t0 + v - 2 (valid for 2 <= v < rows + 2)
+        const int t = sg.t0 + v - 2;
+        const bool store = v >= 2 && v < rows + 2;
+        uint32_t u = 0;
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+          if (b == blk) u = uses[b];
+        if (!mbar_wait(&done[blk], u & 1, abort_flag)) { alive = false; break; }
+        tc_fence_after();
+        uint32_t r[MT][16];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) tmem_ld16(lane_addr + (uint32_t)(mt * kTileCols + blk * NT), r[mt]);
+        tmem_ld_wait();
+        {
+          const uint32_t z = 0;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+                    lane_addr + (uint32_t)(mt * kTileCols + blk * NT)),
+                "r"(z)
+                : "memory");
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(&bfree[blk]);
+        if (store) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int f = sg.f0 + mt * kWsTileM + quad * 32 + lane;
+            if (f < p.F) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float v0 = fmaxf(fmaf(__uint_as_float(r[mt][2 * e]), sc[2 * e], sh[2 * e]), 0.f);
+                const float v1 = fmaxf(fmaf(__uint_as_float(r[mt][2 * e + 1]), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              __nv_bfloat16* dst = p.out + cg8_index(sg.b, t, grp * 2, f, p.T, C, p.F);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+          if (b == blk) uses[b] += 1;
+        blk = blk == 0 ? RB - 1 : blk - 1;  // next index x+1 lives in block blk-1
+      }
+      L += rows;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TcConvWsWeights {
   int C;
   WsCfg cfg;
   __nv_bfloat16* d_pack;
+  __nv_bfloat16* d_pack_rs = nullptr;  // C = 48: row-stacked packing
 };
 
 static bool ws_make_cfg(int C, int F, WsCfg& c) {
@@ -579,6 +846,8 @@ int tc_conv3x3_ws_supported(int T, int F, int C) {
   return ws_make_cfg(C, F, c) ? AC_OK : AC_E_INVALID;
 }
 
+static int ws_pack_rs(const float* h_w, __nv_bfloat16** d_out);
+
 int tc_conv3x3_ws_pack(const float* h_w, int C, TcConvWsWeights** out) {
   *out = nullptr;
   WsCfg c;
@@ -604,17 +873,49 @@ int tc_conv3x3_ws_pack(const float* h_w, int C, TcConvWsWeights** out) {
     delete w;
     return AC_E_CUDA;
   }
+  if (C == 48 && ws_pack_rs(h_w, &w->d_pack_rs) != AC_OK) {
+    cudaFree(w->d_pack);
+    delete w;
+    return AC_E_CUDA;
+  }
   *out = w;
   return AC_OK;
 }
 
 void tc_conv3x3_ws_free(TcConvWsWeights* w) {
   if (!w) return;
+  if (w->d_pack_rs) cudaFree(w->d_pack_rs);
   if (w->d_pack) cudaFree(w->d_pack);
   delete w;
 }
 
+// row-stacked packing for C = 48: [df][C/8][dt*48 + co][8]
+static int ws_pack_rs(const float* h_w, __nv_bfloat16** d_out) {
+  const int C = 48;
+  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  size_t o = 0;
+  for (int df = 0; df < 3; ++df)
+    for (int kg = 0; kg < C / 8; ++kg)
+      for (int dt = 0; dt < 3; ++dt)
+        for (int co = 0; co < C; ++co)
+          for (int e = 0; e < 8; ++e)
+            pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + kg * 8 + e) * 3 + dt) * 3 + df]);
+  *d_out = nullptr;
+  if (cudaMalloc(d_out, pack.size() * 2) != cudaSuccess ||
+      cudaMemcpy(*d_out, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tc rs weight upload failed");
+    return AC_E_CUDA;
+  }
+  return AC_OK;
+}
+
 static bool g_ws_pair_enabled = true;
+// Off by default: at C = 48 the weight-stationary kernel already runs at the practical HBM rate (4.2 TB/s of
+// algorithmic traffic, the streaming 1x1 kernels reach 4.7-4.9), so removing its shared-memory bottleneck
+// changes nothing measurable (572 vs 576 us per 16-window layer, bit-identical output).  Kept as the
+// tensor-bound formulation for narrower channel counts / faster memory; exercised by the tests.
+static bool g_ws_rs_enabled = false;
+void tc_conv3x3_ws_set_rs(int enabled) { g_ws_rs_enabled = enabled != 0; }
 void tc_conv3x3_ws_set_pair(int enabled) { g_ws_pair_enabled = enabled != 0; }
 
 int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStream_t st) {
@@ -668,6 +969,19 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     AC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map, p));
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+  }
+  if (g_ws_rs_enabled && a.C == 48 && w->d_pack_rs && (a.F + kWsTileM - 1) / kWsTileM >= kRsMT) {
+    p.cfg.MT = kRsMT;
+    p.n_strips = ((a.F + kWsTileM - 1) / kWsTileM + kRsMT - 1) / kRsMT;
+    p.total_rows = (long long)a.nB * p.n_strips * a.T;
+    p.wpack = w->d_pack_rs;
+    const int smem = 1024 + 9 * 48 * 48 * 2 + kRsSlots * kRsMT * c.a_tile_bytes;
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int grid = device_sm_count();
+    if ((long long)grid > p.total_rows) grid = (int)p.total_rows;
+    tc_conv3x3_rs_kernel<<<grid, kWsThreads, smem, st>>>(map, p);
     AC_LAUNCH_CHECK();
     return AC_OK;
   }

@@ -264,6 +264,24 @@ def test_unet_tcgen05_matches_simt(ops, dim_f, dim_t, g, B):
     assert s_ref > 30, s_ref
 
 
+@pytest.mark.parametrize("C,T,F,impls", [(48, 24, 640, (2, 3)), (96, 16, 512, (2, 3)), (144, 12, 384, (1, 4)), (192, 8, 256, (1, 4))])
+def test_conv3x3_variants_match_cuda_core_layer(ops, C, T, F, impls):
+    """Layer-level check of every tcgen05 3x3-conv kernel against the CUDA-core implicit GEMM (same bf16
+    inputs, fp32 accumulation): 1 streaming, 2 weight-stationary, 3 row-stacked (C=48) / CTA pair (C=96),
+    4 CTA-pair streaming."""
+    rng = np.random.default_rng(C)
+    x = torch.randn(3, T, F, C, device="cuda").bfloat16()
+    w = (rng.standard_normal((C, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32)
+    scale = torch.rand(C, device="cuda") + 0.5
+    shift = torch.randn(C, device="cuda") * 0.1
+    ref, _ = ops.debug_conv3x3(x, w, scale, shift, 0)
+    for impl in impls:
+        y, _ = ops.debug_conv3x3(x, w, scale, shift, impl)
+        assert _tc_aborted() == 0
+        s = sdr_db(ref.float().cpu().numpy(), y.float().cpu().numpy())
+        assert s > 60, (impl, s)
+
+
 def test_unet_tcgen05_full_geometry(ops):
     net, x, ref = _unet_case(ops, 3072, 256, 48, 1)
     tc = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()).bfloat16())).float().cpu()
