@@ -145,4 +145,75 @@ __device__ __forceinline__ float2* fft_smem(float2* buf0, float2* buf1, const Ff
   return in;
 }
 
+// ---- in-place variant: ONE shared-memory buffer --------------------------------------------------
+// A Stockham pass reads and writes different index patterns, so the two-buffer version above ping-pongs.
+// Here every thread first pulls ALL the butterflies it owns in this pass into registers (N / blockDim
+// complex values, <= 16), the CTA synchronises, and the results go back into the same buffer.  Halving
+// the footprint (61 KB instead of 123 KB at n_fft = 7680) is what lets three STFT CTAs share an SM and
+// hide each other's shared-memory / twiddle latency.
+template <int R, bool INV, int MAXB>
+__device__ __forceinline__ void fft_pass_inplace(float2* __restrict__ buf, int n, int Ns, const float2* __restrict__ tw) {
+  const int nb = n / R;
+  const int tmul = n / (Ns * R);
+  float2 v[MAXB][R];
+#pragma unroll
+  for (int i = 0; i < MAXB; ++i) {
+    const int j = threadIdx.x + i * blockDim.x;
+    if (j < nb) {
+      const int k = j % Ns;
+      const int ts = k * tmul;
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[i][r] = buf[fpad(j + r * nb)];
+      if (k != 0) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+          float2 w = __ldg(&tw[r * ts]);
+          if (INV) w.y = -w.y;
+          v[i][r] = cmul(v[i][r], w);
+        }
+      }
+      dft_small<R, INV>(v[i]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MAXB; ++i) {
+    const int j = threadIdx.x + i * blockDim.x;
+    if (j < nb) {
+      const int k = j % Ns;
+      const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) buf[fpad(j0 + r * Ns)] = v[i][r];
+    }
+  }
+  __syncthreads();
+}
+
+// true when fft_smem_inplace can run this plan with `threads` threads per CTA (register staging bound)
+inline bool fft_inplace_ok(const FftPlan* p, int threads) {
+  for (int s = 0; s < p->n_radix; ++s) {
+    const int R = p->radix[s];
+    const int maxb = R == 2 ? 8 : (R == 3 ? 5 : (R == 4 ? 4 : (R == 5 ? 3 : 2)));
+    if ((p->n / R + threads - 1) / threads > maxb) return false;
+  }
+  return true;
+}
+
+// In-place transform of the n points in buf (index through fpad); result in natural order in buf.
+template <bool INV>
+__device__ __forceinline__ void fft_smem_inplace(float2* buf, const FftDev& p) {
+  int Ns = 1;
+  for (int s = 0; s < p.n_radix; ++s) {
+    const int R = p.radix[s];
+    switch (R) {
+      case 2: fft_pass_inplace<2, INV, 8>(buf, p.n, Ns, p.tw); break;
+      case 3: fft_pass_inplace<3, INV, 5>(buf, p.n, Ns, p.tw); break;
+      case 4: fft_pass_inplace<4, INV, 4>(buf, p.n, Ns, p.tw); break;
+      case 5: fft_pass_inplace<5, INV, 3>(buf, p.n, Ns, p.tw); break;
+      default: fft_pass_inplace<8, INV, 2>(buf, p.n, Ns, p.tw); break;
+    }
+    Ns *= R;
+  }
+}
+
 }  // namespace ac

@@ -88,8 +88,8 @@ __device__ __forceinline__ float4 load_spec4(const __nv_bfloat16* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kFftThreads) stft_mdx_kernel(const float* __restrict__ src, long long ch_stride,
+template <typename T, bool kInplace>
+__global__ void __launch_bounds__(kFftThreads, kInplace ? 2 : 1) stft_mdx_kernel(const float* __restrict__ src, long long ch_stride,
                                                                int n_ch, const WinDesc* __restrict__ wins, FftDev fft,
                                                                const float* __restrict__ hann, int hop, int dim_f,
                                                                int dim_t, int W, T* __restrict__ spec) {
@@ -115,7 +115,13 @@ __global__ void __launch_bounds__(kFftThreads) stft_mdx_kernel(const float* __re
     buf0[fpad(j)] = make_float2(l * w, r * w);
   }
   __syncthreads();
-  const float2* Z = fft_smem<false>(buf0, buf1, fft);
+  const float2* Z;
+  if constexpr (kInplace) {
+    fft_smem_inplace<false>(buf0, fft);
+    Z = buf0;
+  } else {
+    Z = fft_smem<false>(buf0, buf1, fft);
+  }
   T* out = spec + ((size_t)blockIdx.y * dim_t + t) * (size_t)dim_f * 4;
   for (int k = threadIdx.x; k < dim_f; k += kFftThreads) {
     const float2 a = Z[fpad(k)];
@@ -236,22 +242,25 @@ int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, in
                 int n_win, void* d_spec, int dtype, cudaStream_t st) {
   if (n_win <= 0) return AC_OK;
   const ac_mdx_geom& g = plan->g;
-  const size_t smem = stft_smem_bytes(g.n_fft);
+  const bool inplace = fft_inplace_ok(plan->fft, kFftThreads);
+  const size_t smem = inplace ? stft_smem_bytes(g.n_fft) / 2 : stft_smem_bytes(g.n_fft);
   AC_REQUIRE(smem <= 227 * 1024, "n_fft too large for shared memory");
   FftDev fd = make_fft_dev(plan->fft);
   dim3 grid(g.dim_t, n_win);
   const double es = dtype == AC_F32 ? 4.0 : 2.0;
   ProfScope ps(KC_STFT, 0.0, n_win * (2.0 * plan->W * 4 + (double)g.dim_t * g.dim_f * 4 * es), st);
+#define AC_STFT_LAUNCH(TYPE, INPLACE)                                                                                        \
+  do {                                                                                                                       \
+    AC_CHECK_CUDA(cudaFuncSetAttribute(stft_mdx_kernel<TYPE, INPLACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    stft_mdx_kernel<TYPE, INPLACE><<<grid, kFftThreads, smem, st>>>(d_src, ch_stride, n_ch, d_wins, fd, plan->fft->d_hann, g.hop, \
+                                                                    g.dim_f, g.dim_t, plan->W, (TYPE*)d_spec);                 \
+  } while (0)
   if (dtype == AC_F32) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(stft_mdx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stft_mdx_kernel<float><<<grid, kFftThreads, smem, st>>>(d_src, ch_stride, n_ch, d_wins, fd, plan->fft->d_hann,
-                                                            g.hop, g.dim_f, g.dim_t, plan->W, (float*)d_spec);
+    if (inplace) AC_STFT_LAUNCH(float, true); else AC_STFT_LAUNCH(float, false);
   } else {
-    AC_CHECK_CUDA(
-        cudaFuncSetAttribute(stft_mdx_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stft_mdx_kernel<__nv_bfloat16><<<grid, kFftThreads, smem, st>>>(
-        d_src, ch_stride, n_ch, d_wins, fd, plan->fft->d_hann, g.hop, g.dim_f, g.dim_t, plan->W, (__nv_bfloat16*)d_spec);
+    if (inplace) AC_STFT_LAUNCH(__nv_bfloat16, true); else AC_STFT_LAUNCH(__nv_bfloat16, false);
   }
+#undef AC_STFT_LAUNCH
   AC_LAUNCH_CHECK();
   return AC_OK;
 }
