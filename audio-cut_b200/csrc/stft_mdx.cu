@@ -286,9 +286,10 @@ int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDe
   a.blk_lo = pos_lo / g.hop;
   a.blk_hi = (pos_hi + g.hop - 1) / g.hop;
   const int n_blk = a.blk_hi - a.blk_lo;
-  // enough CTAs for ~2 waves, but strips no shorter than 4x the warm-up
-  int strips = (2 * device_sm_count() + n_win - 1) / n_win;
-  int max_strips = n_blk / (4 * a.nb);
+  // One CTA per SM (the kernel needs > 113 KB of shared memory): fill the machine with exactly one wave,
+  // strips no shorter than 2x the nb-1 warm-up frames every strip recomputes.
+  int strips = device_sm_count() / n_win;
+  int max_strips = n_blk / (2 * a.nb);
   if (max_strips < 1) max_strips = 1;
   if (strips > max_strips) strips = max_strips;
   if (strips < 1) strips = 1;
