@@ -179,6 +179,35 @@ def test_separate_track_small_geometry(ops, stereo, output_is_vocal):
     assert w.max() == 2 and w.min() == 1
 
 
+@pytest.mark.parametrize("n_samples", [1, 100, 641, 5000, 16001])
+def test_separate_track_short_and_ragged_inputs(ops, n_samples):
+    """Tracks shorter than one model window / one chunk / not a multiple of anything: the planner returns a single
+    plan (gpu_pipeline.py:341-343), the backend pads to one window (backends.py:306-330)."""
+    import torch
+
+    from audio_cut_b200 import unet_weights as uw
+    from oracle import mdx, pipeline, planner
+    from oracle import unet as ounet
+
+    sr, n_fft, hop, dim_f, dim_t, g = 8000, 640, 128, 256, 32, 16
+    geo = uw.UNetGeometry(dim_f=dim_f, dim_t=dim_t, g=g)
+    st = uw.random_state(geo, seed=1234)
+    net = ops.UNet(st, geo)
+    ref_net = ounet.build_net(st, dim_f, dim_t, g)
+    mg = mdx.MdxGeometry(n_fft, hop, dim_f, dim_t)
+    rng = np.random.default_rng(n_samples)
+    audio = (0.3 * rng.standard_normal((2, n_samples))).astype(np.float32)
+    plans = planner.chunk_schedule(n_samples / float(sr), 2.0, 0.5, 0.1)
+    bounds = [planner.sample_bounds(p, sr, n_samples) for p in plans]
+    ref_v, ref_i = pipeline.separate_track(audio, lambda ch: mdx.infer_chunk(ch, ref_net, mg, align_hop=256), sr=sr, plans=plans)
+    v, i, w = ops.separate_track(net, torch.from_numpy(audio).cuda(), bounds, ops.mdx_geom(n_fft, hop, dim_f, dim_t), align_hop=256)
+    v, i, w = v.cpu().numpy(), i.cpu().numpy(), w.cpu().numpy()
+    assert v.shape == ref_v.shape == (n_samples,)
+    assert w.min() >= 1
+    np.testing.assert_allclose(v, ref_v, atol=2e-4 * max(1e-6, np.abs(ref_v).max()) + 1e-7)
+    np.testing.assert_allclose(i, ref_i, atol=2e-4 * max(1e-6, np.abs(ref_i).max()) + 1e-7)
+
+
 def test_separate_track_full_geometry_30s_stereo(ops):
     """BASELINE config 1: 30 s stereo, Kim_Vocal geometry (n_fft 7680), 4 chunks / 8 windows."""
     ref_v, ref_i, v, i, w, bounds = _track_case(ops, 7680, 1024, 3072, 256, 48, 30.0, True, 44100, 10.0, 2.5, 0.5, 4096)
@@ -211,6 +240,39 @@ def test_chunk_sharded_track_equals_single_gpu_stitch(ops, world, dtype_name):
     mv, mi = sharding.merge_chunk_shards(total, shards)
     np.testing.assert_array_equal(mv, v.cpu().numpy())
     np.testing.assert_array_equal(mi, i.cpu().numpy())
+
+
+def test_full_size_track_properties(ops):
+    """BASELINE configs[1] at full size (4-min stereo, Kim_Vocal geometry, bf16 tensor-core path), checked through
+    size-independent properties: stem arithmetic is linear (vocal + instrumental == mono mix, backends.py:389-406
+    and the uniform overlap average of enhanced_vocal_separator.py:423-458), the overlap weights equal the
+    planner's effective-region counts, and the run is deterministic."""
+    from audio_cut_b200 import synth, unet_weights as uw
+    from audio_cut_b200._lib import AC_BF16
+    from oracle import planner
+
+    sr = 44100
+    geo = uw.UNetGeometry()
+    net = ops.UNet(uw.random_state(geo, seed=1234), geo)
+    audio = synth.synth_track(240.0, sr=sr, seed=0, stereo=True)
+    total = audio.shape[-1]
+    plans = planner.chunk_schedule(total / float(sr), 10.0, 2.5, 0.5)
+    bounds = [planner.sample_bounds(p, sr, total) for p in plans]
+    assert len(bounds) == 32
+    mix = torch.from_numpy(audio).cuda()
+    geom = ops.mdx_geom(7680, 1024, 3072, 256)
+    v, i, w = ops.separate_track(net, mix, bounds, geom, dtype=AC_BF16)
+    v2, i2, _ = ops.separate_track(net, mix, bounds, geom, dtype=AC_BF16)
+    assert _tc_aborted() == 0
+    assert torch.equal(v, v2) and torch.equal(i, i2)
+    wref = np.zeros(total, np.float32)
+    for cs, ce, es, ee in bounds:
+        wref[es:ee] += 1
+    np.testing.assert_array_equal(w.cpu().numpy(), wref)
+    mono = mix.mean(dim=0)
+    err = (v + i - mono).abs().max().item()
+    assert err < 1e-5 * max(1.0, mono.abs().max().item()), err
+    assert torch.isfinite(v).all() and float(v.abs().max()) > 0
 
 
 # --------------------------------------------------------------------------- STFT-2048 features
