@@ -113,6 +113,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every tensor-core kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs call
+// launch_dependents at once (the NEXT kernel's CTAs may then take an SM the moment one of ours leaves it and
+// run their prologue - barrier init, TMEM allocation, scale/shift staging - under our tail) and wait for the
+// PREVIOUS kernel's memory with griddepcontrol.wait after their own prologue.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- CTA-pair (cta_group::2) helpers ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -197,6 +205,35 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_tensor_map_encoder();
+
+// Launch with the PDL attribute (and a cluster of `cluster_x` CTAs when > 1).  AC_TC_NO_PDL=1 turns PDL off.
+bool tc_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int cluster_x,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (tc_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 int* tc_abort_flag();  // device int shared by all tensor-core kernels (allocated on first use)
 
 }  // namespace ac

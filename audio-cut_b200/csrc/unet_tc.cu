@@ -15,6 +15,8 @@
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..13 =
 //     epilogue (tcgen05.ld -> scale/shift/ReLU -> bf16 -> global); smem ring and (when the
 //     accumulators fit twice) a double-buffered TMEM hand-off, all through mbarriers.
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -57,6 +59,7 @@ struct TcParams {
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   const TcCfg& c = p.cfg;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [stages]
   uint64_t* empty = full + 8;                           // [stages]
@@ -93,6 +96,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
   const int steps = 3 * c.nkc;  // pipeline stages consumed per work unit (dt x channel chunk)
 
   auto decode = [&](int u, int& nt, int& b, int& t, int& f0) {
@@ -323,6 +327,15 @@ EncodeTiledFn get_tensor_map_encoder() {
   return fn;
 }
 
+bool tc_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AC_TC_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int* g_abort_flag = nullptr;  // device
 int* tc_abort_flag() {
   if (!g_abort_flag) {
@@ -370,7 +383,7 @@ int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   int grid = device_sm_count();
   if (grid > p.n_units) grid = p.n_units;
   ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
-  tc_conv3x3_kernel<<<grid, kTcThreads, c.smem_bytes, st>>>(map, p);
+  AC_CHECK_CUDA(tc_launch(tc_conv3x3_kernel, grid, kTcThreads, c.smem_bytes, st, 1, map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -54,6 +54,7 @@ __device__ __forceinline__ void cp_tma_load_2d_2sm(void* dst, const CUtensorMap*
 __global__ void __launch_bounds__(kCpThreads, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const CpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   const CpCfg& c = p.cfg;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [stages]  leader: both CTAs' stage landed
   uint64_t* empty = full + kCpMaxStages;                // [stages]
@@ -93,6 +94,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
   const int steps = 3 * c.nkc;  // (dt, channel chunk) pipeline steps per unit
   const int b_rows = c.b_tap_bytes / 128;  // rows of the weight tensor map per tap
 
@@ -371,20 +373,8 @@ int launch_tc_conv3x3_pair(const TcConvPairWeights* w, const TcConvArgs& a, cuda
   }
   int pairs = device_sm_count() / 2;
   if (pairs > p.n_units) pairs = p.n_units;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kCpThreads);
-  cfg.dynamicSmemBytes = c.smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
-  AC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_conv3x3_pair_kernel, in_map, w_map, p));
+  AC_CHECK_CUDA(tc_launch(tc_conv3x3_pair_kernel, 2 * pairs, kCpThreads, c.smem_bytes, st, 2, in_map, w_map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

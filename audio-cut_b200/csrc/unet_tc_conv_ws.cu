@@ -105,6 +105,7 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
   constexpr int kBLbo = NT * 16;
   constexpr int K16 = C / 16;
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [R]
   uint64_t* empty = full + kWsMaxR;                     // [R]
   uint64_t* tfull = full + 2 * kWsMaxR;                 // [2]
@@ -149,6 +150,7 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -341,6 +343,7 @@ tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams
   constexpr int kBLbo = NH * 16;
   constexpr int K16 = C / 16;
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [R]   (used in the leader)
   uint64_t* empty = full + kWsMaxR;                     // [R]
   uint64_t* tfull = full + 2 * kWsMaxR;                 // [2]
@@ -387,6 +390,7 @@ tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams
   cluster_sync_all();  // both CTAs' barriers are initialised before anything can signal them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -573,6 +577,7 @@ tc_conv3x3_rs_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
   constexpr int K16 = C / 16;
   constexpr int kTileCols = RB * NT;               // TMEM columns of one M tile's block ring
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [RA]
   uint64_t* empty = full + kWsMaxR;                     // [RA]
   uint64_t* done = full + 2 * kWsMaxR;                  // [RB]  MMA -> epilogue: block complete
@@ -614,6 +619,7 @@ tc_conv3x3_rs_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one slot per input row =====================
@@ -956,19 +962,7 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
     AC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int pairs = device_sm_count() / 2;
     if ((long long)pairs > p.total_rows) pairs = (int)p.total_rows;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kWsThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    AC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, map, p));
+    AC_CHECK_CUDA(tc_launch(kern, 2 * pairs, kWsThreads, smem, st, 2, map, p));
     AC_LAUNCH_CHECK();
     return AC_OK;
   }
@@ -981,7 +975,7 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
     AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int grid = device_sm_count();
     if ((long long)grid > p.total_rows) grid = (int)p.total_rows;
-    tc_conv3x3_rs_kernel<<<grid, kWsThreads, smem, st>>>(map, p);
+    AC_CHECK_CUDA(tc_launch(tc_conv3x3_rs_kernel, grid, kWsThreads, smem, st, 1, map, p));
     AC_LAUNCH_CHECK();
     return AC_OK;
   }
@@ -995,7 +989,7 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
   int group = device_sm_count() / c.nsplit;
   if ((long long)group > p.total_rows) group = (int)p.total_rows;
   const int grid = group * c.nsplit;
-  kern<<<grid, kWsThreads, c.smem_bytes, st>>>(map, p);
+  AC_CHECK_CUDA(tc_launch(kern, grid, kWsThreads, c.smem_bytes, st, 1, map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

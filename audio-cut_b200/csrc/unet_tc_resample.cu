@@ -48,6 +48,7 @@ struct RsParams {
 
 __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid_constant__ CUtensorMap in_map, const RsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   const RsCfg& c = p.cfg;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + 8;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
   const bool down = c.mode == RS_DOWN;
   const int ndt = down ? 2 : 1;             // K-walk over vertical taps (DOWN only)
   const int steps = ndt * c.nkc;
@@ -437,7 +439,7 @@ int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, cons
   const double pos = (double)nB * T * F;
   const double bytes = down ? pos * 2.0 * (4.0 * c.Cin + c.Cout) : pos * 2.0 * (c.Cin + 8.0 * c.Cout);
   ProfScope ps(KC_RESAMPLE_TC, 2.0 * pos * 4.0 * c.Cin * c.Cout, bytes, st);
-  tc_resample_kernel<<<grid, kRsThreads, c.smem_bytes, st>>>(map, p);
+  AC_CHECK_CUDA(tc_launch(tc_resample_kernel, grid, kRsThreads, c.smem_bytes, st, 1, map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

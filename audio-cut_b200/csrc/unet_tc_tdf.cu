@@ -46,6 +46,7 @@ struct TdfParams {
 
 __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_constant__ CUtensorMap in_map, const TdfParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   const TdfCfg& c = p.cfg;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + 8;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
 
 
   auto decode = [&](int u, int& mg, int& b, int& t0) {
@@ -359,7 +361,7 @@ int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfl
   int grid = device_sm_count();
   if (grid > p.n_units) grid = p.n_units;
   ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB, 2.0 * nB * (double)T * c.C * (c.K + c.M * (residual ? 2 : 1)), st);
-  tc_tdf_kernel<<<grid, kTdfThreads, c.smem_bytes, st>>>(map, p);
+  AC_CHECK_CUDA(tc_launch(tc_tdf_kernel, grid, kTdfThreads, c.smem_bytes, st, 1, map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

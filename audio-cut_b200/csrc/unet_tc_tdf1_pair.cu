@@ -57,6 +57,7 @@ __device__ __forceinline__ void t1_tma_load_2d_2sm(void* dst, const CUtensorMap*
 __global__ void __launch_bounds__(kT1Threads, 1)
 tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map, const T1Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   const T1Cfg& c = p.cfg;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [stages]  leader: both CTAs' stage landed
   uint64_t* empty = full + kT1MaxStages;                 // [stages]
@@ -98,6 +99,7 @@ tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
   const int acc_cols = c.n_mp * c.N;  // columns of one accumulator set
 
   if (warp == 0) {
@@ -366,20 +368,8 @@ int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const __nv_bfloat16* in, __n
   }
   int pairs = device_sm_count() / 2;
   if (pairs > p.n_units) pairs = p.n_units;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kT1Threads);
-  cfg.dynamicSmemBytes = c.smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB, 2.0 * nB * (double)T * c.C * (c.K + c.M), st);
-  AC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_tdf1_pair_kernel, x_map, w_map, p));
+  AC_CHECK_CUDA(tc_launch(tc_tdf1_pair_kernel, 2 * pairs, kT1Threads, c.smem_bytes, st, 2, x_map, w_map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }
