@@ -283,6 +283,20 @@ class PipelineContext:
             meta.setdefault(k, v)
         return meta
 
+    def capture_device_metrics_async(self):
+        """Start the NVML sample on a helper thread WHILE the kernels run (the sample then shows the device
+        under load, and the 10+ ms NVML round trip leaves the caller's critical path); returns a callable
+        that joins the thread and merges the gpu_pipeline_nvml_* keys into ``gpu_meta``."""
+        import threading
+
+        th = threading.Thread(target=self.capture_device_metrics, daemon=True)
+        th.start()
+
+        def finish(timeout: float = 2.0) -> None:
+            th.join(timeout)
+
+        return finish
+
     def capture_device_metrics(self) -> None:
         """gpu_pipeline_nvml_* keys (gpu_pipeline.py:208-259) through pynvml when it is importable."""
         try:

@@ -274,6 +274,7 @@ class B200VocalSeparator:
         ev = bufs.events
         vad_segments: List[Dict[str, float]] = []
         lib = backend.net._lib
+        finish_metrics = None
         with torch.cuda.device(dev), ctx.acquire_inflight():
             parallel_copy(v.pin_in_np, audio.reshape(n_ch, total))  # pageable -> pinned staging
             caller = torch.cuda.current_stream(dev)
@@ -291,6 +292,8 @@ class B200VocalSeparator:
                                    output_is_vocal=backend.get_output_type() == "vocal", dtype=backend.dtype,
                                    out=(v.vocal, v.instr, v.weight))
                 ev[2].record()
+                if self.capture_device_metrics:  # NVML sample taken while the network runs, off the critical path
+                    finish_metrics = ctx.capture_device_metrics_async()
                 # tail, all asynchronous: presence-marker RMS, energies, D2H of the stems and the scalars
                 hop = max(1, int(0.02 * sr))
                 frame = max(hop * 2, int(0.05 * sr))
@@ -343,8 +346,8 @@ class B200VocalSeparator:
             "gpu_pipeline_chunk_invocations": int(perf["chunks"]),
             "mdx23_output_type": backend.get_output_type(),
         })
-        if self.capture_device_metrics:
-            ctx.capture_device_metrics()
+        if finish_metrics is not None:
+            finish_metrics()
         return vocal, instrumental, cache, vad_segments, markers
 
     def _buffers(self, dev: torch.device) -> "_TrackBuffers":
