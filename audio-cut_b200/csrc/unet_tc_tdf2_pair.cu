@@ -222,50 +222,63 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
       my_off[i] = (size_t)tl * t_stride + (size_t)(cq * 2) * plane;
     }
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
-    uint32_t acc_n = 0;
-    bool alive = true;
-    for (int lu = 0; lu < n_my && alive; ++lu) {
+    // Tiles of this pair in order: tile = lu * n_mp + mp.  The residual of tile n + 1 is requested at the start of
+    // tile n (a full tile period ahead), so no global-load latency is left on the epilogue's critical path; the
+    // accumulators are read in two halves to keep {2 x 16 accumulators, 2 x residual sets} within 128 registers.
+    auto tile_base = [&](long long tile) -> size_t {
+      const int lu = (int)(tile / c.n_mp), mp = (int)(tile - (long long)lu * c.n_mp);
       const int u = pair + lu * n_pairs;
       const int b = u / p.n_tg, t0 = (u - b * p.n_tg) * c.NTt;
-      for (int mp = 0; mp < c.n_mp; ++mp, ++acc_n) {
-        const int buf = acc_n & 1;
-        const int m = mp * 256 + (int)rank * 128 + quad * 32 + lane;
-        const size_t base = cg8_index(b, t0, 0, m, p.T, c.C, c.M);
-        if (!mbar_wait(&tfull[buf], (acc_n >> 1) & 1, abort_flag)) { alive = false; break; }
-        tc_fence_after();
-        // 1. all of this warp's accumulator columns -> registers, then hand the TMEM buffer straight back
-        //    (relaxed arrive: it must not wait for the global stores of the previous tile)
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.N);
-        uint32_t r[kMaxMy][16];
+      return cg8_index(b, t0, 0, mp * 256 + (int)rank * 128 + quad * 32 + lane, p.T, c.C, c.M);
+    };
+    auto fetch = [&](size_t base, uint4* q) {
 #pragma unroll
-        for (int i = 0; i < kMaxMy; ++i)
-          if (i < n_mine) tmem_ld16(taddr + my_col[i], r[i]);
+      for (int i = 0; i < kMaxMy; ++i) {
+        if (i < n_mine) {
+          q[2 * i] = ldg_stream_u4(p.residual + base + my_off[i]);
+          q[2 * i + 1] = ldg_stream_u4(p.residual + base + my_off[i] + plane);
+        }
+      }
+    };
+    const long long n_tiles = (long long)n_my * c.n_mp;
+    uint4 q_cur[2 * kMaxMy], q_next[2 * kMaxMy];
+    size_t base = n_tiles ? tile_base(0) : 0;
+    if (n_tiles) fetch(base, q_cur);
+    for (long long tile = 0; tile < n_tiles; ++tile) {
+      const int buf = (int)(tile & 1);
+      const bool has_next = tile + 1 < n_tiles;
+      const size_t next_base = has_next ? tile_base(tile + 1) : base;
+      if (has_next) fetch(next_base, q_next);
+      if (!mbar_wait(&tfull[buf], (uint32_t)((tile >> 1) & 1), abort_flag)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.N);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[2][16];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (2 * h + k < n_mine) tmem_ld16(taddr + my_col[2 * h + k], r[k]);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
-        // 2. residual (all loads in flight together), BN/ReLU, add, store: off the MMA's critical path
-        uint4 q[2 * kMaxMy];
-#pragma unroll
-        for (int i = 0; i < kMaxMy; ++i) {
-          if (i < n_mine) {
-            q[2 * i] = ldg_stream_u4(p.residual + base + my_off[i]);
-            q[2 * i + 1] = ldg_stream_u4(p.residual + base + my_off[i] + plane);
-          }
+        if (h == 1) {  // every accumulator column of this warp is in registers: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
         }
 #pragma unroll
-        for (int i = 0; i < kMaxMy; ++i) {
+        for (int k = 0; k < 2; ++k) {
+          const int i = 2 * h + k;
           if (i < n_mine) {
-            const uint32_t w[8] = {q[2 * i].x, q[2 * i].y, q[2 * i].z, q[2 * i].w, q[2 * i + 1].x, q[2 * i + 1].y, q[2 * i + 1].z, q[2 * i + 1].w};
+            const uint4 q0 = q_cur[2 * i], q1 = q_cur[2 * i + 1];
+            const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int ch = my_ch[i] + 2 * e;
               const float2 res = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-              const float v0 = fmaxf(fmaf(__uint_as_float(r[i][2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
-              const float v1 = fmaxf(fmaf(__uint_as_float(r[i][2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[k][2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[k][2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
+              __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+              pk[e] = *reinterpret_cast<uint32_t*>(&hh);
             }
             const size_t idx = base + my_off[i];
             *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -273,6 +286,9 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
           }
         }
       }
+#pragma unroll
+      for (int i = 0; i < 2 * kMaxMy; ++i) q_cur[i] = q_next[i];
+      base = next_base;
     }
   }
   tc_fence_before();
