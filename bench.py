@@ -124,6 +124,15 @@ def cpu_reference_pass(sample_seconds: float, n_fft: int, threads: int, state=No
     return n / float(SR), time.perf_counter() - t0
 
 
+def bench_config(n_fft: int, world: int, chunks: int = 32, windows: int = 64) -> dict:
+    """The workload description shared by both arms (the reference arm runs a bounded sample of it)."""
+    return {"workload": "v2.2_mdd hot path, one 4-min 44.1 kHz stereo track per GPU per step (configs[1]; track-sharded at N>1 = configs[3])",
+            "n_fft": n_fft, "hop": 1024, "dim_f": 3072, "dim_t": 256, "chunk_s": 10.0, "overlap_s": 2.5, "halo_s": 0.5,
+            "chunks_per_track": chunks, "windows_per_track": windows, "weights": "random-init TFC-TDF (Kim_Vocal geometry, seed 1234)",
+            "l2": "working set per step (>4 GB of activations, 85 MB track) exceeds the 126 MB L2; no explicit flush",
+            "parallelism": f"track-sharded x{world}, no collective"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,8 +154,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "v2.2_mdd hot path, 4-min 44.1 kHz stereo track (configs[1]); bounded sample per step",
-                   "n_fft": args.n_fft, "chunk_s": 10.0, "overlap_s": 2.5, "halo_s": 0.5},
+        "config": bench_config(args.n_fft, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample_s:.0f} s stereo (1 chunk, 2 MDX windows + its features) per step, {args.steps} steps; "
                                    "oracle port: torch-CPU TFC-TDF net + numpy/scipy librosa restatement (onnxruntime/librosa absent)"},
@@ -313,11 +321,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "v2.2_mdd hot path, one 4-min 44.1 kHz stereo track per GPU per step (configs[1]; track-sharded at N>1 = configs[3])",
-                       "n_fft": args.n_fft, "hop": 1024, "dim_f": 3072, "dim_t": 256, "chunk_s": 10.0, "overlap_s": 2.5, "halo_s": 0.5,
-                       "chunks_per_track": len(plans), "windows_per_track": n_windows, "weights": "random-init TFC-TDF (Kim_Vocal geometry, seed 1234)",
-                       "l2": "working set per step (>4 GB of activations, 85 MB track) exceeds the 126 MB L2; no explicit flush",
-                       "parallelism": f"track-sharded x{world}, no collective"},
+            "config": bench_config(args.n_fft, world, len(plans), n_windows),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(audio.nbytes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps, "call": "B200VocalSeparator.separate_for_detection(host ndarray)"},
