@@ -189,3 +189,15 @@ def test_lpc_burg_recovers_an_ar2_process_and_ragged_tracks():
     counts = np.array([3, 1, 0, 2])
     t1, t2, t3 = ops.formant_tracks(mags, counts)
     assert t1.tolist() == [3.0, 5.0, 0.0, 7.0] and t2.tolist() == [2.0, 0.0, 6.0] and t3.tolist() == [1.0, 0.0]
+
+
+def test_public_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/audiocut_b200.h must compile as C99 (and as C++) on its own."""
+    import shutil
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "audiocut_b200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    subprocess.run(["gcc", "-fsyntax-only", "-std=c99", "-Wall", "-Werror", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-fsyntax-only", "-std=c++17", "-x", "c++", hdr], check=True)
