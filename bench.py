@@ -214,10 +214,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; rank 0 must print ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to stdout when the first communicator is created; rank 0 must print
+        # exactly ONE JSON line there, so file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = torch.device("cuda", local)
 
     geo = uw.UNetGeometry()
