@@ -21,7 +21,7 @@ EXPORTS = [
     "ac_track_workspace_bytes", "ac_separate_track", "ac_stft_features_workspace_bytes", "ac_stft_features",
     "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
     "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3", "ac_pyin_frame_count", "ac_pyin_workspace_bytes", "ac_pyin",
-    "ac_lpc_frame_count", "ac_lpc_formants",
+    "ac_lpc_frame_count", "ac_lpc_formants", "ac_refine_cut_points", "ac_quiet_lookup_db",
 ]
 
 
@@ -107,6 +107,10 @@ def load() -> C.CDLL:
     lib.ac_pyin.argtypes, lib.ac_pyin.restype = [vp, ll, i, i, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp], i
     lib.ac_lpc_frame_count.argtypes, lib.ac_lpc_frame_count.restype = [ll, i, i], ll
     lib.ac_lpc_formants.argtypes, lib.ac_lpc_formants.restype = [vp, ll, i, i, i, vp, vp, vp], i
+    d = C.c_double
+    lib.ac_refine_cut_points.argtypes = [vp, vp, ll, i, vp, i, i, i, i, d, d, i, i, i, vp, vp, vp]
+    lib.ac_refine_cut_points.restype = i
+    lib.ac_quiet_lookup_db.argtypes, lib.ac_quiet_lookup_db.restype = [vp, ll, i, vp, vp], i
     lib.ac_profile_begin.argtypes, lib.ac_profile_begin.restype = [], i
     lib.ac_profile_collect.argtypes, lib.ac_profile_collect.restype = [C.POINTER(KernelStat), i], i
     _lib = lib

@@ -291,3 +291,38 @@ def formant_tracks(mags: np.ndarray, counts: np.ndarray):
         keep = (counts > j) | (counts == 0)
         tracks.append(np.where(counts[keep] == 0, 0.0, mags[keep, j]).astype(mags.dtype))
     return tracks
+
+
+def refine_cut_points(mix: torch.Tensor, vocal: Optional[torch.Tensor], sr: int, times: Sequence[float], *,
+                      zero_cross_half: int, search: int, win: int, guard_db: float, floor_db: float,
+                      use_vocal_guard_first: bool = True, enable_vocal_guard: bool = True,
+                      enable_mix_guard: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """The per-point loop of finalize_cut_points (refine.py:318-371) for all points in one launch.
+
+    ``mix`` / ``vocal``: mono float32 CUDA tensors of the same length (``vocal`` may be None).  Returns
+    (guard_times, final_times) as float64 numpy arrays."""
+    lib = _lib.init(_dev_index(mix))
+    mix = mix.contiguous().float()
+    if vocal is not None:
+        vocal = vocal.contiguous().float()
+        if vocal.numel() != mix.numel():
+            raise _lib.AudioCutError("mix and vocal must have the same length")
+    p = len(times)
+    t_in = torch.tensor(np.asarray(times, dtype=np.float64), dtype=torch.float64, device=mix.device)
+    out = torch.empty((2, max(p, 1)), dtype=torch.float64, device=mix.device)
+    check(lib.ac_refine_cut_points(ptr(mix), ptr(vocal), mix.numel(), int(sr), ptr(t_in), p, int(zero_cross_half),
+                                   int(search), int(win), float(guard_db), float(floor_db),
+                                   int(bool(use_vocal_guard_first)), int(bool(enable_vocal_guard)),
+                                   int(bool(enable_mix_guard)), ptr(out[0]), ptr(out[1]), stream_ptr()),
+          "ac_refine_cut_points")
+    host = out.cpu().numpy()
+    return host[0, :p].copy(), host[1, :p].copy()
+
+
+def quiet_lookup_db(wave: torch.Tensor, win: int) -> torch.Tensor:
+    """QuietGuardLookup.rms_db (refine.py:161-173) of a mono float32 CUDA tensor, float64 on the device."""
+    lib = _lib.init(_dev_index(wave))
+    wave = wave.contiguous().float()
+    out = torch.empty(wave.numel(), dtype=torch.float64, device=wave.device)
+    check(lib.ac_quiet_lookup_db(ptr(wave), wave.numel(), int(win), ptr(out), stream_ptr()), "ac_quiet_lookup_db")
+    return out

@@ -229,6 +229,24 @@ AC_API int ac_tempogram_stats(const float* d_env, long long n, int win, const fl
 AC_API int ac_host_beat_dp(const float* h_localscore, int n, int period, float tightness, long long* h_backlink,
                            float* h_cumscore);
 
+/* ---- cut-point refinement -------------------------------------------
+ * The per-point loop of finalize_cut_points (src/audio_cut/cutting/refine.py:318-371) in one launch, one
+ * CTA per NMS-pruned candidate: align_to_zero_cross (:72-110) on the vocal stem -> _apply_quiet_guard_fast
+ * (:184-214; the 10 ms boxcar RMS-dB of _prepare_quiet_lookup :161-173 is evaluated only over the
+ * [idx, idx+search) samples the point consults, never for the whole track) -> apply_quiet_guard (:113-158)
+ * when the fast guard did not move the point -> the same three steps on the mix -> clip to [0, n/sr].
+ * d_mix / d_vocal: mono float32 [n] device arrays (d_vocal may be NULL = ctx.vocal_wave is None);
+ * d_times [n_points] fp64 seconds in, d_guard_times / d_final_times [n_points] fp64 out (CutAdjustment.
+ * guard_time / final_time).  zero_cross_half = max(1, round(zero_cross_win_ms/1000*sr)), search = max(1,
+ * round(search_right_ms/1000*sr)), win = max(1, round(guard_win_ms/1000*sr)) - the reference's own integers. */
+AC_API int ac_refine_cut_points(const float* d_mix, const float* d_vocal, long long n, int sr, const double* d_times,
+                                int n_points, int zero_cross_half, int search, int win, double guard_db,
+                                double floor_db, int use_vocal_guard_first, int enable_vocal_guard,
+                                int enable_mix_guard, double* d_guard_times, double* d_final_times, void* stream);
+/* QuietGuardLookup.rms_db of _prepare_quiet_lookup (refine.py:161-173) for the whole track, fp64 [n]:
+ * 20*log10(sqrt(convolve(wave^2, ones(win)/win, "same") + 1e-12) + 1e-12). */
+AC_API int ac_quiet_lookup_db(const float* d_wave, long long n, int win, double* d_rms_db, void* stream);
+
 /* librosa.feature.zero_crossing_rate(y, frame_length, hop_length, center=True) (edge padding,
  * |y| <= 1e-10 -> 0): pure_vocal_pause_detector.py:444. */
 AC_API int ac_zero_crossing_rate(const float* d_x, long long n, int frame, int hop, float* d_out, void* stream);

@@ -179,11 +179,47 @@ def gen_pipeline():
 
 def main():
     torch.set_num_threads(4)
+    if "--cuts44k" in sys.argv:
+        return gen_cuts_44k()
     if "--cuts" not in sys.argv:
         gen_chunk_schedule()
         gen_infer_chunk()
         gen_pipeline()
     gen_cuts()
+    gen_cuts_44k()
+
+
+def _load_ref_refine():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_refine", os.path.join(REF, "src/audio_cut/cutting/refine.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_refine"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_cuts_44k():
+    """finalize_cut_points of the reference at 44.1 / 22.05 kHz with its default guard geometry, including every
+    CutAdjustment (raw / guard / final time), stereo mixes, a missing vocal stem, digital silence, points at the
+    track ends and disabled guards: the fixture of the GPU refinement (audio_cut_b200.refine)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import cut_case
+
+    mod = _load_ref_refine()
+    cases = []
+    for seed in range(8):
+        mix, vocal, sr, pts, kw = cut_case(seed)
+        res = mod.finalize_cut_points(mod.CutContext(sr=sr, mix_wave=mix, vocal_wave=vocal),
+                                      [mod.CutPoint(t=a, score=b) for a, b in pts], **kw)
+        cases.append({"seed": seed, "sample_boundaries": [int(v) for v in res.sample_boundaries],
+                      "final_times": [repr(float(p.t)) for p in res.final_points],
+                      "adjustments": [[repr(float(a.raw_time)), repr(float(a.guard_time)), repr(float(a.final_time))]
+                                      for a in res.adjustments],
+                      "n_suppressed": len(res.suppressed_points)})
+    with open(os.path.join(HERE, "cuts_44k.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+    print("cuts_44k.json", [(len(c["sample_boundaries"]), sum(a[0] != a[2] for a in c["adjustments"])) for c in cases])
 
 
 def gen_cuts():

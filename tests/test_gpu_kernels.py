@@ -434,3 +434,91 @@ def test_lpc_formants_match_oracle(ops):
     tr = ops.formant_tracks(mags, counts)
     assert len(tr[0]) >= len(tr[1]) >= len(tr[2])
     assert len(tr[0]) == int(np.sum((counts > 0) | (counts == 0)))
+
+
+# --------------------------------------------------------------------------- cut-point refinement
+def _refine_on_gpu(mix, vocal, sr, pts, kw, as_tensor=False):
+    from audio_cut_b200 import refine as R
+
+    if as_tensor:
+        mix = torch.from_numpy(mix).cuda()
+        vocal = None if vocal is None else torch.from_numpy(vocal).cuda()
+    return R.finalize_cut_points(R.CutContext(sr=sr, mix_wave=mix, vocal_wave=vocal), [R.CutPoint(t=a, score=b) for a, b in pts], **kw)
+
+
+def test_refine_cut_points_matches_reference_fixture_44k():
+    """audio_cut_b200.refine.finalize_cut_points vs the REFERENCE's refine.py (tests/golden/cuts_44k.json): sample
+    boundaries, final times and every kept adjustment (raw / guard / final) bit-exact - integer and fp64 outputs."""
+    import json, os
+    from helpers import cut_case
+
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cuts_44k.json")))
+    for case in cases:
+        mix, vocal, sr, pts, kw = cut_case(case["seed"])
+        res = _refine_on_gpu(mix, vocal, sr, pts, kw, as_tensor=(case["seed"] % 2 == 1 and mix.ndim == 1))
+        assert res.sample_boundaries == case["sample_boundaries"], case["seed"]
+        assert [repr(float(p.t)) for p in res.final_points] == case["final_times"], case["seed"]
+        got = [[repr(a.raw_time), repr(a.guard_time), repr(a.final_time)] for a in res.adjustments]
+        assert got == case["adjustments"], case["seed"]
+        assert len(res.suppressed_points) == case["n_suppressed"]
+
+
+def test_refine_cut_points_matches_reference_fixture_8k():
+    """The 8 kHz fixture the oracle is pinned with (tests/golden/cuts.json; 450 ms search, 80 ms guard window)."""
+    import json, os
+
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cuts.json")))
+    for case in cases:
+        seed = case["seed"]
+        rng = np.random.default_rng(seed)
+        sr = 8000
+        n = int(24.0 * sr)
+        t = np.arange(n) / sr
+        s = seed - 100
+        gate = (np.sin(2 * np.pi * 0.23 * t + s) > -0.3).astype(np.float64)
+        vocal = (0.3 * np.sin(2 * np.pi * 180 * t) * gate + 1e-4 * rng.standard_normal(n)).astype(np.float32)
+        mix = (vocal + 0.1 * np.sin(2 * np.pi * 55 * t) * (np.sin(2 * np.pi * 0.11 * t) > 0) + 1e-3 * rng.standard_normal(n)).astype(np.float32)
+        res = _refine_on_gpu(mix, vocal, sr, [tuple(p) for p in case["points"]], case["kwargs"])
+        assert res.sample_boundaries == case["sample_boundaries"], seed
+        assert [repr(float(p.t)) for p in res.final_points] == case["final_times"], seed
+
+
+def test_refine_cut_points_full_track_matches_oracle(ops):
+    """4-minute stems (BASELINE configs[1] length), 120 candidates, default parameters: every per-point time equals the
+    oracle's (fp64, compared exactly); the whole-track lookup array agrees to 1e-9 dB where it is evaluated."""
+    from audio_cut_b200 import synth
+    from oracle import cuts
+
+    mix2 = synth.synth_track(240.0, seed=11)
+    mix = mix2.mean(axis=0).astype(np.float32)
+    vocal = (0.6 * mix * (np.sin(2 * np.pi * 0.2 * np.arange(mix.size) / SR) > 0)).astype(np.float32)
+    rng = np.random.default_rng(5)
+    pts = [(float(a), float(b)) for a, b in zip(rng.uniform(0.3, 239.7, 120), rng.uniform(0, 1, 120))]
+    kw = dict(min_gap_s=1.0, topk_per_10s=6, floor_db=-50.0)
+    res = _refine_on_gpu(mix, vocal, SR, pts, kw, as_tensor=True)
+    bounds, times = cuts.finalize_cut_points(mix, vocal, SR, pts, **kw)
+    assert res.sample_boundaries == bounds
+    assert [p.t for p in res.final_points] == times
+    assert len(times) > 20
+    win = 441
+    got = ops.quiet_lookup_db(torch.from_numpy(vocal[: 30 * SR]).cuda(), win).cpu().numpy()
+    ref, _ = cuts.prepare_quiet_lookup(vocal[: 30 * SR], SR, 10.0, -60.0)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+
+
+def test_refine_cut_points_edge_cases():
+    from audio_cut_b200 import refine as R
+
+    z = np.zeros(4410, np.float32)
+    res = R.finalize_cut_points(R.CutContext(sr=SR, mix_wave=z), [])
+    assert res.sample_boundaries == [0, 4410] and res.final_points == []
+    # all-zero track: every window ties exactly, nothing may move; a single sample; a point beyond the end
+    res = R.finalize_cut_points(R.CutContext(sr=SR, mix_wave=np.zeros(3 * SR, np.float32), vocal_wave=np.zeros(3 * SR, np.float32)),
+                                [R.CutPoint(1.0, 0.5), R.CutPoint(2.2, 0.9), R.CutPoint(7.0, 0.1)], min_boundary_s=0.1)
+    from oracle import cuts
+
+    zz = np.zeros(3 * SR, np.float32)
+    _, times = cuts.finalize_cut_points(zz, zz, SR, [(1.0, 0.5), (2.2, 0.9), (7.0, 0.1)], min_boundary_s=0.1)
+    assert [a.final_time for a in res.adjustments] == times == [1.0, 2.2]
+    res = R.finalize_cut_points(R.CutContext(sr=SR, mix_wave=np.ones(1, np.float32)), [R.CutPoint(0.0, 1.0)])
+    assert res.sample_boundaries == [0, 1]

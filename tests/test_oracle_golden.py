@@ -133,3 +133,19 @@ def test_finalize_cut_points_matches_reference(golden_dir):
         bounds, times = cuts.finalize_cut_points(mix, vocal, sr, [tuple(p) for p in case["points"]], **case["kwargs"])
         assert bounds == case["sample_boundaries"], seed
         assert [repr(float(x)) for x in times] == case["final_times"], seed
+
+
+def test_finalize_cut_points_44k_matches_reference(golden_dir):
+    """oracle.cuts vs the reference's refine.py at 44.1 / 22.05 kHz with the default guard geometry: stereo mixes, no
+    vocal stem, digital silence, points at the track ends, disabled guards (tests/golden/cuts_44k.json)."""
+    from helpers import cut_case
+    from oracle import cuts
+
+    cases = json.load(open(os.path.join(golden_dir, "cuts_44k.json")))
+    assert len(cases) == 8
+    with np.errstate(invalid="ignore"):
+        for case in cases:
+            mix, vocal, sr, pts, kw = cut_case(case["seed"])
+            bounds, times = cuts.finalize_cut_points(mix, vocal, sr, pts, **kw)
+            assert bounds == case["sample_boundaries"], case["seed"]
+            assert [repr(float(x)) for x in times] == case["final_times"], case["seed"]
