@@ -324,6 +324,7 @@ class B200VocalSeparator:
         if instrumental is not None:
             parallel_copy(instrumental, v.pin_out_np[1])
         markers = vocal_presence_markers_from_rms(mark.pin.numpy()[:n_mark].copy(), total, sr, hop, self._marker_threshold_db)
+        self._last_device = (v.mono, v.vocal, v.instr if any_instr else None)
         self._energies = (float(stats[0]) / max(total, 1), float(stats[1]) / max(total, 1) if any_instr else None,
                           float(stats[2]) / max(total, 1))
         if self._vad_fn is not None:  # hook kept from SileroChunkVAD (silero_chunk_vad.py:34, 56-116)
@@ -349,6 +350,15 @@ class B200VocalSeparator:
         if finish_metrics is not None:
             finish_metrics()
         return vocal, instrumental, cache, vad_segments, markers
+
+    def last_device_stems(self) -> Dict[str, Optional[torch.Tensor]]:
+        """The last track's mono mix, vocal and instrumental stems as they lie in HBM (views of the persistent
+        track buffers: valid until the next ``separate_for_detection`` call).  ``audio_cut_b200.refine.
+        finalize_cut_points`` takes them as ``CutContext.mix_wave / vocal_wave`` without any copy."""
+        last = getattr(self, "_last_device", None)
+        if last is None:
+            raise RuntimeError("no track has been separated yet")
+        return {"mix": last[0], "vocal": last[1], "instrumental": last[2]}
 
     def _buffers(self, dev: torch.device) -> "_TrackBuffers":
         b = self._bufs.get(dev)

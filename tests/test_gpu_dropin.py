@@ -89,6 +89,31 @@ def test_separator_dropin_matches_oracle_pipeline():
                                         "vocal_presence_segments", "pure_music_segments"}
 
 
+def test_cut_refinement_on_device_resident_stems():
+    """separate_for_detection -> finalize_cut_points with the stems still in HBM: the cut samples equal the oracle's
+    finalize_cut_points run on the host copies of the same stems (bit-exact sample boundaries)."""
+    from audio_cut_b200 import refine as R, synth
+    from audio_cut_b200.gpu_pipeline import PipelineConfig
+    from audio_cut_b200.separator import B200VocalSeparator
+    from oracle import cuts
+
+    sr = 8000
+    be, _, _ = _small_backend()
+    sep = B200VocalSeparator(sr, backend=be, pipeline_config=PipelineConfig(chunk_s=4.0, overlap_s=1.0, halo_s=0.25, align_hop=256))
+    audio = synth.synth_track(17.3, sr=sr, seed=9, stereo=False)
+    res = sep.separate_for_detection(audio)
+    dev = sep.last_device_stems()
+    np.testing.assert_array_equal(dev["vocal"].cpu().numpy(), res.vocal_track)
+    np.testing.assert_array_equal(dev["mix"].cpu().numpy(), audio)
+    rng = np.random.default_rng(2)
+    pts = [(float(a), float(b)) for a, b in zip(rng.uniform(0.2, 17.0, 24), rng.uniform(0, 1, 24))]
+    kw = dict(min_gap_s=0.5, floor_db=-30.0, guard_db=1.0)
+    got = R.finalize_cut_points(R.CutContext(sr=sr, mix_wave=dev["mix"], vocal_wave=dev["vocal"]),
+                                [R.CutPoint(a, b) for a, b in pts], **kw)
+    bounds, times = cuts.finalize_cut_points(audio, res.vocal_track, sr, pts, **kw)
+    assert got.sample_boundaries == bounds and [p.t for p in got.final_points] == times and len(times) >= 8
+
+
 def test_vad_hook_is_called_per_chunk():
     from audio_cut_b200 import synth
     from audio_cut_b200.gpu_pipeline import PipelineConfig
