@@ -212,6 +212,9 @@ class B200VocalSeparator:
         self._marker_threshold_db = marker_threshold_db
         self.enable_fallback = False
         self.backend_pref = "mdx23"
+        # stems are returned as numpy views of page-locked memory (no pinned -> pageable copy after the D2H);
+        # set False to get ordinary pageable arrays (e.g. when thousands of results are kept alive at once)
+        self.pinned_outputs = True
         self.capture_device_metrics = True  # NVML / nvidia-smi sample per call (gpu_pipeline.py:208-259)
         self._bufs: Dict[torch.device, "_TrackBuffers"] = {}
         self._energies = (0.0, None, 1e-8)
@@ -274,6 +277,8 @@ class B200VocalSeparator:
         ev = bufs.events
         vad_segments: List[Dict[str, float]] = []
         lib = backend.net._lib
+        out_pin = ([torch.empty(total, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+                   if self.pinned_outputs else None)
         finish_metrics = None
         with torch.cuda.device(dev), ctx.acquire_inflight():
             parallel_copy(v.pin_in_np, audio.reshape(n_ch, total))  # pageable -> pinned staging
@@ -303,7 +308,11 @@ class B200VocalSeparator:
                 stream.wait_event(ev[4])
                 ops.check(lib.ac_track_stats(ops.ptr(v.vocal), ops.ptr(v.instr), ops.ptr(v.mono), total, ops.ptr(bufs.stats_dev),
                                              ops.stream_ptr()), "ac_track_stats")
-                v.pin_out.copy_(v.stems2, non_blocking=True)
+                if out_pin is not None:  # D2H straight into the arrays the caller will own
+                    out_pin[0].copy_(v.vocal, non_blocking=True)
+                    out_pin[1].copy_(v.instr, non_blocking=True)
+                else:
+                    v.pin_out.copy_(v.stems2, non_blocking=True)
                 mark.pin.copy_(mark.dev, non_blocking=True)
                 bufs.stats_pin.copy_(bufs.stats_dev, non_blocking=True)
                 ev[3].record()
@@ -317,12 +326,18 @@ class B200VocalSeparator:
             caller.wait_stream(stream)
             caller.wait_stream(feat_stream)
         stats = bufs.stats_pin.numpy().copy()
-        vocal = np.empty(total, dtype=np.float32)
         any_instr = stats[3] > 0
-        instrumental = np.empty(total, dtype=np.float32) if any_instr else None
-        parallel_copy(vocal, v.pin_out_np[0])
-        if instrumental is not None:
-            parallel_copy(instrumental, v.pin_out_np[1])
+        if out_pin is not None:
+            # numpy views of page-locked tensors: freshly allocated, caller-owned (the array keeps its tensor alive;
+            # torch's caching host allocator recycles the block once the caller drops the array)
+            vocal = out_pin[0].numpy()
+            instrumental = out_pin[1].numpy() if any_instr else None
+        else:
+            vocal = np.empty(total, dtype=np.float32)
+            instrumental = np.empty(total, dtype=np.float32) if any_instr else None
+            parallel_copy(vocal, v.pin_out_np[0])
+            if instrumental is not None:
+                parallel_copy(instrumental, v.pin_out_np[1])
         markers = vocal_presence_markers_from_rms(mark.pin.numpy()[:n_mark].copy(), total, sr, hop, self._marker_threshold_db)
         self._last_device = (v.mono, v.vocal, v.instr if any_instr else None)
         self._energies = (float(stats[0]) / max(total, 1), float(stats[1]) / max(total, 1) if any_instr else None,
