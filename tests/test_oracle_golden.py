@@ -149,3 +149,21 @@ def test_finalize_cut_points_44k_matches_reference(golden_dir):
             bounds, times = cuts.finalize_cut_points(mix, vocal, sr, pts, **kw)
             assert bounds == case["sample_boundaries"], case["seed"]
             assert [repr(float(x)) for x in times] == case["final_times"], case["seed"]
+
+
+def test_mel_db_matches_transformers_audio_utils():
+    """Second independent pin of the librosa restatement (librosa itself is absent): transformers.audio_utils
+    re-implements librosa's STFT power spectrogram, slaney mel filterbank and power_to_db(top_db=80)."""
+    au = __import__("pytest").importorskip("transformers.audio_utils")
+    rng = np.random.default_rng(0)
+    sr = 44100
+    t = np.arange(2 * sr) / sr
+    y = (0.3 * np.sin(2 * np.pi * 220 * t) * (np.sin(2 * np.pi * 2 * t) > 0) + 0.01 * rng.standard_normal(t.size)).astype(np.float32)
+    fb = au.mel_filter_bank(1025, 128, 0.0, sr / 2, sr, norm="slaney", mel_scale="slaney")
+    win = au.window_function(2048, "hann")
+    for hop in (512, 2205):
+        P = au.spectrogram(y.astype(np.float64), win, 2048, hop, power=2.0, center=True, pad_mode="constant", dtype=np.float64)
+        np.testing.assert_allclose(OF.stft_mag2(y, 2048, hop), P.T, rtol=0, atol=1e-6 * P.max())
+        S = au.spectrogram(y.astype(np.float64), win, 2048, hop, power=2.0, center=True, pad_mode="constant", mel_filters=fb,
+                           log_mel="dB", db_range=80.0, mel_floor=1e-10, dtype=np.float64)
+        np.testing.assert_allclose(OF.mel_db(y, sr, 2048, hop, 128), S.T, rtol=0, atol=1e-5)
