@@ -468,8 +468,10 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.kclass = KC_TDF_SIMT;
     return launch_gemm_simt(a, dtype, st);
   };
-  // X is clobbered, Y is scratch, result lands in Z (Z != Y)
-  auto run_block = [&](const Block& b, void* X, void* Y, void* Z) -> int {
+  // The network's last TDF2 can apply the final 1x1 conv in its epilogue (debug mode 3 keeps them separate)
+  bool final_fused = false;
+  // X is clobbered, Y is scratch, result lands in Z (Z != Y); last = the block that feeds the final conv
+  auto run_block = [&](const Block& b, void* X, void* Y, void* Z, bool last = false) -> int {
     void* src = X;
     void* dst = Y;
     for (int j = 0; j < g.l; ++j) {
@@ -480,6 +482,12 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     void* tfc = src;
     if (Z == tfc) return (set_error("internal: block output aliases TFC output"), AC_E_INVALID);
     if ((rc = tdf(b.tdf1, b, tfc, nullptr, H))) return rc;
+    if (last && use_tc && net->force_simt == 0 && b.tdf2.pair && tc_tdf2_pair_can_fuse_final(b.tdf2.pair) && b.c == g.g &&
+        b.T == g.dim_t && b.tdf2.M == g.dim_f) {
+      final_fused = true;
+      return launch_tc_tdf2_pair(b.tdf2.pair, (const __nv_bfloat16*)H, (const __nv_bfloat16*)tfc, (__nv_bfloat16*)d_out, B, b.T,
+                                 b.tdf2.af.scale, b.tdf2.af.shift, st, net->final_w, net->final_b);
+    }
     return tdf(b.tdf2, b, H, tfc, Z);
   };
 
@@ -540,9 +548,10 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     }
     { void* t = cur; cur = oth; oth = t; }
     void* Z = (g.l & 1) ? cur : oth;
-    if ((rc = run_block(b, cur, oth, Z))) return rc;
+    if ((rc = run_block(b, cur, oth, Z, i == g.n - 1))) return rc;
     if (Z != cur) { void* t = cur; cur = oth; oth = t; }
   }
+  if (final_fused) return AC_OK;
   if (use_tc) return launch_final_conv_cg8(cur, d_out, (long long)B * g.dim_t, g.dim_f, g.g, net->final_w, net->final_b, st);
   return launch_final_conv(cur, d_out, P0, g.g, net->final_w, net->final_b, dtype, st);
 }

@@ -104,8 +104,11 @@ int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfl
 struct TcTdf2PairWeights;
 int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf2PairWeights** out);
 void tc_tdf2_pair_free(TcTdf2PairWeights* w);
+// final_w/final_b != nullptr: fused final 1x1 conv (C -> 4): `out` is then the [nB*T*M][4] network output
+bool tc_tdf2_pair_can_fuse_final(const TcTdf2PairWeights* w);
 int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                        int nB, int T, const float* scale, const float* shift, cudaStream_t st);
+                        int nB, int T, const float* scale, const float* shift, cudaStream_t st, const float* final_w = nullptr,
+                        const float* final_b = nullptr);
 
 // CTA-pair kernel for the first TDF layer (no residual); *out stays nullptr for unsupported shapes
 struct TcTdf1PairWeights;

@@ -23,9 +23,12 @@ namespace ac {
 
 constexpr int kT2AProducers = 1;
 constexpr int kT2EpiGroups = 3;
-constexpr int kT2EpiWarps = 4 * kT2EpiGroups;
-constexpr int kT2FirstEpiWarp = kT2AProducers + 2;  // warps: 0 weight producer, 1 H producer, 2 MMA, 3..14 epilogue
-constexpr int kT2Threads = (kT2FirstEpiWarp + kT2EpiWarps) * 32;
+constexpr int kT2FirstEpiWarp = kT2AProducers + 2;  // warps: 0 weight producer, 1 H producer, 2 MMA, 3.. epilogue
+// FINAL variant (the network's last TDF2, C = 48, 4 time rows per unit): 4 epilogue groups, one per time row, so
+// that a thread sees all 48 channels of its (t, f) position and can apply the final 1x1 convolution itself.
+constexpr int t2_groups(bool fin) { return fin ? 4 : kT2EpiGroups; }
+constexpr int t2_epi_warps(bool fin) { return 4 * t2_groups(fin); }
+constexpr int t2_threads(bool fin) { return (kT2FirstEpiWarp + t2_epi_warps(fin)) * 32; }
 constexpr int kT2Header = 4096;
 constexpr int kT2MaxStages = 12;
 
@@ -52,6 +55,10 @@ struct T2Params {
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
   int* abort_flag;
+  // FINAL variant only: out4[(b*T + t)*M + m][0..3] = bias[o] + sum_c final_w[o][c] * bf16(Y[b][t][m][c]); Y is not stored
+  const float* final_w;
+  const float* final_b;
+  __nv_bfloat16* out4;
 };
 
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -61,7 +68,8 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       : "memory");
 }
 
-__global__ void __launch_bounds__(kT2Threads, 1)
+template <bool FINAL>
+__global__ void __launch_bounds__(t2_threads(FINAL), 1)
 tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_constant__ CUtensorMap w_map, const T2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
@@ -75,6 +83,8 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [C] (<= 256)
   float* s_shift = s_scale + 256;
+  float* s_fw = s_shift + 256;  // FINAL: [4][C] weights + 4 biases (C = 48: 784 B, ends below kT2Header)
+  constexpr int kEpiWarps = t2_epi_warps(FINAL);
   uint8_t* h_smem = smem + kT2Header;                   // 2 x h_bytes
   uint8_t* ring = h_smem + c.n_hbuf * c.h_bytes;
   volatile int* abort_flag = p.abort_flag;
@@ -94,7 +104,7 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
       mbar_init(&hfull[b], 1);
       mbar_init(&hempty[b], 1);
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 2 * kT2EpiWarps);
+      mbar_init(&tempty[b], 2 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -102,6 +112,8 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
   }
+  if (FINAL)
+    for (int i = threadIdx.x; i < 4 * c.C + 4; i += blockDim.x) s_fw[i] = i < 4 * c.C ? p.final_w[i] : p.final_b[i - 4 * c.C];
   if (warp == kT2AProducers + 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -205,6 +217,79 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
     // ===================== epilogue (12 warps per CTA: own 128 rows x all N columns) =====================
     const int quad = warp & 3;  // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
     const int grp = (warp - kT2FirstEpiWarp) >> 2;
+    if constexpr (FINAL) {
+      // ---- last layer of the network: 16 warps, group = time row; residual add, then the 1x1 conv to 4 channels ----
+      const int tl = grp;  // NTt == 4
+      const size_t plane = (size_t)c.M * 8;
+      const size_t t_off = (size_t)tl * (size_t)(c.C >> 3) * plane;
+      const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
+      const int m_in = (int)rank * 128 + quad * 32 + lane;
+      auto tile_bt = [&](long long tile, int& b, int& t0, int& mp) {
+        const int lu = (int)(tile / c.n_mp);
+        mp = (int)(tile - (long long)lu * c.n_mp);
+        const int u = pair + lu * n_pairs;
+        b = u / p.n_tg;
+        t0 = (u - b * p.n_tg) * c.NTt;
+      };
+      auto res_base = [&](long long tile) -> size_t {
+        int b, t0, mp;
+        tile_bt(tile, b, t0, mp);
+        return cg8_index(b, t0, 0, mp * 256 + m_in, p.T, c.C, c.M) + t_off;
+      };
+      const long long n_tiles = (long long)n_my * c.n_mp;
+      uint4 q[6];
+      if (n_tiles) {
+        const size_t b0 = res_base(0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[k] = ldg_stream_u4(p.residual + b0 + (size_t)k * plane);
+      }
+      for (long long tile = 0; tile < n_tiles; ++tile) {
+        const int buf = (int)(tile & 1);
+        const bool has_next = tile + 1 < n_tiles;
+        const size_t next_base = has_next ? res_base(tile + 1) : 0;
+        if (!mbar_wait(&tfull[buf], (uint32_t)((tile >> 1) & 1), abort_flag)) break;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.N + tl * 48);
+        uint32_t r[3][16];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tmem_ld16(taddr + k * 16, r[k]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
+        float o0 = s_fw[4 * 48], o1 = s_fw[4 * 48 + 1], o2 = s_fw[4 * 48 + 2], o3 = s_fw[4 * 48 + 3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint4 q0 = q[2 * k], q1 = q[2 * k + 1];
+          if (has_next) {  // the residual of the next tile: a full tile period ahead of its use
+            q[2 * k] = ldg_stream_u4(p.residual + next_base + (size_t)(2 * k) * plane);
+            q[2 * k + 1] = ldg_stream_u4(p.residual + next_base + (size_t)(2 * k + 1) * plane);
+          }
+          const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ch = k * 16 + 2 * e;
+            const float2 res = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+            const float v0 = fmaxf(fmaf(__uint_as_float(r[k][2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
+            const float v1 = fmaxf(fmaf(__uint_as_float(r[k][2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
+            // rounded to bf16 exactly like the stored activation the separate 1x1 kernel would read
+            const float2 y = __bfloat1622float2(__floats2bfloat162_rn(v0, v1));
+            o0 = fmaf(s_fw[ch], y.x, o0); o0 = fmaf(s_fw[ch + 1], y.y, o0);
+            o1 = fmaf(s_fw[48 + ch], y.x, o1); o1 = fmaf(s_fw[48 + ch + 1], y.y, o1);
+            o2 = fmaf(s_fw[96 + ch], y.x, o2); o2 = fmaf(s_fw[96 + ch + 1], y.y, o2);
+            o3 = fmaf(s_fw[144 + ch], y.x, o3); o3 = fmaf(s_fw[144 + ch + 1], y.y, o3);
+          }
+        }
+        int b, t0, mp;
+        tile_bt(tile, b, t0, mp);
+        const size_t pos = ((size_t)b * p.T + t0 + tl) * c.M + mp * 256 + m_in;
+        __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), bb = __floats2bfloat162_rn(o2, o3);
+        uint2 ov;
+        ov.x = *reinterpret_cast<uint32_t*>(&a);
+        ov.y = *reinterpret_cast<uint32_t*>(&bb);
+        *reinterpret_cast<uint2*>(p.out4 + pos * 4) = ov;
+      }
+    } else {
     const int chunks_c = c.C >> 4;
     const int per_row = chunks_c > grp ? (chunks_c - grp + kT2EpiGroups - 1) / kT2EpiGroups : 0;
     const int n_mine = c.NTt * per_row;  // 16-column chunks this warp owns per accumulator tile
@@ -290,6 +375,7 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
       for (int i = 0; i < 2 * kMaxMy; ++i) q_cur[i] = q_next[i];
       base = next_base;
     }
+    }  // !FINAL
   }
   tc_fence_before();
   __syncthreads();
@@ -383,10 +469,17 @@ void tc_tdf2_pair_free(TcTdf2PairWeights* w) {
   delete w;
 }
 
+bool tc_tdf2_pair_can_fuse_final(const TcTdf2PairWeights* w) { return w && w->cfg.C == 48 && w->cfg.NTt == 4; }
+
+// final_w != nullptr: the FINAL variant - `out` is then the network output [nB*T*M][4] bf16 and the layer's own
+// activation is never written (unet.cu uses it for the last TDF2 of the network).
 int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                        int nB, int T, const float* scale, const float* shift, cudaStream_t st) {
+                        int nB, int T, const float* scale, const float* shift, cudaStream_t st, const float* final_w,
+                        const float* final_b) {
   AC_REQUIRE(w && in && residual && out, "tc tdf2 pair: null");
   const T2Cfg& c = w->cfg;
+  const bool fin = final_w != nullptr;
+  AC_REQUIRE(!fin || (final_b && tc_tdf2_pair_can_fuse_final(w)), "tc tdf2 pair: final 1x1 fusion needs C == 48, 4 time rows per unit");
   AC_REQUIRE(T % c.NTt == 0, "tc tdf2 pair: T not divisible by the time tile");
   EncodeTiledFn enc = get_tensor_map_encoder();
   AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
@@ -427,17 +520,25 @@ int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, con
   p.n_units = p.n_tg * nB;
   p.scale = scale; p.shift = shift;
   p.residual = residual;
-  p.out = out;
+  p.out = fin ? nullptr : out;
+  p.out4 = fin ? out : nullptr;
+  p.final_w = final_w;
+  p.final_b = final_b;
   p.abort_flag = tc_abort_flag();
   static bool attr_set = false;
   if (!attr_set) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int pairs = device_sm_count() / 2;
   if (pairs > p.n_units) pairs = p.n_units;
-  ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB, 2.0 * nB * (double)T * c.C * (c.K + c.M * 2), st);
-  AC_CHECK_CUDA(tc_launch(tc_tdf2_pair_kernel, 2 * pairs, kT2Threads, c.smem_bytes, st, 2, h_map, w_map, p));
+  ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB + (fin ? 8.0 * c.M * c.C * T * nB : 0.0),
+               2.0 * nB * (double)T * (c.C * (c.K + c.M * (fin ? 1 : 2)) + (fin ? 4 * c.M : 0)), st);
+  if (fin)
+    AC_CHECK_CUDA(tc_launch(tc_tdf2_pair_kernel<true>, 2 * pairs, t2_threads(true), c.smem_bytes, st, 2, h_map, w_map, p));
+  else
+    AC_CHECK_CUDA(tc_launch(tc_tdf2_pair_kernel<false>, 2 * pairs, t2_threads(false), c.smem_bytes, st, 2, h_map, w_map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }
