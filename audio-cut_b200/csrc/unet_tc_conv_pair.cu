@@ -19,7 +19,8 @@ namespace ac {
 
 constexpr int kCpEpiGroups = 3;
 constexpr int kCpEpiWarps = 4 * kCpEpiGroups;
-constexpr int kCpThreads = (2 + kCpEpiWarps) * 32;
+constexpr int kCpWeightWarp = 2 + kCpEpiWarps;  // warps: 0 activation producer, 1 MMA, 2..13 epilogue, 14 weight producer
+constexpr int kCpThreads = (3 + kCpEpiWarps) * 32;
 constexpr int kCpHeader = 5120;
 constexpr int kCpTileM = 128;
 constexpr int kCpRowPos = kCpTileM + 2;
@@ -126,6 +127,27 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
             for (int mt = 0; mt < c.MT; ++mt)
               tma_load_5d_2sm(st + mt * c.a_tile_bytes, &in_map, bar, 0, f0 + (2 * mt + (int)rank) * kCpTileM - 1, kc * (c.KC / 8),
                               t + dt - 1, b);
+            if (++s == c.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kCpWeightWarp) {
+    // ===================== second TMA producer: this CTA's half of the weight slab of every stage ==============
+    // (one issuing thread moves ~14 B/clk, scripts/microbench/tma_box.cu; a stage needs twice that.  Its bytes are
+    //  part of the expect_tx the activation producer posts; a complete_tx that lands first just runs the count negative)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (int u = pair; u < p.n_units && alive; u += n_pairs) {
+        int nt, b, t, f0;
+        decode(u, nt, b, t, f0);
+        for (int dt = 0; dt < 3 && alive; ++dt) {
+          for (int kc = 0; kc < c.nkc; ++kc) {
+            if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+            const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+            uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
             // weights: slab (nt, rank, dt, kc) = 3 taps of b_rows rows each
             const int slab = ((nt * 2 + (int)rank) * 3 + dt) * c.nkc + kc;
             for (int df = 0; df < 3; ++df)

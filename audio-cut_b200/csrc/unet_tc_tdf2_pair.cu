@@ -21,7 +21,7 @@
 
 namespace ac {
 
-constexpr int kT2AProducers = 1;
+constexpr int kT2AProducers = 2;
 constexpr int kT2EpiGroups = 3;
 constexpr int kT2FirstEpiWarp = kT2AProducers + 2;  // warps: 0 weight producer, 1 H producer, 2 MMA, 3.. epilogue
 // FINAL variant (the network's last TDF2, C = 48, 4 time rows per unit): 4 epilogue groups, one per time row, so
