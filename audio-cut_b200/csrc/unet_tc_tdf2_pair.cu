@@ -21,14 +21,14 @@
 
 namespace ac {
 
-constexpr int kT2AProducers = 2;
+constexpr int t2_producers(bool) { return 2; }  // weight producer warps (round-robin over the ring stages)
 constexpr int kT2EpiGroups = 3;
-constexpr int kT2FirstEpiWarp = kT2AProducers + 2;  // warps: 0 weight producer, 1 H producer, 2 MMA, 3.. epilogue
+// warps: [0, P) weight producers, P = H producer, P + 1 = MMA issuer, P + 2 ... epilogue
 // FINAL variant (the network's last TDF2, C = 48, 4 time rows per unit): 4 epilogue groups, one per time row, so
 // that a thread sees all 48 channels of its (t, f) position and can apply the final 1x1 convolution itself.
 constexpr int t2_groups(bool fin) { return fin ? 4 : kT2EpiGroups; }
 constexpr int t2_epi_warps(bool fin) { return 4 * t2_groups(fin); }
-constexpr int t2_threads(bool fin) { return (kT2FirstEpiWarp + t2_epi_warps(fin)) * 32; }
+constexpr int t2_threads(bool fin) { return (t2_producers(fin) + 2 + t2_epi_warps(fin)) * 32; }
 constexpr int kT2Header = 4096;
 constexpr int kT2MaxStages = 12;
 
@@ -81,10 +81,12 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
   uint64_t* tfull = hempty + 2;                         // [2]
   uint64_t* tempty = tfull + 2;                         // [2]       leader: both CTAs' epilogues drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [C] (<= 256)
-  float* s_shift = s_scale + 256;
-  float* s_fw = s_shift + 256;  // FINAL: [4][C] weights + 4 biases (C = 48: 784 B, ends below kT2Header)
+  // per channel pair {scale[c], shift[c], scale[c+1], shift[c+1]}: one 128-bit shared load per two outputs
+  float4* s_ss = reinterpret_cast<float4*>(smem + 1024);   // [C/2] (C <= 256: 2 KB)
+  float4* s_fw = s_ss + 128;  // FINAL: [C] x {w0..w3 of that input channel} + the 4 biases (C = 48: 784 B, below kT2Header)
   constexpr int kEpiWarps = t2_epi_warps(FINAL);
+  constexpr int kT2AProducers = t2_producers(FINAL);
+  constexpr int kT2FirstEpiWarp = kT2AProducers + 2;
   uint8_t* h_smem = smem + kT2Header;                   // 2 x h_bytes
   uint8_t* ring = h_smem + c.n_hbuf * c.h_bytes;
   volatile int* abort_flag = p.abort_flag;
@@ -109,11 +111,14 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < c.C; i += blockDim.x) {
-    s_scale[i] = p.scale[i];
-    s_shift[i] = p.shift[i];
+    reinterpret_cast<float*>(s_ss)[(i >> 1) * 4 + (i & 1) * 2] = p.scale[i];
+    reinterpret_cast<float*>(s_ss)[(i >> 1) * 4 + (i & 1) * 2 + 1] = p.shift[i];
   }
   if (FINAL)
-    for (int i = threadIdx.x; i < 4 * c.C + 4; i += blockDim.x) s_fw[i] = i < 4 * c.C ? p.final_w[i] : p.final_b[i - 4 * c.C];
+    for (int i = threadIdx.x; i < 4 * c.C + 4; i += blockDim.x) {  // final_w is [4][C]
+      const int o = i / c.C, ch = i - o * c.C;
+      reinterpret_cast<float*>(s_fw)[i < 4 * c.C ? ch * 4 + o : i] = i < 4 * c.C ? p.final_w[i] : p.final_b[i - 4 * c.C];
+    }
   if (warp == kT2AProducers + 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -217,164 +222,162 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
     // ===================== epilogue (12 warps per CTA: own 128 rows x all N columns) =====================
     const int quad = warp & 3;  // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
     const int grp = (warp - kT2FirstEpiWarp) >> 2;
+    // Tiles of this pair in order (unit lu, output row pair mp).  Index arithmetic is incremental (no divisions on the
+    // per-tile path) and the residual registers of a chunk are re-requested for the NEXT tile right after they have
+    // been consumed, one tile period ahead of their use: one register set instead of two, no spills at 128 registers
+    // (the spilled version spent ~25 % of its stall samples on local-memory reloads in the epilogue's serial chain).
+    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
+    const size_t plane = (size_t)c.M * 8;
+    const int m_in = (int)rank * 128 + quad * 32 + lane;
+    auto unit_base = [&](int lu, int& b, int& t0) -> size_t {  // once per unit
+      const int u = pair + lu * n_pairs;
+      b = u / p.n_tg;
+      t0 = (u - b * p.n_tg) * c.NTt;
+      return cg8_index(b, t0, 0, m_in, p.T, c.C, c.M);
+    };
+    const long long n_tiles = (long long)n_my * c.n_mp;
+    int lu = 0, mp = 0, ub = 0, ut0 = 0;
+    size_t base = n_tiles ? unit_base(0, ub, ut0) : 0;
     if constexpr (FINAL) {
       // ---- last layer of the network: 16 warps, group = time row; residual add, then the 1x1 conv to 4 channels ----
       const int tl = grp;  // NTt == 4
-      const size_t plane = (size_t)c.M * 8;
       const size_t t_off = (size_t)tl * (size_t)(c.C >> 3) * plane;
-      const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
-      const int m_in = (int)rank * 128 + quad * 32 + lane;
-      auto tile_bt = [&](long long tile, int& b, int& t0, int& mp) {
-        const int lu = (int)(tile / c.n_mp);
-        mp = (int)(tile - (long long)lu * c.n_mp);
-        const int u = pair + lu * n_pairs;
-        b = u / p.n_tg;
-        t0 = (u - b * p.n_tg) * c.NTt;
-      };
-      auto res_base = [&](long long tile) -> size_t {
-        int b, t0, mp;
-        tile_bt(tile, b, t0, mp);
-        return cg8_index(b, t0, 0, mp * 256 + m_in, p.T, c.C, c.M) + t_off;
-      };
-      const long long n_tiles = (long long)n_my * c.n_mp;
       uint4 q[6];
       if (n_tiles) {
-        const size_t b0 = res_base(0);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) q[k] = ldg_stream_u4(p.residual + b0 + (size_t)k * plane);
+        for (int k = 0; k < 6; ++k) q[k] = ldg_stream_u4(p.residual + base + t_off + (size_t)k * plane);
       }
       for (long long tile = 0; tile < n_tiles; ++tile) {
         const int buf = (int)(tile & 1);
         const bool has_next = tile + 1 < n_tiles;
-        const size_t next_base = has_next ? res_base(tile + 1) : 0;
+        const size_t pos = ((size_t)ub * p.T + ut0 + tl) * c.M + mp * 256 + m_in;
+        size_t next_base = base + 256 * 8;
+        if (++mp == c.n_mp) {
+          mp = 0;
+          ++lu;
+          if (has_next) next_base = unit_base(lu, ub, ut0);
+        }
         if (!mbar_wait(&tfull[buf], (uint32_t)((tile >> 1) & 1), abort_flag)) break;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.N + tl * 48);
-        uint32_t r[3][16];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) tmem_ld16(taddr + k * 16, r[k]);
+        uint32_t r[2][16];
+        tmem_ld16(taddr, r[0]);
+        tmem_ld16(taddr + 16, r[1]);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
-        float o0 = s_fw[4 * 48], o1 = s_fw[4 * 48 + 1], o2 = s_fw[4 * 48 + 2], o3 = s_fw[4 * 48 + 3];
+        const float4 bias = s_fw[48];
+        float o0 = bias.x, o1 = bias.y, o2 = bias.z, o3 = bias.w;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
+          if (k == 2) {  // third chunk was requested into r[0] while the second was processed
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
+          }
           const uint4 q0 = q[2 * k], q1 = q[2 * k + 1];
           if (has_next) {  // the residual of the next tile: a full tile period ahead of its use
-            q[2 * k] = ldg_stream_u4(p.residual + next_base + (size_t)(2 * k) * plane);
-            q[2 * k + 1] = ldg_stream_u4(p.residual + next_base + (size_t)(2 * k + 1) * plane);
+            q[2 * k] = ldg_stream_u4(p.residual + next_base + t_off + (size_t)(2 * k) * plane);
+            q[2 * k + 1] = ldg_stream_u4(p.residual + next_base + t_off + (size_t)(2 * k + 1) * plane);
           }
           const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+          float y[16];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int ch = k * 16 + 2 * e;
+            const float4 ss = s_ss[k * 8 + e];
             const float2 res = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-            const float v0 = fmaxf(fmaf(__uint_as_float(r[k][2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
-            const float v1 = fmaxf(fmaf(__uint_as_float(r[k][2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
+            const float v0 = fmaxf(fmaf(__uint_as_float(r[k & 1][2 * e]), ss.x, ss.y), 0.f) + res.x;
+            const float v1 = fmaxf(fmaf(__uint_as_float(r[k & 1][2 * e + 1]), ss.z, ss.w), 0.f) + res.y;
             // rounded to bf16 exactly like the stored activation the separate 1x1 kernel would read
-            const float2 y = __bfloat1622float2(__floats2bfloat162_rn(v0, v1));
-            o0 = fmaf(s_fw[ch], y.x, o0); o0 = fmaf(s_fw[ch + 1], y.y, o0);
-            o1 = fmaf(s_fw[48 + ch], y.x, o1); o1 = fmaf(s_fw[48 + ch + 1], y.y, o1);
-            o2 = fmaf(s_fw[96 + ch], y.x, o2); o2 = fmaf(s_fw[96 + ch + 1], y.y, o2);
-            o3 = fmaf(s_fw[144 + ch], y.x, o3); o3 = fmaf(s_fw[144 + ch + 1], y.y, o3);
+            const float2 yy = __bfloat1622float2(__floats2bfloat162_rn(v0, v1));
+            y[2 * e] = yy.x;
+            y[2 * e + 1] = yy.y;
+          }
+          if (k == 0) tmem_ld16(taddr + 32, r[0]);  // r[0] is consumed: fetch the third chunk behind the second's math
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float4 fw = s_fw[k * 16 + e];
+            o0 = fmaf(fw.x, y[e], o0);
+            o1 = fmaf(fw.y, y[e], o1);
+            o2 = fmaf(fw.z, y[e], o2);
+            o3 = fmaf(fw.w, y[e], o3);
           }
         }
-        int b, t0, mp;
-        tile_bt(tile, b, t0, mp);
-        const size_t pos = ((size_t)b * p.T + t0 + tl) * c.M + mp * 256 + m_in;
         __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), bb = __floats2bfloat162_rn(o2, o3);
         uint2 ov;
         ov.x = *reinterpret_cast<uint32_t*>(&a);
         ov.y = *reinterpret_cast<uint32_t*>(&bb);
         *reinterpret_cast<uint2*>(p.out4 + pos * 4) = ov;
+        base = next_base;
       }
     } else {
-    const int chunks_c = c.C >> 4;
-    const int per_row = chunks_c > grp ? (chunks_c - grp + kT2EpiGroups - 1) / kT2EpiGroups : 0;
-    const int n_mine = c.NTt * per_row;  // 16-column chunks this warp owns per accumulator tile
-    constexpr int kMaxMy = 4;
-    const size_t plane = (size_t)c.M * 8;
-    const size_t t_stride = (size_t)(c.C >> 3) * plane;
-    int my_col[kMaxMy], my_ch[kMaxMy];
-    size_t my_off[kMaxMy];
+      const int chunks_c = c.C >> 4;
+      const int per_row = chunks_c > grp ? (chunks_c - grp + kT2EpiGroups - 1) / kT2EpiGroups : 0;
+      const int n_mine = c.NTt * per_row;  // 16-column chunks this warp owns per accumulator tile (<= 4)
+      constexpr int kMaxMy = 4;
+      const size_t t_stride = (size_t)(c.C >> 3) * plane;
+      // chunk i -> (time row tl, k-th chunk of this group in the row); i is a compile-time constant after unrolling
+      auto chunk_tl = [&](int i) { return (int)(i >= per_row) + (int)(i >= 2 * per_row) + (int)(i >= 3 * per_row); };
+      auto chunk_cq = [&](int i) { return grp + kT2EpiGroups * (i - chunk_tl(i) * per_row); };
+      auto chunk_off = [&](int i) { return (size_t)chunk_tl(i) * t_stride + (size_t)(chunk_cq(i) * 2) * plane; };
+      // the residual of tile n + 1 is requested at the start of tile n (before the accumulator wait); accumulators are
+      // read one 16-column chunk at a time so that {16 accumulators, 2 x residual sets} stay within 128 registers
+      auto fetch = [&](size_t from, uint4* q) {
 #pragma unroll
-    for (int i = 0; i < kMaxMy; ++i) {
-      const int tl = per_row ? i / per_row : 0, k = per_row ? i - tl * per_row : 0;
-      const int cq = grp + kT2EpiGroups * k;
-      my_ch[i] = cq * 16;
-      my_col[i] = tl * c.C + cq * 16;
-      my_off[i] = (size_t)tl * t_stride + (size_t)(cq * 2) * plane;
-    }
-    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), 0);
-    // Tiles of this pair in order: tile = lu * n_mp + mp.  The residual of tile n + 1 is requested at the start of
-    // tile n (a full tile period ahead), so no global-load latency is left on the epilogue's critical path; the
-    // accumulators are read in two halves to keep {2 x 16 accumulators, 2 x residual sets} within 128 registers.
-    auto tile_base = [&](long long tile) -> size_t {
-      const int lu = (int)(tile / c.n_mp), mp = (int)(tile - (long long)lu * c.n_mp);
-      const int u = pair + lu * n_pairs;
-      const int b = u / p.n_tg, t0 = (u - b * p.n_tg) * c.NTt;
-      return cg8_index(b, t0, 0, mp * 256 + (int)rank * 128 + quad * 32 + lane, p.T, c.C, c.M);
-    };
-    auto fetch = [&](size_t base, uint4* q) {
-#pragma unroll
-      for (int i = 0; i < kMaxMy; ++i) {
-        if (i < n_mine) {
-          q[2 * i] = ldg_stream_u4(p.residual + base + my_off[i]);
-          q[2 * i + 1] = ldg_stream_u4(p.residual + base + my_off[i] + plane);
-        }
-      }
-    };
-    const long long n_tiles = (long long)n_my * c.n_mp;
-    uint4 q_cur[2 * kMaxMy], q_next[2 * kMaxMy];
-    size_t base = n_tiles ? tile_base(0) : 0;
-    if (n_tiles) fetch(base, q_cur);
-    for (long long tile = 0; tile < n_tiles; ++tile) {
-      const int buf = (int)(tile & 1);
-      const bool has_next = tile + 1 < n_tiles;
-      const size_t next_base = has_next ? tile_base(tile + 1) : base;
-      if (has_next) fetch(next_base, q_next);
-      if (!mbar_wait(&tfull[buf], (uint32_t)((tile >> 1) & 1), abort_flag)) break;
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.N);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t r[2][16];
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          if (2 * h + k < n_mine) tmem_ld16(taddr + my_col[2 * h + k], r[k]);
-        tmem_ld_wait();
-        if (h == 1) {  // every accumulator column of this warp is in registers: hand the TMEM buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int i = 2 * h + k;
+        for (int i = 0; i < kMaxMy; ++i)
           if (i < n_mine) {
+            q[2 * i] = ldg_stream_u4(p.residual + from + chunk_off(i));
+            q[2 * i + 1] = ldg_stream_u4(p.residual + from + chunk_off(i) + plane);
+          }
+      };
+      uint4 q_cur[2 * kMaxMy], q_next[2 * kMaxMy];
+      if (n_tiles) fetch(base, q_cur);
+      for (long long tile = 0; tile < n_tiles; ++tile) {
+        const int buf = (int)(tile & 1);
+        const bool has_next = tile + 1 < n_tiles;
+        size_t next_base = base + 256 * 8;
+        if (++mp == c.n_mp) {
+          mp = 0;
+          ++lu;
+          if (has_next) next_base = unit_base(lu, ub, ut0);
+        }
+        if (has_next) fetch(next_base, q_next);
+        if (!mbar_wait(&tfull[buf], (uint32_t)((tile >> 1) & 1), abort_flag)) break;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.N);
+#pragma unroll
+        for (int i = 0; i < kMaxMy; ++i) {
+          if (i < n_mine) {
+            uint32_t r[16];
+            tmem_ld16(taddr + chunk_tl(i) * c.C + chunk_cq(i) * 16, r);
+            tmem_ld_wait();
+            if (i == n_mine - 1) {  // every accumulator column of this warp is in registers: hand the TMEM buffer back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
+            }
+            const size_t off = chunk_off(i);
             const uint4 q0 = q_cur[2 * i], q1 = q_cur[2 * i + 1];
             const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            const int ch0 = chunk_cq(i) * 16;
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const int ch = my_ch[i] + 2 * e;
+              const float4 ss = s_ss[(ch0 >> 1) + e];
               const float2 res = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-              const float v0 = fmaxf(fmaf(__uint_as_float(r[k][2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
-              const float v1 = fmaxf(fmaf(__uint_as_float(r[k][2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), ss.x, ss.y), 0.f) + res.x;
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), ss.z, ss.w), 0.f) + res.y;
               __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
               pk[e] = *reinterpret_cast<uint32_t*>(&hh);
             }
-            const size_t idx = base + my_off[i];
+            const size_t idx = base + off;
             *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(p.out + idx + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < 2 * kMaxMy; ++i) q_cur[i] = q_next[i];
-      base = next_base;
-    }
+        for (int i = 0; i < 2 * kMaxMy; ++i) q_cur[i] = q_next[i];
+        base = next_base;
+      }
     }  // !FINAL
   }
   tc_fence_before();
