@@ -20,7 +20,8 @@ namespace ac {
 constexpr int kT1EpiGroups = 3;
 constexpr int kT1EpiWarps = 4 * kT1EpiGroups;
 constexpr int kT1FirstEpiWarp = 2;  // warps: 0 producer, 1 MMA, 2..13 epilogue
-constexpr int kT1Threads = (kT1FirstEpiWarp + kT1EpiWarps) * 32;
+constexpr int kT1WeightWarp = kT1FirstEpiWarp + kT1EpiWarps;  // second TMA producer: the weight blobs of every stage
+constexpr int kT1Threads = (kT1FirstEpiWarp + kT1EpiWarps + 1) * 32;
 constexpr int kT1Header = 4096;
 constexpr int kT1MaxStages = 8;
 
@@ -116,15 +117,30 @@ tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
           if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)c.stage_bytes);
           const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
           uint8_t* st = ring + (size_t)s * c.stage_bytes;
-          for (int mp = 0; mp < c.n_mp; ++mp) {
-            const int blob = (mp * 2 + (int)rank) * c.nk + kc;
-            t1_tma_load_2d_2sm(st + (size_t)mp * c.a_blob_bytes, &w_map, bar, 0, blob * (c.a_blob_bytes / 512));
-          }
           uint8_t* xb = st + (size_t)c.n_mp * c.a_blob_bytes;
           if (c.split_t)
             tma_load_5d_2sm(xb, &x_map, bar, 0, kc * c.Kt, 0, t0 + (int)rank * (c.NTt / 2), b);
           else
             tma_load_5d_2sm(xb, &x_map, bar, 0, kc * c.Kt, (int)rank * (c.C / 16), t0, b);
+        }
+      }
+    }
+  } else if (warp == kT1WeightWarp) {
+    // ===================== second producer: the n_mp weight blobs of every stage (their bytes are part of the
+    // expect_tx the first producer posts; one issuing thread alone tops out near 14 B/clk) =====================
+    if (lane == 0) {
+      long long i = 0;
+      bool alive = true;
+      for (int lu = 0; lu < n_my && alive; ++lu) {
+        for (int kc = 0; kc < c.nk; ++kc, ++i) {
+          const int s = (int)(i % c.stages);
+          if (!mbar_wait(&empty[s], (uint32_t)(((i / c.stages) & 1) ^ 1), abort_flag)) { alive = false; break; }
+          const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+          uint8_t* st = ring + (size_t)s * c.stage_bytes;
+          for (int mp = 0; mp < c.n_mp; ++mp) {
+            const int blob = (mp * 2 + (int)rank) * c.nk + kc;
+            t1_tma_load_2d_2sm(st + (size_t)mp * c.a_blob_bytes, &w_map, bar, 0, blob * (c.a_blob_bytes / 512));
+          }
         }
       }
     }
