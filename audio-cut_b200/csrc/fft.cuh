@@ -10,6 +10,7 @@ struct FftDev {
   int n;
   int n_radix;
   int radix[12];
+  unsigned magic[12];  // ceil(2^32 / Ns) of every pass: j / Ns == __umulhi(j, magic) for j < 2^16, Ns <= 2^15
   const float2* tw;
 };
 
@@ -17,7 +18,12 @@ inline FftDev make_fft_dev(const FftPlan* p) {
   FftDev d;
   d.n = p->n;
   d.n_radix = p->n_radix;
-  for (int i = 0; i < 12; ++i) d.radix[i] = i < p->n_radix ? p->radix[i] : 1;
+  unsigned long long ns = 1;
+  for (int i = 0; i < 12; ++i) {
+    d.radix[i] = i < p->n_radix ? p->radix[i] : 1;
+    d.magic[i] = ns == 1 ? 0u : (unsigned)((0x100000000ull + ns - 1) / ns);
+    ns *= (unsigned long long)d.radix[i];
+  }
   d.tw = p->d_twiddle;
   return d;
 }
@@ -96,11 +102,12 @@ __device__ __forceinline__ void dft_small(float2* v) {
 
 template <int R, bool INV>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* __restrict__ out, int n, int Ns,
-                                         const float2* __restrict__ tw) {
+                                         unsigned magic, const float2* __restrict__ tw) {
   const int nb = n / R;
   const int tmul = n / (Ns * R);
   for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-    const int k = j % Ns;
+    const int q = Ns == 1 ? j : (int)__umulhi((unsigned)j, magic);  // j / Ns without a division
+    const int k = j - q * Ns;
     const int ts = k * tmul;
     float2 v[R];
 #pragma unroll
@@ -114,7 +121,7 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
       }
     }
     dft_small<R, INV>(v);
-    const int j0 = (j / Ns) * Ns * R + k;
+    const int j0 = q * Ns * R + k;
 #pragma unroll
     for (int r = 0; r < R; ++r) out[fpad(j0 + r * Ns)] = v[r];
   }
@@ -130,11 +137,11 @@ __device__ __forceinline__ float2* fft_smem(float2* buf0, float2* buf1, const Ff
   for (int s = 0; s < p.n_radix; ++s) {
     const int R = p.radix[s];
     switch (R) {
-      case 2: fft_pass<2, INV>(in, out, p.n, Ns, p.tw); break;
-      case 3: fft_pass<3, INV>(in, out, p.n, Ns, p.tw); break;
-      case 4: fft_pass<4, INV>(in, out, p.n, Ns, p.tw); break;
-      case 5: fft_pass<5, INV>(in, out, p.n, Ns, p.tw); break;
-      default: fft_pass<8, INV>(in, out, p.n, Ns, p.tw); break;
+      case 2: fft_pass<2, INV>(in, out, p.n, Ns, p.magic[s], p.tw); break;
+      case 3: fft_pass<3, INV>(in, out, p.n, Ns, p.magic[s], p.tw); break;
+      case 4: fft_pass<4, INV>(in, out, p.n, Ns, p.magic[s], p.tw); break;
+      case 5: fft_pass<5, INV>(in, out, p.n, Ns, p.magic[s], p.tw); break;
+      default: fft_pass<8, INV>(in, out, p.n, Ns, p.magic[s], p.tw); break;
     }
     __syncthreads();
     float2* t = in;
@@ -152,7 +159,8 @@ __device__ __forceinline__ float2* fft_smem(float2* buf0, float2* buf1, const Ff
 // the footprint (61 KB instead of 123 KB at n_fft = 7680) is what lets three STFT CTAs share an SM and
 // hide each other's shared-memory / twiddle latency.
 template <int R, bool INV, int MAXB>
-__device__ __forceinline__ void fft_pass_inplace(float2* __restrict__ buf, int n, int Ns, const float2* __restrict__ tw) {
+__device__ __forceinline__ void fft_pass_inplace(float2* __restrict__ buf, int n, int Ns, unsigned magic,
+                                                 const float2* __restrict__ tw) {
   const int nb = n / R;
   const int tmul = n / (Ns * R);
   float2 v[MAXB][R];
@@ -160,7 +168,7 @@ __device__ __forceinline__ void fft_pass_inplace(float2* __restrict__ buf, int n
   for (int i = 0; i < MAXB; ++i) {
     const int j = threadIdx.x + i * blockDim.x;
     if (j < nb) {
-      const int k = j % Ns;
+      const int k = Ns == 1 ? 0 : j - (int)__umulhi((unsigned)j, magic) * Ns;
       const int ts = k * tmul;
 #pragma unroll
       for (int r = 0; r < R; ++r) v[i][r] = buf[fpad(j + r * nb)];
@@ -180,8 +188,9 @@ __device__ __forceinline__ void fft_pass_inplace(float2* __restrict__ buf, int n
   for (int i = 0; i < MAXB; ++i) {
     const int j = threadIdx.x + i * blockDim.x;
     if (j < nb) {
-      const int k = j % Ns;
-      const int j0 = (j / Ns) * Ns * R + k;
+      const int q = Ns == 1 ? j : (int)__umulhi((unsigned)j, magic);
+      const int k = j - q * Ns;
+      const int j0 = q * Ns * R + k;
 #pragma unroll
       for (int r = 0; r < R; ++r) buf[fpad(j0 + r * Ns)] = v[i][r];
     }
@@ -206,11 +215,11 @@ __device__ __forceinline__ void fft_smem_inplace(float2* buf, const FftDev& p) {
   for (int s = 0; s < p.n_radix; ++s) {
     const int R = p.radix[s];
     switch (R) {
-      case 2: fft_pass_inplace<2, INV, 8>(buf, p.n, Ns, p.tw); break;
-      case 3: fft_pass_inplace<3, INV, 5>(buf, p.n, Ns, p.tw); break;
-      case 4: fft_pass_inplace<4, INV, 4>(buf, p.n, Ns, p.tw); break;
-      case 5: fft_pass_inplace<5, INV, 3>(buf, p.n, Ns, p.tw); break;
-      default: fft_pass_inplace<8, INV, 2>(buf, p.n, Ns, p.tw); break;
+      case 2: fft_pass_inplace<2, INV, 8>(buf, p.n, Ns, p.magic[s], p.tw); break;
+      case 3: fft_pass_inplace<3, INV, 5>(buf, p.n, Ns, p.magic[s], p.tw); break;
+      case 4: fft_pass_inplace<4, INV, 4>(buf, p.n, Ns, p.magic[s], p.tw); break;
+      case 5: fft_pass_inplace<5, INV, 3>(buf, p.n, Ns, p.magic[s], p.tw); break;
+      default: fft_pass_inplace<8, INV, 2>(buf, p.n, Ns, p.magic[s], p.tw); break;
     }
     Ns *= R;
   }

@@ -58,6 +58,10 @@ def _device_mono(wave: Optional[Wave], device: torch.device) -> Optional[torch.T
     """``_ensure_mono`` (refine.py:59-66) + residency: 1-D stays, 2-D is the float32 channel mean, else flatten."""
     if wave is None:
         return None
+    if (wave.dtype if isinstance(wave, torch.Tensor) else np.asarray(wave).dtype) not in (torch.float32, np.float32):
+        # the reference computes in the dtype it is given; the kernel reproduces its float32 arithmetic (the pipeline's
+        # dtype: librosa.load and the separator both return float32) - refuse anything else rather than drift silently
+        raise TypeError("finalize_cut_points on the GPU expects float32 waves")
     t = wave if isinstance(wave, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(wave))
     t = t.to(device=device, dtype=torch.float32, non_blocking=True)
     if t.dim() == 1:

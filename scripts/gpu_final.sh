@@ -3,6 +3,7 @@ set -x
 R=${1:-r01}
 python -m pytest tests -m gpu -x -q > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${R}_pytest_gpu.log
 tail -2 gpurun_out/${R}_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${R}_smoke.log 2>&1; tail -1 gpurun_out/${R}_smoke.log
 python bench.py > gpurun_out/${R}_bench_final.json 2> gpurun_out/${R}_bench_final.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference.json 2> gpurun_out/${R}_bench_reference.err; echo "ref rc=$?"
 # launch list of the bench command itself (times under ncu are cold-cache and serialised: shares, not absolutes)
@@ -15,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
     python scripts/dev_unet_tc_once.py 16 > /dev/null 2>&1
 python scripts/launch_table.py gpurun_out/${R}_launches_unet.csv > gpurun_out/${R}_unet_launches.txt
 # full-set capture of every tensor-core kernel of one forward (second forward), report kept on the box, summary exported
-ncu --set full --clock-control none --import-source on -k regex:"tc_|conv_cg8|tdf_small" -s 66 -c 66 -o /tmp/prof_unet \
+ncu --set full --clock-control none --import-source on -k regex:"tc_conv3x3|tc_tdf|tc_resample" -s 64 -c 64 -o /tmp/prof_unet \
     python scripts/dev_unet_tc_once.py 16 > gpurun_out/${R}_ncu_unet_full.log 2>&1
 python scripts/ncu_summary.py rep /tmp/prof_unet.ncu-rep > gpurun_out/${R}_unet_ncu_full.md
 rm -f gpurun_out/${R}_launches_bench.csv
