@@ -103,7 +103,16 @@ static int launch_frame_reduce(const float* d_x, long long n, int frame, int hop
   AC_REQUIRE(frame + 8 <= kRmsMaxTileFloats, "frame too long");
   const long long n_frames = ac_frame_count(n, frame, hop, center);
   if (n_frames <= 0) return AC_OK;
-  int fr = 1 + (kRmsMaxTileFloats - 8 - frame) / hop;
+  // Tile size: small tiles put 3-4 CTAs on an SM, so one CTA's load phase overlaps the others' reduce phase (the
+  // 94 KB tile, 2 CTAs per SM, ran at 2.8-3.4 TB/s; 32-46 KB tiles reach 3.9-4.9 TB/s on one hour of audio).  Frames
+  // overlap by frame - hop samples, re-read once per tile: take the smallest tile that keeps that below ~26 %.
+  const int caps[4] = {8192, 11776, 15600, kRmsMaxTileFloats};
+  int fr = 1;
+  for (int i = 0; i < 4; ++i) {
+    if (caps[i] - 8 < frame) continue;
+    fr = 1 + (caps[i] - 8 - frame) / hop;
+    if ((double)(frame > hop ? frame - hop : 0) <= 0.26 * (double)fr * hop) break;
+  }
   if (fr > 64) fr = 64;
   // keep at least ~4 CTAs per SM worth of work when the signal is short
   const long long want = 4LL * device_sm_count();

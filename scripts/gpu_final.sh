@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
     python scripts/dev_unet_tc_once.py 16 > /dev/null 2>&1
 python scripts/launch_table.py gpurun_out/${R}_launches_unet.csv > gpurun_out/${R}_unet_launches.txt
 # full-set capture of every tensor-core kernel of one forward (second forward), report kept on the box, summary exported
-ncu --set full --clock-control none --import-source on -k regex:"tc_conv3x3|tc_tdf|tc_resample" -s 64 -c 64 -o /tmp/prof_unet \
+ncu --set full --clock-control none --import-source on -k regex:"tc_conv3x3|tc_tdf|tc_resample" -s 59 -c 59 -o /tmp/prof_unet \
     python scripts/dev_unet_tc_once.py 16 > gpurun_out/${R}_ncu_unet_full.log 2>&1
 python scripts/ncu_summary.py rep /tmp/prof_unet.ncu-rep > gpurun_out/${R}_unet_ncu_full.md
 rm -f gpurun_out/${R}_launches_bench.csv
