@@ -15,6 +15,7 @@
 //                          predecessors; back pointers go to global memory;
 //   3. pyin_backtrack_kernel  pointer chase from the best final state.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -328,12 +329,23 @@ struct VitParams {
   int* final_state;
 };
 
+// adj is stored with kVitPad cells of -inf on either side of each [nb] row, so the fixed-width fast path can read its
+// whole band without clipping (an out-of-range predecessor is -inf + logtri = -inf and never wins a strict >).
+constexpr int kVitPad = kVitMaxHalf + 2;
+__host__ __device__ inline int vit_row(int nb) { return nb + 2 * kVitPad; }
+
+// HALF > 0: compile-time band half width (librosa's default geometry gives 20): the triangle lives in registers
+// (it is symmetric: HALF + 1 values), a thread owns TWO adjacent pitch bins and slides one window of
+// 2*HALF + 2 predecessors over both, i.e. per step 84 shared loads for 164 candidates instead of 246 -
+// the loop was shared-memory bound.  HALF == 0: run-time width (any hop / sr), one bin per thread.
+template <int HALF>
 __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitParams p) {
   extern __shared__ double vsm[];
   const int nb = p.nb, S = 2 * nb, half = p.half;
+  const int row = vit_row(nb);
   double* val = vsm;                 // [2][S] raw values (double buffered)
-  double* adj = val + 2 * S;         // [2][S] value - lognorm[k]
-  double* obs = adj + 2 * S;         // [2][nb] log observation of the voiced states (double buffered)
+  double* adj = val + 2 * S;         // [2][2][row] value - lognorm[k], padded rows (voiced, unvoiced)
+  double* obs = adj + 4 * row;       // [2][nb] log observation of the voiced states (double buffered)
   double* tri = obs + 2 * nb;        // [2*half+1]
   double* lnorm = tri + (2 * kVitMaxHalf + 1);  // [nb]
   double* redv = lnorm + nb;         // [32]
@@ -344,7 +356,11 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
 
   for (int i = tid; i < 2 * half + 1; i += kVitThreads) tri[i] = p.logtri[i];
   for (int i = tid; i < nb; i += kVitThreads) { lnorm[i] = p.lognorm[i]; obs[i] = kLogTiny; obs[nb + i] = kLogTiny; }
+  for (int i = tid; i < 4 * row; i += kVitThreads) adj[i] = -INFINITY;
   __syncthreads();
+  double T[HALF + 1];  // T[d] = logtri[half + d] = logtri[half - d]
+#pragma unroll
+  for (int d = 0; d <= HALF; ++d) T[d] = tri[half + d];
   // Observation inputs are software-pipelined through registers two steps ahead, so no global-memory
   // latency sits on the per-step critical path: thread i owns candidate i of a frame (n_cand <= 328 < 640).
   struct ObsIn {
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
       const int k = s < nb ? s : s - nb;
       const double v = (s < nb ? obs[s] : lu0) + p.log_init;
       val[s] = v;
-      adj[s] = v - lnorm[k];
+      adj[(s < nb ? 0 : row) + kVitPad + k] = v - lnorm[k];
     }
   }
   __syncthreads();
@@ -398,7 +414,7 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
   for (long long t = 1; t < p.n_steps; ++t) {
     const int ob = (int)(t & 1);
     const double* cv = val + cur * S;
-    const double* ca = adj + cur * S;
+    const double* ca = adj + cur * 2 * row + kVitPad;  // ca[k] voiced, ca[row + k] unvoiced
     const ObsIn in3 = fetch(t + 2);  // issued now, consumed two steps later
     // ---- P1: per-warp (max, first argmax) of the previous values + the in-band maxima
     {
@@ -417,18 +433,47 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
       if (lane == 0) { redv[warp] = bv; redi[warp] = bi; }
       if (tid == kVitThreads - 1) redv[31] = log((1.0 - (double)in1.vp) / (double)nb + tiny);
     }
-    double mv = -INFINITY, mu = -INFINITY;
-    int av = 0, au = 0;
-    if (tid < nb) {
-      const int j = tid;
-      const int k_lo = j - half < 0 ? 0 : j - half;
-      const int k_hi = j + half > nb - 1 ? nb - 1 : j + half;
-      const double* tr = tri + (half - j);  // tr[k] = logtri[k - j + half]: the triangle is symmetric
-      for (int k = k_lo; k <= k_hi; ++k) {
-        const double l = tr[k];
-        const double a = ca[k] + l, b = ca[nb + k] + l;
-        if (a > mv) { mv = a; av = k; }
-        if (b > mu) { mu = b; au = k; }
+    // bins owned by this thread: HALF > 0 -> {2 tid, 2 tid + 1}, else {tid}
+    constexpr int kOwn = HALF > 0 ? 2 : 1;
+    const int jbase = kOwn * tid;
+    double mv[kOwn], mu[kOwn];
+    int av[kOwn], au[kOwn];
+#pragma unroll
+    for (int o = 0; o < kOwn; ++o) { mv[o] = -INFINITY; mu[o] = -INFINITY; av[o] = 0; au[o] = 0; }
+    if (jbase < nb) {
+      if constexpr (HALF > 0) {
+        // window k = jbase - HALF + i, i = 0 .. 2 HALF + 1; bin jbase sees d = i - HALF (i <= 2 HALF), bin jbase + 1
+        // sees d = i - HALF - 1 (i >= 1); candidates are visited in increasing k for either bin, as before
+        const double* wv = ca + (jbase - HALF);
+        const double* wu = wv + row;
+#pragma unroll
+        for (int i = 0; i <= 2 * HALF + 1; ++i) {
+          const double cvk = wv[i], cuk = wu[i];
+          const int k = jbase - HALF + i;
+          if (i <= 2 * HALF) {
+            const double l = T[i >= HALF ? i - HALF : HALF - i];
+            const double a = cvk + l, b = cuk + l;
+            if (a > mv[0]) { mv[0] = a; av[0] = k; }
+            if (b > mu[0]) { mu[0] = b; au[0] = k; }
+          }
+          if (i >= 1) {
+            const double l = T[i - 1 >= HALF ? i - 1 - HALF : HALF - (i - 1)];
+            const double a = cvk + l, b = cuk + l;
+            if (a > mv[kOwn - 1]) { mv[kOwn - 1] = a; av[kOwn - 1] = k; }
+            if (b > mu[kOwn - 1]) { mu[kOwn - 1] = b; au[kOwn - 1] = k; }
+          }
+        }
+      } else {
+        const int j = jbase;
+        const int k_lo = j - half < 0 ? 0 : j - half;
+        const int k_hi = j + half > nb - 1 ? nb - 1 : j + half;
+        const double* tr = tri + (half - j);  // tr[k] = logtri[k - j + half]: the triangle is symmetric
+        for (int k = k_lo; k <= k_hi; ++k) {
+          const double l = tr[k];
+          const double a = ca[k] + l, b = ca[row + k] + l;
+          if (a > mv[0]) { mv[0] = a; av[0] = k; }
+          if (b > mu[0]) { mu[0] = b; au[0] = k; }
+        }
       }
     }
     __syncthreads();  // S1: warp partials visible
@@ -444,27 +489,30 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
         const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
         if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
       }
-      if (tid < nb) {
-        const int j = tid;
-        const double oob = gv + kLogTiny;
-        // candidates in increasing state index: voiced k, then unvoiced k; replace only on strict improvement
-        double best_v = mv + p.log_stay, best_u = mv + p.log_switch;
-        int arg_v = av, arg_u = av;
-        const double c2v = mu + p.log_switch, c2u = mu + p.log_stay;
-        if (c2v > best_v) { best_v = c2v; arg_v = nb + au; }
-        if (c2u > best_u) { best_u = c2u; arg_u = nb + au; }
-        if (oob > best_v || (oob == best_v && gi < arg_v)) { best_v = oob; arg_v = gi; }
-        if (oob > best_u || (oob == best_u && gi < arg_u)) { best_u = oob; arg_u = gi; }
-        const double lu = redv[31];  // log observation of the unvoiced states, published in P1
-        const double nv = obs[ob * nb + j] + best_v, nu = lu + best_u;
-        double* wv = val + (cur ^ 1) * S;
-        double* wa = adj + (cur ^ 1) * S;
-        const double ln = lnorm[j];
-        wv[j] = nv; wv[nb + j] = nu;
-        wa[j] = nv - ln; wa[nb + j] = nu - ln;
-        unsigned short* pr = p.ptr + t * (long long)S;
-        pr[j] = (unsigned short)arg_v;
-        pr[nb + j] = (unsigned short)arg_u;
+#pragma unroll
+      for (int o = 0; o < kOwn; ++o) {
+        const int j = jbase + o;
+        if (j < nb) {
+          const double oob = gv + kLogTiny;
+          // candidates in increasing state index: voiced k, then unvoiced k; replace only on strict improvement
+          double best_v = mv[o] + p.log_stay, best_u = mv[o] + p.log_switch;
+          int arg_v = av[o], arg_u = av[o];
+          const double c2v = mu[o] + p.log_switch, c2u = mu[o] + p.log_stay;
+          if (c2v > best_v) { best_v = c2v; arg_v = nb + au[o]; }
+          if (c2u > best_u) { best_u = c2u; arg_u = nb + au[o]; }
+          if (oob > best_v || (oob == best_v && gi < arg_v)) { best_v = oob; arg_v = gi; }
+          if (oob > best_u || (oob == best_u && gi < arg_u)) { best_u = oob; arg_u = gi; }
+          const double lu = redv[31];  // log observation of the unvoiced states, published in P1
+          const double nv = obs[ob * nb + j] + best_v, nu = lu + best_u;
+          double* wv = val + (cur ^ 1) * S;
+          double* wa = adj + (cur ^ 1) * 2 * row + kVitPad;
+          const double ln = lnorm[j];
+          wv[j] = nv; wv[nb + j] = nu;
+          wa[j] = nv - ln; wa[row + j] = nu - ln;
+          unsigned short* pr = p.ptr + t * (long long)S;
+          pr[j] = (unsigned short)arg_v;
+          pr[nb + j] = (unsigned short)arg_u;
+        }
       }
       wrote_next = scatter(in2, ob ^ 1);
     }
@@ -492,6 +540,225 @@ __global__ void __launch_bounds__(kVitThreads, 1) pyin_viterbi_kernel(const VitP
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
     if (tid == 0) *p.final_state = bi;
+  }
+}
+
+// ---- fast Viterbi: ONE barrier per step ---------------------------------------------------------------------
+// Same recurrence, same arithmetic and visiting order as pyin_viterbi_kernel (outputs are bit-identical; the
+// generic kernel stays as the fallback for other band widths and as the cross-check), restructured so that the
+// only things left on the sequential critical path are the 2 x 42-predecessor window and one block barrier:
+//   * warps 0-9 own two adjacent pitch bins per thread (triangle in registers, see above); the block maximum the
+//     out-of-band transitions need is reduced from the NEW values while they are still in registers (one partial
+//     per warp, published with the step's barrier) instead of a separate pass over shared memory;
+//   * warps 10-20 own the candidates: they prefetch frame t+3, take the fp64 log of frame t+2's probabilities,
+//     scatter frame t+1's observations into a 3-deep ring and un-scatter frame t-1's - all concurrently with the
+//     compute warps, never between two barriers of the same step; thread 320 does the same for the unvoiced term.
+constexpr int kVitFastThreads = 672;
+constexpr int kVitFastComp = 320;  // threads of the compute warps
+template <int HALF>
+__global__ void __launch_bounds__(kVitFastThreads, 1) pyin_viterbi_fast_kernel(const VitParams p) {
+  extern __shared__ double vsm[];
+  const int nb = p.nb, S = 2 * nb;
+  const int row = vit_row(nb);
+  double* adj = vsm;               // [2][2][row] value - lognorm[k], padded rows (voiced, unvoiced), double buffered
+  double* obs = adj + 4 * row;     // [3][nb] log observation of the voiced states, ring over steps
+  double* lnorm = obs + 3 * nb;    // [nb]
+  double* redv = lnorm + nb;       // [2][16] per-warp maxima of the values of a step
+  double* lu_s = redv + 32;        // [2] log observation of the unvoiced states
+  int* redi = reinterpret_cast<int*>(lu_s + 2);  // [2][16]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double tiny = 2.2250738585072014e-308;
+  constexpr int kCompWarps = kVitFastComp / 32;
+  const int jbase = 2 * tid;
+  const bool is_comp = tid < kVitFastComp;
+  const int cidx = kVitFastThreads - 1 - tid;  // candidate slot (threads >= 320: slots 351 .. 0; >= kYinMaxCand unused)
+  const bool is_cand = !is_comp && cidx < kYinMaxCand;
+  const bool is_lu = tid == kVitFastComp;
+
+  for (int i = tid; i < nb; i += kVitFastThreads) lnorm[i] = p.lognorm[i];
+  for (int i = tid; i < 3 * nb; i += kVitFastThreads) obs[i] = kLogTiny;
+  for (int i = tid; i < 4 * row; i += kVitFastThreads) adj[i] = -INFINITY;
+  double T[HALF + 1];  // T[d] = logtri[half + d] = logtri[half - d]
+#pragma unroll
+  for (int d = 0; d <= HALF; ++d) T[d] = p.logtri[HALF + d];
+  __syncthreads();
+
+  struct Stage {
+    int nc;
+    unsigned bin, nbin;
+    float prob;
+  };
+  auto fetch = [&](long long t) {
+    Stage st;
+    st.nc = 0; st.bin = 0; st.nbin = 0xffffffffu; st.prob = 0.f;
+    if (is_cand && t < p.n_steps) {
+      st.nc = p.n_cand[t];
+      const uint2* c = p.cand + t * (long long)kYinMaxCand;
+      const uint2 me = c[cidx];
+      st.bin = me.x;
+      st.prob = __uint_as_float(me.y);
+      st.nbin = cidx + 1 < kYinMaxCand ? c[cidx + 1].x : 0xffffffffu;
+    }
+    return st;
+  };
+  // the last candidate of a run of equal bins wins (numpy fancy assignment)
+  auto writes = [&](const Stage& st) { return cidx < st.nc && (cidx == st.nc - 1 || st.nbin != st.bin) && (int)st.bin < nb; };
+  auto lu_of = [&](long long t) { return log((1.0 - (double)p.voiced_prob[t]) / (double)nb + tiny); };
+  // warp partial (max, first index) of this thread's new values -> red[buf][warp]
+  auto publish = [&](double bv, int bi, int buf) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { redv[buf * 16 + warp] = bv; redi[buf * 16 + warp] = bi; }
+  };
+
+  // ---- step 0 ----
+  Stage s0 = fetch(0), s1 = fetch(1), sA = fetch(2), sB = fetch(3);
+  int wr0 = -1, wr1 = -1;  // bins this thread scattered for the previous / the current step
+  if (is_cand) {
+    if (writes(s0)) { obs[s0.bin] = log((double)s0.prob + tiny); wr0 = (int)s0.bin; }
+    if (writes(s1)) { obs[nb + s1.bin] = log((double)s1.prob + tiny); wr1 = (int)s1.bin; }
+  }
+  double lgA = is_cand ? log((double)sA.prob + tiny) : 0.0;
+  if (is_lu) {
+    lu_s[0] = lu_of(0);
+    if (p.n_steps > 1) lu_s[1] = lu_of(1);
+  }
+  __syncthreads();
+  if (is_comp) {
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+    const double lu0 = lu_s[0];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const int j = jbase + o;
+      if (j < nb) {
+        const double vv = obs[j] + p.log_init, vu = lu0 + p.log_init;
+        adj[kVitPad + j] = vv - lnorm[j];
+        adj[row + kVitPad + j] = vu - lnorm[j];
+        if (vv > bv || (vv == bv && j < bi)) { bv = vv; bi = j; }
+      }
+    }
+    // unvoiced states have higher indices than every voiced one: they win only on a strictly larger value here,
+    // but a LOWER-indexed unvoiced state must beat a higher-indexed one on ties -> second pass in index order
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const int j = jbase + o;
+      if (j < nb) {
+        const double vu = lu0 + p.log_init;
+        if (vu > bv || (vu == bv && nb + j < bi)) { bv = vu; bi = nb + j; }
+      }
+    }
+    publish(bv, bi, 0);
+  }
+  __syncthreads();
+
+  for (long long t = 1; t < p.n_steps; ++t) {
+    const int rb = (int)((t - 1) & 1), wb = (int)(t & 1);  // adj / partial buffers read and written by this step
+    if (is_comp) {
+      // block maximum (and its first index) of the previous step's values, from the per-warp partials
+      double gv = -INFINITY;
+      int gi = 0x7fffffff;
+#pragma unroll
+      for (int w = 0; w < kCompWarps; ++w) {
+        const double ov = redv[rb * 16 + w];
+        const int oi = redi[rb * 16 + w];
+        if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
+      }
+      double mv[2], mu[2];
+      int av[2], au[2];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) { mv[o] = -INFINITY; mu[o] = -INFINITY; av[o] = 0; au[o] = 0; }
+      double bv = -INFINITY;
+      int bi = 0x7fffffff;
+      if (jbase < nb) {
+        const double* wv = adj + rb * 2 * row + kVitPad + (jbase - HALF);
+        const double* wu = wv + row;
+#pragma unroll
+        for (int i = 0; i <= 2 * HALF + 1; ++i) {
+          const double cvk = wv[i], cuk = wu[i];
+          const int k = jbase - HALF + i;
+          if (i <= 2 * HALF) {
+            const double l = T[i >= HALF ? i - HALF : HALF - i];
+            const double a = cvk + l, b = cuk + l;
+            if (a > mv[0]) { mv[0] = a; av[0] = k; }
+            if (b > mu[0]) { mu[0] = b; au[0] = k; }
+          }
+          if (i >= 1) {
+            const double l = T[i - 1 >= HALF ? i - 1 - HALF : HALF - (i - 1)];
+            const double a = cvk + l, b = cuk + l;
+            if (a > mv[1]) { mv[1] = a; av[1] = k; }
+            if (b > mu[1]) { mu[1] = b; au[1] = k; }
+          }
+        }
+        const double oob = gv + kLogTiny;
+        const double lu = lu_s[wb];
+        const double* ob = obs + (int)(t % 3) * nb;
+        double* wa = adj + wb * 2 * row + kVitPad;
+        unsigned short* pr = p.ptr + t * (long long)S;
+        double nvv[2], nuu[2];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int j = jbase + o;
+          nvv[o] = -INFINITY; nuu[o] = -INFINITY;
+          if (j < nb) {
+            // candidates in increasing state index: voiced k, then unvoiced k; replace only on strict improvement
+            double best_v = mv[o] + p.log_stay, best_u = mv[o] + p.log_switch;
+            int arg_v = av[o], arg_u = av[o];
+            const double c2v = mu[o] + p.log_switch, c2u = mu[o] + p.log_stay;
+            if (c2v > best_v) { best_v = c2v; arg_v = nb + au[o]; }
+            if (c2u > best_u) { best_u = c2u; arg_u = nb + au[o]; }
+            if (oob > best_v || (oob == best_v && gi < arg_v)) { best_v = oob; arg_v = gi; }
+            if (oob > best_u || (oob == best_u && gi < arg_u)) { best_u = oob; arg_u = gi; }
+            const double nv = ob[j] + best_v, nu = lu + best_u;
+            const double ln = lnorm[j];
+            wa[j] = nv - ln;
+            wa[row + j] = nu - ln;
+            pr[j] = (unsigned short)arg_v;
+            pr[nb + j] = (unsigned short)arg_u;
+            nvv[o] = nv; nuu[o] = nu;
+          }
+        }
+        // first maximum in state-index order: voiced j, j+1, then unvoiced nb+j, nb+j+1
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+          if (jbase + o < nb && (nvv[o] > bv || (nvv[o] == bv && jbase + o < bi))) { bv = nvv[o]; bi = jbase + o; }
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+          if (jbase + o < nb && (nuu[o] > bv || (nuu[o] == bv && nb + jbase + o < bi))) { bv = nuu[o]; bi = nb + jbase + o; }
+      }
+      publish(bv, bi, wb);
+    } else {
+      // ---- candidate / unvoiced-term warps: everything here targets buffers no compute warp touches in this step ----
+      if (is_cand) {
+        if (wr0 >= 0) obs[(int)((t - 1) % 3) * nb + wr0] = kLogTiny;  // un-scatter step t-1 (read before the last barrier)
+        int wrn = -1;
+        if (writes(sA)) { obs[(int)((t + 1) % 3) * nb + sA.bin] = lgA; wrn = (int)sA.bin; }  // step t+1's observations
+        wr0 = wr1;
+        wr1 = wrn;
+        const Stage sC = fetch(t + 3);
+        lgA = log((double)sB.prob + tiny);  // step t+2's, scattered during step t+1
+        sA = sB;
+        sB = sC;
+      }
+      if (is_lu && t + 1 < p.n_steps) lu_s[(t + 1) & 1] = lu_of(t + 1);
+    }
+    __syncthreads();
+  }
+  // final state = first argmax of the last step's values
+  if (tid == 0) {
+    const int rb = (int)((p.n_steps - 1) & 1);
+    double gv = -INFINITY;
+    int gi = 0x7fffffff;
+    for (int w = 0; w < kCompWarps; ++w) {
+      const double ov = redv[rb * 16 + w];
+      const int oi = redi[rb * 16 + w];
+      if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
+    }
+    *p.final_state = gi;
   }
 }
 
@@ -645,10 +912,22 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
     vp.log_init = log(1.0 / (2.0 * g.nb) + 2.2250738585072014e-308);
     vp.ptr = ptr; vp.final_state = final_state;
     AC_REQUIRE(g.half <= kVitMaxHalf, "ac_pyin: transition band too wide");
-    const size_t smem = (size_t)(4 * 2 * g.nb + 2 * g.nb + (2 * kVitMaxHalf + 1) + g.nb + 32) * sizeof(double) + 32 * sizeof(int);
-    AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)(2 * 2 * g.nb + 4 * vit_row(g.nb) + 2 * g.nb + (2 * kVitMaxHalf + 1) + g.nb + 32) * sizeof(double) +
+                        32 * sizeof(int);
+    AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(KC_MISC, 0.0, (double)nf * 2 * g.nb * 2, st);
-    pyin_viterbi_kernel<<<1, kVitThreads, smem, st>>>(vp);
+    static const char* mode = getenv("AC_PYIN_VITERBI");  // test hook: "generic" / "tiled" force the older kernels
+    const bool want_generic = mode && mode[0] == 'g', want_tiled = mode && mode[0] == 't';
+    if (g.half == 20 && !want_generic && !want_tiled && (g.nb + 1) / 2 <= kVitFastComp) {
+      const size_t fsmem = (size_t)(4 * vit_row(g.nb) + 3 * g.nb + g.nb + 32 + 2) * sizeof(double) + 32 * sizeof(int);
+      AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_fast_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      pyin_viterbi_fast_kernel<20><<<1, kVitFastThreads, fsmem, st>>>(vp);
+    } else if (g.half == 20 && !want_generic) {
+      pyin_viterbi_kernel<20><<<1, kVitThreads, smem, st>>>(vp);
+    } else {
+      pyin_viterbi_kernel<0><<<1, kVitThreads, smem, st>>>(vp);
+    }
     AC_LAUNCH_CHECK();
     const size_t bt_smem = (size_t)kBtSteps * 2 * g.nb * sizeof(unsigned short);
     AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));

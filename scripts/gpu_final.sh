@@ -6,6 +6,8 @@ tail -2 gpurun_out/${R}_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${R}_smoke.log 2>&1; tail -1 gpurun_out/${R}_smoke.log
 python bench.py > gpurun_out/${R}_bench_final.json 2> gpurun_out/${R}_bench_final.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${R}_bench_reference.json 2> gpurun_out/${R}_bench_reference.err; echo "ref rc=$?"
+python scripts/dev_feature_bench.py 3600 > gpurun_out/${R}_features_1h.json 2>/dev/null; echo "features rc=$?"
+python scripts/dev_refine_bench.py > /dev/null 2>&1; cp gpurun_out/r01_refine.json gpurun_out/${R}_refine.json 2>/dev/null
 # launch list of the bench command itself (times under ncu are cold-cache and serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/${R}_launches_bench.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${R}_ncu_bench.log 2>&1
