@@ -917,7 +917,7 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
     AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(KC_MISC, 0.0, (double)nf * 2 * g.nb * 2, st);
-    static const char* mode = getenv("AC_PYIN_VITERBI");  // test hook: "generic" / "tiled" force the older kernels
+    const char* mode = getenv("AC_PYIN_VITERBI");  // test hook: "generic" / "tiled" force the older kernels
     const bool want_generic = mode && mode[0] == 'g', want_tiled = mode && mode[0] == 't';
     if (g.half == 20 && !want_generic && !want_tiled && (g.nb + 1) / 2 <= kVitFastComp) {
       const size_t fsmem = (size_t)(4 * vit_row(g.nb) + 3 * g.nb + g.nb + 32 + 2) * sizeof(double) + 32 * sizeof(int);

@@ -522,3 +522,28 @@ def test_refine_cut_points_edge_cases():
     assert [a.final_time for a in res.adjustments] == times == [1.0, 2.2]
     res = R.finalize_cut_points(R.CutContext(sr=SR, mix_wave=np.ones(1, np.float32)), [R.CutPoint(0.0, 1.0)])
     assert res.sample_boundaries == [0, 1]
+
+
+def test_pyin_viterbi_kernels_agree_bit_for_bit(ops):
+    """The production Viterbi (one barrier per step, two bins per thread, triangle in registers) against the run-time
+    band-width kernel and the intermediate tiled one: identical back pointers, hence identical f0 / flags."""
+    import os
+    from audio_cut_b200 import synth
+
+    y = synth.synth_track(20.0, seed=8, stereo=False).astype(np.float32)
+    x = torch.from_numpy(y).cuda()
+    outs = {}
+    try:
+        for mode in ("", "generic", "tiled"):
+            if mode:
+                os.environ["AC_PYIN_VITERBI"] = mode
+            else:
+                os.environ.pop("AC_PYIN_VITERBI", None)
+            f0, fl, vp = ops.pyin(x)
+            outs[mode] = (f0.cpu().numpy(), fl.cpu().numpy(), vp.cpu().numpy())
+    finally:
+        os.environ.pop("AC_PYIN_VITERBI", None)
+    assert outs[""][1].sum() > 100
+    for mode in ("generic", "tiled"):
+        for a, b in zip(outs[""], outs[mode]):
+            np.testing.assert_array_equal(a, b)
