@@ -22,6 +22,7 @@ EXPORTS = [
     "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
     "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3", "ac_pyin_frame_count", "ac_pyin_workspace_bytes", "ac_pyin",
     "ac_lpc_frame_count", "ac_lpc_formants", "ac_refine_cut_points", "ac_quiet_lookup_db",
+    "ac_host_is_pinned", "ac_copy_h2d_async",
 ]
 
 
@@ -111,6 +112,8 @@ def load() -> C.CDLL:
     lib.ac_refine_cut_points.argtypes = [vp, vp, ll, i, vp, i, i, i, i, d, d, i, i, i, vp, vp, vp]
     lib.ac_refine_cut_points.restype = i
     lib.ac_quiet_lookup_db.argtypes, lib.ac_quiet_lookup_db.restype = [vp, ll, i, vp, vp], i
+    lib.ac_host_is_pinned.argtypes, lib.ac_host_is_pinned.restype = [vp, sz], i
+    lib.ac_copy_h2d_async.argtypes, lib.ac_copy_h2d_async.restype = [vp, vp, sz, vp], i
     lib.ac_profile_begin.argtypes, lib.ac_profile_begin.restype = [], i
     lib.ac_profile_collect.argtypes, lib.ac_profile_collect.restype = [C.POINTER(KernelStat), i], i
     _lib = lib

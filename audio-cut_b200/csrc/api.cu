@@ -130,6 +130,23 @@ int ac_profile_collect(ac_kernel_stat* out, int max_classes) {
 }
 
 int ac_abi_version(void) { return 1; }
+
+int ac_host_is_pinned(const void* h_ptr, size_t bytes) {
+  if (!h_ptr || bytes == 0) return 0;
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, h_ptr) != cudaSuccess ||
+      cudaPointerGetAttributes(&a1, static_cast<const char*>(h_ptr) + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();  // unregistered host memory reports an error on old drivers: not an error for the caller
+    return 0;
+  }
+  return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
+int ac_copy_h2d_async(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+  AC_REQUIRE(d_dst && h_src, "null pointer");
+  AC_CHECK_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return AC_OK;
+}
 const char* ac_last_error(void) { return ac::t_error.c_str(); }
 long long ac_launch_count(void) { return ac::g_launches.load(); }
 

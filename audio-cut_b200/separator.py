@@ -281,12 +281,21 @@ class B200VocalSeparator:
                    if self.pinned_outputs else None)
         finish_metrics = None
         with torch.cuda.device(dev), ctx.acquire_inflight():
-            parallel_copy(v.pin_in_np, audio.reshape(n_ch, total))  # pageable -> pinned staging
+            # a page-locked caller array (e.g. ``torch.empty(..., pin_memory=True).numpy()``) goes to the device as it
+            # is; anything else is staged through the persistent pinned buffer first (pageable -> pinned, threaded)
+            direct = (audio.dtype == np.float32 and audio.flags.c_contiguous and
+                      lib.ac_host_is_pinned(audio.ctypes.data, audio.nbytes) == 1)
+            if not direct:
+                parallel_copy(v.pin_in_np, audio.reshape(n_ch, total))
             caller = torch.cuda.current_stream(dev)
             stream.wait_stream(caller)
             with torch.cuda.stream(stream):
                 ev[0].record()
-                v.mix.copy_(v.pin_in, non_blocking=True)
+                if direct:
+                    ops.check(lib.ac_copy_h2d_async(ops.ptr(v.mix), audio.ctypes.data, audio.nbytes, ops.stream_ptr()),
+                              "ac_copy_h2d_async")
+                else:
+                    v.mix.copy_(v.pin_in, non_blocking=True)
                 ev[1].record()
             feat_stream.wait_event(ev[1])
             with torch.cuda.stream(feat_stream):

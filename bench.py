@@ -273,24 +273,36 @@ def run_b200(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- e2e through the reference-facing call, host buffers in / out
+    # The step's input lives in page-locked host memory (the contract's "host->device copy of that step's inputs from
+    # pinned host memory"); the drop-in recognises that and skips its own pageable->pinned staging.  The same loop
+    # with an ordinary pageable ndarray is timed as well and reported beside it.
     sep = B200VocalSeparator(SR, backend=be, pipeline_config=PipelineConfig())
-    for _ in range(min(args.warmup, 2)):
-        res = sep.separate_for_detection(audio)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = sep.separate_for_detection(audio)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    audio_pin_t = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True)
+    audio_pin = audio_pin_t.numpy()
+    audio_pin[...] = audio
+
+    def e2e_loop(host_audio):
+        for _ in range(min(args.warmup, 2)):
+            r = sep.separate_for_detection(host_audio)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = sep.separate_for_detection(host_audio)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return r, dt
+
+    _, e2e_pageable_s = e2e_loop(audio)
+    res, e2e_s = e2e_loop(audio_pin)
     fc = res.feature_cache
     d2h = res.vocal_track.nbytes + (res.instrumental_track.nbytes if res.instrumental_track is not None else 0) + \
         4 * (fc.rms_series.size + fc.spectral_flatness.size + fc.onset_envelope.size) + 4 * (1 + (n + 1323000) // 512) + 4 * (1 + n // 882)
 
-    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, e2e_pageable_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, e2e_pageable_ms = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         peaks = _peaks()
         audio_total = TRACK_SECONDS * world * args.steps
@@ -333,7 +345,9 @@ def run_b200(args):
             "config": bench_config(args.n_fft, world, len(plans), n_windows),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(audio.nbytes), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / args.steps, "call": "B200VocalSeparator.separate_for_detection(host ndarray)"},
+                    "ms_per_step": e2e_ms / args.steps,
+                    "call": "B200VocalSeparator.separate_for_detection(page-locked host ndarray) -> host ndarrays",
+                    "ms_per_step_pageable_input": e2e_pageable_ms / args.steps},
             "gpu_launches": launches,
             "roofline": roof,
             "kernels": [{k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in k.items()} for k in kstats],

@@ -49,6 +49,12 @@ AC_API const char* ac_last_error(void);
 AC_API int ac_abi_version(void);
 /* Number of kernels this library has launched since load (for bench.py "gpu_launches"). */
 AC_API long long ac_launch_count(void);
+/* Host staging helpers for the Python drop-in (enhanced_vocal_separator.py:378-389 stages every chunk through a
+ * pinned pool and copies it straight back).  ac_host_is_pinned: 1 when [p, p+bytes) is page-locked memory CUDA
+ * knows about (cudaHostAlloc / cudaHostRegister / torch pin_memory), 0 otherwise.  ac_copy_h2d_async: a
+ * cudaMemcpyAsync host -> device on `stream`; truly asynchronous only for page-locked sources. */
+AC_API int ac_host_is_pinned(const void* h_ptr, size_t bytes);
+AC_API int ac_copy_h2d_async(void* d_dst, const void* h_src, size_t bytes, void* stream);
 
 /* Per-kernel-class device timing with CUDA events on the launching stream (for bench.py's
  * roofline line): begin, run the workload, collect (synchronises the device).  `flops` / `bytes`

@@ -114,6 +114,37 @@ def test_cut_refinement_on_device_resident_stems():
     assert got.sample_boundaries == bounds and [p.t for p in got.final_points] == times and len(times) >= 8
 
 
+def test_pinned_input_and_output_arrays():
+    """A page-locked caller array goes to the device without the staging copy; results equal the pageable path, are
+    float32 numpy arrays of the input length that stay valid (and writable) after later calls."""
+    from audio_cut_b200 import _lib, synth
+    from audio_cut_b200.gpu_pipeline import PipelineConfig
+    from audio_cut_b200.separator import B200VocalSeparator
+
+    sr = 8000
+    be, _, _ = _small_backend()
+    sep = B200VocalSeparator(sr, backend=be, pipeline_config=PipelineConfig(chunk_s=4.0, overlap_s=1.0, halo_s=0.25, align_hop=256))
+    audio = synth.synth_track(9.7, sr=sr, seed=6, stereo=False)
+    pinned = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True).numpy()
+    pinned[...] = audio
+    lib = _lib.load()
+    assert lib.ac_host_is_pinned(pinned.ctypes.data, pinned.nbytes) == 1
+    assert lib.ac_host_is_pinned(audio.ctypes.data, audio.nbytes) == 0
+    a = sep.separate_for_detection(audio)
+    va, ia = a.vocal_track.copy(), a.instrumental_track.copy()
+    b = sep.separate_for_detection(pinned)
+    np.testing.assert_array_equal(b.vocal_track, va)
+    np.testing.assert_array_equal(b.instrumental_track, ia)
+    for _ in range(3):  # later calls must not recycle memory the caller still holds
+        sep.separate_for_detection(audio * np.float32(0.5))
+    np.testing.assert_array_equal(a.vocal_track, va)
+    np.testing.assert_array_equal(b.instrumental_track, ia)
+    assert a.vocal_track.dtype == np.float32 and a.vocal_track.shape == audio.shape and a.vocal_track.flags.writeable
+    sep.pinned_outputs = False
+    c = sep.separate_for_detection(audio)
+    np.testing.assert_array_equal(c.vocal_track, va)
+
+
 def test_vad_hook_is_called_per_chunk():
     from audio_cut_b200 import synth
     from audio_cut_b200.gpu_pipeline import PipelineConfig
