@@ -83,21 +83,13 @@ __global__ void __launch_bounds__(kRmsThreads) frame_reduce_kernel(const float* 
       acc = warp_sum(acc);
       if (lane == 0) out[t0 + f] = sqrtf(acc / (float)frame);
     } else {
-      // one shared load and one threshold per sample: the left neighbour's sign comes from the previous lane
-      // (lane 0: from lane 31 of the previous 32-sample group); counts are integers, so the order is irrelevant
-      unsigned prev_last = 0;  // sign bit of sample 32*g - 1 (sample -1 of the first group is never used)
-      unsigned cnt = 0;
-      for (int j0 = 0; j0 < frame; j0 += 32) {
-        const int j = j0 + lane;
-        float b = j < frame ? fr[j] : 0.f;
+      for (int j = lane + 1; j < frame; j += 32) {
+        float a = fr[j - 1], b = fr[j];
+        a = fabsf(a) <= 1e-10f ? 0.f : a;
         b = fabsf(b) <= 1e-10f ? 0.f : b;
-        const unsigned sb = __float_as_uint(b) >> 31;
-        unsigned sa = __shfl_up_sync(0xffffffffu, sb, 1);
-        if (lane == 0) sa = prev_last;
-        if (j >= 1 && j < frame) cnt += sa ^ sb;
-        prev_last = __shfl_sync(0xffffffffu, sb, 31);
+        acc += (signbit(a) != signbit(b)) ? 1.f : 0.f;
       }
-      acc = warp_sum((float)cnt);
+      acc = warp_sum(acc);
       if (lane == 0) out[t0 + f] = acc / (float)frame;
     }
   }

@@ -17,6 +17,8 @@
 //     row's MMAs run - with a single warp per scheduler the epilogue's dependent ALU chains, not the
 //     tensor pipe, set the pace (ncu: 75 % of the stall samples sat in the epilogue).
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2..13 = epilogue.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "tc_common.cuh"
@@ -834,7 +836,8 @@ static bool ws_make_cfg(int C, int F, WsCfg& c) {
   const int tiles = (F + kWsTileM - 1) / kWsTileM;
   const int budget = 227 * 1024 - 1024 - c.w_bytes;
   c.MT = 1;
-  for (int mt = 3; mt >= 1; --mt) {
+  static const int mt_cap = getenv("AC_WS_MT") ? atoi(getenv("AC_WS_MT")) : 3;  // dev hook: tiles per row step
+  for (int mt = mt_cap < 1 ? 1 : (mt_cap > 3 ? 3 : mt_cap); mt >= 1; --mt) {
     if (mt > tiles) continue;
     if (2 * mt * c.NT > 512) continue;
     if (4 * mt * c.a_tile_bytes <= budget) { c.MT = mt; break; }
