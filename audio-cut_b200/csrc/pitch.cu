@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kVitFastThreads, 1) pyin_viterbi_fast_kernel(c
     if (writes(s0)) { obs[s0.bin] = log((double)s0.prob + tiny); wr0 = (int)s0.bin; }
     if (writes(s1)) { obs[nb + s1.bin] = log((double)s1.prob + tiny); wr1 = (int)s1.bin; }
   }
-  double lgA = is_cand ? log((double)sA.prob + tiny) : 0.0;
+  double lgA = (is_cand && cidx < sA.nc) ? log((double)sA.prob + tiny) : 0.0;
   if (is_lu) {
     lu_s[0] = lu_of(0);
     if (p.n_steps > 1) lu_s[1] = lu_of(1);
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(kVitFastThreads, 1) pyin_viterbi_fast_kernel(c
         wr0 = wr1;
         wr1 = wrn;
         const Stage sC = fetch(t + 3);
-        lgA = log((double)sB.prob + tiny);  // step t+2's, scattered during step t+1
+        lgA = cidx < sB.nc ? log((double)sB.prob + tiny) : 0.0;  // step t+2's, scattered during step t+1
         sA = sB;
         sB = sC;
       }
