@@ -201,3 +201,28 @@ def test_public_header_is_plain_c():
         pytest.skip("gcc not available")
     subprocess.run(["gcc", "-fsyntax-only", "-std=c99", "-Wall", "-Werror", "-x", "c", hdr], check=True)
     subprocess.run(["g++", "-fsyntax-only", "-std=c++17", "-x", "c++", hdr], check=True)
+
+
+def test_refine_host_logic_matches_oracle():
+    """Host half of the finalize_cut_points drop-in (score-ordered NMS with per-window cap, boundary / gap filter)
+    against the oracle restatement that is pinned to the reference's refine.py (no GPU needed for this part)."""
+    import importlib.util, os, sys, types
+
+    # audio_cut_b200.refine imports .ops (ctypes binding only; nothing is called here)
+    from audio_cut_b200 import refine as R
+    from oracle import cuts
+
+    rng = np.random.default_rng(3)
+    for case in range(20):
+        n = int(rng.integers(1, 40))
+        pts = [(float(t), float(s)) for t, s in zip(rng.uniform(0, 60, n), rng.choice([0.1, 0.5, 0.5, 0.9, 0.3], n))]
+        gap = float(rng.choice([0.2, 1.0, 2.5]))
+        cap = [None, 1, 3][case % 3]
+        topk = [None, 5][case % 2]
+        win = float(rng.choice([5.0, 10.0]))
+        ref = cuts.nms_min_gap(pts, gap, topk=topk, max_per_window=cap, window_s=win)
+        got = R.nms_min_gap([R.CutPoint(t, s) for t, s in pts], gap, topk, max_per_window=cap, window_s=win)
+        assert [(p.t, p.score) for p in got] == [tuple(p) for p in ref]
+    times = [0.2, 0.49, 0.5, 0.51, 3.0, 3.4, 5.0, 9.6, 9.5, 9.51]
+    assert R._filter_cut_times(times, duration_s=10.0, min_gap_s=1.0, min_boundary_s=0.5) == [0.51, 3.0, 5.0]
+    assert R._filter_cut_times(times, duration_s=0.0, min_gap_s=1.0, min_boundary_s=0.5) == []
