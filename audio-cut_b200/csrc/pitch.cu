@@ -623,9 +623,11 @@ __global__ void __launch_bounds__(kVitFastThreads, 1) pyin_viterbi_fast_kernel(c
     if (writes(s1)) { obs[nb + s1.bin] = log((double)s1.prob + tiny); wr1 = (int)s1.bin; }
   }
   double lgA = (is_cand && cidx < sA.nc) ? log((double)sA.prob + tiny) : 0.0;
+  float vp_next = 0.f;  // voiced_prob of the NEXT step, loaded one step before its logarithm is taken
   if (is_lu) {
     lu_s[0] = lu_of(0);
     if (p.n_steps > 1) lu_s[1] = lu_of(1);
+    if (p.n_steps > 2) vp_next = p.voiced_prob[2];
   }
   __syncthreads();
   if (is_comp) {
@@ -744,7 +746,10 @@ __global__ void __launch_bounds__(kVitFastThreads, 1) pyin_viterbi_fast_kernel(c
         sA = sB;
         sB = sC;
       }
-      if (is_lu && t + 1 < p.n_steps) lu_s[(t + 1) & 1] = lu_of(t + 1);
+      if (is_lu && t + 1 < p.n_steps) {  // invariant: vp_next = voiced_prob[t + 1] on entry to step t
+        lu_s[(t + 1) & 1] = log((1.0 - (double)vp_next) / (double)nb + tiny);
+        vp_next = t + 2 < p.n_steps ? p.voiced_prob[t + 2] : 0.f;
+      }
     }
     __syncthreads();
   }
@@ -756,6 +761,231 @@ __global__ void __launch_bounds__(kVitFastThreads, 1) pyin_viterbi_fast_kernel(c
     for (int w = 0; w < kCompWarps; ++w) {
       const double ov = redv[rb * 16 + w];
       const int oi = redi[rb * 16 + w];
+      if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
+    }
+    *p.final_state = gi;
+  }
+}
+
+// ---- cluster Viterbi: the pitch bins split over a 4-CTA cluster ------------------------------------------------
+// One SM issues the ~7.7 k warp-instructions of a step (601 bins x 82 predecessors x {add, compare, 3 selects}) in
+// ~6 k cycles; four SMs each take a quarter of the bins.  A CTA keeps the adj rows of its own bins plus a HALF-wide
+// halo on either side; after a step it stores its new values locally, pushes its outermost HALF bins into the two
+// neighbours' halos and its per-warp maxima into every CTA's partial table through distributed shared memory
+// (st.shared::cluster), then all CTAs meet at ONE cluster barrier (arrive.release / wait.acquire).  Arithmetic,
+// visiting order and tie rules are those of the single-CTA kernels: the outputs are bit-identical.
+constexpr int kVcN = 4;
+constexpr int kVcThreads = 512;
+constexpr int kVcComp = 160;  // compute threads per CTA (one pitch bin each; Q = ceil(nb / 4) <= 160)
+__device__ __forceinline__ uint32_t vc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t vc_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void vc_st_f64(uint32_t cluster_addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void vc_st_s32(uint32_t cluster_addr, int v) {
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void vc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int HALF>
+__global__ void __cluster_dims__(kVcN, 1, 1) __launch_bounds__(kVcThreads, 1) pyin_viterbi_cluster_kernel(const VitParams p) {
+  extern __shared__ double vsm[];
+  const int nb = p.nb, S = 2 * nb;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int Q = (nb + kVcN - 1) / kVcN;           // bins per CTA (the last CTA may own fewer)
+  const int j0 = (int)rank * Q;
+  const int nq = max(0, min(Q, nb - j0));
+  const int rowlen = Q + 2 * HALF + 2;            // local index of bin j: j - j0 + HALF
+  constexpr int kCompWarps = kVcComp / 32;
+  constexpr int kParts = kVcN * kCompWarps;       // warp partials of the whole cluster
+  double* adj = vsm;                              // [2][2][rowlen]
+  double* obs = adj + 4 * rowlen;                 // [3][Q]
+  double* lnorm = obs + 3 * Q;                    // [Q]
+  double* partv = lnorm + Q;                      // [2][kParts]
+  double* lu_s = partv + 2 * kParts;              // [2]
+  int* parti = reinterpret_cast<int*>(lu_s + 2);  // [2][kParts]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double tiny = 2.2250738585072014e-308;
+  const bool is_comp = tid < kVcComp;
+  const int c = tid;                              // local bin of a compute thread
+  const int j = j0 + c;
+  const bool owns = is_comp && c < nq;
+  const int cidx = kVcThreads - 1 - tid;          // candidate slot (threads >= 160: slots 351 .. 0)
+  const bool is_cand = !is_comp && cidx < kYinMaxCand;
+  const bool is_lu = tid == kVcComp;
+
+  for (int i = tid; i < Q; i += kVcThreads) lnorm[i] = j0 + i < nb ? p.lognorm[j0 + i] : 0.0;
+  for (int i = tid; i < 3 * Q; i += kVcThreads) obs[i] = kLogTiny;
+  for (int i = tid; i < 4 * rowlen; i += kVcThreads) adj[i] = -INFINITY;
+  for (int i = tid; i < 2 * kParts; i += kVcThreads) { partv[i] = -INFINITY; parti[i] = 0x7fffffff; }
+  double T[HALF + 1];
+#pragma unroll
+  for (int d = 0; d <= HALF; ++d) T[d] = p.logtri[HALF + d];
+  __syncthreads();
+  vc_cluster_sync();  // every CTA's shared memory is initialised before anybody stores into it
+
+  struct Stage {
+    int nc;
+    unsigned bin, nbin;
+    float prob;
+  };
+  auto fetch = [&](long long t) {
+    Stage st;
+    st.nc = 0; st.bin = 0; st.nbin = 0xffffffffu; st.prob = 0.f;
+    if (is_cand && t < p.n_steps) {
+      st.nc = p.n_cand[t];
+      const uint2* cd = p.cand + t * (long long)kYinMaxCand;
+      const uint2 me = cd[cidx];
+      st.bin = me.x;
+      st.prob = __uint_as_float(me.y);
+      st.nbin = cidx + 1 < kYinMaxCand ? cd[cidx + 1].x : 0xffffffffu;
+    }
+    return st;
+  };
+  // last candidate of a run of equal bins wins; only bins of this CTA are scattered (local index returned, else -1)
+  auto target = [&](const Stage& st) -> int {
+    if (cidx < st.nc && (cidx == st.nc - 1 || st.nbin != st.bin) && (int)st.bin < nb) {
+      const int li = (int)st.bin - j0;
+      if (li >= 0 && li < nq) return li;
+    }
+    return -1;
+  };
+  auto lu_of = [&](long long t) { return log((1.0 - (double)p.voiced_prob[t]) / (double)nb + tiny); };
+  // new values -> local adj row, the neighbours' halos, the cluster-wide partial table
+  auto publish = [&](double nv, double nu, int wb) {
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+    if (owns) {
+      const double ln = lnorm[c];
+      const double av_ = nv - ln, au_ = nu - ln;
+      double* row_v = adj + (wb * 2 + 0) * rowlen;
+      double* row_u = adj + (wb * 2 + 1) * rowlen;
+      row_v[c + HALF] = av_;
+      row_u[c + HALF] = au_;
+      if (c < HALF && rank > 0) {  // left neighbour's right halo: its local index of bin j is c + Q + HALF
+        vc_st_f64(vc_mapa(vc_smem_u32(row_v + c + Q + HALF), rank - 1), av_);
+        vc_st_f64(vc_mapa(vc_smem_u32(row_u + c + Q + HALF), rank - 1), au_);
+      }
+      if (c >= Q - HALF && rank + 1 < kVcN) {  // right neighbour's left halo: local index c - Q + HALF
+        vc_st_f64(vc_mapa(vc_smem_u32(row_v + c - Q + HALF), rank + 1), av_);
+        vc_st_f64(vc_mapa(vc_smem_u32(row_u + c - Q + HALF), rank + 1), au_);
+      }
+      bv = nv; bi = j;
+      if (nu > bv) { bv = nu; bi = nb + j; }  // equal values: the voiced state has the lower index
+    }
+    if (is_comp) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane < kVcN) {  // lane q stores this warp's partial into CTA q's table
+        const int slot = wb * kParts + (int)rank * kCompWarps + warp;
+        vc_st_f64(vc_mapa(vc_smem_u32(partv + slot), (uint32_t)lane), bv);
+        vc_st_s32(vc_mapa(vc_smem_u32(parti + slot), (uint32_t)lane), bi);
+      }
+    }
+  };
+
+  // ---- step 0 ----
+  Stage s0 = fetch(0), s1 = fetch(1), sA = fetch(2), sB = fetch(3);
+  int wr0 = -1, wr1 = -1;
+  if (is_cand) {
+    const int t0 = target(s0), t1 = target(s1);
+    if (t0 >= 0) { obs[t0] = log((double)s0.prob + tiny); wr0 = t0; }
+    if (t1 >= 0) { obs[Q + t1] = log((double)s1.prob + tiny); wr1 = t1; }
+  }
+  double lgA = (is_cand && cidx < sA.nc) ? log((double)sA.prob + tiny) : 0.0;
+  float vp_next = 0.f;  // voiced_prob of the NEXT step, loaded one step before its logarithm is taken
+  if (is_lu) {
+    lu_s[0] = lu_of(0);
+    if (p.n_steps > 1) lu_s[1] = lu_of(1);
+    if (p.n_steps > 2) vp_next = p.voiced_prob[2];
+  }
+  __syncthreads();
+  {
+    double nv = -INFINITY, nu = -INFINITY;
+    if (owns) {
+      nv = obs[c] + p.log_init;
+      nu = lu_s[0] + p.log_init;
+    }
+    publish(nv, nu, 0);
+  }
+  vc_cluster_sync();
+
+  for (long long t = 1; t < p.n_steps; ++t) {
+    const int rb = (int)((t - 1) & 1), wb = (int)(t & 1);
+    if (is_comp) {
+      double gv = -INFINITY;
+      int gi = 0x7fffffff;
+#pragma unroll
+      for (int w = 0; w < kParts; ++w) {
+        const double ov = partv[rb * kParts + w];
+        const int oi = parti[rb * kParts + w];
+        if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
+      }
+      double nv = -INFINITY, nu = -INFINITY;
+      if (owns) {
+        double mv = -INFINITY, mu = -INFINITY;
+        int av = 0, au = 0;
+        const double* wv = adj + (rb * 2 + 0) * rowlen + c;  // local index of bin j - HALF
+        const double* wu = adj + (rb * 2 + 1) * rowlen + c;
+#pragma unroll
+        for (int i = 0; i <= 2 * HALF; ++i) {
+          const double l = T[i >= HALF ? i - HALF : HALF - i];
+          const double a = wv[i] + l, b = wu[i] + l;
+          const int k = j - HALF + i;
+          if (a > mv) { mv = a; av = k; }
+          if (b > mu) { mu = b; au = k; }
+        }
+        const double oob = gv + kLogTiny;
+        double best_v = mv + p.log_stay, best_u = mv + p.log_switch;
+        int arg_v = av, arg_u = av;
+        const double c2v = mu + p.log_switch, c2u = mu + p.log_stay;
+        if (c2v > best_v) { best_v = c2v; arg_v = nb + au; }
+        if (c2u > best_u) { best_u = c2u; arg_u = nb + au; }
+        if (oob > best_v || (oob == best_v && gi < arg_v)) { best_v = oob; arg_v = gi; }
+        if (oob > best_u || (oob == best_u && gi < arg_u)) { best_u = oob; arg_u = gi; }
+        nv = obs[(int)(t % 3) * Q + c] + best_v;
+        nu = lu_s[wb] + best_u;
+        unsigned short* pr = p.ptr + t * (long long)S;
+        pr[j] = (unsigned short)arg_v;
+        pr[nb + j] = (unsigned short)arg_u;
+      }
+      publish(nv, nu, wb);
+    } else {
+      if (is_cand) {
+        if (wr0 >= 0) obs[(int)((t - 1) % 3) * Q + wr0] = kLogTiny;
+        const int tn = target(sA);
+        if (tn >= 0) obs[(int)((t + 1) % 3) * Q + tn] = lgA;
+        wr0 = wr1;
+        wr1 = tn;
+        const Stage sC = fetch(t + 3);
+        lgA = cidx < sB.nc ? log((double)sB.prob + tiny) : 0.0;
+        sA = sB;
+        sB = sC;
+      }
+      if (is_lu && t + 1 < p.n_steps) {  // invariant: vp_next = voiced_prob[t + 1] on entry to step t
+        lu_s[(t + 1) & 1] = log((1.0 - (double)vp_next) / (double)nb + tiny);
+        vp_next = t + 2 < p.n_steps ? p.voiced_prob[t + 2] : 0.f;
+      }
+    }
+    vc_cluster_sync();
+  }
+  if (rank == 0 && tid == 0) {
+    const int rb = (int)((p.n_steps - 1) & 1);
+    double gv = -INFINITY;
+    int gi = 0x7fffffff;
+    for (int w = 0; w < kParts; ++w) {
+      const double ov = partv[rb * kParts + w];
+      const int oi = parti[rb * kParts + w];
       if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; }
     }
     *p.final_state = gi;
@@ -802,6 +1032,89 @@ __global__ void __launch_bounds__(256) pyin_backtrack_kernel(const unsigned shor
   }
 }
 
+// ---- parallel backtrack -----------------------------------------------------------------------------------
+// The serial kernel above stages ALL 2*nb back pointers of every step through one CTA to follow ONE of them
+// (2.1 us per step: as long as the forward pass).  Back pointers are maps state(t) -> state(t-1), and maps compose:
+//   A  (one CTA per 64-step block, whole GPU): compose the block's maps -> G[b][s] = state at the step below the
+//      block for every possible state s at its top (64 shared-memory lookups per state);
+//   B  (one CTA): chase the block tops through G, 64 tables at a time in shared memory;
+//   C  (one CTA per block): walk the block's 64 steps from its known top state, emit f0 / voiced flags.
+// The pointers are read once at full bandwidth instead of once through a single SM.
+constexpr int kBpSteps = 64;
+constexpr int kBpThreads = 640;
+__device__ __forceinline__ void bp_stage(unsigned short* dst, const unsigned short* src, long long n_elems) {
+  // src is 16-byte aligned (block starts are multiples of 64 rows of 4*nb bytes); bulk as uint4, tail as ushort
+  const long long n16 = n_elems / 8;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (long long i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  for (long long i = n16 * 8 + threadIdx.x; i < n_elems; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(kBpThreads) pyin_bp_compose_kernel(const unsigned short* __restrict__ ptr, long long n_steps, int nb,
+                                                                     unsigned short* __restrict__ G) {
+  extern __shared__ __align__(16) unsigned short bsm[];  // [cnt][2*nb]
+  const int S = 2 * nb;
+  const long long b = blockIdx.x;
+  if (b == 0) return;  // nothing lies below block 0
+  const long long lo = b * kBpSteps;
+  const int cnt = (int)min((long long)kBpSteps, n_steps - lo);
+  bp_stage(bsm, ptr + lo * (long long)S, (long long)cnt * S);
+  __syncthreads();
+  for (int s0 = threadIdx.x; s0 < S; s0 += kBpThreads) {
+    int x = s0;
+    for (int r = cnt - 1; r >= 0; --r) x = bsm[(size_t)r * S + x];
+    G[b * (long long)S + s0] = (unsigned short)x;
+  }
+}
+__global__ void __launch_bounds__(256) pyin_bp_tops_kernel(const unsigned short* __restrict__ G, const int* __restrict__ final_state,
+                                                           long long n_blk, int nb, int* __restrict__ top) {
+  extern __shared__ __align__(16) unsigned short bsm[];  // [<=64][2*nb]
+  __shared__ int carry;
+  const int S = 2 * nb;
+  if (threadIdx.x == 0) { carry = *final_state; top[n_blk - 1] = carry; }
+  __syncthreads();
+  // batches of 64 tables, aligned at multiples of 64 blocks so that every batch starts on a 16-byte boundary
+  for (long long q = (n_blk - 1) / kBpSteps; q >= 0; --q) {
+    const long long b_lo = q * kBpSteps, b_hi = min(n_blk - 1, b_lo + kBpSteps - 1);
+    const int cnt = (int)(b_hi - b_lo + 1);
+    bp_stage(bsm, G + b_lo * (long long)S, (long long)cnt * S);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = carry;  // state at the top of block b_hi
+      for (long long b = b_hi; b >= max(b_lo, 1LL); --b) {
+        s = bsm[(size_t)(b - b_lo) * S + s];  // state at the top of block b - 1
+        top[b - 1] = s;
+      }
+      carry = s;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(kBpSteps) pyin_bp_emit_kernel(const unsigned short* __restrict__ ptr, const int* __restrict__ top,
+                                                                long long n_steps, int nb, float fmin, int bins_per_semitone,
+                                                                float* __restrict__ f0, unsigned char* __restrict__ voiced_flag) {
+  __shared__ int states[kBpSteps];
+  const int S = 2 * nb;
+  const long long lo = (long long)blockIdx.x * kBpSteps;
+  const int cnt = (int)min((long long)kBpSteps, n_steps - lo);
+  if (threadIdx.x == 0) {
+    int s = top[blockIdx.x];
+    for (int r = cnt - 1; r >= 0; --r) {
+      states[r] = s;
+      if (r > 0) s = ptr[(lo + r) * (long long)S + s];
+    }
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < cnt) {
+    const int s = states[r];
+    const bool v = s < nb;
+    const int k = v ? s : s - nb;
+    if (f0) f0[lo + r] = v ? fmin * exp2f((float)k / (12.f * (float)bins_per_semitone)) : __int_as_float(0x7fc00000);
+    if (voiced_flag) voiced_flag[lo + r] = v ? 1 : 0;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 static double beta_cdf_int(double x, int a, int b) {  // regularised incomplete beta for integer a, b
   const int n = a + b - 1;
@@ -845,6 +1158,9 @@ extern "C" size_t ac_pyin_workspace_bytes(long long n, int hop, int sr, float fm
   b += align_up((size_t)nf * 2 * g.nb * sizeof(unsigned short), 256);
   b += align_up((size_t)(g.nb + 2 * g.half + 1) * sizeof(double), 256);
   b += align_up((size_t)kNThresholds * sizeof(float), 256);
+  const size_t n_blk = (size_t)((nf + kBpSteps - 1) / kBpSteps);
+  b += align_up(n_blk * 2 * g.nb * sizeof(unsigned short), 256);  // composed back-pointer maps, one per 64 steps
+  b += align_up(n_blk * sizeof(int), 256);                         // state at the top of every block
   b += 256;
   return b;
 }
@@ -866,6 +1182,9 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
   unsigned short* ptr = reinterpret_cast<unsigned short*>(w); w += align_up((size_t)nf * 2 * g.nb * sizeof(unsigned short), 256);
   double* logtab = reinterpret_cast<double*>(w); w += align_up((size_t)(g.nb + 2 * g.half + 1) * sizeof(double), 256);
   float* beta = reinterpret_cast<float*>(w); w += align_up((size_t)kNThresholds * sizeof(float), 256);
+  const long long n_blk = (nf + kBpSteps - 1) / kBpSteps;
+  unsigned short* bp_maps = reinterpret_cast<unsigned short*>(w); w += align_up((size_t)n_blk * 2 * g.nb * sizeof(unsigned short), 256);
+  int* bp_top = reinterpret_cast<int*>(w); w += align_up((size_t)n_blk * sizeof(int), 256);
   int* final_state = reinterpret_cast<int*>(w);
 
   // beta(2, 18) weights of the 100 thresholds and the banded log transition (row-normalised triangle)
@@ -919,7 +1238,15 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
     ProfScope ps(KC_MISC, 0.0, (double)nf * 2 * g.nb * 2, st);
     const char* mode = getenv("AC_PYIN_VITERBI");  // test hook: "generic" / "tiled" force the older kernels
     const bool want_generic = mode && mode[0] == 'g', want_tiled = mode && mode[0] == 't';
-    if (g.half == 20 && !want_generic && !want_tiled && (g.nb + 1) / 2 <= kVitFastComp) {
+    // default: the 4-CTA cluster kernel; "fast" = single-CTA one-barrier kernel, "tiled" / "generic" = the older ones
+    const bool want_fast = mode && mode[0] == 'f';
+    if (g.half == 20 && !want_generic && !want_tiled && !want_fast && (g.nb + kVcN - 1) / kVcN <= kVcComp &&
+        (g.nb + kVcN - 1) / kVcN > 20) {
+      const int Q = (g.nb + kVcN - 1) / kVcN;
+      const size_t csmem = (size_t)(4 * (Q + 2 * 20 + 2) + 3 * Q + Q + 2 * kVcN * (kVcComp / 32) + 2) * sizeof(double) +
+                           (size_t)2 * kVcN * (kVcComp / 32) * sizeof(int);
+      pyin_viterbi_cluster_kernel<20><<<kVcN, kVcThreads, csmem, st>>>(vp);
+    } else if (g.half == 20 && !want_generic && !want_tiled && (g.nb + 1) / 2 <= kVitFastComp) {
       const size_t fsmem = (size_t)(4 * vit_row(g.nb) + 3 * g.nb + g.nb + 32 + 2) * sizeof(double) + 32 * sizeof(int);
       AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_viterbi_fast_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       pyin_viterbi_fast_kernel<20><<<1, kVitFastThreads, fsmem, st>>>(vp);
@@ -931,7 +1258,18 @@ extern "C" int ac_pyin(const float* d_x, long long n, int sr, int hop, float fmi
     AC_LAUNCH_CHECK();
     const size_t bt_smem = (size_t)kBtSteps * 2 * g.nb * sizeof(unsigned short);
     AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
-    pyin_backtrack_kernel<<<1, 256, bt_smem, st>>>(ptr, final_state, nf, g.nb, fmin, g.bps, d_f0, d_voiced_flag);
+    const char* bt_mode = getenv("AC_PYIN_BACKTRACK");  // test hook: "serial" runs the single-CTA kernel
+    if (bt_mode && bt_mode[0] == 's') {
+      pyin_backtrack_kernel<<<1, 256, bt_smem, st>>>(ptr, final_state, nf, g.nb, fmin, g.bps, d_f0, d_voiced_flag);
+    } else {
+      AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_bp_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
+      AC_CHECK_CUDA(cudaFuncSetAttribute(pyin_bp_tops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
+      pyin_bp_compose_kernel<<<(unsigned)n_blk, kBpThreads, bt_smem, st>>>(ptr, nf, g.nb, bp_maps);
+      count_launch();
+      pyin_bp_tops_kernel<<<1, 256, bt_smem, st>>>(bp_maps, final_state, n_blk, g.nb, bp_top);
+      count_launch();
+      pyin_bp_emit_kernel<<<(unsigned)n_blk, kBpSteps, 0, st>>>(ptr, bp_top, nf, g.nb, fmin, g.bps, d_f0, d_voiced_flag);
+    }
     AC_LAUNCH_CHECK();
   }
   return AC_OK;

@@ -525,8 +525,8 @@ def test_refine_cut_points_edge_cases():
 
 
 def test_pyin_viterbi_kernels_agree_bit_for_bit(ops):
-    """The production Viterbi (one barrier per step, two bins per thread, triangle in registers) against the run-time
-    band-width kernel and the intermediate tiled one: identical back pointers, hence identical f0 / flags."""
+    """The production pYIN decode (4-CTA cluster Viterbi + map-composition backtrack) against the single-CTA
+    one-barrier kernel, the tiled and the run-time band-width kernels and the serial backtrack: identical f0 / flags."""
     import os
     from audio_cut_b200 import synth
 
@@ -534,16 +534,19 @@ def test_pyin_viterbi_kernels_agree_bit_for_bit(ops):
     x = torch.from_numpy(y).cuda()
     outs = {}
     try:
-        for mode in ("", "generic", "tiled"):
-            if mode:
+        for mode in ("", "generic", "tiled", "fast", "serial-backtrack"):
+            os.environ.pop("AC_PYIN_VITERBI", None)
+            os.environ.pop("AC_PYIN_BACKTRACK", None)
+            if mode == "serial-backtrack":
+                os.environ["AC_PYIN_BACKTRACK"] = "serial"
+            elif mode:
                 os.environ["AC_PYIN_VITERBI"] = mode
-            else:
-                os.environ.pop("AC_PYIN_VITERBI", None)
             f0, fl, vp = ops.pyin(x)
             outs[mode] = (f0.cpu().numpy(), fl.cpu().numpy(), vp.cpu().numpy())
     finally:
         os.environ.pop("AC_PYIN_VITERBI", None)
+        os.environ.pop("AC_PYIN_BACKTRACK", None)
     assert outs[""][1].sum() > 100
-    for mode in ("generic", "tiled"):
+    for mode in ("generic", "tiled", "fast", "serial-backtrack"):
         for a, b in zip(outs[""], outs[mode]):
             np.testing.assert_array_equal(a, b)
