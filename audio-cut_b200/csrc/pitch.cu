@@ -775,8 +775,11 @@ __global__ void __launch_bounds__(kVitFastThreads, 1) pyin_viterbi_fast_kernel(c
 // (st.shared::cluster), then all CTAs meet at ONE cluster barrier (arrive.release / wait.acquire).  Arithmetic,
 // visiting order and tie rules are those of the single-CTA kernels: the outputs are bit-identical.
 constexpr int kVcN = 4;
-constexpr int kVcThreads = 512;
-constexpr int kVcComp = 160;  // compute threads per CTA (one pitch bin each; Q = ceil(nb / 4) <= 160)
+constexpr int kVcComp = 160;   // compute threads per CTA (one pitch bin each; Q = ceil(nb / 4) <= 160)
+constexpr int kVcCand = 96;    // candidate threads per CTA; each owns kVcSlots candidate slots (slot = ct + 96 k).  Few
+constexpr int kVcSlots = 4;    // warps on purpose: the cluster barrier of a step gets slower with every warp that joins it
+constexpr int kVcThreads = kVcComp + kVcCand;
+static_assert(kVcCand * kVcSlots >= kYinMaxCand, "candidate slots");
 __device__ __forceinline__ uint32_t vc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t vc_mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -816,8 +819,8 @@ __global__ void __cluster_dims__(kVcN, 1, 1) __launch_bounds__(kVcThreads, 1) py
   const int c = tid;                              // local bin of a compute thread
   const int j = j0 + c;
   const bool owns = is_comp && c < nq;
-  const int cidx = kVcThreads - 1 - tid;          // candidate slot (threads >= 160: slots 351 .. 0)
-  const bool is_cand = !is_comp && cidx < kYinMaxCand;
+  const int ct = tid - kVcComp;                   // candidate thread index (0 .. 95) of the non-compute warps
+  const bool is_cand = !is_comp;
   const bool is_lu = tid == kVcComp;
 
   for (int i = tid; i < Q; i += kVcThreads) lnorm[i] = j0 + i < nb ? p.lognorm[j0 + i] : 0.0;
@@ -832,26 +835,35 @@ __global__ void __cluster_dims__(kVcN, 1, 1) __launch_bounds__(kVcThreads, 1) py
 
   struct Stage {
     int nc;
-    unsigned bin, nbin;
-    float prob;
+    unsigned bin[kVcSlots], nbin[kVcSlots];
+    float prob[kVcSlots];
   };
   auto fetch = [&](long long t) {
     Stage st;
-    st.nc = 0; st.bin = 0; st.nbin = 0xffffffffu; st.prob = 0.f;
+    st.nc = 0;
+#pragma unroll
+    for (int k = 0; k < kVcSlots; ++k) { st.bin[k] = 0; st.nbin[k] = 0xffffffffu; st.prob[k] = 0.f; }
     if (is_cand && t < p.n_steps) {
       st.nc = p.n_cand[t];
       const uint2* cd = p.cand + t * (long long)kYinMaxCand;
-      const uint2 me = cd[cidx];
-      st.bin = me.x;
-      st.prob = __uint_as_float(me.y);
-      st.nbin = cidx + 1 < kYinMaxCand ? cd[cidx + 1].x : 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < kVcSlots; ++k) {
+        const int idx = ct + kVcCand * k;
+        if (idx < st.nc) {
+          const uint2 me = cd[idx];
+          st.bin[k] = me.x;
+          st.prob[k] = __uint_as_float(me.y);
+          st.nbin[k] = idx + 1 < kYinMaxCand ? cd[idx + 1].x : 0xffffffffu;
+        }
+      }
     }
     return st;
   };
   // last candidate of a run of equal bins wins; only bins of this CTA are scattered (local index returned, else -1)
-  auto target = [&](const Stage& st) -> int {
-    if (cidx < st.nc && (cidx == st.nc - 1 || st.nbin != st.bin) && (int)st.bin < nb) {
-      const int li = (int)st.bin - j0;
+  auto target = [&](const Stage& st, int k) -> int {
+    const int idx = ct + kVcCand * k;
+    if (idx < st.nc && (idx == st.nc - 1 || st.nbin[k] != st.bin[k]) && (int)st.bin[k] < nb) {
+      const int li = (int)st.bin[k] - j0;
       if (li >= 0 && li < nq) return li;
     }
     return -1;
@@ -896,13 +908,18 @@ __global__ void __cluster_dims__(kVcN, 1, 1) __launch_bounds__(kVcThreads, 1) py
 
   // ---- step 0 ----
   Stage s0 = fetch(0), s1 = fetch(1), sA = fetch(2), sB = fetch(3);
-  int wr0 = -1, wr1 = -1;
-  if (is_cand) {
-    const int t0 = target(s0), t1 = target(s1);
-    if (t0 >= 0) { obs[t0] = log((double)s0.prob + tiny); wr0 = t0; }
-    if (t1 >= 0) { obs[Q + t1] = log((double)s1.prob + tiny); wr1 = t1; }
+  int wr0[kVcSlots], wr1[kVcSlots];
+  double lgA[kVcSlots];
+#pragma unroll
+  for (int k = 0; k < kVcSlots; ++k) {
+    wr0[k] = -1; wr1[k] = -1; lgA[k] = 0.0;
+    if (is_cand) {
+      const int t0 = target(s0, k), t1 = target(s1, k);
+      if (t0 >= 0) { obs[t0] = log((double)s0.prob[k] + tiny); wr0[k] = t0; }
+      if (t1 >= 0) { obs[Q + t1] = log((double)s1.prob[k] + tiny); wr1[k] = t1; }
+      if (ct + kVcCand * k < sA.nc) lgA[k] = log((double)sA.prob[k] + tiny);
+    }
   }
-  double lgA = (is_cand && cidx < sA.nc) ? log((double)sA.prob + tiny) : 0.0;
   float vp_next = 0.f;  // voiced_prob of the NEXT step, loaded one step before its logarithm is taken
   if (is_lu) {
     lu_s[0] = lu_of(0);
@@ -962,13 +979,16 @@ __global__ void __cluster_dims__(kVcN, 1, 1) __launch_bounds__(kVcThreads, 1) py
       publish(nv, nu, wb);
     } else {
       if (is_cand) {
-        if (wr0 >= 0) obs[(int)((t - 1) % 3) * Q + wr0] = kLogTiny;
-        const int tn = target(sA);
-        if (tn >= 0) obs[(int)((t + 1) % 3) * Q + tn] = lgA;
-        wr0 = wr1;
-        wr1 = tn;
         const Stage sC = fetch(t + 3);
-        lgA = cidx < sB.nc ? log((double)sB.prob + tiny) : 0.0;
+#pragma unroll
+        for (int k = 0; k < kVcSlots; ++k) {
+          if (wr0[k] >= 0) obs[(int)((t - 1) % 3) * Q + wr0[k]] = kLogTiny;
+          const int tn = target(sA, k);
+          if (tn >= 0) obs[(int)((t + 1) % 3) * Q + tn] = lgA[k];
+          wr0[k] = wr1[k];
+          wr1[k] = tn;
+          lgA[k] = ct + kVcCand * k < sB.nc ? log((double)sB.prob[k] + tiny) : 0.0;
+        }
         sA = sB;
         sB = sC;
       }
