@@ -550,3 +550,28 @@ def test_pyin_viterbi_kernels_agree_bit_for_bit(ops):
     for mode in ("generic", "tiled", "fast", "serial-backtrack"):
         for a, b in zip(outs[""], outs[mode]):
             np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("n", [300, 441, 900, 1400, 441 * 65 + 7, 441 * 129])
+def test_pyin_decode_on_very_short_inputs(ops, n):
+    """1, 2, 3, 4 frames and lengths around the 64-step backtrack blocks: the cluster Viterbi + composed backtrack agree
+    with the run-time-width kernel + serial backtrack (pipeline prologues, block boundaries, empty tails)."""
+    import os
+
+    rng = np.random.default_rng(n)
+    t = np.arange(n) / SR
+    y = (0.4 * np.sin(2 * np.pi * 220.0 * t) + 0.01 * rng.standard_normal(n)).astype(np.float32)
+    x = torch.from_numpy(y).cuda()
+    try:
+        os.environ.pop("AC_PYIN_VITERBI", None)
+        os.environ.pop("AC_PYIN_BACKTRACK", None)
+        a = [v.cpu().numpy() for v in ops.pyin(x)]
+        os.environ["AC_PYIN_VITERBI"] = "generic"
+        os.environ["AC_PYIN_BACKTRACK"] = "serial"
+        b = [v.cpu().numpy() for v in ops.pyin(x)]
+    finally:
+        os.environ.pop("AC_PYIN_VITERBI", None)
+        os.environ.pop("AC_PYIN_BACKTRACK", None)
+    assert a[0].shape == (1 + n // 441,)
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
