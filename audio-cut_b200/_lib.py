@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaudiocut_b200.so")
 
-AC_F32, AC_BF16 = 0, 1
+AC_F32, AC_BF16, AC_F16 = 0, 1, 2
 
 EXPORTS = [
     "ac_init", "ac_last_error", "ac_abi_version", "ac_launch_count", "ac_frame_count", "ac_frame_rms",

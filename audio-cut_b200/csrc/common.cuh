@@ -1,6 +1,7 @@
 // Shared helpers for libaudiocut_b200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -58,15 +59,52 @@ struct ProfScope {  // brackets the launches issued during its lifetime with two
   ~ProfScope() { if (idx >= 0) prof_stop(idx, st); }
 };
 
-// storage type helpers: activations are float or __nv_bfloat16, math is always fp32
+// storage type helpers: activations are float, __half or __nv_bfloat16, math is always fp32
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
 template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// ---- 16-bit storage of the tensor-core path ---------------------------------------------------
+// The tcgen05 kernels are templated on the operand format FMT of tcgen05.mma kind::f16: IEEE half (11-bit
+// significand; the production format: its rounding noise is 18 dB below bfloat16's, which is what the >= 40 dB
+// stem-SDR gate of the 16-bit path needs) or bfloat16 (fp32 range, 8-bit significand).  Both run at the same
+// tensor-core rate and move the same bytes.  `h16` is the opaque storage element; pack2 / unpack2 convert
+// a pair through one 32-bit register.
+constexpr int kFmtF16 = 0, kFmtBF16 = 1;
+struct h16 { uint16_t bits; };
+inline bool is_h16_dtype(int dtype) { return dtype == AC_BF16 || dtype == AC_F16; }
+inline int fmt_of_dtype(int dtype) { return dtype == AC_BF16 ? kFmtBF16 : kFmtF16; }
+inline h16 h16_rn(float v, int fmt) {  // host: round to nearest even
+  h16 r;
+  if (fmt == kFmtBF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); r.bits = *reinterpret_cast<uint16_t*>(&b); }
+  else { __half h = __float2half_rn(v); r.bits = *reinterpret_cast<uint16_t*>(&h); }
+  return r;
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  if constexpr (FMT == kFmtBF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // |x| > 65504 saturates instead of inf
+  return r;
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if constexpr (FMT == kFmtBF16) return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  else return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+template <int FMT>
+__device__ __forceinline__ float unpack1(h16 v) {
+  if constexpr (FMT == kFmtBF16) return __uint_as_float((uint32_t)v.bits << 16);
+  else return __half2float(*reinterpret_cast<const __half*>(&v));
+}
 
 // streaming 128-bit global load (read once: keep it out of L1)
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {

@@ -80,7 +80,19 @@ __device__ __forceinline__ void store_spec4<__nv_bfloat16>(__nv_bfloat16* p, flo
   v.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(p) = v;
 }
+template <>
+__device__ __forceinline__ void store_spec4<__half>(__half* p, float a, float b, float c, float d) {
+  uint2 v;
+  v.x = pack2<kFmtF16>(a, b);
+  v.y = pack2<kFmtF16>(c, d);
+  *reinterpret_cast<uint2*>(p) = v;
+}
 __device__ __forceinline__ float4 load_spec4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load_spec4(const __half* p) {
+  uint2 v = *reinterpret_cast<const uint2*>(p);
+  float2 a = unpack2<kFmtF16>(v.x), b = unpack2<kFmtF16>(v.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ float4 load_spec4(const __nv_bfloat16* p) {
   uint2 v = *reinterpret_cast<const uint2*>(p);
   __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&v.x), hi = *reinterpret_cast<__nv_bfloat162*>(&v.y);
@@ -257,6 +269,8 @@ int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, in
   } while (0)
   if (dtype == AC_F32) {
     if (inplace) AC_STFT_LAUNCH(float, true); else AC_STFT_LAUNCH(float, false);
+  } else if (dtype == AC_F16) {
+    if (inplace) AC_STFT_LAUNCH(__half, true); else AC_STFT_LAUNCH(__half, false);
   } else {
     if (inplace) AC_STFT_LAUNCH(__nv_bfloat16, true); else AC_STFT_LAUNCH(__nv_bfloat16, false);
   }
@@ -314,6 +328,9 @@ int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDe
   if (dtype == AC_F32) {
     AC_CHECK_CUDA(cudaFuncSetAttribute(istft_mdx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_mdx_kernel<float><<<grid, kFftThreads, smem, st>>>((const float*)d_spec, a);
+  } else if (dtype == AC_F16) {
+    AC_CHECK_CUDA(cudaFuncSetAttribute(istft_mdx_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    istft_mdx_kernel<__half><<<grid, kFftThreads, smem, st>>>((const __half*)d_spec, a);
   } else {
     AC_CHECK_CUDA(
         cudaFuncSetAttribute(istft_mdx_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -359,7 +376,7 @@ const ac::WinDesc* batch_windows(int B, int W) {
 
 extern "C" int ac_stft_mdx(const float* d_wave, void* d_spec, int B, const ac_mdx_geom* g, int dtype, void* stream) {
   AC_REQUIRE(d_wave && d_spec && g && B >= 0, "null pointer");
-  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16, "dtype");
+  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16 || dtype == AC_F16, "dtype");
   const ac::MdxPlan* plan = ac::get_mdx_plan(*g);
   if (!plan) return AC_E_INVALID;
   const ac::WinDesc* w = batch_windows(B, plan->W);
@@ -369,7 +386,7 @@ extern "C" int ac_stft_mdx(const float* d_wave, void* d_spec, int B, const ac_md
 
 extern "C" int ac_istft_mdx(const void* d_spec, float* d_wave, int B, const ac_mdx_geom* g, int dtype, void* stream) {
   AC_REQUIRE(d_wave && d_spec && g && B >= 0, "null pointer");
-  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16, "dtype");
+  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16 || dtype == AC_F16, "dtype");
   const ac::MdxPlan* plan = ac::get_mdx_plan(*g);
   if (!plan) return AC_E_INVALID;
   const ac::WinDesc* w = batch_windows(B, plan->W);

@@ -86,9 +86,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
+// kind::f16 instruction descriptor: D = f32 (bit 4), A / B format in bits [7,10) / [10,13) (0 = f16, 1 = bf16),
+// both K-major, M = 128, N = n
+template <int FMT>
+__device__ __forceinline__ uint32_t idesc_ab() { return FMT == kFmtBF16 ? ((1u << 7) | (1u << 10)) : 0u; }
+template <int FMT>
 __device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  return (1u << 4) | idesc_ab<FMT>() | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -157,8 +161,9 @@ __device__ __forceinline__ void tma_load_5d_2sm(void* dst, const CUtensorMap* ma
       : "memory");
 }
 // kind::f16 idesc for the pair: M = 256 (128 rows per CTA), N = n, both operands K-major
+template <int FMT>
 __device__ __forceinline__ uint32_t make_idesc_2sm(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  return (1u << 4) | idesc_ab<FMT>() | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 template <bool kAcc>
 __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
@@ -190,7 +195,8 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_by
   return make_desc(saddr, lbo_bytes, sbo_bytes);
 }
 // kind::f16 idesc with B MN-major (bit 16)
-__device__ __forceinline__ uint32_t make_idesc_bmn(int n) { return make_idesc(n) | (1u << 16); }
+template <int FMT>
+__device__ __forceinline__ uint32_t make_idesc_bmn(int n) { return make_idesc<FMT>(n) | (1u << 16); }
 
 // Activation layout of the tensor-core path ("CG8", channel-group planar):
 //   X[b][t][c/8][f][c%8]   element index (((b*T + t)*(C/8) + c/8)*F + f)*8 + c%8

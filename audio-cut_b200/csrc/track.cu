@@ -162,7 +162,7 @@ extern "C" int ac_separate_track(ac_unet* net, const float* d_mix, long long n_s
   AC_REQUIRE(net && d_mix && h_chunks && p && d_vocal && d_instr && d_weight && d_ws, "null pointer");
   AC_REQUIRE(n_samples > 0 && n_chunks >= 0, "bad sizes");
   AC_REQUIRE(p->n_channels == 1 || p->n_channels == 2, "n_channels must be 1 or 2");
-  AC_REQUIRE(p->dtype == AC_F32 || p->dtype == AC_BF16, "dtype");
+  AC_REQUIRE(p->dtype == AC_F32 || p->dtype == AC_BF16 || p->dtype == AC_F16, "dtype");
   for (int c = 0; c < n_chunks; ++c) {
     AC_REQUIRE(h_chunks[c].chunk_start >= 0 && h_chunks[c].chunk_start + h_chunks[c].chunk_len <= n_samples,
                "chunk outside the track");

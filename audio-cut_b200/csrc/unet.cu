@@ -10,24 +10,28 @@ struct Affine {
   const float* scale;
   const float* shift;
 };
-struct ConvLayer {  // implicit-GEMM B operand [K][N] in both dtypes
+// Everything 16-bit exists once per operand format (index kFmtF16 / kFmtBF16) and is built lazily by
+// ensure_h16() on the first forward in that format: the arena copy and the per-layer tcgen05 packings.
+struct ConvLayer {  // implicit-GEMM B operand [K][N]
   const float* w32;
-  const __nv_bfloat16* w16;
+  size_t w_off;      // arena offset of w32 (the 16-bit arena copies use the same offsets)
+  size_t raw_off;    // offset of the layer's weights in the caller's blob order (host copy kept in ac_unet)
+  int cin, cout;
   Affine af;
   int K, N;
-  TcConvWeights* tc = nullptr;  // tcgen05 packing (3x3 convs only)
-  TcConvWsWeights* ws = nullptr;  // weight-stationary tcgen05 packing (3x3 convs, C = 48 / 96)
-  TcConvPairWeights* cp = nullptr;  // CTA-pair streaming packing (3x3 convs, C >= 144)
-  TcResampleWeights* rs = nullptr;  // tcgen05 packing (down / up convs only)
+  TcConvWeights* tc[2] = {nullptr, nullptr};      // tcgen05 packing (3x3 convs only)
+  TcConvWsWeights* ws[2] = {nullptr, nullptr};    // weight-stationary tcgen05 packing (3x3 convs, C = 48 / 96)
+  TcConvPairWeights* cp[2] = {nullptr, nullptr};  // CTA-pair streaming packing (3x3 convs, C >= 144)
+  TcResampleWeights* rs[2] = {nullptr, nullptr};  // tcgen05 packing (down / up convs only)
 };
 struct TdfLayer {  // GEMM A operand [M][K] (PyTorch Linear weight as is)
   const float* w32;
-  const __nv_bfloat16* w16;
+  size_t w_off, raw_off;
   Affine af;
   int M, K;
-  TcTdfWeights* tc = nullptr;
-  TcTdf2PairWeights* pair = nullptr;  // CTA-pair kernel (second TDF layer of a block only)
-  TcTdf1PairWeights* pair1 = nullptr;  // CTA-pair kernel (first TDF layer of a block only)
+  TcTdfWeights* tc[2] = {nullptr, nullptr};
+  TcTdf2PairWeights* pair[2] = {nullptr, nullptr};   // CTA-pair kernel (second TDF layer of a block only)
+  TcTdf1PairWeights* pair1[2] = {nullptr, nullptr};  // CTA-pair kernel (first TDF layer of a block only)
 };
 struct Block {
   int c, T, F;
@@ -47,10 +51,13 @@ struct ac_unet {
   const float* final_w;
   const float* final_b;
   float* d_f32 = nullptr;           // arena: all fp32 params (repacked)
-  __nv_bfloat16* d_bf16 = nullptr;  // arena: bf16 copies, same offsets
+  ac::h16* d_h16[2] = {nullptr, nullptr};  // arena: 16-bit copies (f16 / bf16), same offsets
+  bool h16_ready[2] = {false, false};
+  bool tc_ok[2] = {false, false};  // every layer has a CG8 / tcgen05 implementation: the 16-bit path runs on tensor cores
+  std::vector<float> h_blob;        // the caller's parameter blob (the packers read the original weight order)
   size_t arena_floats = 0;
   int force_simt = 0;
-  bool tc_ok = false;  // every layer has a CG8 / tcgen05 implementation: the bf16 path runs on tensor cores
+  int device = 0;
 };
 
 namespace ac {
@@ -103,6 +110,8 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
   ac_unet* net = new ac_unet();
   net->g = g;
   net->arena_floats = n_floats;
+  net->h_blob.assign(h_blob, h_blob + n_floats);
+  cudaGetDevice(&net->device);
   size_t rd = 0, wr = 0;
   struct Fix {  // pointer fix-ups recorded as arena offsets
     size_t off;
@@ -188,25 +197,22 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
     return AC_E_INVALID;
   }
 
-  std::vector<__nv_bfloat16> arena16(n_floats);
-  for (size_t i = 0; i < n_floats; ++i) arena16[i] = __float2bfloat16_rn(arena[i]);
-  if (cudaMalloc(&net->d_f32, n_floats * 4) != cudaSuccess || cudaMalloc(&net->d_bf16, n_floats * 2) != cudaSuccess ||
-      cudaMemcpy(net->d_f32, arena.data(), n_floats * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(net->d_bf16, arena16.data(), n_floats * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (cudaMalloc(&net->d_f32, n_floats * 4) != cudaSuccess ||
+      cudaMemcpy(net->d_f32, arena.data(), n_floats * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
     set_error(std::string("unet parameter upload: ") + cudaGetErrorString(cudaGetLastError()));
     ac_unet_destroy(net);
     return AC_E_CUDA;
   }
   auto mk_conv = [&](const ConvOff& o) {
     ConvLayer L;
-    L.w32 = net->d_f32 + o.w; L.w16 = net->d_bf16 + o.w;
+    L.w32 = net->d_f32 + o.w; L.w_off = o.w; L.raw_off = (size_t)(o.raw - h_blob); L.cin = o.cin; L.cout = o.cout;
     L.af = Affine{net->d_f32 + o.sc, net->d_f32 + o.sh};
     L.K = o.K; L.N = o.N;
     return L;
   };
   auto mk_tdf = [&](const TdfOff& o) {
     TdfLayer L;
-    L.w32 = net->d_f32 + o.w; L.w16 = net->d_bf16 + o.w;
+    L.w32 = net->d_f32 + o.w; L.w_off = o.w; L.raw_off = (size_t)(o.raw - h_blob);
     L.af = Affine{net->d_f32 + o.sc, net->d_f32 + o.sh};
     L.M = o.M; L.K = o.K;
     return L;
@@ -214,82 +220,101 @@ extern "C" int ac_unet_create(const ac_unet_geom* gp, const float* h_blob, size_
   for (auto& bo : boffs) {
     Block b;
     b.c = bo.c; b.T = bo.T; b.F = bo.F;
-    for (int j = 0; j < g.l; ++j) {
-      b.conv[j] = mk_conv(bo.conv[j]);
-      if (tc_conv3x3_supported(bo.T, bo.F, bo.c) == AC_OK) {
-        if (tc_conv3x3_pack(bo.conv[j].raw, bo.c, &b.conv[j].tc) != AC_OK) {
-          ac_unet_destroy(net);
-          return AC_E_CUDA;
-        }
-      }
-      if (tc_conv3x3_pair_supported(bo.T, bo.F, bo.c) == AC_OK) {
-        if (tc_conv3x3_pair_pack(bo.conv[j].raw, bo.c, &b.conv[j].cp) != AC_OK) {
-          ac_unet_destroy(net);
-          return AC_E_CUDA;
-        }
-      }
-      if (tc_conv3x3_ws_supported(bo.T, bo.F, bo.c) == AC_OK) {
-        if (tc_conv3x3_ws_pack(bo.conv[j].raw, bo.c, &b.conv[j].ws) != AC_OK) {
-          ac_unet_destroy(net);
-          return AC_E_CUDA;
-        }
-      }
-    }
+    for (int j = 0; j < g.l; ++j) b.conv[j] = mk_conv(bo.conv[j]);
     b.tdf1 = mk_tdf(bo.t1);
     b.tdf2 = mk_tdf(bo.t2);
-    if (tc_tdf_pack(bo.t1.raw, bo.t1.M, bo.t1.K, bo.c, bo.T, &b.tdf1.tc) != AC_OK ||
-        tc_tdf_pack(bo.t2.raw, bo.t2.M, bo.t2.K, bo.c, bo.T, &b.tdf2.tc) != AC_OK ||
-        tc_tdf2_pair_pack(bo.t2.raw, bo.t2.M, bo.t2.K, bo.c, bo.T, &b.tdf2.pair) != AC_OK ||
-        tc_tdf1_pair_pack(bo.t1.raw, bo.t1.M, bo.t1.K, bo.c, bo.T, &b.tdf1.pair1) != AC_OK) {
-      ac_unet_destroy(net);
-      return AC_E_CUDA;
-    }
     net->blocks.push_back(b);
   }
-  for (auto& o : dsoffs) {
-    ConvLayer L = mk_conv(o);
-    if (tc_resample_pack(0, o.raw, o.cin, o.cout, &L.rs) != AC_OK) { ac_unet_destroy(net); return AC_E_CUDA; }
-    net->ds.push_back(L);
-  }
-  for (auto& o : usoffs) {
-    ConvLayer L = mk_conv(o);
-    if (tc_resample_pack(1, o.raw, o.cin, o.cout, &L.rs) != AC_OK) { ac_unet_destroy(net); return AC_E_CUDA; }
-    net->us.push_back(L);
-  }
+  for (auto& o : dsoffs) net->ds.push_back(mk_conv(o));
+  for (auto& o : usoffs) net->us.push_back(mk_conv(o));
   net->first_w = net->d_f32 + first_w;
   net->first_af = Affine{net->d_f32 + first_sc, net->d_f32 + first_sh};
   net->final_w = net->d_f32 + final_w;
   net->final_b = net->d_f32 + final_b;
   net->n_blocks = (int)net->blocks.size();
-  net->tc_ok = cg8_ends_supported(g.g) == AC_OK;
-  for (auto& b : net->blocks)
-    for (int j = 0; j < g.l; ++j) net->tc_ok = net->tc_ok && b.conv[j].tc != nullptr;
-  for (auto& L : net->ds) net->tc_ok = net->tc_ok && L.rs != nullptr;
-  for (auto& L : net->us) net->tc_ok = net->tc_ok && L.rs != nullptr;
   *out = net;
   return AC_OK;
 }
 
 extern "C" void ac_unet_destroy(ac_unet* net) {
   if (!net) return;
-  for (auto& b : net->blocks) {
-    for (int j = 0; j < net->g.l; ++j)
-    {
-      if (b.conv[j].tc) ac::tc_conv3x3_free(b.conv[j].tc);
-      if (b.conv[j].ws) ac::tc_conv3x3_ws_free(b.conv[j].ws);
-      if (b.conv[j].cp) ac::tc_conv3x3_pair_free(b.conv[j].cp);
+  for (int f = 0; f < 2; ++f) {
+    for (auto& b : net->blocks) {
+      for (int j = 0; j < net->g.l; ++j) {
+        if (b.conv[j].tc[f]) ac::tc_conv3x3_free(b.conv[j].tc[f]);
+        if (b.conv[j].ws[f]) ac::tc_conv3x3_ws_free(b.conv[j].ws[f]);
+        if (b.conv[j].cp[f]) ac::tc_conv3x3_pair_free(b.conv[j].cp[f]);
+      }
+      ac::tc_tdf_free(b.tdf1.tc[f]);
+      ac::tc_tdf_free(b.tdf2.tc[f]);
+      ac::tc_tdf2_pair_free(b.tdf2.pair[f]);
+      ac::tc_tdf1_pair_free(b.tdf1.pair1[f]);
     }
-    ac::tc_tdf_free(b.tdf1.tc);
-    ac::tc_tdf_free(b.tdf2.tc);
-    ac::tc_tdf2_pair_free(b.tdf2.pair);
-    ac::tc_tdf1_pair_free(b.tdf1.pair1);
+    for (auto& L : net->ds) ac::tc_resample_free(L.rs[f]);
+    for (auto& L : net->us) ac::tc_resample_free(L.rs[f]);
+    if (net->d_h16[f]) cudaFree(net->d_h16[f]);
   }
-  for (auto& L : net->ds) ac::tc_resample_free(L.rs);
-  for (auto& L : net->us) ac::tc_resample_free(L.rs);
   if (net->d_f32) cudaFree(net->d_f32);
-  if (net->d_bf16) cudaFree(net->d_bf16);
   delete net;
 }
+
+namespace ac {
+template <int FMT>
+__global__ void arena_to_h16_kernel(const float* __restrict__ src, h16* __restrict__ dst, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    *reinterpret_cast<uint32_t*>(dst + i) = pack2<FMT>(src[i], src[i + 1]);
+  } else if (i < n) {
+    const uint32_t v = pack2<FMT>(src[i], 0.f);
+    dst[i].bits = (uint16_t)(v & 0xffffu);
+  }
+}
+
+// Builds, once per operand format, the 16-bit arena copy and every per-layer tcgen05 packing.  A pack that fails
+// half-way is owned by the net already (the layer pointer is set by the packer's out-parameter), so
+// ac_unet_destroy frees whatever exists.
+static int ensure_h16(ac_unet* net, int fmt) {
+  if (net->h16_ready[fmt]) return AC_OK;
+  const ac_unet_geom& g = net->g;
+  const size_t n = net->arena_floats;
+  if (!net->d_h16[fmt]) {
+    AC_CHECK_CUDA(cudaMalloc(&net->d_h16[fmt], (n + 2) * 2));
+    const unsigned grid = (unsigned)((n / 2 + 1 + 255) / 256);
+    if (fmt == kFmtBF16) arena_to_h16_kernel<kFmtBF16><<<grid, 256>>>(net->d_f32, net->d_h16[fmt], n);
+    else arena_to_h16_kernel<kFmtF16><<<grid, 256>>>(net->d_f32, net->d_h16[fmt], n);
+    AC_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  const float* blob = net->h_blob.data();
+  int rc;
+  for (auto& b : net->blocks) {
+    for (int j = 0; j < g.l; ++j) {
+      ConvLayer& L = b.conv[j];
+      const float* raw = blob + L.raw_off;
+      if (!L.tc[fmt] && tc_conv3x3_supported(b.T, b.F, b.c) == AC_OK && (rc = tc_conv3x3_pack(raw, b.c, fmt, &L.tc[fmt]))) return rc;
+      if (!L.cp[fmt] && tc_conv3x3_pair_supported(b.T, b.F, b.c) == AC_OK && (rc = tc_conv3x3_pair_pack(raw, b.c, fmt, &L.cp[fmt]))) return rc;
+      if (!L.ws[fmt] && tc_conv3x3_ws_supported(b.T, b.F, b.c) == AC_OK && (rc = tc_conv3x3_ws_pack(raw, b.c, fmt, &L.ws[fmt]))) return rc;
+    }
+    TdfLayer& t1 = b.tdf1;
+    TdfLayer& t2 = b.tdf2;
+    if (!t1.tc[fmt] && (rc = tc_tdf_pack(blob + t1.raw_off, t1.M, t1.K, b.c, b.T, fmt, &t1.tc[fmt]))) return rc;
+    if (!t2.tc[fmt] && (rc = tc_tdf_pack(blob + t2.raw_off, t2.M, t2.K, b.c, b.T, fmt, &t2.tc[fmt]))) return rc;
+    if (!t2.pair[fmt] && (rc = tc_tdf2_pair_pack(blob + t2.raw_off, t2.M, t2.K, b.c, b.T, fmt, &t2.pair[fmt]))) return rc;
+    if (!t1.pair1[fmt] && (rc = tc_tdf1_pair_pack(blob + t1.raw_off, t1.M, t1.K, b.c, b.T, fmt, &t1.pair1[fmt]))) return rc;
+  }
+  for (auto& L : net->ds)
+    if (!L.rs[fmt] && (rc = tc_resample_pack(0, blob + L.raw_off, L.cin, L.cout, fmt, &L.rs[fmt]))) return rc;
+  for (auto& L : net->us)
+    if (!L.rs[fmt] && (rc = tc_resample_pack(1, blob + L.raw_off, L.cin, L.cout, fmt, &L.rs[fmt]))) return rc;
+  bool ok = cg8_ends_supported(g.g) == AC_OK;
+  for (auto& b : net->blocks)
+    for (int j = 0; j < g.l; ++j) ok = ok && b.conv[j].tc[fmt] != nullptr;
+  for (auto& L : net->ds) ok = ok && L.rs[fmt] != nullptr;
+  for (auto& L : net->us) ok = ok && L.rs[fmt] != nullptr;
+  net->tc_ok[fmt] = ok;
+  net->h16_ready[fmt] = true;
+  return AC_OK;
+}
+}  // namespace ac
 
 namespace ac { int tc_check_abort(); }
 extern "C" int ac_debug_tc_aborted(void) { return ac::tc_check_abort(); }
@@ -307,29 +332,31 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
   using namespace ac;
   AC_REQUIRE(d_in && d_out && h_w && d_scale && d_shift && iters >= 1, "null pointer / iters");
   cudaStream_t st = (cudaStream_t)stream;
-  TcConvArgs ta{(const __nv_bfloat16*)d_in, (__nv_bfloat16*)d_out, B, T, F, C, nullptr, d_scale, d_shift};
+  const int fmt = (impl & 16) ? kFmtF16 : kFmtBF16;  // impl + 16: IEEE half operands
+  impl &= 15;
+  TcConvArgs ta{(const h16*)d_in, (h16*)d_out, B, T, F, C, nullptr, d_scale, d_shift};
   TcConvWeights* tc = nullptr;
   TcConvWsWeights* ws = nullptr;
   TcConvPairWeights* cp = nullptr;
-  __nv_bfloat16* d_w16 = nullptr;
+  h16* d_w16 = nullptr;
   int rc = AC_OK;
   if (impl == 1) {
     AC_REQUIRE(tc_conv3x3_supported(T, F, C) == AC_OK, "streaming tc conv does not support this shape");
-    if ((rc = tc_conv3x3_pack(h_w, C, &tc))) return rc;
+    if ((rc = tc_conv3x3_pack(h_w, C, fmt, &tc))) return rc;
     ta.w = tc;
   } else if (impl == 4) {
     AC_REQUIRE(tc_conv3x3_pair_supported(T, F, C) == AC_OK, "pair streaming tc conv does not support this shape");
-    if ((rc = tc_conv3x3_pair_pack(h_w, C, &cp))) return rc;
+    if ((rc = tc_conv3x3_pair_pack(h_w, C, fmt, &cp))) return rc;
   } else if (impl == 2 || impl == 3) {
     tc_conv3x3_ws_set_pair(impl == 3);
     tc_conv3x3_ws_set_rs(impl == 3);
     AC_REQUIRE(tc_conv3x3_ws_supported(T, F, C) == AC_OK, "ws tc conv does not support this shape");
-    if ((rc = tc_conv3x3_ws_pack(h_w, C, &ws))) return rc;
+    if ((rc = tc_conv3x3_ws_pack(h_w, C, fmt, &ws))) return rc;
   } else {
-    std::vector<__nv_bfloat16> w16((size_t)9 * C * C);  // [(tap*C+ci)][co]
+    std::vector<h16> w16((size_t)9 * C * C);  // [(tap*C+ci)][co]
     for (int co = 0; co < C; ++co)
       for (int ci = 0; ci < C; ++ci)
-        for (int t = 0; t < 9; ++t) w16[((size_t)t * C + ci) * C + co] = __float2bfloat16_rn(h_w[((size_t)co * C + ci) * 9 + t]);
+        for (int t = 0; t < 9; ++t) w16[((size_t)t * C + ci) * C + co] = h16_rn(h_w[((size_t)co * C + ci) * 9 + t], fmt);
     AC_CHECK_CUDA(cudaMalloc(&d_w16, w16.size() * 2));
     AC_CHECK_CUDA(cudaMemcpy(d_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
   }
@@ -343,7 +370,7 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
     a.Bm = d_w16;
     a.epi = EPI_AFFINE_RELU; a.scale = d_scale; a.shift = d_shift; a.cmod = C; a.out = d_out;
     a.kclass = KC_CONV_SIMT;
-    return launch_gemm_simt(a, AC_BF16, st);
+    return launch_gemm_simt(a, fmt == kFmtF16 ? AC_F16 : AC_BF16, st);
   };
   rc = once();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -409,7 +436,12 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
   using namespace ac;
   AC_REQUIRE(net && d_in && d_out && d_ws, "null pointer");
   AC_REQUIRE(B > 0, "batch must be positive");
-  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16, "dtype");
+  AC_REQUIRE(dtype == AC_F32 || dtype == AC_BF16 || dtype == AC_F16, "dtype");
+  const int fmt = fmt_of_dtype(dtype);
+  if (dtype != AC_F32) {
+    int rc0 = ensure_h16(net, fmt);
+    if (rc0) return rc0;
+  }
   if (ws_bytes < ac_unet_workspace_bytes(net, B, dtype)) {
     set_error("unet workspace too small");
     return AC_E_WORKSPACE;
@@ -423,24 +455,24 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
   void* P = ptr(wp.P);
   void* Q = ptr(wp.Q);
   void* H = ptr(wp.H);
-  auto wsel = [&](const float* w32, const __nv_bfloat16* w16) { return dtype == AC_F32 ? (const void*)w32 : (const void*)w16; };
+  auto wsel = [&](const float* w32, size_t w_off) { return dtype == AC_F32 ? (const void*)w32 : (const void*)(net->d_h16[fmt] + w_off); };
   int rc;
 
   // bf16 runs on the tensor-core path (all activations in the CG8 layout) unless the geometry has a layer
   // without a tcgen05 kernel or the test hook forces the CUDA-core kernels (channels-last layout).
-  const bool use_tc = dtype == AC_BF16 && net->tc_ok && net->force_simt != 1;
+  const bool use_tc = dtype != AC_F32 && net->tc_ok[fmt] && net->force_simt != 1;
 
   auto conv3x3 = [&](const ConvLayer& L, const void* x, void* y, int T, int F, int C) -> int {
     if (use_tc) {
-      TcConvArgs ta{(const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, T, F, C, L.tc, L.af.scale, L.af.shift};
-      if (L.ws && net->force_simt != 2 && tc_conv3x3_ws_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_ws(L.ws, ta, st);
-      if (L.cp && net->force_simt != 2 && tc_conv3x3_pair_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_pair(L.cp, ta, st);
+      TcConvArgs ta{(const h16*)x, (h16*)y, B, T, F, C, L.tc[fmt], L.af.scale, L.af.shift};
+      if (L.ws[fmt] && net->force_simt != 2 && tc_conv3x3_ws_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_ws(L.ws[fmt], ta, st);
+      if (L.cp[fmt] && net->force_simt != 2 && tc_conv3x3_pair_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_pair(L.cp[fmt], ta, st);
       return launch_tc_conv3x3(ta, st);
     }
     GemmArgs a{};
     a.M = B * T * F; a.N = L.N; a.K = L.K; a.batch = 1;
     a.a_mode = A_CONV3; a.A = x; a.T = T; a.F = F; a.C = C;
-    a.Bm = wsel(L.w32, L.w16);
+    a.Bm = wsel(L.w32, L.w_off);
     a.epi = EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = L.N; a.out = y;
     a.kclass = KC_CONV_SIMT;
     return launch_gemm_simt(a, dtype, st);
@@ -448,20 +480,20 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
   // out = relu(affine(W * in)) (+ residual)
   auto tdf = [&](const TdfLayer& L, const Block& b, const void* in, const void* residual, void* out) -> int {
     if (use_tc) {
-      if (L.pair && residual && net->force_simt != 2)
-        return launch_tc_tdf2_pair(L.pair, (const __nv_bfloat16*)in, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, B, b.T,
+      if (L.pair[fmt] && residual && net->force_simt != 2)
+        return launch_tc_tdf2_pair(L.pair[fmt], (const h16*)in, (const h16*)residual, (h16*)out, B, b.T,
                                    L.af.scale, L.af.shift, st);
-      if (L.pair1 && !residual && net->force_simt != 2)
-        return launch_tc_tdf1_pair(L.pair1, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, b.T, L.af.scale, L.af.shift, st);
-      if (L.tc)
-        return launch_tc_tdf(L.tc, (const __nv_bfloat16*)in, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, B, b.T,
+      if (L.pair1[fmt] && !residual && net->force_simt != 2)
+        return launch_tc_tdf1_pair(L.pair1[fmt], (const h16*)in, (h16*)out, B, b.T, L.af.scale, L.af.shift, st);
+      if (L.tc[fmt])
+        return launch_tc_tdf(L.tc[fmt], (const h16*)in, (const h16*)residual, (h16*)out, B, b.T,
                              L.af.scale, L.af.shift, st);
-      return launch_tdf_small_cg8((const __nv_bfloat16*)in, L.w16, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, B, b.T,
-                                  b.c, L.M, L.K, L.af.scale, L.af.shift, st);
+      return launch_tdf_small_cg8((const h16*)in, net->d_h16[fmt] + L.w_off, (const h16*)residual, (h16*)out, B, b.T,
+                                  b.c, L.M, L.K, L.af.scale, L.af.shift, fmt, st);
     }
     GemmArgs a{};
     a.M = L.M; a.N = b.c; a.K = L.K; a.batch = B * b.T;
-    a.a_mode = A_PLAIN; a.A = wsel(L.w32, L.w16); a.a_batch_stride = 0;
+    a.a_mode = A_PLAIN; a.A = wsel(L.w32, L.w_off); a.a_batch_stride = 0;
     a.Bm = in; a.b_batch_stride = (long long)L.K * b.c;
     a.epi = residual ? EPI_RESIDUAL : EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = b.c;
     a.out = out; a.c_batch_stride = (long long)L.M * b.c; a.extra = residual;
@@ -482,10 +514,10 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     void* tfc = src;
     if (Z == tfc) return (set_error("internal: block output aliases TFC output"), AC_E_INVALID);
     if ((rc = tdf(b.tdf1, b, tfc, nullptr, H))) return rc;
-    if (last && use_tc && net->force_simt == 0 && b.tdf2.pair && tc_tdf2_pair_can_fuse_final(b.tdf2.pair) && b.c == g.g &&
+    if (last && use_tc && net->force_simt == 0 && b.tdf2.pair[fmt] && tc_tdf2_pair_can_fuse_final(b.tdf2.pair[fmt]) && b.c == g.g &&
         b.T == g.dim_t && b.tdf2.M == g.dim_f) {
       final_fused = true;
-      return launch_tc_tdf2_pair(b.tdf2.pair, (const __nv_bfloat16*)H, (const __nv_bfloat16*)tfc, (__nv_bfloat16*)d_out, B, b.T,
+      return launch_tc_tdf2_pair(b.tdf2.pair[fmt], (const h16*)H, (const h16*)tfc, (h16*)d_out, B, b.T,
                                  b.tdf2.af.scale, b.tdf2.af.shift, st, net->final_w, net->final_b);
     }
     return tdf(b.tdf2, b, H, tfc, Z);
@@ -494,7 +526,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
   const long long P0 = (long long)B * g.dim_t * g.dim_f;
   if (use_tc)
     rc = launch_first_conv_cg8(d_in, P, (long long)B * g.dim_t, g.dim_f, g.g, net->first_w, net->first_af.scale,
-                               net->first_af.shift, st);
+                               net->first_af.shift, fmt, st);
   else
     rc = launch_first_conv(d_in, P, P0, g.g, net->first_w, net->first_af.scale, net->first_af.shift, dtype, st);
   if (rc) return rc;
@@ -507,7 +539,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     if ((rc = run_block(b, cur, oth, skip))) return rc;
     const ConvLayer& d = net->ds[i];
     if (use_tc) {
-      if ((rc = launch_tc_resample(d.rs, (const __nv_bfloat16*)skip, nullptr, (__nv_bfloat16*)cur, B, b.T / 2, b.F / 2,
+      if ((rc = launch_tc_resample(d.rs[fmt], (const h16*)skip, nullptr, (h16*)cur, B, b.T / 2, b.F / 2,
                                    d.af.scale, d.af.shift, st)))
         return rc;
       continue;
@@ -515,7 +547,7 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     GemmArgs a{};
     a.M = B * (b.T / 2) * (b.F / 2); a.N = d.N; a.K = d.K; a.batch = 1;
     a.a_mode = A_DOWN2; a.A = skip; a.T = b.T / 2; a.F = b.F / 2; a.C = b.c;
-    a.Bm = wsel(d.w32, d.w16);
+    a.Bm = wsel(d.w32, d.w_off);
     a.epi = EPI_AFFINE_RELU; a.scale = d.af.scale; a.shift = d.af.shift; a.cmod = d.N; a.out = cur;
     a.kclass = KC_RESAMPLE_SIMT;
     if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
@@ -533,14 +565,14 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     const ConvLayer& u = net->us[i];
     void* skip = ptr(wp.skip_off[lvl]);
     if (use_tc) {
-      if ((rc = launch_tc_resample(u.rs, (const __nv_bfloat16*)cur, (const __nv_bfloat16*)skip, (__nv_bfloat16*)oth, B, b.T / 2,
+      if ((rc = launch_tc_resample(u.rs[fmt], (const h16*)cur, (const h16*)skip, (h16*)oth, B, b.T / 2,
                                    b.F / 2, u.af.scale, u.af.shift, st)))
         return rc;
     } else {
     GemmArgs a{};
     a.M = B * (b.T / 2) * (b.F / 2); a.N = u.N; a.K = u.K; a.batch = 1;
     a.a_mode = A_PLAIN; a.A = cur; a.a_batch_stride = 0;
-    a.Bm = wsel(u.w32, u.w16);
+    a.Bm = wsel(u.w32, u.w_off);
     a.epi = EPI_UP_SKIP; a.scale = u.af.scale; a.shift = u.af.shift; a.cmod = b.c; a.out = oth; a.extra = skip;
     a.up_T = b.T / 2; a.up_F = b.F / 2;
     a.kclass = KC_RESAMPLE_SIMT;
@@ -552,6 +584,6 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     if (Z != cur) { void* t = cur; cur = oth; oth = t; }
   }
   if (final_fused) return AC_OK;
-  if (use_tc) return launch_final_conv_cg8(cur, d_out, (long long)B * g.dim_t, g.dim_f, g.g, net->final_w, net->final_b, st);
+  if (use_tc) return launch_final_conv_cg8(cur, d_out, (long long)B * g.dim_t, g.dim_f, g.g, net->final_w, net->final_b, fmt, st);
   return launch_final_conv(cur, d_out, P0, g.g, net->final_w, net->final_b, dtype, st);
 }

@@ -1,6 +1,6 @@
 // Internal interface between the U-Net orchestration (unet.cu) and its kernels.
 // CUDA-core kernels (fp32 path, bf16 cross-check path): activations are channels-last [B][T][F][C].
-// tcgen05 kernels (bf16 production path): activations are "CG8" = [B][T][C/8][F][8], see tc_common.cuh.
+// tcgen05 kernels (16-bit production path, operands f16 or bf16 = `fmt`, common.cuh): activations are "CG8" = [B][T][C/8][F][8], see tc_common.cuh.
 #pragma once
 #include "common.cuh"
 
@@ -41,11 +41,11 @@ int launch_first_conv(const void* in, void* out, long long P, int g, const float
 int launch_final_conv(const void* in, void* out, long long P, int g, const float* w /*[4][g]*/, const float* bias,
                       int dtype, cudaStream_t st);
 
-// ---- tcgen05 path (bf16) -------------------------------------------------------------------
+// ---- tcgen05 path (f16 / bf16 operands: every *_pack takes the format, kFmtF16 / kFmtBF16) -------------------------------------------------------------------
 struct TcConvWeights;  // opaque: packed smem images for one 3x3 conv layer
 struct TcConvArgs {
-  const __nv_bfloat16* in;  // CG8 [nB][T][C/8][F][8]
-  __nv_bfloat16* out;       // CG8 [nB][T][C/8][F][8]
+  const h16* in;  // CG8 [nB][T][C/8][F][8]
+  h16* out;       // CG8 [nB][T][C/8][F][8]
   int nB, T, F, C;
   const TcConvWeights* w;
   const float* scale;
@@ -53,14 +53,14 @@ struct TcConvArgs {
 };
 // returns AC_OK, or AC_E_INVALID when the shape is not supported by the tensor-core kernel
 int tc_conv3x3_supported(int T, int F, int C);
-int tc_conv3x3_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWeights** out);
+int tc_conv3x3_pack(const float* h_w /*[C][C][3][3]*/, int C, int fmt, TcConvWeights** out);
 void tc_conv3x3_free(TcConvWeights* w);
 int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st);
 
 // weight-stationary variant for C = 48 / 96 (unet_tc_conv_ws.cu); *out stays nullptr for other widths
 struct TcConvWsWeights;
 int tc_conv3x3_ws_supported(int T, int F, int C);
-int tc_conv3x3_ws_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvWsWeights** out);
+int tc_conv3x3_ws_pack(const float* h_w /*[C][C][3][3]*/, int C, int fmt, TcConvWsWeights** out);
 void tc_conv3x3_ws_free(TcConvWsWeights* w);
 int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStream_t st);
 void tc_conv3x3_ws_set_rs(int enabled);    // test hook: 0 = never use the row-stacked (N = 144) kernel for C = 48
@@ -70,51 +70,51 @@ void tc_conv3x3_ws_set_pair(int enabled);  // test hook: 0 = never use the CTA-p
 int cg8_ends_supported(int g);
 // spec [rows*F][4] bf16 -> CG8 [rows][g/8][F][8] (rows = nB*T);  and back with bias
 int launch_first_conv_cg8(const void* in, void* out, long long rows, int F, int g, const float* w /*[g][4]*/,
-                          const float* scale, const float* shift, cudaStream_t st);
+                          const float* scale, const float* shift, int fmt, cudaStream_t st);
 int launch_final_conv_cg8(const void* in, void* out, long long rows, int F, int g, const float* w /*[4][g]*/,
-                          const float* bias, cudaStream_t st);
+                          const float* bias, int fmt, cudaStream_t st);
 // TDF layer too small for a UMMA tile: in CG8 [nB][T][C/8][K][8], w bf16 [M][K], residual/out CG8 [nB][T][C/8][M][8]
-int launch_tdf_small_cg8(const __nv_bfloat16* in, const __nv_bfloat16* w, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                         int nB, int T, int C, int M, int K, const float* scale, const float* shift, cudaStream_t st);
+int launch_tdf_small_cg8(const h16* in, const h16* w, const h16* residual, h16* out,
+                         int nB, int T, int C, int M, int K, const float* scale, const float* shift, int fmt, cudaStream_t st);
 
 // CTA-pair streaming variant for C >= 144 (unet_tc_conv_pair.cu); *out stays nullptr for other widths
 struct TcConvPairWeights;
 int tc_conv3x3_pair_supported(int T, int F, int C);
-int tc_conv3x3_pair_pack(const float* h_w /*[C][C][3][3]*/, int C, TcConvPairWeights** out);
+int tc_conv3x3_pair_pack(const float* h_w /*[C][C][3][3]*/, int C, int fmt, TcConvPairWeights** out);
 void tc_conv3x3_pair_free(TcConvPairWeights* w);
 int launch_tc_conv3x3_pair(const TcConvPairWeights* w, const TcConvArgs& a, cudaStream_t st);
 
 struct TcResampleWeights;  // opaque: packed smem images of a 2x2/s2 conv (down) or transposed conv (up)
-int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeights** out);
+int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, int fmt, TcResampleWeights** out);
 void tc_resample_free(TcResampleWeights* w);
 // all tensors CG8.  DOWN: in (2T x 2F, Cin) -> out (T x F, Cout).  UP: in (T x F, Cin); skip, out (2T x 2F, Cout)
-int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* skip, __nv_bfloat16* out,
+int launch_tc_resample(const TcResampleWeights* w, const h16* in, const h16* skip, h16* out,
                        int nB, int T, int F, const float* scale, const float* shift, cudaStream_t st);
 
 struct TcTdfWeights;  // opaque: packed smem images of one TDF linear layer
 // *out stays nullptr when the shape is left to the CUDA-core kernel (tiny deep-level layers)
-int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdfWeights** out);
+int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, int fmt, TcTdfWeights** out);
 void tc_tdf_free(TcTdfWeights* w);
 // out[b][t][m][c] = relu(scale[c]*sum_k W[m][k]*in[b][t][k][c] + shift[c]) (+ residual[b][t][m][c]); tensors CG8
-int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+int launch_tc_tdf(const TcTdfWeights* w, const h16* in, const h16* residual, h16* out,
                   int nB, int T, const float* scale, const float* shift, cudaStream_t st);
 
 // CTA-pair (cta_group::2), activation-stationary kernel for the second TDF layer (with residual);
 // *out stays nullptr when the shape is not supported (M % 256, K % 32, N = NTt*C <= 256 ...)
 struct TcTdf2PairWeights;
-int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf2PairWeights** out);
+int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, int fmt, TcTdf2PairWeights** out);
 void tc_tdf2_pair_free(TcTdf2PairWeights* w);
 // final_w/final_b != nullptr: fused final 1x1 conv (C -> 4): `out` is then the [nB*T*M][4] network output
 bool tc_tdf2_pair_can_fuse_final(const TcTdf2PairWeights* w);
-int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const h16* in, const h16* residual, h16* out,
                         int nB, int T, const float* scale, const float* shift, cudaStream_t st, const float* final_w = nullptr,
                         const float* final_b = nullptr);
 
 // CTA-pair kernel for the first TDF layer (no residual); *out stays nullptr for unsupported shapes
 struct TcTdf1PairWeights;
-int tc_tdf1_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf1PairWeights** out);
+int tc_tdf1_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, int fmt, TcTdf1PairWeights** out);
 void tc_tdf1_pair_free(TcTdf1PairWeights* w);
-int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const __nv_bfloat16* in, __nv_bfloat16* out, int nB, int T, const float* scale,
+int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const h16* in, h16* out, int nB, int T, const float* scale,
                         const float* shift, cudaStream_t st);
 
 }  // namespace ac

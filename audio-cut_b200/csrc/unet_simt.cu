@@ -32,6 +32,18 @@ __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, flo
   }
 }
 
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float* r) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    r[2 * i] = f.x;
+    r[2 * i + 1] = f.y;
+  }
+}
+
 template <typename T, int BN>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
   constexpr int BM = 128, BK = 16, LDA = BM + 4, NB = BN / 16, NBL = (BK * BN + 255) / 256;
@@ -172,7 +184,8 @@ static int launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
 
 int launch_gemm_simt(const GemmArgs& a, int dtype, cudaStream_t st) {
   if (a.a_mode != A_PLAIN) AC_REQUIRE(a.C % 16 == 0, "gemm: channels must be a multiple of 16");
-  return dtype == AC_F32 ? launch_gemm_t<float>(a, st) : launch_gemm_t<__nv_bfloat16>(a, st);
+  if (dtype == AC_F32) return launch_gemm_t<float>(a, st);
+  return dtype == AC_F16 ? launch_gemm_t<__half>(a, st) : launch_gemm_t<__nv_bfloat16>(a, st);
 }
 
 // ---- 1x1 convs -------------------------------------------------------------------------------
@@ -236,6 +249,8 @@ int launch_first_conv(const void* in, void* out, long long P, int g, const float
   ProfScope ps(KC_CONV1X1, 2.0 * P * g * 4, (double)P * (4 + g) * (dtype == AC_F32 ? 4 : 2), st);
   if (dtype == AC_F32)
     first_conv_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, P, g, w, scale, shift);
+  else if (dtype == AC_F16)
+    first_conv_kernel<__half><<<grid, 256, 0, st>>>((const __half*)in, (__half*)out, P, g, w, scale, shift);
   else
     first_conv_kernel<__nv_bfloat16>
         <<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, P, g, w, scale, shift);
@@ -250,6 +265,8 @@ int launch_final_conv(const void* in, void* out, long long P, int g, const float
   ProfScope ps(KC_CONV1X1, 2.0 * P * g * 4, (double)P * (4 + g) * (dtype == AC_F32 ? 4 : 2), st);
   if (dtype == AC_F32)
     final_conv_kernel<float><<<grid, 256, smem, st>>>((const float*)in, (float*)out, P, g, w, bias);
+  else if (dtype == AC_F16)
+    final_conv_kernel<__half><<<grid, 256, smem, st>>>((const __half*)in, (__half*)out, P, g, w, bias);
   else
     final_conv_kernel<__nv_bfloat16>
         <<<grid, 256, smem, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, P, g, w, bias);

@@ -49,13 +49,14 @@ struct TcParams {
   int nB, T, F;
   int n_fg;       // groups of MT tiles per row
   int n_units;    // nsplit * nB * T * n_fg
-  const __nv_bfloat16* wpack;
+  const h16* wpack;
   const float* scale;
   const float* shift;
-  __nv_bfloat16* out;
+  h16* out;
   int* abort_flag;
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -125,7 +126,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
             mbar_expect_tx(&full[s], (uint32_t)(c.MT * (c.KC / 8) * (kRowPos * 16) + c.b_stage_bytes));
             for (int mt = 0; mt < c.MT; ++mt)
               tma_load_5d(st + mt * c.a_tile_bytes, &in_map, &full[s], 0, f0 + mt * kTileM - 1, kc * (c.KC / 8), t + dt - 1, b);
-            const __nv_bfloat16* wsrc =
+            const h16* wsrc =
                 p.wpack + ((size_t)((nt * 3 + dt) * c.nkc + kc)) * (size_t)(3 * c.KC * c.NT);
             bulk_load_1d(st + c.MT * c.a_tile_bytes, wsrc, (uint32_t)c.b_stage_bytes, &full[s]);
             if (++s == c.stages) { s = 0; ph ^= 1; }
@@ -137,7 +138,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
     // ===================== MMA issuer =====================
     // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
     {
-      const uint32_t idesc = make_idesc(c.NT);
+      const uint32_t idesc = make_idesc<FMT>(c.NT);
       const uint32_t a_lbo = kRowStride * 16, b_lbo = (uint32_t)c.NT * 16;
       const uint64_t a_proto = make_desc(0, a_lbo, 128), b_proto = make_desc(0, b_lbo, 128);
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
@@ -192,13 +193,13 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
       decode(u, nt, b, t, f0);
       const int n0 = nt * c.NT;
       const int f_lane = f0 + quad * 32 + lane;
-      __nv_bfloat16* dst0 = p.out + cg8_index(b, t, n0 >> 3, f_lane, p.T, c.C, p.F);
+      h16* dst0 = p.out + cg8_index(b, t, n0 >> 3, f_lane, p.T, c.C, p.F);
       if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
       tc_fence_after();
       for (int mt = 0; mt < c.MT; ++mt) {
         const bool valid = f_lane + mt * kTileM < p.F;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
-        __nv_bfloat16* dst = dst0 + (size_t)mt * kTileM * 8;
+        h16* dst = dst0 + (size_t)mt * kTileM * 8;
         for (int j = grp * 16; j < c.NT; j += 16 * kTcEpiGroups) {
           uint32_t r[16];
           tmem_ld16(taddr + j, r);
@@ -210,8 +211,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
               const int ch = n0 + j + 2 * e;
               const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
               const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              pk[e] = pack2<FMT>(v0, v1);
             }
             *reinterpret_cast<uint4*>(dst + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(dst + (size_t)((j >> 3) + 1) * plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -237,8 +237,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap in_map, const TcParams p) 
 // ------------------------------------------------------------------------------------------------
 struct TcConvWeights {
   int C;
+  int fmt;
   TcCfg cfg;
-  __nv_bfloat16* d_pack;
+  h16* d_pack;
 };
 
 static bool make_cfg(int C, int F, TcCfg& c) {
@@ -278,12 +279,12 @@ int tc_conv3x3_supported(int T, int F, int C) {
   return make_cfg(C, F, c) ? AC_OK : AC_E_INVALID;
 }
 
-int tc_conv3x3_pack(const float* h_w, int C, TcConvWeights** out) {
+int tc_conv3x3_pack(const float* h_w, int C, int fmt, TcConvWeights** out) {
   *out = nullptr;
   TcCfg c;
   if (!make_cfg(C, 1 << 20, c)) return AC_OK;  // unsupported shape: caller keeps the CUDA-core kernel
   // [nt][dt][kc][df][KC/8][NT][8]  <-  W[co][ci][kh=dt][kw=df]
-  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  std::vector<h16> pack((size_t)9 * C * C);
   size_t o = 0;
   for (int nt = 0; nt < c.nsplit; ++nt)
     for (int dt = 0; dt < 3; ++dt)
@@ -293,10 +294,11 @@ int tc_conv3x3_pack(const float* h_w, int C, TcConvWeights** out) {
             for (int n = 0; n < c.NT; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int co = nt * c.NT + n, ci = kc * c.KC + kg * 8 + e;
-                pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df]);
+                pack[o++] = h16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df], fmt);
               }
   TcConvWeights* w = new TcConvWeights();
   w->C = C;
+  w->fmt = fmt;
   w->d_pack = nullptr;
   if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
       cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -359,7 +361,7 @@ int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   const cuuint64_t strides[4] = {16, (cuuint64_t)a.F * 16, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
   const cuuint32_t box[5] = {8, (cuuint32_t)kRowPos, (cuuint32_t)(c.KC / 8), 1, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(a.in), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -377,13 +379,14 @@ int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   p.abort_flag = g_abort_flag;
   static int max_smem_set = 0;
   if (max_smem_set < c.smem_bytes) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<kFmtF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     max_smem_set = 227 * 1024;
   }
   int grid = device_sm_count();
   if (grid > p.n_units) grid = p.n_units;
   ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
-  AC_CHECK_CUDA(tc_launch(tc_conv3x3_kernel, grid, kTcThreads, c.smem_bytes, st, 1, map, p));
+  AC_CHECK_CUDA(tc_launch(a.w->fmt == kFmtBF16 ? tc_conv3x3_kernel<kFmtBF16> : tc_conv3x3_kernel<kFmtF16>, grid, kTcThreads, c.smem_bytes, st, 1, map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -41,7 +41,7 @@ struct CpParams {
   int n_units;   // nsplit * nB * T * n_fg
   const float* scale;
   const float* shift;
-  __nv_bfloat16* out;
+  h16* out;
   int* abort_flag;
 };
 
@@ -52,6 +52,7 @@ __device__ __forceinline__ void cp_tma_load_2d_2sm(void* dst, const CUtensorMap*
       : "memory");
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kCpThreads, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const CpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -160,7 +161,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader; warp-uniform loop, one elected lane issues) =====================
     if (leader) {
-      const uint32_t idesc = make_idesc_2sm(c.NT);
+      const uint32_t idesc = make_idesc_2sm<FMT>(c.NT);
       const uint32_t a_lbo = kCpRowPos * 16, b_lbo = (uint32_t)(c.NT / 2) * 16;
       const uint64_t a_proto = make_desc(0, a_lbo, 128), b_proto = make_desc(0, b_lbo, 128);
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
@@ -222,7 +223,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
         const int f = f0 + (2 * mt + (int)rank) * kCpTileM + quad * 32 + lane;
         const bool valid = f < p.F;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
-        __nv_bfloat16* dst = p.out + cg8_index(b, t, n0 >> 3, valid ? f : 0, p.T, c.C, p.F);
+        h16* dst = p.out + cg8_index(b, t, n0 >> 3, valid ? f : 0, p.T, c.C, p.F);
         for (int j = grp * 16; j < c.NT; j += 16 * kCpEpiGroups) {
           uint32_t r[16];
           tmem_ld16(taddr + j, r);
@@ -234,8 +235,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
               const int ch = n0 + j + 2 * e;
               const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
               const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              pk[e] = pack2<FMT>(v0, v1);
             }
             *reinterpret_cast<uint4*>(dst + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(dst + (size_t)((j >> 3) + 1) * plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -261,8 +261,9 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
 // ------------------------------------------------------------------------------------------------
 struct TcConvPairWeights {
   int C;
+  int fmt;
   CpCfg cfg;
-  __nv_bfloat16* d_pack;
+  h16* d_pack;
   size_t pack_elems;
 };
 
@@ -306,13 +307,13 @@ int tc_conv3x3_pair_supported(int T, int F, int C) {
   return cp_make_cfg(C, F, c) ? AC_OK : AC_E_INVALID;
 }
 
-int tc_conv3x3_pair_pack(const float* h_w, int C, TcConvPairWeights** out) {
+int tc_conv3x3_pair_pack(const float* h_w, int C, int fmt, TcConvPairWeights** out) {
   *out = nullptr;
   CpCfg c;
   if (!cp_make_cfg(C, 1 << 20, c)) return AC_OK;
   // [nt][rank][dt][kc][df][KC/8][NT/2][8]  <-  W[co][ci][kh=dt][kw=df]
   const int NH = c.NT / 2;
-  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  std::vector<h16> pack((size_t)9 * C * C);
   size_t o = 0;
   for (int nt = 0; nt < c.nsplit; ++nt)
     for (int r = 0; r < 2; ++r)
@@ -323,10 +324,11 @@ int tc_conv3x3_pair_pack(const float* h_w, int C, TcConvPairWeights** out) {
               for (int n = 0; n < NH; ++n)
                 for (int e = 0; e < 8; ++e) {
                   const int co = nt * c.NT + r * NH + n, ci = kc * c.KC + kg * 8 + e;
-                  pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df]);
+                  pack[o++] = h16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df], fmt);
                 }
   TcConvPairWeights* w = new TcConvPairWeights();
   w->C = C;
+  w->fmt = fmt;
   w->d_pack = nullptr;
   w->pack_elems = pack.size();
   if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
@@ -358,7 +360,7 @@ int launch_tc_conv3x3_pair(const TcConvPairWeights* w, const TcConvArgs& a, cuda
     const cuuint64_t dims[5] = {8, (cuuint64_t)a.F, (cuuint64_t)(a.C / 8), (cuuint64_t)a.T, (cuuint64_t)a.nB};
     const cuuint64_t strides[4] = {16, (cuuint64_t)a.F * 16, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
     const cuuint32_t box[5] = {8, (cuuint32_t)kCpRowPos, (cuuint32_t)(c.KC / 8), 1, 1};
-    CUresult r = enc(&in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
+    CUresult r = enc(&in_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(a.in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -390,13 +392,14 @@ int launch_tc_conv3x3_pair(const TcConvPairWeights* w, const TcConvArgs& a, cuda
   p.abort_flag = tc_abort_flag();
   static bool attr_set = false;
   if (!attr_set) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_pair_kernel<kFmtF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_pair_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int pairs = device_sm_count() / 2;
   if (pairs > p.n_units) pairs = p.n_units;
   ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
-  AC_CHECK_CUDA(tc_launch(tc_conv3x3_pair_kernel, 2 * pairs, kCpThreads, c.smem_bytes, st, 2, in_map, w_map, p));
+  AC_CHECK_CUDA(tc_launch(w->fmt == kFmtBF16 ? tc_conv3x3_pair_kernel<kFmtBF16> : tc_conv3x3_pair_kernel<kFmtF16>, 2 * pairs, kCpThreads, c.smem_bytes, st, 2, in_map, w_map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -47,10 +47,10 @@ struct WsParams {
   int nB, T, F;
   int n_strips;          // strips of MT*128 positions per image row
   long long total_rows;  // nB * n_strips * T
-  const __nv_bfloat16* wpack;
+  const h16* wpack;
   const float* scale;
   const float* shift;
-  __nv_bfloat16* out;
+  h16* out;
   int* abort_flag;
 };
 
@@ -95,7 +95,7 @@ __device__ __forceinline__ void umma_f16_c(uint32_t tmem_d, uint64_t adesc, uint
         : "memory");
 }
 
-template <int C, int MT, int R>
+template <int C, int MT, int R, int FMT>
 __global__ void __launch_bounds__(kWsThreads, 1)
 tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams p) {
   constexpr int NT = 48;
@@ -182,7 +182,7 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
     // The whole warp runs the (uniform) loop and one elected lane issues, so descriptors and TMEM
     // addresses stay in uniform registers instead of being broadcast (R2UR) before every MMA.
     {
-      const uint32_t idesc = make_idesc(NT);
+      const uint32_t idesc = make_idesc<FMT>(NT);
       const uint64_t a_proto = make_desc(0, kALbo, 128), b_proto = make_desc(0, kBLbo, 128);
       const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
       const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
@@ -278,7 +278,7 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
     for (long long L = lo; L < hi && alive;) {
       const WsSeg sg = ws_segment(p, L, hi);
       // CG8: plane (b, t, c/8) is [F][8], so the 32 lanes of a warp store 512 contiguous bytes
-      __nv_bfloat16* row0 = p.out + cg8_index(sg.b, sg.t0, nt * (NT / 8) + grp * 2, sg.f0 + quad * 32 + lane, p.T, C, p.F);
+      h16* row0 = p.out + cg8_index(sg.b, sg.t0, nt * (NT / 8) + grp * 2, sg.f0 + quad * 32 + lane, p.T, C, p.F);
       const size_t row_stride = (size_t)(C / 8) * plane;
       for (int t = sg.t0; t < sg.t1; ++t, ++orow, row0 += row_stride) {
         const int buf = orow & 1;
@@ -301,10 +301,9 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
             for (int e = 0; e < 8; ++e) {
               const float v0 = fmaxf(fmaf(__uint_as_float(r[mt][2 * e]), sc[2 * e], sh[2 * e]), 0.f);
               const float v1 = fmaxf(fmaf(__uint_as_float(r[mt][2 * e + 1]), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              pk[e] = pack2<FMT>(v0, v1);
             }
-            __nv_bfloat16* dst = row0 + (size_t)mt * kWsTileM * 8;
+            h16* dst = row0 + (size_t)mt * kWsTileM * 8;
             *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
@@ -331,7 +330,7 @@ tc_conv3x3_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
 //   commits are multicast to the empty[] / tfull[] barriers of both CTAs; the peer's epilogue warps
 //   release the accumulators by arriving remotely on the leader's tempty[] barrier.
 // ------------------------------------------------------------------------------------------------
-template <int C, int R>
+template <int C, int R, int FMT>
 __global__ void __launch_bounds__(kWsThreads, 1)
 tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams p) {
   constexpr int NH = C / 2;               // output channels whose weights live in this CTA
@@ -426,7 +425,7 @@ tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams
       if (alive && lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(wbar_peer), 0));  // "my weights are in place"
     } else {
       alive = alive && wait_all(wbar_peer, 0);
-      const uint32_t idesc = make_idesc_2sm(C);
+      const uint32_t idesc = make_idesc_2sm<FMT>(C);
       const uint64_t a_proto = make_desc(0, kALbo, 128), b_proto = make_desc(0, kBLbo, 128);
       const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
       const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
@@ -505,7 +504,7 @@ tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams
     for (long long L = lo; L < hi && alive;) {
       const WsSeg sg = ws_segment(p, L, hi);
       const int f = sg.f0 + (int)rank * kWsTileM + quad * 32 + lane;
-      __nv_bfloat16* row0 = p.out + cg8_index(sg.b, sg.t0, grp * (kGrpCh / 8), f, p.T, C, p.F);
+      h16* row0 = p.out + cg8_index(sg.b, sg.t0, grp * (kGrpCh / 8), f, p.T, C, p.F);
       const size_t row_stride = (size_t)(C / 8) * plane;
       for (int t = sg.t0; t < sg.t1; ++t, ++orow, row0 += row_stride) {
         const int buf = orow & 1;
@@ -528,8 +527,7 @@ tc_conv3x3_ws2_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams
               const int ch = grp * kGrpCh + j + 2 * e;
               const float v0 = fmaxf(fmaf(__uint_as_float(r[j + 2 * e]), s_scale[ch], s_shift[ch]), 0.f);
               const float v1 = fmaxf(fmaf(__uint_as_float(r[j + 2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
-              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              pk[e] = pack2<FMT>(v0, v1);
             }
             *reinterpret_cast<uint4*>(row0 + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
@@ -567,6 +565,7 @@ constexpr int kRsBlocks = 5;
 constexpr int kRsMT = 2;
 constexpr int kRsSlots = 6;
 
+template <int FMT>
 __global__ void __launch_bounds__(kWsThreads, 1)
 tc_conv3x3_rs_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams p) {
   constexpr int C = 48, NT = 48, MT = kRsMT, RB = kRsBlocks, RA = kRsSlots;
@@ -648,7 +647,7 @@ tc_conv3x3_rs_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t idesc144 = make_idesc(144), idesc96 = make_idesc(96), idesc48 = make_idesc(48);
+    const uint32_t idesc144 = make_idesc<FMT>(144), idesc96 = make_idesc<FMT>(96), idesc48 = make_idesc<FMT>(48);
     const uint64_t a_proto = make_desc(0, kALbo, 128), b_proto = make_desc(0, kBLbo, 128);
     const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
     const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
@@ -790,10 +789,9 @@ tc_conv3x3_rs_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
               for (int e = 0; e < 8; ++e) {
                 const float v0 = fmaxf(fmaf(__uint_as_float(r[mt][2 * e]), sc[2 * e], sh[2 * e]), 0.f);
                 const float v1 = fmaxf(fmaf(__uint_as_float(r[mt][2 * e + 1]), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
-                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                pk[e] = pack2<FMT>(v0, v1);
               }
-              __nv_bfloat16* dst = p.out + cg8_index(sg.b, t, grp * 2, f, p.T, C, p.F);
+              h16* dst = p.out + cg8_index(sg.b, t, grp * 2, f, p.T, C, p.F);
               *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
@@ -820,9 +818,10 @@ tc_conv3x3_rs_kernel(const __grid_constant__ CUtensorMap in_map, const WsParams 
 // ------------------------------------------------------------------------------------------------
 struct TcConvWsWeights {
   int C;
+  int fmt;
   WsCfg cfg;
-  __nv_bfloat16* d_pack;
-  __nv_bfloat16* d_pack_rs = nullptr;  // C = 48: row-stacked packing
+  h16* d_pack;
+  h16* d_pack_rs = nullptr;  // C = 48: row-stacked packing
 };
 
 static bool ws_make_cfg(int C, int F, WsCfg& c) {
@@ -855,14 +854,14 @@ int tc_conv3x3_ws_supported(int T, int F, int C) {
   return ws_make_cfg(C, F, c) ? AC_OK : AC_E_INVALID;
 }
 
-static int ws_pack_rs(const float* h_w, __nv_bfloat16** d_out);
+static int ws_pack_rs(const float* h_w, int fmt, h16** d_out);
 
-int tc_conv3x3_ws_pack(const float* h_w, int C, TcConvWsWeights** out) {
+int tc_conv3x3_ws_pack(const float* h_w, int C, int fmt, TcConvWsWeights** out) {
   *out = nullptr;
   WsCfg c;
   if (!ws_make_cfg(C, 1 << 20, c)) return AC_OK;
   // [nt][dt][df][C/8][NT][8]  <-  W[co][ci][kh=dt][kw=df]
-  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  std::vector<h16> pack((size_t)9 * C * C);
   size_t o = 0;
   for (int nt = 0; nt < c.nsplit; ++nt)
     for (int dt = 0; dt < 3; ++dt)
@@ -871,10 +870,11 @@ int tc_conv3x3_ws_pack(const float* h_w, int C, TcConvWsWeights** out) {
           for (int n = 0; n < c.NT; ++n)
             for (int e = 0; e < 8; ++e) {
               const int co = nt * c.NT + n, ci = kg * 8 + e;
-              pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df]);
+              pack[o++] = h16_rn(h_w[(((size_t)co * C + ci) * 3 + dt) * 3 + df], fmt);
             }
   TcConvWsWeights* w = new TcConvWsWeights();
   w->C = C;
+  w->fmt = fmt;
   w->d_pack = nullptr;
   if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
       cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -882,7 +882,7 @@ int tc_conv3x3_ws_pack(const float* h_w, int C, TcConvWsWeights** out) {
     delete w;
     return AC_E_CUDA;
   }
-  if (C == 48 && ws_pack_rs(h_w, &w->d_pack_rs) != AC_OK) {
+  if (C == 48 && ws_pack_rs(h_w, fmt, &w->d_pack_rs) != AC_OK) {
     cudaFree(w->d_pack);
     delete w;
     return AC_E_CUDA;
@@ -899,16 +899,16 @@ void tc_conv3x3_ws_free(TcConvWsWeights* w) {
 }
 
 // row-stacked packing for C = 48: [df][C/8][dt*48 + co][8]
-static int ws_pack_rs(const float* h_w, __nv_bfloat16** d_out) {
+static int ws_pack_rs(const float* h_w, int fmt, h16** d_out) {
   const int C = 48;
-  std::vector<__nv_bfloat16> pack((size_t)9 * C * C);
+  std::vector<h16> pack((size_t)9 * C * C);
   size_t o = 0;
   for (int df = 0; df < 3; ++df)
     for (int kg = 0; kg < C / 8; ++kg)
       for (int dt = 0; dt < 3; ++dt)
         for (int co = 0; co < C; ++co)
           for (int e = 0; e < 8; ++e)
-            pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * C + kg * 8 + e) * 3 + dt) * 3 + df]);
+            pack[o++] = h16_rn(h_w[(((size_t)co * C + kg * 8 + e) * 3 + dt) * 3 + df], fmt);
   *d_out = nullptr;
   if (cudaMalloc(d_out, pack.size() * 2) != cudaSuccess ||
       cudaMemcpy(*d_out, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -940,7 +940,7 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
   const cuuint64_t strides[4] = {16, (cuuint64_t)a.F * 16, (cuuint64_t)a.F * a.C * 2, (cuuint64_t)a.T * a.F * a.C * 2};
   const cuuint32_t box[5] = {8, (cuuint32_t)kWsRowPos, (cuuint32_t)(a.C / 8), 1, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(a.in), dims, strides, box, estr,
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(a.in), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -960,7 +960,7 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
   p.abort_flag = tc_abort_flag();
   ProfScope ps(KC_CONV_TC, 2.0 * 9.0 * a.nB * (double)a.T * a.F * a.C * a.C, 4.0 * a.nB * (double)a.T * a.F * a.C, st);
   if (pair) {
-    auto kern = tc_conv3x3_ws2_kernel<96, 5>;
+    auto kern = w->fmt == kFmtBF16 ? tc_conv3x3_ws2_kernel<96, 5, kFmtBF16> : tc_conv3x3_ws2_kernel<96, 5, kFmtF16>;
     const int smem = 1024 + 9 * 96 * 48 * 2 + 5 * c.a_tile_bytes;
     AC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int pairs = device_sm_count() / 2;
@@ -975,18 +975,20 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
     p.total_rows = (long long)a.nB * p.n_strips * a.T;
     p.wpack = w->d_pack_rs;
     const int smem = 1024 + 9 * 48 * 48 * 2 + kRsSlots * kRsMT * c.a_tile_bytes;
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_conv3x3_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    auto rs_kern = w->fmt == kFmtBF16 ? tc_conv3x3_rs_kernel<kFmtBF16> : tc_conv3x3_rs_kernel<kFmtF16>;
+    AC_CHECK_CUDA(cudaFuncSetAttribute(rs_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int grid = device_sm_count();
     if ((long long)grid > p.total_rows) grid = (int)p.total_rows;
-    AC_CHECK_CUDA(tc_launch(tc_conv3x3_rs_kernel, grid, kWsThreads, smem, st, 1, map, p));
+    AC_CHECK_CUDA(tc_launch(rs_kern, grid, kWsThreads, smem, st, 1, map, p));
     AC_LAUNCH_CHECK();
     return AC_OK;
   }
   void (*kern)(const CUtensorMap, const WsParams) = nullptr;
-  if (c.C == 48 && c.MT == 3) kern = tc_conv3x3_ws_kernel<48, 3, 5>;
-  else if (c.C == 48 && c.MT == 2) kern = tc_conv3x3_ws_kernel<48, 2, 6>;
-  else if (c.C == 48 && c.MT == 1) kern = tc_conv3x3_ws_kernel<48, 1, 6>;
-  else if (c.C == 96 && c.MT == 1) kern = tc_conv3x3_ws_kernel<96, 1, 5>;
+  const bool bf = w->fmt == kFmtBF16;
+  if (c.C == 48 && c.MT == 3) kern = bf ? tc_conv3x3_ws_kernel<48, 3, 5, kFmtBF16> : tc_conv3x3_ws_kernel<48, 3, 5, kFmtF16>;
+  else if (c.C == 48 && c.MT == 2) kern = bf ? tc_conv3x3_ws_kernel<48, 2, 6, kFmtBF16> : tc_conv3x3_ws_kernel<48, 2, 6, kFmtF16>;
+  else if (c.C == 48 && c.MT == 1) kern = bf ? tc_conv3x3_ws_kernel<48, 1, 6, kFmtBF16> : tc_conv3x3_ws_kernel<48, 1, 6, kFmtF16>;
+  else if (c.C == 96 && c.MT == 1) kern = bf ? tc_conv3x3_ws_kernel<96, 1, 5, kFmtBF16> : tc_conv3x3_ws_kernel<96, 1, 5, kFmtF16>;
   AC_REQUIRE(kern != nullptr, "tc ws conv: no instantiation for this shape");
   AC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int group = device_sm_count() / c.nsplit;

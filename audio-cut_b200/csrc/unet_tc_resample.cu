@@ -38,14 +38,15 @@ struct RsParams {
   RsCfg cfg;
   int nB, T, F;  // DOWN: OUTPUT grid.  UP: INPUT grid
   int n_fg, n_units;
-  const __nv_bfloat16* wpack;
+  const h16* wpack;
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* skip;  // UP only
-  __nv_bfloat16* out;
+  const h16* skip;  // UP only
+  h16* out;
   int* abort_flag;
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid_constant__ CUtensorMap in_map, const RsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
               }
             }
             const size_t blob = (size_t)c.ntap * c.KC * c.NT;
-            const __nv_bfloat16* wsrc = p.wpack + ((size_t)((ns * ndt + dt) * c.nkc + kc)) * blob;
+            const h16* wsrc = p.wpack + ((size_t)((ns * ndt + dt) * c.nkc + kc)) * blob;
             bulk_load_1d(st + a_per_stage * c.a_tile_bytes, wsrc, (uint32_t)c.b_stage_bytes, &full[s]);
             if (++s == c.stages) { s = 0; ph ^= 1; }
           }
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
   } else if (warp == 1) {
     // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
     {
-      const uint32_t idesc = make_idesc(c.NT);
+      const uint32_t idesc = make_idesc<FMT>(c.NT);
       const uint32_t b_lbo = (uint32_t)c.NT * 16;
       const uint64_t a_proto = make_desc(0, 2048, 128), b_proto = make_desc(0, b_lbo, 128);
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
@@ -245,11 +246,10 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int ch = n0 + j + 2 * e;
-          const float2 mul = down ? make_float2(1.f, 1.f) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+          const float2 mul = down ? make_float2(1.f, 1.f) : unpack2<FMT>(w[e]);
           const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f) * mul.x;
           const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) * mul.y;
-          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-          pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          pk[e] = pack2<FMT>(v0, v1);
         }
         *reinterpret_cast<uint4*>(p.out + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(p.out + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -278,8 +278,9 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
 }
 
 struct TcResampleWeights {
+  int fmt;
   RsCfg cfg;
-  __nv_bfloat16* d_pack;
+  h16* d_pack;
 };
 
 static bool make_rs_cfg(int mode, int Cin, int Cout, RsCfg& c) {
@@ -326,11 +327,11 @@ static bool make_rs_cfg(int mode, int Cin, int Cout, RsCfg& c) {
 }
 
 // DOWN: h_w = Conv2d weight [Cout][Cin][2][2].  UP: h_w = ConvTranspose2d weight [Cin][Cout][2][2].
-int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeights** out) {
+int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, int fmt, TcResampleWeights** out) {
   *out = nullptr;
   RsCfg c;
   if (!make_rs_cfg(up ? RS_UP : RS_DOWN, Cin, Cout, c)) return AC_OK;
-  std::vector<__nv_bfloat16> pack((size_t)4 * Cin * Cout);
+  std::vector<h16> pack((size_t)4 * Cin * Cout);
   size_t o = 0;
   if (!up) {
     // [ns][dt][kc][df][KC/8][NT][8]
@@ -342,7 +343,7 @@ int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeig
               for (int n = 0; n < c.NT; ++n)
                 for (int e = 0; e < 8; ++e) {
                   const int co = ns * c.NT + n, ci = kc * c.KC + kg * 8 + e;
-                  pack[o++] = __float2bfloat16_rn(h_w[(((size_t)co * Cin + ci) * 2 + dt) * 2 + df]);
+                  pack[o++] = h16_rn(h_w[(((size_t)co * Cin + ci) * 2 + dt) * 2 + df], fmt);
                 }
   } else {
     // [tap group][kc][tp][KC/8][NT][8]
@@ -353,11 +354,12 @@ int tc_resample_pack(int up, const float* h_w, int Cin, int Cout, TcResampleWeig
             for (int n = 0; n < c.NT; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int tap = tg * c.ntap + tp, ci = kc * c.KC + kg * 8 + e;
-                pack[o++] = __float2bfloat16_rn(h_w[((size_t)ci * Cout + n) * 4 + tap]);
+                pack[o++] = h16_rn(h_w[((size_t)ci * Cout + n) * 4 + tap], fmt);
               }
   }
   TcResampleWeights* w = new TcResampleWeights();
   w->cfg = c;
+  w->fmt = fmt;
   w->d_pack = nullptr;
   if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
       cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -376,7 +378,7 @@ void tc_resample_free(TcResampleWeights* w) {
 }
 
 // All tensors CG8.  DOWN: in (2T x 2F, Cin) -> out (T x F, Cout).   UP: in (T x F, Cin); skip, out (2T x 2F, Cout).
-int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* skip, __nv_bfloat16* out,
+int launch_tc_resample(const TcResampleWeights* w, const h16* in, const h16* skip, h16* out,
                        int nB, int T, int F, const float* scale, const float* shift, cudaStream_t st) {
   AC_REQUIRE(w && in && out, "tc resample: null");
   RsCfg c = w->cfg;
@@ -403,7 +405,7 @@ int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, cons
     const cuuint64_t dims[5] = {8, 2, (cuuint64_t)F, (cuuint64_t)(c.Cin / 8), (cuuint64_t)nB * 2 * T};
     const cuuint64_t strides[4] = {16, 32, (cuuint64_t)(2 * F) * 16, (cuuint64_t)(2 * F) * c.Cin * 2};
     const cuuint32_t box[5] = {8, 1, 128, (cuuint32_t)(c.KC / 8), 1};
-    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(in), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
@@ -411,7 +413,7 @@ int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, cons
     const cuuint64_t dims[5] = {8, (cuuint64_t)F, (cuuint64_t)(c.Cin / 8), (cuuint64_t)T, (cuuint64_t)nB};
     const cuuint64_t strides[4] = {16, (cuuint64_t)F * 16, (cuuint64_t)F * c.Cin * 2, (cuuint64_t)T * F * c.Cin * 2};
     const cuuint32_t box[5] = {8, 128, (cuuint32_t)(c.KC / 8), 1, 1};
-    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(in), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -431,7 +433,8 @@ int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, cons
   p.abort_flag = tc_abort_flag();
   static bool attr = false;
   if (!attr) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_resample_kernel<kFmtF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_resample_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   int grid = device_sm_count();
@@ -439,7 +442,7 @@ int launch_tc_resample(const TcResampleWeights* w, const __nv_bfloat16* in, cons
   const double pos = (double)nB * T * F;
   const double bytes = down ? pos * 2.0 * (4.0 * c.Cin + c.Cout) : pos * 2.0 * (c.Cin + 8.0 * c.Cout);
   ProfScope ps(KC_RESAMPLE_TC, 2.0 * pos * 4.0 * c.Cin * c.Cout, bytes, st);
-  AC_CHECK_CUDA(tc_launch(tc_resample_kernel, grid, kRsThreads, c.smem_bytes, st, 1, map, p));
+  AC_CHECK_CUDA(tc_launch(w->fmt == kFmtBF16 ? tc_resample_kernel<kFmtBF16> : tc_resample_kernel<kFmtF16>, grid, kRsThreads, c.smem_bytes, st, 1, map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -36,14 +36,15 @@ struct TdfParams {
   TdfCfg cfg;
   int nB, T;
   int n_tg, n_units;
-  const __nv_bfloat16* wpack;
+  const h16* wpack;
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* residual;  // nullable
-  __nv_bfloat16* out;             // CG8 [nB][T][C/8][M][8]
+  const h16* residual;  // nullable
+  h16* out;             // CG8 [nB][T][C/8][M][8]
   int* abort_flag;
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_constant__ CUtensorMap in_map, const TdfParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
           if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
           uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
           mbar_expect_tx(&full[s], (uint32_t)(c.mt * c.a_tile_bytes + c.b_stage_bytes));
-          const __nv_bfloat16* wsrc = p.wpack + ((size_t)mg * c.nk + kc) * (size_t)(c.mt * 128 * c.Kt);
+          const h16* wsrc = p.wpack + ((size_t)mg * c.nk + kc) * (size_t)(c.mt * 128 * c.Kt);
           bulk_load_1d(st, wsrc, (uint32_t)(c.mt * c.a_tile_bytes), &full[s]);
           uint8_t* sb = st + c.mt * c.a_tile_bytes;
           tma_load_5d(sb, &in_map, &full[s], 0, kc * c.Kt, 0, t0, b);  // [NTt][C/8][Kt][8]
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
   } else if (warp == 1) {
     // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
     {
-      const uint32_t idesc = make_idesc_bmn(c.N);
+      const uint32_t idesc = make_idesc_bmn<FMT>(c.N);
       const uint64_t a_proto = make_desc(0, 128 * 16, 128), b_proto = make_desc_mn(0, 128, (uint32_t)c.Kt * 16);
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
         return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
@@ -210,11 +211,10 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int ch = ch0 + 2 * e;
-          const float2 res = p.residual ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e])) : make_float2(0.f, 0.f);
+          const float2 res = p.residual ? unpack2<FMT>(w[e]) : make_float2(0.f, 0.f);
           const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f) + res.x;
           const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f) + res.y;
-          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-          pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          pk[e] = pack2<FMT>(v0, v1);
         }
         *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(p.out + idx + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(kTdfThreads, 1) tc_tdf_kernel(const __grid_con
 
 struct TcTdfWeights {
   TdfCfg cfg;
-  __nv_bfloat16* d_pack;
+  int fmt;
+  h16* d_pack;
 };
 
 static bool make_tdf_cfg(int M, int K, int C, int T, TdfCfg& c) {
@@ -286,13 +287,13 @@ static bool make_tdf_cfg(int M, int K, int C, int T, TdfCfg& c) {
   return true;
 }
 
-int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdfWeights** out) {
+int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, int fmt, TcTdfWeights** out) {
   *out = nullptr;
   TdfCfg c;
   if (!make_tdf_cfg(M, K, C, T, c)) return AC_OK;
   // [m_group][k_chunk][mt][Kt/8][128][8]; rows >= M are zero
   const size_t total = (size_t)c.n_mg * c.nk * c.mt * 128 * c.Kt;
-  std::vector<__nv_bfloat16> pack(total, __float2bfloat16_rn(0.f));
+  std::vector<h16> pack(total, h16_rn(0.f, fmt));
   size_t o = 0;
   for (int mg = 0; mg < c.n_mg; ++mg)
     for (int kc = 0; kc < c.nk; ++kc)
@@ -301,10 +302,11 @@ int tc_tdf_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdfWe
           for (int r = 0; r < 128; ++r)
             for (int e = 0; e < 8; ++e, ++o) {
               const int m = (mg * c.mt + mi) * 128 + r, k = kc * c.Kt + kg * 8 + e;
-              if (m < M) pack[o] = __float2bfloat16_rn(h_w[(size_t)m * K + k]);
+              if (m < M) pack[o] = h16_rn(h_w[(size_t)m * K + k], fmt);
             }
   TcTdfWeights* w = new TcTdfWeights();
   w->cfg = c;
+  w->fmt = fmt;
   w->d_pack = nullptr;
   if (cudaMalloc(&w->d_pack, total * 2) != cudaSuccess ||
       cudaMemcpy(w->d_pack, pack.data(), total * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -322,7 +324,7 @@ void tc_tdf_free(TcTdfWeights* w) {
   delete w;
 }
 
-int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+int launch_tc_tdf(const TcTdfWeights* w, const h16* in, const h16* residual, h16* out,
                   int nB, int T, const float* scale, const float* shift, cudaStream_t st) {
   AC_REQUIRE(w && in && out, "tc tdf: null");
   const TdfCfg& c = w->cfg;
@@ -336,7 +338,7 @@ int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfl
   const cuuint64_t strides[4] = {16, (cuuint64_t)c.K * 16, (cuuint64_t)c.K * c.C * 2, (cuuint64_t)T * c.K * c.C * 2};
   const cuuint32_t box[5] = {8, (cuuint32_t)c.Kt, (cuuint32_t)(c.C / 8), (cuuint32_t)c.NTt, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(in), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -355,13 +357,14 @@ int launch_tc_tdf(const TcTdfWeights* w, const __nv_bfloat16* in, const __nv_bfl
   p.abort_flag = tc_abort_flag();
   static bool attr = false;
   if (!attr) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf_kernel<kFmtF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   int grid = device_sm_count();
   if (grid > p.n_units) grid = p.n_units;
   ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB, 2.0 * nB * (double)T * c.C * (c.K + c.M * (residual ? 2 : 1)), st);
-  AC_CHECK_CUDA(tc_launch(tc_tdf_kernel, grid, kTdfThreads, c.smem_bytes, st, 1, map, p));
+  AC_CHECK_CUDA(tc_launch(w->fmt == kFmtBF16 ? tc_tdf_kernel<kFmtBF16> : tc_tdf_kernel<kFmtF16>, grid, kTdfThreads, c.smem_bytes, st, 1, map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -44,7 +44,7 @@ struct T1Params {
   int n_tg, n_units;
   const float* scale;
   const float* shift;
-  __nv_bfloat16* out;
+  h16* out;
   int* abort_flag;
 };
 
@@ -55,6 +55,7 @@ __device__ __forceinline__ void t1_tma_load_2d_2sm(void* dst, const CUtensorMap*
       : "memory");
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kT1Threads, 1)
 tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map, const T1Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -150,7 +151,7 @@ tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
         return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
       };
-      const uint32_t idesc = make_idesc_2sm(c.N) | (1u << 16);  // B is MN-major
+      const uint32_t idesc = make_idesc_2sm<FMT>(c.N) | (1u << 16);  // B is MN-major
       const uint64_t a_proto = make_desc(0, 128 * 16, 128);
       const uint64_t b_proto = make_desc_mn(0, 128, (uint32_t)c.Kt * 16);
       long long i = 0;
@@ -237,8 +238,7 @@ tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
                 const int ch = my_ch[i] + 2 * e;
                 const float v0 = fmaxf(fmaf(__uint_as_float(r[i][2 * e]), s_scale[ch], s_shift[ch]), 0.f);
                 const float v1 = fmaxf(fmaf(__uint_as_float(r[i][2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
-                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                pk[e] = pack2<FMT>(v0, v1);
               }
               const size_t idx = base + my_off[i];
               *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -262,8 +262,9 @@ tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TcTdf1PairWeights {
+  int fmt;
   T1Cfg cfg;
-  __nv_bfloat16* d_pack;
+  h16* d_pack;
   size_t pack_elems;
 };
 
@@ -296,13 +297,13 @@ static bool make_t1_cfg(int M, int K, int C, int T, T1Cfg& c) {
   return true;
 }
 
-int tc_tdf1_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf1PairWeights** out) {
+int tc_tdf1_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, int fmt, TcTdf1PairWeights** out) {
   *out = nullptr;
   T1Cfg c;
   if (!make_t1_cfg(M, K, C, T, c)) return AC_OK;
   // [mp][rank][kc][Kt/8][128][8]; rows >= M are zero
   const size_t total = (size_t)c.n_mp * 256 * K;
-  std::vector<__nv_bfloat16> pack(total, __float2bfloat16_rn(0.f));
+  std::vector<h16> pack(total, h16_rn(0.f, fmt));
   size_t o = 0;
   for (int mp = 0; mp < c.n_mp; ++mp)
     for (int r = 0; r < 2; ++r)
@@ -311,10 +312,11 @@ int tc_tdf1_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, T
           for (int row = 0; row < 128; ++row)
             for (int e = 0; e < 8; ++e, ++o) {
               const int m = mp * 256 + r * 128 + row;
-              if (m < M) pack[o] = __float2bfloat16_rn(h_w[(size_t)m * K + kc * c.Kt + kg * 8 + e]);
+              if (m < M) pack[o] = h16_rn(h_w[(size_t)m * K + kc * c.Kt + kg * 8 + e], fmt);
             }
   TcTdf1PairWeights* w = new TcTdf1PairWeights();
   w->cfg = c;
+  w->fmt = fmt;
   w->d_pack = nullptr;
   w->pack_elems = total;
   if (cudaMalloc(&w->d_pack, total * 2) != cudaSuccess ||
@@ -333,7 +335,7 @@ void tc_tdf1_pair_free(TcTdf1PairWeights* w) {
   delete w;
 }
 
-int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const __nv_bfloat16* in, __nv_bfloat16* out, int nB, int T, const float* scale,
+int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const h16* in, h16* out, int nB, int T, const float* scale,
                         const float* shift, cudaStream_t st) {
   AC_REQUIRE(w && in && out, "tc tdf1 pair: null");
   const T1Cfg& c = w->cfg;
@@ -349,7 +351,7 @@ int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const __nv_bfloat16* in, __n
     const cuuint64_t strides[4] = {16, (cuuint64_t)c.K * 16, (cuuint64_t)c.K * c.C * 2, (cuuint64_t)T * c.K * c.C * 2};
     const cuuint32_t box[5] = {8, (cuuint32_t)c.Kt, (cuuint32_t)(c.split_t ? c.C / 8 : c.C / 16),
                                (cuuint32_t)(c.split_t ? c.NTt / 2 : 1), 1};
-    CUresult r = enc(&x_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+    CUresult r = enc(&x_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -379,13 +381,14 @@ int launch_tc_tdf1_pair(const TcTdf1PairWeights* w, const __nv_bfloat16* in, __n
   p.abort_flag = tc_abort_flag();
   static bool attr_set = false;
   if (!attr_set) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf1_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf1_pair_kernel<kFmtF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf1_pair_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int pairs = device_sm_count() / 2;
   if (pairs > p.n_units) pairs = p.n_units;
   ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB, 2.0 * nB * (double)T * c.C * (c.K + c.M), st);
-  AC_CHECK_CUDA(tc_launch(tc_tdf1_pair_kernel, 2 * pairs, kT1Threads, c.smem_bytes, st, 2, x_map, w_map, p));
+  AC_CHECK_CUDA(tc_launch(w->fmt == kFmtBF16 ? tc_tdf1_pair_kernel<kFmtBF16> : tc_tdf1_pair_kernel<kFmtF16>, 2 * pairs, kT1Threads, c.smem_bytes, st, 2, x_map, w_map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

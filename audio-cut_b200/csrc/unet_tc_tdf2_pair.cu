@@ -52,13 +52,13 @@ struct T2Params {
   int n_tg, n_units;
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out;
+  const h16* residual;
+  h16* out;
   int* abort_flag;
   // FINAL variant only: out4[(b*T + t)*M + m][0..3] = bias[o] + sum_c final_w[o][c] * bf16(Y[b][t][m][c]); Y is not stored
   const float* final_w;
   const float* final_b;
-  __nv_bfloat16* out4;
+  h16* out4;
 };
 
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -68,7 +68,7 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       : "memory");
 }
 
-template <bool FINAL>
+template <bool FINAL, int FMT>
 __global__ void __launch_bounds__(t2_threads(FINAL), 1)
 tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_constant__ CUtensorMap w_map, const T2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -175,7 +175,7 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
         return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
       };
-      const uint32_t idesc = make_idesc_2sm(c.N) | (1u << 16);  // B is MN-major
+      const uint32_t idesc = make_idesc_2sm<FMT>(c.N) | (1u << 16);  // B is MN-major
       const uint64_t a_proto = make_desc(0, 128 * 16, 128);
       const uint64_t b_proto = make_desc_mn(0, 128, (uint32_t)c.Kb * 16);
       const uint32_t hbox_bytes = (uint32_t)(c.h_bytes / c.nkb);
@@ -284,11 +284,11 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float4 ss = s_ss[k * 8 + e];
-            const float2 res = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+            const float2 res = unpack2<FMT>(w[e]);
             const float v0 = fmaxf(fmaf(__uint_as_float(r[k & 1][2 * e]), ss.x, ss.y), 0.f) + res.x;
             const float v1 = fmaxf(fmaf(__uint_as_float(r[k & 1][2 * e + 1]), ss.z, ss.w), 0.f) + res.y;
             // rounded to bf16 exactly like the stored activation the separate 1x1 kernel would read
-            const float2 yy = __bfloat1622float2(__floats2bfloat162_rn(v0, v1));
+            const float2 yy = unpack2<FMT>(pack2<FMT>(v0, v1));
             y[2 * e] = yy.x;
             y[2 * e + 1] = yy.y;
           }
@@ -302,10 +302,9 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
             o3 = fmaf(fw.w, y[e], o3);
           }
         }
-        __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), bb = __floats2bfloat162_rn(o2, o3);
         uint2 ov;
-        ov.x = *reinterpret_cast<uint32_t*>(&a);
-        ov.y = *reinterpret_cast<uint32_t*>(&bb);
+        ov.x = pack2<FMT>(o0, o1);
+        ov.y = pack2<FMT>(o2, o3);
         *reinterpret_cast<uint2*>(p.out4 + pos * 4) = ov;
         base = next_base;
       }
@@ -363,11 +362,10 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float4 ss = s_ss[(ch0 >> 1) + e];
-              const float2 res = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+              const float2 res = unpack2<FMT>(w[e]);
               const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), ss.x, ss.y), 0.f) + res.x;
               const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), ss.z, ss.w), 0.f) + res.y;
-              __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-              pk[e] = *reinterpret_cast<uint32_t*>(&hh);
+              pk[e] = pack2<FMT>(v0, v1);
             }
             const size_t idx = base + off;
             *reinterpret_cast<uint4*>(p.out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -393,8 +391,9 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TcTdf2PairWeights {
+  int fmt;
   T2Cfg cfg;
-  __nv_bfloat16* d_pack;
+  h16* d_pack;
   size_t pack_elems;
 };
 
@@ -437,13 +436,13 @@ static bool make_t2_cfg(int M, int K, int C, int T, T2Cfg& c) {
   return true;
 }
 
-int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, TcTdf2PairWeights** out) {
+int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, int fmt, TcTdf2PairWeights** out) {
   *out = nullptr;
   T2Cfg c;
   if (!make_t2_cfg(M, K, C, T, c)) return AC_OK;
   // [mp][rank][kc][Kt/8][128][8]
   const size_t total = (size_t)M * K;
-  std::vector<__nv_bfloat16> pack(total);
+  std::vector<h16> pack(total);
   size_t o = 0;
   for (int mp = 0; mp < c.n_mp; ++mp)
     for (int r = 0; r < 2; ++r)
@@ -451,9 +450,10 @@ int tc_tdf2_pair_pack(const float* h_w /*[M][K]*/, int M, int K, int C, int T, T
         for (int kg = 0; kg < c.Kt / 8; ++kg)
           for (int row = 0; row < 128; ++row)
             for (int e = 0; e < 8; ++e)
-              pack[o++] = __float2bfloat16_rn(h_w[(size_t)(mp * 256 + r * 128 + row) * K + kc * c.Kt + kg * 8 + e]);
+              pack[o++] = h16_rn(h_w[(size_t)(mp * 256 + r * 128 + row) * K + kc * c.Kt + kg * 8 + e], fmt);
   TcTdf2PairWeights* w = new TcTdf2PairWeights();
   w->cfg = c;
+  w->fmt = fmt;
   w->d_pack = nullptr;
   w->pack_elems = total;
   if (cudaMalloc(&w->d_pack, total * 2) != cudaSuccess ||
@@ -476,7 +476,7 @@ bool tc_tdf2_pair_can_fuse_final(const TcTdf2PairWeights* w) { return w && w->cf
 
 // final_w != nullptr: the FINAL variant - `out` is then the network output [nB*T*M][4] bf16 and the layer's own
 // activation is never written (unet.cu uses it for the last TDF2 of the network).
-int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const h16* in, const h16* residual, h16* out,
                         int nB, int T, const float* scale, const float* shift, cudaStream_t st, const float* final_w,
                         const float* final_b) {
   AC_REQUIRE(w && in && residual && out, "tc tdf2 pair: null");
@@ -495,7 +495,7 @@ int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, con
     const cuuint64_t strides[4] = {16, (cuuint64_t)c.K * 16, (cuuint64_t)c.K * c.C * 2, (cuuint64_t)T * c.K * c.C * 2};
     const cuuint32_t box[5] = {8, (cuuint32_t)c.Kb, (cuuint32_t)(c.split_t ? c.C / 8 : c.C / 16),
                                (cuuint32_t)(c.split_t ? c.NTt / 2 : 1), 1};
-    CUresult r = enc(&h_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+    CUresult r = enc(&h_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -530,8 +530,10 @@ int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, con
   p.abort_flag = tc_abort_flag();
   static bool attr_set = false;
   if (!attr_set) {
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<false, kFmtF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<true, kFmtF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<false, kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AC_CHECK_CUDA(cudaFuncSetAttribute(tc_tdf2_pair_kernel<true, kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int pairs = device_sm_count() / 2;
@@ -539,9 +541,9 @@ int launch_tc_tdf2_pair(const TcTdf2PairWeights* w, const __nv_bfloat16* in, con
   ProfScope ps(KC_TDF_TC, 2.0 * c.M * (double)c.K * c.C * T * nB + (fin ? 8.0 * c.M * c.C * T * nB : 0.0),
                2.0 * nB * (double)T * (c.C * (c.K + c.M * (fin ? 1 : 2)) + (fin ? 4 * c.M : 0)), st);
   if (fin)
-    AC_CHECK_CUDA(tc_launch(tc_tdf2_pair_kernel<true>, 2 * pairs, t2_threads(true), c.smem_bytes, st, 2, h_map, w_map, p));
+    AC_CHECK_CUDA(tc_launch(w->fmt == kFmtBF16 ? tc_tdf2_pair_kernel<true, kFmtBF16> : tc_tdf2_pair_kernel<true, kFmtF16>, 2 * pairs, t2_threads(true), c.smem_bytes, st, 2, h_map, w_map, p));
   else
-    AC_CHECK_CUDA(tc_launch(tc_tdf2_pair_kernel<false>, 2 * pairs, t2_threads(false), c.smem_bytes, st, 2, h_map, w_map, p));
+    AC_CHECK_CUDA(tc_launch(w->fmt == kFmtBF16 ? tc_tdf2_pair_kernel<false, kFmtBF16> : tc_tdf2_pair_kernel<false, kFmtF16>, 2 * pairs, t2_threads(false), c.smem_bytes, st, 2, h_map, w_map, p));
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

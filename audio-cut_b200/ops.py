@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import AC_BF16, AC_F32, ChunkDesc, FeatSegment, MdxGeom, TrackParams, UNetGeom, check, ptr, stream_ptr
+from ._lib import AC_BF16, AC_F16, AC_F32, ChunkDesc, FeatSegment, MdxGeom, TrackParams, UNetGeom, check, ptr, stream_ptr
 from .unet_weights import UNetGeometry, pack_blob
 
 
@@ -19,7 +19,14 @@ def _dev_index(t: torch.Tensor) -> int:
 
 
 def _torch_dtype(dtype: int):
-    return torch.float32 if dtype == AC_F32 else torch.bfloat16
+    return {AC_F32: torch.float32, AC_BF16: torch.bfloat16, AC_F16: torch.float16}[dtype]
+
+
+def _ac_dtype(t: torch.Tensor) -> int:
+    try:
+        return {torch.float32: AC_F32, torch.bfloat16: AC_BF16, torch.float16: AC_F16}[t.dtype]
+    except KeyError:
+        raise _lib.AudioCutError(f"unsupported tensor dtype {t.dtype} (float32, float16 or bfloat16)") from None
 
 
 def frame_count(n: int, frame: int, hop: int, center: bool = True) -> int:
@@ -68,7 +75,7 @@ def stft_mdx(wave: torch.Tensor, geom: MdxGeom, dtype: int = AC_F32) -> torch.Te
 
 def istft_mdx(spec: torch.Tensor, geom: MdxGeom) -> torch.Tensor:
     lib = _lib.init(_dev_index(spec))
-    dtype = AC_F32 if spec.dtype == torch.float32 else AC_BF16
+    dtype = _ac_dtype(spec)
     spec = spec.contiguous()
     B = spec.shape[0]
     assert tuple(spec.shape[1:]) == (geom.dim_t, geom.dim_f, 4), spec.shape
@@ -125,8 +132,8 @@ class UNet:
         return self._ws
 
     def forward(self, spec: torch.Tensor) -> torch.Tensor:
-        """spec [B,dim_t,dim_f,4] float32 or bfloat16 (TFC layout) -> same shape/dtype."""
-        dtype = AC_F32 if spec.dtype == torch.float32 else AC_BF16
+        """spec [B,dim_t,dim_f,4] float32, float16 or bfloat16 (TFC layout) -> same shape/dtype."""
+        dtype = _ac_dtype(spec)
         spec = spec.contiguous()
         B = spec.shape[0]
         assert tuple(spec.shape[1:]) == (self.geo.dim_t, self.geo.dim_f, 4), spec.shape
@@ -143,18 +150,20 @@ def debug_conv3x3(x: torch.Tensor, w: np.ndarray, scale: torch.Tensor, shift: to
     impl 0 = CUDA cores, 1 = streaming tcgen05, 2 = weight-stationary tcgen05; the tensor-core kernels
     work on the CG8 layout [B,T,C/8,F,8], the conversion to and from channels-last is done here."""
     lib = _lib.init(_dev_index(x))
-    assert x.dtype == torch.bfloat16 and x.dim() == 4
+    assert x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4
+    if x.dtype == torch.float16:
+        impl |= 16  # IEEE-half operands
     B, T, F, Cc = x.shape
-    if impl != 0:
+    if impl & 15:
         x = x.view(B, T, F, Cc // 8, 8).permute(0, 1, 3, 2, 4)
     x = x.contiguous()
     w = np.ascontiguousarray(w, dtype=np.float32)
     assert w.shape == (Cc, Cc, 3, 3)
-    y = torch.empty((B, T, F, Cc), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((B, T, F, Cc), dtype=x.dtype, device=x.device)
     ms = C.c_float(0.0)
     check(lib.ac_debug_conv3x3(ptr(x), ptr(y), B, T, F, Cc, w.ctypes.data_as(C.c_void_p), ptr(scale.float().contiguous()),
                                ptr(shift.float().contiguous()), impl, iters, C.byref(ms), stream_ptr()), "ac_debug_conv3x3")
-    if impl != 0:
+    if impl & 15:
         y = y.view(B, T, Cc // 8, F, 8).permute(0, 1, 3, 2, 4).contiguous().view(B, T, F, Cc)
     return y, float(ms.value)
 

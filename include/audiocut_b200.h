@@ -41,7 +41,9 @@ extern "C" {
 #define AC_E_WORKSPACE (-4) /* workspace too small */
 
 #define AC_F32 0  /* fp32 storage, fp32 FFMA math (the >=60 dB parity path) */
-#define AC_BF16 1 /* bf16 storage, tcgen05 tensor-core math with fp32 accumulation */
+#define AC_BF16 1 /* bfloat16 storage, tcgen05 tensor-core math with fp32 accumulation (fp32 range, 8-bit significand) */
+#define AC_F16 2  /* IEEE half storage, the same tcgen05 kernels and rate (11-bit significand: the 16-bit path that
+                     meets the >= 40 dB stem-SDR gate; values beyond +-65504 saturate) */
 
 /* Library / device bring-up.  Replaces torch.cuda device selection in gpu_pipeline.py:87-130. */
 AC_API int ac_init(int device);
