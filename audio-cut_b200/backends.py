@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
+from .onnx_weights import load_onnx
 from .unet_weights import UNetGeometry, load_npz, random_state
 
 
@@ -57,9 +58,11 @@ def resolve_output_type(model_name: str, pref: str = "auto") -> str:
 class B200Mdx23Backend(IVocalSeparatorBackend):
     """MDX23 (Kim_Vocal geometry) separation on one B200.
 
-    ``weights``: a ``{name: ndarray}`` state dict, a path to an ``.npz`` of one, or ``None`` ->
-    the first ``*.npz`` in ``model_dir`` (``MDX23_MODEL_FILENAME`` / ``model_filename`` select one),
-    or - only when ``allow_random_init`` - seeded random weights of the architecture.
+    ``weights``: a ``{name: ndarray}`` state dict, a path to an ``.onnx`` (the reference's model file, read by
+    ``onnx_weights.load_onnx``) or an ``.npz`` of one, or ``None`` -> the first ``*.onnx`` (else ``*.npz``) in
+    ``model_dir`` (``MDX23_MODEL_FILENAME`` / ``model_filename`` select one, backends.py:144-160), or - only when
+    ``allow_random_init`` - seeded random weights of the architecture.  ``n_fft`` defaults to 6144 like the reference
+    (backends.py:264; env ``MDX23_N_FFT`` overrides), Kim_Vocal's native 7680 is an explicit choice.
     """
 
     def __init__(self, model_dir: Union[str, Path, None] = None, *, weights=None, device: str = "cuda:0",
@@ -79,7 +82,7 @@ class B200Mdx23Backend(IVocalSeparatorBackend):
         self._precision = precision
         self._dtype = {"fp16": _lib.AC_F16, "bf16": _lib.AC_BF16, "fp32": _lib.AC_F32}[precision]
         self._geo = geometry or UNetGeometry()
-        self._n_fft = int(n_fft if n_fft is not None else os.getenv("MDX23_N_FFT", 7680))
+        self._n_fft = int(n_fft if n_fft is not None else os.getenv("MDX23_N_FFT", 6144))
         self._hop = int(hop)
         self._align_hop = int(align_hop if align_hop is not None else os.getenv("MDX23_ALIGN_HOP", 4096))
         self._output_pref = output_type
@@ -120,8 +123,7 @@ class B200Mdx23Backend(IVocalSeparatorBackend):
     def load_model(self) -> None:
         state = self._weights
         if isinstance(state, (str, Path)):
-            self._model_name = Path(state).name
-            state = load_npz(str(state))
+            state = self._read_weight_file(Path(state))
         if state is None and self._model_dir is not None:
             if self._model_filename:
                 cand = self._model_dir / self._model_filename
@@ -129,18 +131,28 @@ class B200Mdx23Backend(IVocalSeparatorBackend):
                     raise FileNotFoundError(f"MDX23 weights not found: {cand}")
                 files = [cand]
             else:
-                files = sorted(self._model_dir.glob("*.npz"))
+                files = sorted(self._model_dir.glob("*.onnx")) or sorted(self._model_dir.glob("*.npz"))
             if files:
-                self._model_name = files[0].name
-                state = load_npz(str(files[0]))
+                state = self._read_weight_file(files[0])
         if state is None:
             if not self._allow_random:
-                raise FileNotFoundError("no MDX23 weights (.npz) found and allow_random_init is False")
+                where = self._model_dir if self._model_dir is not None else "(no model_dir given)"
+                raise FileNotFoundError(f"no MDX23 model (.onnx / .npz) found in {where} and allow_random_init is False")
             state = random_state(self._geo)
         self._resolved_output_type = resolve_output_type(self._model_name, self._output_pref)
         idx = self._device.index if self._device.index is not None else 0
         self._net = ops.UNet(state, self._geo, device=idx)
         self.reset_performance_metrics()
+
+    def _read_weight_file(self, path: Path):
+        if not path.exists():
+            raise FileNotFoundError(f"MDX23 weights not found: {path}")
+        self._model_name = path.name
+        if path.suffix.lower() == ".onnx":
+            state, geo = load_onnx(str(path), dim_t=self._geo.dim_t)
+            self._geo = geo  # the file decides g / n / l / bn / dim_f
+            return state
+        return load_npz(str(path))
 
     def reset_performance_metrics(self) -> None:
         self._perf = {"h2d_ms": 0.0, "dtoh_ms": 0.0, "compute_ms": 0.0, "chunks": 0.0, "max_alloc_bytes": 0.0}
@@ -188,6 +200,8 @@ class B200Mdx23Backend(IVocalSeparatorBackend):
             out = torch.stack([v, i]).cpu()
             ev[3].record()
             ev[3].synchronize()
+        if _lib.load().ac_debug_tc_aborted() != 0:
+            raise _lib.AudioCutError("a tcgen05 kernel hit its mbarrier watchdog during this chunk: separation output is invalid")
         self.record_perf("h2d_ms", ev[0].elapsed_time(ev[1]))
         self.record_perf("compute_ms", ev[1].elapsed_time(ev[2]))
         self.record_perf("dtoh_ms", ev[2].elapsed_time(ev[3]))

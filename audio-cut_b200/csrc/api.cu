@@ -11,6 +11,7 @@ namespace ac {
 static thread_local std::string t_error;
 std::atomic<long long> g_launches{0};
 static int g_sm_count = 0;
+static int g_bound_device = -1;  // the library keeps per-device tables (FFT plans, window caches, abort flag): one device per process
 static std::mutex g_plan_mu;
 static std::map<int, FftPlan*> g_plans;
 
@@ -158,6 +159,11 @@ int ac_init(int device) {
     return AC_E_NODEVICE;
   }
   AC_REQUIRE(device >= 0 && device < n, "device index out of range");
+  if (ac::g_bound_device >= 0 && ac::g_bound_device != device) {
+    ac::set_error("libaudiocut_b200 is bound to cuda:" + std::to_string(ac::g_bound_device) + " in this process (its cached device tables "
+                  "live there); use one process per GPU (torchrun / CUDA_VISIBLE_DEVICES), as bench.py --gpus N does");
+    return AC_E_INVALID;
+  }
   AC_CHECK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   AC_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -167,6 +173,7 @@ int ac_init(int device) {
     return AC_E_NODEVICE;
   }
   ac::g_sm_count = prop.multiProcessorCount;
+  ac::g_bound_device = device;
   return AC_OK;
 }
 

@@ -1322,7 +1322,7 @@ __global__ void __launch_bounds__(kLpcThreads) lpc_formant_kernel(const float* _
   __shared__ double fwd[kLpcMaxFrame], bwd[kLpcMaxFrame];
   __shared__ double ar[kLpcMaxOrder + 1], ar_prev[kLpcMaxOrder + 1];
   __shared__ double red[8];
-  __shared__ float mag[kLpcFreq];
+  __shared__ double mag[kLpcFreq];  // fp64 like scipy.signal.freqz: the peak rule compares neighbours, float32 storage created ties
   __shared__ int peak_idx[4];
   __shared__ int n_peaks_s;
   const long long fr = blockIdx.x;
@@ -1384,7 +1384,7 @@ __global__ void __launch_bounds__(kLpcThreads) lpc_formant_kernel(const float* _
     __syncthreads();
   }
   // |1 / A(e^{jw})|, w_k = pi * k / 512
-  float local_max = 0.f;
+  double local_max = 0.0;
   for (int k = tid; k < kLpcFreq; k += kLpcThreads) {
     const double w = 3.14159265358979323846 * (double)k / (double)kLpcFreq;
     double re = 0.0, im = 0.0;
@@ -1394,20 +1394,21 @@ __global__ void __launch_bounds__(kLpcThreads) lpc_formant_kernel(const float* _
       re += a_cur[m] * c;
       im -= a_cur[m] * s;
     }
-    const float v = (float)(1.0 / sqrt(re * re + im * im));
+    const double v = 1.0 / sqrt(re * re + im * im);
     mag[k] = v;
-    local_max = fmaxf(local_max, v);
+    local_max = fmax(local_max, v);
   }
-  local_max = warp_max(local_max);
-  __shared__ float mx_s[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  __shared__ double mx_s[8];
   if ((tid & 31) == 0) mx_s[tid >> 5] = local_max;
   __syncthreads();
-  float mx = 0.f;
-  for (int i = 0; i < kLpcThreads / 32; ++i) mx = fmaxf(mx, mx_s[i]);
+  double mx = 0.0;
+  for (int i = 0; i < kLpcThreads / 32; ++i) mx = fmax(mx, mx_s[i]);
   if (tid == 0) {
     int np = 0;
     if (ok && isfinite(mx)) {
-      const float height = mx * 0.1f;
+      const double height = mx * 0.1;
       int i = 1;
       while (i < kLpcFreq - 1 && np < 3) {
         if (mag[i - 1] < mag[i]) {
@@ -1426,7 +1427,7 @@ __global__ void __launch_bounds__(kLpcThreads) lpc_formant_kernel(const float* _
     n_peaks_s = np;
   }
   __syncthreads();
-  if (tid < 3) mags[fr * 3 + tid] = tid < n_peaks_s ? mag[peak_idx[tid]] : 0.f;
+  if (tid < 3) mags[fr * 3 + tid] = tid < n_peaks_s ? (float)mag[peak_idx[tid]] : 0.f;
   if (tid == 0) counts[fr] = n_peaks_s;
 }
 }  // namespace ac

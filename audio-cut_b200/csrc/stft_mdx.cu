@@ -161,6 +161,7 @@ struct IstftArgs {
   float* vocal;
   float* instr;
   float* weight;
+  float* side_vocal;  // nullable: per-chunk vocal before halo trimming
 };
 
 template <typename T>
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(kFftThreads) istft_mdx_kernel(const T* __restr
           const int o = n - half;  // trim = n_fft/2 on both sides (backends.py:377)
           if (o < 0 || o >= wd.out_len || n >= a.W - half) continue;
           const long long tp = wd.out_base + o;
-          if (tp < wd.eff_start || tp >= wd.eff_end) continue;
+          const bool in_eff = tp >= wd.eff_start && tp < wd.eff_end;
+          if (!in_eff && !a.side_vocal) continue;
           const float m0 = __ldg(a.mix + tp);
           const float m1 = __ldg(a.mix + (a.n_ch > 1 ? a.mix_stride : 0) + tp);
           float v, ins;
@@ -237,6 +239,8 @@ __global__ void __launch_bounds__(kFftThreads) istft_mdx_kernel(const T* __restr
             ins = (y0 + y1) * 0.5f;
             v = ((m0 - y0) + (m1 - y1)) * 0.5f;
           }
+          if (a.side_vocal) a.side_vocal[wd.side_base + o] = v;
+          if (!in_eff) continue;
           atomicAdd(a.vocal + tp, v);
           atomicAdd(a.instr + tp, ins);
           atomicAdd(a.weight + tp, 1.0f);
@@ -281,7 +285,7 @@ int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, in
 
 int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDesc* d_wins, int n_win, int mode,
                  float* d_wave, const float* d_mix, long long mix_stride, int n_ch, int output_is_vocal,
-                 float* d_vocal, float* d_instr, float* d_weight, cudaStream_t st) {
+                 float* d_vocal, float* d_instr, float* d_weight, cudaStream_t st, float* d_chunk_vocal) {
   if (n_win <= 0) return AC_OK;
   const ac_mdx_geom& g = plan->g;
   IstftArgs a;
@@ -318,6 +322,7 @@ int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDe
   a.vocal = d_vocal;
   a.instr = d_instr;
   a.weight = d_weight;
+  a.side_vocal = mode == 1 ? d_chunk_vocal : nullptr;
   const size_t smem = stft_smem_bytes(g.n_fft) + sizeof(float2) * (size_t)a.nb * g.hop;
   AC_REQUIRE(smem <= 227 * 1024, "n_fft too large for shared memory");
   dim3 grid(strips, n_win);

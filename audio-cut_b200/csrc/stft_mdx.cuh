@@ -13,6 +13,7 @@ struct WinDesc {
   int p_lo, p_hi;       // window positions holding real samples; outside -> 0 (zero padding)
   int out_len;          // stems mode: outputs n = trim .. trim+out_len-1 are valid (<= gen)
   int pad_;
+  long long side_base;  // stems mode: index in the per-chunk side buffer of this window's first output (see launch_istft)
 };
 
 struct MdxPlan {
@@ -32,6 +33,8 @@ int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, in
 //         mix, averages the two channels and atomically accumulates vocal / instrumental / weight.
 int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDesc* d_wins, int n_win, int mode,
                  float* d_wave, const float* d_mix, long long mix_stride, int n_ch, int output_is_vocal,
-                 float* d_vocal, float* d_instr, float* d_weight, cudaStream_t st);
+                 float* d_vocal, float* d_instr, float* d_weight, cudaStream_t st, float* d_chunk_vocal = nullptr);
+// d_chunk_vocal (stems mode, nullable): every chunk's OWN vocal output before halo trimming and overlap averaging,
+// chunks back to back (WinDesc::side_base) - what the reference hands its per-chunk VAD (enhanced_vocal_separator.py:412-417).
 
 }  // namespace ac

@@ -13,6 +13,12 @@
 
 namespace ac {
 
+// hop*(dim_t-1) must exceed n_fft (gen > 0), everything positive: otherwise the window arithmetic divides by zero
+static bool track_geom_ok(const ac_track_params& p) {
+  return p.mdx.hop > 0 && p.mdx.dim_t > 1 && p.mdx.n_fft > 0 && p.mdx.dim_f > 0 && p.align_hop >= 0 &&
+         (long long)p.mdx.hop * (p.mdx.dim_t - 1) > (long long)p.mdx.n_fft;
+}
+
 static int chunk_windows(int chunk_len, const ac_track_params& p) {
   const int hop = p.align_hop > 0 ? p.align_hop : 1;
   const long long L = (long long)chunk_len + ((hop - chunk_len % hop) % hop);
@@ -27,7 +33,8 @@ static void build_windows(const ac_chunk_desc* ch, int n_chunks, const ac_track_
   const int trim = p.mdx.n_fft / 2;
   const int gen = W - p.mdx.n_fft;
   out.clear();
-  for (int c = 0; c < n_chunks; ++c) {
+  long long side = 0;  // chunks lie back to back in the per-chunk side buffer
+  for (int c = 0; c < n_chunks; side += ch[c].chunk_len > 0 ? ch[c].chunk_len : 0, ++c) {
     if (ch[c].chunk_len <= 0) continue;
     const int nw = chunk_windows(ch[c].chunk_len, p);
     for (int w = 0; w < nw; ++w) {
@@ -48,6 +55,7 @@ static void build_windows(const ac_chunk_desc* ch, int n_chunks, const ac_track_
       d.eff_start = ch[c].eff_start;
       d.eff_end = ch[c].eff_end;
       d.pad_ = 0;
+      d.side_base = side + (long long)w * gen;
       out.push_back(d);
     }
   }
@@ -108,7 +116,11 @@ __global__ void downmix_kernel(const float* __restrict__ mix, int n_ch, long lon
 
 // sum of squares of up to three arrays + count of non-zero samples of the second one (fp64 accumulators)
 __global__ void track_stats_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
-                                   long long n, double* __restrict__ out) {
+                                   long long n, double* __restrict__ out, int* __restrict__ abort_flag) {
+  if (abort_flag && blockIdx.x == 0 && threadIdx.x == 0) {  // hand the tcgen05 watchdog flag to the host and re-arm it
+    const int f = *abort_flag;
+    if (f) { out[4] = (double)f; *abort_flag = 0; }
+  }
   double sa = 0, sb = 0, sc = 0, nz = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float x = a ? a[i] : 0.f, y = b ? b[i] : 0.f, z = c ? c[i] : 0.f;
@@ -136,7 +148,7 @@ __global__ void track_stats_kernel(const float* __restrict__ a, const float* __r
 }  // namespace ac
 
 extern "C" int ac_track_window_count(const ac_chunk_desc* h_chunks, int n_chunks, const ac_track_params* p) {
-  if (!h_chunks || !p || n_chunks < 0) return -1;
+  if (!h_chunks || !p || n_chunks < 0 || !ac::track_geom_ok(*p)) return -1;
   std::vector<ac::WinDesc> w;
   ac::build_windows(h_chunks, n_chunks, *p, w);
   return (int)w.size();
@@ -158,8 +170,16 @@ extern "C" size_t ac_track_workspace_bytes(const ac_unet* net, const ac_chunk_de
 extern "C" int ac_separate_track(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
                                  int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr,
                                  float* d_weight, void* d_ws, size_t ws_bytes, void* stream) {
+  return ac_separate_track_ex(net, d_mix, n_samples, h_chunks, n_chunks, p, d_vocal, d_instr, d_weight, nullptr, d_ws, ws_bytes,
+                              stream);
+}
+
+extern "C" int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
+                                    int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr,
+                                    float* d_weight, float* d_chunk_vocal, void* d_ws, size_t ws_bytes, void* stream) {
   using namespace ac;
   AC_REQUIRE(net && d_mix && h_chunks && p && d_vocal && d_instr && d_weight && d_ws, "null pointer");
+  AC_REQUIRE(track_geom_ok(*p), "MDX geometry: hop*(dim_t-1) must exceed n_fft, all sizes positive");
   AC_REQUIRE(n_samples > 0 && n_chunks >= 0, "bad sizes");
   AC_REQUIRE(p->n_channels == 1 || p->n_channels == 2, "n_channels must be 1 or 2");
   AC_REQUIRE(p->dtype == AC_F32 || p->dtype == AC_BF16 || p->dtype == AC_F16, "dtype");
@@ -210,7 +230,7 @@ extern "C" int ac_separate_track(ac_unet* net, const float* d_mix, long long n_s
     rc = ac_unet_forward(net, d_spec, d_spec, b, p->dtype, d_uws, uws_bytes, st);
     if (rc) return rc;
     rc = launch_istft(plan, d_spec, p->dtype, d_wins + w0, b, 1, nullptr, d_mix, n_samples, p->n_channels,
-                      p->output_is_vocal, d_vocal, d_instr, d_weight, st);
+                      p->output_is_vocal, d_vocal, d_instr, d_weight, st, d_chunk_vocal);
     if (rc) return rc;
   }
   finalize_stems_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, st>>>(d_vocal, d_instr, d_weight, n_samples);
@@ -229,16 +249,18 @@ extern "C" int ac_downmix_mono(const float* d_mix, int n_channels, long long n, 
   return AC_OK;
 }
 
-extern "C" int ac_track_stats(const float* d_a, const float* d_b, const float* d_c, long long n, double* d_out4, void* stream) {
+namespace ac { int* tc_abort_flag_if_any(); }
+extern "C" int ac_track_stats(const float* d_a, const float* d_b, const float* d_c, long long n, double* d_out5, void* stream) {
   using namespace ac;
-  AC_REQUIRE(d_out4 && n >= 0, "null pointer");
+  AC_REQUIRE(d_out5 && n >= 0, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  AC_CHECK_CUDA(cudaMemsetAsync(d_out4, 0, 4 * sizeof(double), st));
-  if (n == 0) return AC_OK;
+  AC_CHECK_CUDA(cudaMemsetAsync(d_out5, 0, 5 * sizeof(double), st));
+  double* d_out4 = d_out5;
+  if (n == 0) n = 1, d_a = d_b = d_c = nullptr;  // still report (and re-arm) the watchdog flag
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)device_sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  track_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_a, d_b, d_c, n, d_out4);
+  track_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_a, d_b, d_c, n, d_out4, tc_abort_flag_if_any());
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -391,6 +391,8 @@ int launch_tc_conv3x3(const TcConvArgs& a, cudaStream_t st) {
   return AC_OK;
 }
 
+int* tc_abort_flag_if_any() { return g_abort_flag; }
+
 // returns 1 if any tensor-core kernel hit its wait watchdog since the last call (synchronises)
 int tc_check_abort() {
   if (!g_abort_flag) return 0;

@@ -177,8 +177,10 @@ def make_chunk_descs(bounds: Sequence[Tuple[int, int, int, int]]):
 
 
 def separate_track(net: UNet, mix: torch.Tensor, bounds: Sequence[Tuple[int, int, int, int]], geom: MdxGeom, *,
-                   align_hop: int = 4096, output_is_vocal: bool = True, dtype: int = AC_F32, max_batch: int = 0, out=None):
-    """mix [n_ch, N] f32 on the GPU -> (vocal [N], instrumental [N], weight [N]); ``out`` = preallocated triple."""
+                   align_hop: int = 4096, output_is_vocal: bool = True, dtype: int = AC_F32, max_batch: int = 0, out=None,
+                   chunk_vocal: Optional[torch.Tensor] = None):
+    """mix [n_ch, N] f32 on the GPU -> (vocal [N], instrumental [N], weight [N]); ``out`` = preallocated triple.
+    ``chunk_vocal`` (optional, float32 [sum of chunk lengths]): receives every chunk's own pre-stitch vocal output."""
     assert mix.dim() == 2 and mix.shape[0] in (1, 2)
     mix = mix.contiguous().float()
     n = mix.shape[1]
@@ -195,8 +197,11 @@ def separate_track(net: UNet, mix: torch.Tensor, bounds: Sequence[Tuple[int, int
         vocal = torch.empty(n, dtype=torch.float32, device=mix.device)
         instr = torch.empty_like(vocal)
         weight = torch.empty_like(vocal)
-    check(lib.ac_separate_track(net.handle, ptr(mix), n, descs, len(bounds), C.byref(tp), ptr(vocal), ptr(instr), ptr(weight),
-                                ptr(ws), ws.numel(), stream_ptr()), "ac_separate_track")
+    if chunk_vocal is not None:
+        need = sum(max(0, ce - cs) for cs, ce, _, _ in bounds)
+        assert chunk_vocal.is_cuda and chunk_vocal.dtype == torch.float32 and chunk_vocal.is_contiguous() and chunk_vocal.numel() >= need
+    check(lib.ac_separate_track_ex(net.handle, ptr(mix), n, descs, len(bounds), C.byref(tp), ptr(vocal), ptr(instr), ptr(weight),
+                                   ptr(chunk_vocal), ptr(ws), ws.numel(), stream_ptr()), "ac_separate_track_ex")
     return vocal, instr, weight
 
 

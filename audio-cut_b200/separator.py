@@ -5,12 +5,16 @@ contract of /root/reference/src/vocal_smart_splitter/core/enhanced_vocal_separat
 result dataclass :45-58, same ``gpu_meta`` keys) but runs the whole track in one
 go: one pinned H2D of the mix, every chunk's windows batched through STFT -> U-Net -> fused iSTFT /
 overlap-average on the device (``ac_separate_track``), per-chunk features in two launches, one D2H of
-the stems.  When a VAD hook is installed the reference's per-chunk order of calls is preserved through
-``infer_chunk``.  There is no fallback backend: failures are recorded in ``gpu_pipeline_failures`` and
+the stems.  When a VAD hook is installed (``vad_fn`` or a ``chunk_vad`` object with the ``SileroChunkVAD``
+interface) it receives, chunk by chunk in plan order, each chunk's OWN vocal output - the whole chunk
+including its halos, before trimming and overlap averaging - exactly what the reference passes at
+enhanced_vocal_separator.py:412-417; the kernels emit those per-chunk stems into a side buffer
+(``ac_separate_track_ex``).  There is no fallback backend: failures are recorded in ``gpu_pipeline_failures`` and
 re-raised (the reference's ``strict_gpu`` behaviour).
 """
 from __future__ import annotations
 
+import os
 import time
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
@@ -19,7 +23,7 @@ from typing import Callable, Dict, List, Optional
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .backends import B200Mdx23Backend, IVocalSeparatorBackend
 from .features_cache import B200ChunkFeatureBuilder, TrackFeatureCache
 from .gpu_pipeline import PipelineConfig, PipelineContext, build_pipeline_context, chunk_schedule
@@ -164,8 +168,8 @@ class _TrackBuffers:
         self.s_sep = torch.cuda.Stream(device=dev)
         self.s_feat = torch.cuda.Stream(device=dev, priority=-1)
         self.events = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        self.stats_dev = torch.zeros(4, dtype=torch.float64, device=dev)
-        self.stats_pin = torch.zeros(4, dtype=torch.float64, pin_memory=True)
+        self.stats_dev = torch.zeros(5, dtype=torch.float64, device=dev)
+        self.stats_pin = torch.zeros(5, dtype=torch.float64, pin_memory=True)
         self._small: Optional[_SmallBuf] = None
 
     def small(self, n: int) -> _SmallBuf:
@@ -202,13 +206,24 @@ class B200VocalSeparator:
     def __init__(self, sample_rate: int = 44100, *, backend: Optional[B200Mdx23Backend] = None,
                  pipeline_config: Optional[PipelineConfig] = None,
                  vad_fn: Optional[Callable[[object, np.ndarray, int], List[Dict[str, float]]]] = None,
-                 marker_threshold_db: float = -50.0):
+                 chunk_vad=None, marker_threshold_db: float = -50.0):
         self.sample_rate = sample_rate
         self._pipeline_cfg = pipeline_config or PipelineConfig()
-        self._primary_backend: IVocalSeparatorBackend = backend if backend is not None else B200Mdx23Backend(allow_random_init=True)
+        if backend is None:
+            # enhanced_vocal_separator.py:83-137: the model directory of the checkout (env MDX23_MODELS_PATH as in the
+            # reference's tests/conftest.py:25-48); no model -> RuntimeError, never silent random weights
+            model_dir = os.getenv("MDX23_MODELS_PATH") or os.path.join(os.getcwd(), "MVSEP-MDX23-music-separation-model", "models")
+            backend = B200Mdx23Backend(model_dir, align_hop=self._pipeline_cfg.align_hop)
+        self._primary_backend: IVocalSeparatorBackend = backend
         if getattr(self._primary_backend, "_net", None) is None:
-            self._primary_backend.load_model()
+            try:
+                self._primary_backend.load_model()
+            except FileNotFoundError as exc:
+                raise RuntimeError(f"no usable separation backend: {{'mdx23': {str(exc)!r}}}") from exc
         self._vad_fn = vad_fn
+        # chunk_vad: a FACTORY ``(sample_rate) -> object with process_chunk(plan, vocal_chunk, sr) / finalize()`` (one
+        # instance per track, like SileroChunkVAD at enhanced_vocal_separator.py:329-333), e.g. chunk_vad.B200ChunkVAD
+        self._chunk_vad_factory = chunk_vad
         self._marker_threshold_db = marker_threshold_db
         self.enable_fallback = False
         self.backend_pref = "mdx23"
@@ -280,6 +295,10 @@ class B200VocalSeparator:
         out_pin = ([torch.empty(total, dtype=torch.float32, pin_memory=True) for _ in range(2)]
                    if self.pinned_outputs else None)
         finish_metrics = None
+        want_chunks = self._vad_fn is not None or self._chunk_vad_factory is not None
+        side_n = sum(ce - cs for _, (cs, ce, _, _) in live) if want_chunks else 0
+        side_dev = torch.empty(side_n, dtype=torch.float32, device=dev) if side_n else None
+        side_pin = torch.empty(side_n, dtype=torch.float32, pin_memory=True) if side_n else None
         with torch.cuda.device(dev), ctx.acquire_inflight():
             # a page-locked caller array (e.g. ``torch.empty(..., pin_memory=True).numpy()``) goes to the device as it
             # is; anything else is staged through the persistent pinned buffer first (pageable -> pinned, threaded)
@@ -304,7 +323,7 @@ class B200VocalSeparator:
             with torch.cuda.stream(stream):
                 ops.separate_track(backend.net, v.mix, [b for _, b in live], backend.geom, align_hop=backend.align_hop,
                                    output_is_vocal=backend.get_output_type() == "vocal", dtype=backend.dtype,
-                                   out=(v.vocal, v.instr, v.weight))
+                                   out=(v.vocal, v.instr, v.weight), chunk_vocal=side_dev)
                 ev[2].record()
                 if self.capture_device_metrics:  # NVML sample taken while the network runs, off the critical path
                     finish_metrics = ctx.capture_device_metrics_async()
@@ -322,6 +341,8 @@ class B200VocalSeparator:
                     out_pin[1].copy_(v.instr, non_blocking=True)
                 else:
                     v.pin_out.copy_(v.stems2, non_blocking=True)
+                if side_dev is not None:
+                    side_pin.copy_(side_dev, non_blocking=True)
                 mark.pin.copy_(mark.dev, non_blocking=True)
                 bufs.stats_pin.copy_(bufs.stats_dev, non_blocking=True)
                 ev[3].record()
@@ -335,6 +356,8 @@ class B200VocalSeparator:
             caller.wait_stream(stream)
             caller.wait_stream(feat_stream)
         stats = bufs.stats_pin.numpy().copy()
+        if stats[4] != 0:  # tc_common.cuh:mbar_wait watchdog: the tensor-core kernels drained out early, the stems are invalid
+            raise _lib.AudioCutError("a tcgen05 kernel hit its mbarrier watchdog during this track: separation output is invalid")
         any_instr = stats[3] > 0
         if out_pin is not None:
             # numpy views of page-locked tensors: freshly allocated, caller-owned (the array keeps its tensor alive;
@@ -351,9 +374,18 @@ class B200VocalSeparator:
         self._last_device = (v.mono, v.vocal, v.instr if any_instr else None)
         self._energies = (float(stats[0]) / max(total, 1), float(stats[1]) / max(total, 1) if any_instr else None,
                           float(stats[2]) / max(total, 1))
-        if self._vad_fn is not None:  # hook kept from SileroChunkVAD (silero_chunk_vad.py:34, 56-116)
+        if want_chunks:  # per-chunk VAD, in plan order, on each chunk's own output (enhanced_vocal_separator.py:412-417)
+            chunk_vad = self._chunk_vad_factory(sr) if self._chunk_vad_factory is not None else None
+            side_np, off = side_pin.numpy(), 0
             for p, (cs, ce, _, _) in live:
-                vad_segments.extend(self._vad_fn(p, vocal[cs:ce], sr) or [])
+                chunk = side_np[off : off + (ce - cs)]
+                off += ce - cs
+                if self._vad_fn is not None:
+                    vad_segments.extend(self._vad_fn(p, chunk, sr) or [])
+                if chunk_vad is not None:
+                    chunk_vad.process_chunk(p, chunk, sr)
+            if chunk_vad is not None:
+                vad_segments = vad_segments + list(chunk_vad.finalize())
         backend.record_perf("h2d_ms", ev[0].elapsed_time(ev[1]))
         backend.record_perf("compute_ms", ev[1].elapsed_time(ev[2]))
         backend.record_perf("dtoh_ms", ev[2].elapsed_time(ev[3]))

@@ -88,7 +88,7 @@ typedef struct ac_mdx_geom {
   int dim_t; /* 256 frames; window length W = hop*(dim_t-1) */
 } ac_mdx_geom;
 
-/* d_wave [B][2][W] f32 -> d_spec [B][dim_t][dim_f][4] (dtype AC_F32 or AC_BF16). */
+/* d_wave [B][2][W] f32 -> d_spec [B][dim_t][dim_f][4] (dtype AC_F32, AC_F16 or AC_BF16). */
 AC_API int ac_stft_mdx(const float* d_wave, void* d_spec, int B, const ac_mdx_geom* g, int dtype, void* stream);
 /* d_spec [B][dim_t][dim_f][4] -> d_wave [B][2][W] f32 (full torch.istft output, no trim). */
 AC_API int ac_istft_mdx(const void* d_spec, float* d_wave, int B, const ac_mdx_geom* g, int dtype, void* stream);
@@ -156,7 +156,7 @@ typedef struct ac_track_params {
   int align_hop;        /* 4096 (gpu_pipeline.align_hop / MDX23_ALIGN_HOP, backends.py:113)  */
   int n_channels;       /* 1: mono duplicated to both network channels (backends.py:269-270); 2: stereo */
   int output_is_vocal;  /* 1: network output is the vocal stem, other = mix - out (backends.py:395-401) */
-  int dtype;            /* AC_F32 / AC_BF16 */
+  int dtype;            /* AC_F32 / AC_F16 / AC_BF16 */
   int max_batch;        /* windows per network launch (0 = library default) */
   int reserved;
 } ac_track_params;
@@ -169,14 +169,24 @@ AC_API size_t ac_track_workspace_bytes(const ac_unet* net, const ac_chunk_desc* 
 AC_API int ac_separate_track(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
                       int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr, float* d_weight,
                       void* d_ws, size_t ws_bytes, void* stream);
+/* The same, additionally writing every chunk's OWN vocal output - before halo trimming and overlap averaging,
+ * chunks with chunk_len > 0 back to back in h_chunks order - to d_chunk_vocal [sum of chunk_len] (nullable).
+ * This is what the reference hands its per-chunk VAD hook inside the chunk loop:
+ * chunk_vad.process_chunk(plan, outputs.vocal, ...) at enhanced_vocal_separator.py:412-417. */
+AC_API int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
+                         int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr, float* d_weight,
+                         float* d_chunk_vocal, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Stereo -> mono mean (np.mean(mix, axis=0) at features_cache.py:137-139 / enhanced_vocal_separator.py
  * mono handling); n_channels == 1 copies.  d_mix [n_channels][n] -> d_out [n]. */
 AC_API int ac_downmix_mono(const float* d_mix, int n_channels, long long n, float* d_out, void* stream);
 /* Energies for EnhancedVocalSeparator._estimate_separation_confidence (enhanced_vocal_separator.py:490-501)
  * and the all-zero test of the instrumental accumulator (:456-458), without a host pass over the stems:
- * d_out4 = { sum a^2, sum b^2, sum c^2, count(b != 0) } in fp64.  Any of d_a/d_b/d_c may be NULL. */
-AC_API int ac_track_stats(const float* d_a, const float* d_b, const float* d_c, long long n, double* d_out4, void* stream);
+ * d_out5 = { sum a^2, sum b^2, sum c^2, count(b != 0), watchdog } in fp64.  Any of d_a/d_b/d_c may be NULL.
+ * watchdog != 0: a tcgen05 kernel launched before this call (stream order) gave up on an mbarrier wait (a wrong
+ * descriptor / byte count would otherwise hang the GPU) and every tensor-core kernel after it drained out early -
+ * the stems of this track are INVALID.  Reading the slot re-arms the flag; the Python drop-in raises on it. */
+AC_API int ac_track_stats(const float* d_a, const float* d_b, const float* d_c, long long n, double* d_out5, void* stream);
 
 /* ---- STFT-2048 framewise features ----------------------------------------------------------------
  * One pass over the signal per call; n_fft = 2048, periodic hann, center=True, zero padding

@@ -150,17 +150,51 @@ def test_vad_hook_is_called_per_chunk():
     from audio_cut_b200.gpu_pipeline import PipelineConfig
     from audio_cut_b200.separator import B200VocalSeparator
 
-    be, _, _ = _small_backend()
-    seen = []
+    be, st, geo = _small_backend()
+    from audio_cut_b200.chunk_vad import B200ChunkVAD
+    from oracle import mdx
+    from oracle import unet as ounet
+
+    ref_net = ounet.build_net(st, geo.dim_f, geo.dim_t, geo.g)
+    mg = mdx.MdxGeometry(640, 128, 256, 32)
+
+    seen, chunks = [], []
 
     def vad(plan, vocal_chunk, sr):
         seen.append((plan.index, len(vocal_chunk)))
+        chunks.append(np.array(vocal_chunk))
         return [{"start": plan.start_s, "end": plan.end_s}]
 
-    sep = B200VocalSeparator(8000, backend=be, pipeline_config=PipelineConfig(chunk_s=4.0, overlap_s=1.0, halo_s=0.25, align_hop=256), vad_fn=vad)
-    res = sep.separate_for_detection(synth.synth_track(9.0, sr=8000, stereo=False))
-    assert [i for i, _ in seen] == list(range(len(seen))) and len(res.vad_segments) == len(seen)
-    assert res.gpu_meta["silero_vad_segments"] == len(seen)
+    made = []
+
+    def factory(sr):
+        made.append(B200ChunkVAD(sr, inference_fn=lambda x: [{"start": 0, "end": len(x)}]))
+        return made[-1]
+
+    cfg = PipelineConfig(chunk_s=4.0, overlap_s=1.0, halo_s=0.25, align_hop=256)
+    sep = B200VocalSeparator(8000, backend=be, pipeline_config=cfg, vad_fn=vad, chunk_vad=factory)
+    audio = synth.synth_track(9.0, sr=8000, stereo=False)
+    res = sep.separate_for_detection(audio)
+    assert [i for i, _ in seen] == list(range(len(seen)))
+    assert res.gpu_meta["silero_vad_segments"] == len(res.vad_segments)
+    # the hook sees each chunk's OWN output (whole chunk, halos included, before the overlap average):
+    # enhanced_vocal_separator.py:412-417 passes outputs.vocal of infer_chunk
+    from audio_cut_b200.gpu_pipeline import chunk_schedule
+
+    plans = chunk_schedule(len(audio) / 8000.0, chunk_s=4.0, overlap_s=1.0, halo_s=0.25)
+    assert len(plans) == len(chunks) >= 2
+    for p, got in zip(plans, chunks):
+        cs, ce, _, _ = p.sample_bounds(8000, len(audio))
+        assert len(got) == ce - cs
+        ref_v, _ = mdx.infer_chunk(audio[cs:ce], ref_net, mg, align_hop=256)
+        assert sdr_db(ref_v, got) > 60
+    # interior chunks differ from the stitched track inside the seams (the stitched samples are averages)
+    cs, ce, es, ee = plans[1].sample_bounds(8000, len(audio))
+    assert not np.allclose(chunks[1][: es - cs + 100], res.vocal_track[cs : es + 100], atol=1e-7)
+    # the SileroChunkVAD-style adapter: every chunk reports all-speech -> one merged span over the whole track
+    merged = made[0].finalize()
+    assert len(merged) == 1 and abs(merged[0]["start"]) < 1e-9 and abs(merged[0]["end"] - len(audio) / 8000.0) < 1e-3
+    assert len(res.vad_segments) == len(seen) + 1
 
 
 def test_vocal_features_dropin_matches_oracle():

@@ -91,14 +91,26 @@ def test_istft_mdx_matches_torch(ops, n_fft, hop, dim_f, dim_t):
     assert sdr_db(ref.numpy(), got.numpy()) > 100
 
 
-def test_stft_bf16_output(ops):
+# 16-bit formats of the tensor-core path: (name, AC_* dtype, torch dtype).  fp16 (IEEE half, 11-bit significand) is
+# the production format - it is the one that meets north_star's >= 40 dB stem-SDR gate; bf16 (8-bit significand)
+# runs through the same kernels and is held to what its rounding noise allows.
+H16 = [("fp16", 2, torch.float16), ("bf16", 1, torch.bfloat16)]
+
+
+@pytest.mark.parametrize("name,dtype,tdtype", H16)
+def test_stft_16bit_output(ops, name, dtype, tdtype):
     from oracle import mdx
 
     g = mdx.MdxGeometry(1280, 256, 512, 64)
     x = torch.randn(1, 2, g.chunk_size, generator=torch.Generator().manual_seed(1)) * 0.3
     ref = mdx.stft(x, g)
-    got = ops.tfc_to_onnx(ops.stft_mdx(x.cuda(), ops.mdx_geom(1280, 256, 512, 64), dtype=1)).float().cpu()
-    assert sdr_db(ref.numpy(), got.numpy()) > 45  # bf16 rounding of the output only
+    got = ops.stft_mdx(x.cuda(), ops.mdx_geom(1280, 256, 512, 64), dtype=dtype)
+    assert got.dtype == tdtype
+    got = ops.tfc_to_onnx(got).float().cpu()
+    assert sdr_db(ref.numpy(), got.numpy()) > (65 if name == "fp16" else 45)  # rounding of the output only
+    back = ops.istft_mdx(ops.stft_mdx(x.cuda(), ops.mdx_geom(1280, 256, 512, 64), dtype=dtype), ops.mdx_geom(1280, 256, 512, 64))
+    ref_back = mdx.istft(ref, g)
+    assert sdr_db(ref_back.numpy(), back.cpu().numpy()) > (60 if name == "fp16" else 40)
 
 
 # --------------------------------------------------------------------------- U-Net
@@ -125,13 +137,14 @@ def test_unet_fp32_matches_oracle(ops, dim_f, dim_t, g, B):
     assert s > 80, s  # north_star asks >= 60 dB on stems for the fp32 path
 
 
+@pytest.mark.parametrize("name,dtype,tdtype", H16)
 @pytest.mark.parametrize("dim_f,dim_t,g,B", [(256, 32, 16, 2), (512, 64, 48, 1)])
-def test_unet_bf16_simt_close_to_oracle(ops, dim_f, dim_t, g, B):
+def test_unet_16bit_simt_close_to_oracle(ops, dim_f, dim_t, g, B, name, dtype, tdtype):
     net, x, ref = _unet_case(ops, dim_f, dim_t, g, B)
     net.set_debug(True)
-    got = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()).bfloat16())).float().cpu()
+    got = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()).to(tdtype))).float().cpu()
     s = sdr_db(ref.numpy(), got.numpy())
-    assert s > 30, s
+    assert s > (50 if name == "fp16" else 32), s
 
 
 def test_unet_full_geometry_fp32(ops):
@@ -216,13 +229,49 @@ def test_separate_track_full_geometry_30s_stereo(ops):
     assert sv > 60 and si > 60, (sv, si)
 
 
-@pytest.mark.parametrize("world,dtype_name", [(2, "f32"), (3, "bf16")])
+# north_star / BASELINE.md: separated-stem SDR >= 40 dB for the 16-bit tensor-core path (>= 60 dB for fp32), both stems,
+# against the CPU oracle on the same input at FULL geometry.  fp16 is the format that carries the gate (measured 48.5 dB
+# vocal / 69.8 dB instrumental on this track); bf16's 8-bit significand gives 30.8 / 52.1 dB on the same random-init
+# network whichever points are kept in fp32 (profiles/r02_bf16_emulation.md) - it is kept as an option and held
+# to a regression floor only.
+STEM_GATE_DB = 40.0
+
+
+@pytest.mark.parametrize("n_fft", [7680, 6144])
+def test_16bit_stem_sdr_gate_30s_full_geometry(ops, n_fft):
+    """BASELINE configs[0] (30 s stereo, 4 chunks / 8 windows) on the tcgen05 path, both n_fft the survey names."""
+    ref_v, ref_i, v, i, w, bounds = _track_case(ops, n_fft, 1024, 3072, 256, 48, 30.0, True, 44100, 10.0, 2.5, 0.5, 4096, dtype=2)
+    assert _tc_aborted() == 0
+    sv, si = sdr_db(ref_v, v), sdr_db(ref_i, i)
+    print(f"fp16 stems n_fft={n_fft}: vocal {sv:.1f} dB, instrumental {si:.1f} dB")
+    assert sv >= STEM_GATE_DB and si >= STEM_GATE_DB, (sv, si)
+
+
+def test_bf16_stem_sdr_floor_30s_full_geometry(ops):
+    ref_v, ref_i, v, i, w, bounds = _track_case(ops, 7680, 1024, 3072, 256, 48, 30.0, True, 44100, 10.0, 2.5, 0.5, 4096, dtype=1)
+    assert _tc_aborted() == 0
+    sv, si = sdr_db(ref_v, v), sdr_db(ref_i, i)
+    print(f"bf16 stems: vocal {sv:.1f} dB, instrumental {si:.1f} dB")
+    assert sv > 28 and si > 48, (sv, si)
+
+
+def test_16bit_stem_sdr_gate_4min_full_geometry(ops):
+    """BASELINE configs[1]: the benchmarked workload itself (4-min stereo track, 32 chunks / 64 windows, n_fft 7680) on
+    the benchmarked fp16 tcgen05 path against the oracle's full CPU pass (about a minute on the box's cores)."""
+    ref_v, ref_i, v, i, w, bounds = _track_case(ops, 7680, 1024, 3072, 256, 48, 240.0, True, 44100, 10.0, 2.5, 0.5, 4096, dtype=2)
+    assert len(bounds) == 32 and _tc_aborted() == 0
+    sv, si = sdr_db(ref_v, v), sdr_db(ref_i, i)
+    print(f"fp16 stems 4 min: vocal {sv:.1f} dB, instrumental {si:.1f} dB")
+    assert sv >= STEM_GATE_DB and si >= STEM_GATE_DB, (sv, si)
+
+
+@pytest.mark.parametrize("world,dtype_name", [(2, "f32"), (3, "bf16"), (3, "fp16")])
 def test_chunk_sharded_track_equals_single_gpu_stitch(ops, world, dtype_name):
     """BASELINE configs[4]: every rank separates a contiguous block of chunks of ONE track (halo recomputed
     locally, only its own samples uploaded); the host merge of the shards is sample-identical to the
     single-GPU result.  The ranks are emulated one after the other on this GPU."""
     from audio_cut_b200 import sharding, synth, unet_weights as uw
-    from audio_cut_b200._lib import AC_BF16, AC_F32
+    from audio_cut_b200._lib import AC_BF16, AC_F16, AC_F32
     from oracle import planner
 
     sr, n_fft, hop, dim_f, dim_t, g = 8000, 640, 128, 256, 32, 16
@@ -233,7 +282,7 @@ def test_chunk_sharded_track_equals_single_gpu_stitch(ops, world, dtype_name):
     total = audio.shape[-1]
     plans = planner.chunk_schedule(total / float(sr), 2.0, 0.5, 0.1)
     bounds = [planner.sample_bounds(p, sr, total) for p in plans]
-    dtype = AC_F32 if dtype_name == "f32" else AC_BF16
+    dtype = {"f32": AC_F32, "bf16": AC_BF16, "fp16": AC_F16}[dtype_name]
     v, i, w = ops.separate_track(net, torch.from_numpy(audio).cuda(), bounds, geom, align_hop=256, dtype=dtype)
     shards = [sharding.separate_chunk_shard(net, geom, audio, bounds, r, world, align_hop=256, dtype=dtype) for r in range(world)]
     assert sum(len(s["weight"]) for s in shards) > total  # neighbouring ranks overlap at the seams
@@ -243,12 +292,12 @@ def test_chunk_sharded_track_equals_single_gpu_stitch(ops, world, dtype_name):
 
 
 def test_full_size_track_properties(ops):
-    """BASELINE configs[1] at full size (4-min stereo, Kim_Vocal geometry, bf16 tensor-core path), checked through
+    """BASELINE configs[1] at full size (4-min stereo, Kim_Vocal geometry, fp16 tensor-core path), checked through
     size-independent properties: stem arithmetic is linear (vocal + instrumental == mono mix, backends.py:389-406
     and the uniform overlap average of enhanced_vocal_separator.py:423-458), the overlap weights equal the
     planner's effective-region counts, and the run is deterministic."""
     from audio_cut_b200 import synth, unet_weights as uw
-    from audio_cut_b200._lib import AC_BF16
+    from audio_cut_b200._lib import AC_F16
     from oracle import planner
 
     sr = 44100
@@ -261,8 +310,8 @@ def test_full_size_track_properties(ops):
     assert len(bounds) == 32
     mix = torch.from_numpy(audio).cuda()
     geom = ops.mdx_geom(7680, 1024, 3072, 256)
-    v, i, w = ops.separate_track(net, mix, bounds, geom, dtype=AC_BF16)
-    v2, i2, _ = ops.separate_track(net, mix, bounds, geom, dtype=AC_BF16)
+    v, i, w = ops.separate_track(net, mix, bounds, geom, dtype=AC_F16)
+    v2, i2, _ = ops.separate_track(net, mix, bounds, geom, dtype=AC_F16)
     assert _tc_aborted() == 0
     assert torch.equal(v, v2) and torch.equal(i, i2)
     wref = np.zeros(total, np.float32)
@@ -310,29 +359,31 @@ def _tc_aborted():
     return _lib.load().ac_debug_tc_aborted()
 
 
+@pytest.mark.parametrize("name,dtype,tdtype", H16)
 @pytest.mark.parametrize("dim_f,dim_t,g,B", [(256, 32, 16, 2), (512, 64, 48, 1), (512, 32, 32, 2)])
-def test_unet_tcgen05_matches_simt(ops, dim_f, dim_t, g, B):
-    """Same bf16 storage, same fp32 accumulation: tensor-core layers vs the CUDA-core kernels."""
+def test_unet_tcgen05_matches_simt(ops, dim_f, dim_t, g, B, name, dtype, tdtype):
+    """Same 16-bit storage, same fp32 accumulation: tensor-core layers vs the CUDA-core kernels."""
     net, x, ref = _unet_case(ops, dim_f, dim_t, g, B)
-    xin = ops.onnx_to_tfc(x.cuda()).bfloat16()
+    xin = ops.onnx_to_tfc(x.cuda()).to(tdtype)
     net.set_debug(True)
     simt = net.forward(xin).float().cpu().numpy()
     net.set_debug(False)
     tc = net.forward(xin).float().cpu().numpy()
     assert _tc_aborted() == 0, "a tcgen05 kernel hit its mbarrier watchdog"
     s = sdr_db(simt, tc)
-    assert s > 40, s
+    assert s > (58 if name == "fp16" else 40), s
     s_ref = sdr_db(ops.onnx_to_tfc(ref).numpy(), tc)
-    assert s_ref > 30, s_ref
+    assert s_ref > (50 if name == "fp16" else 32), s_ref
 
 
+@pytest.mark.parametrize("name,dtype,tdtype", H16)
 @pytest.mark.parametrize("C,T,F,impls", [(48, 24, 640, (2, 3)), (96, 16, 512, (2, 3)), (144, 12, 384, (1, 4)), (192, 8, 256, (1, 4))])
-def test_conv3x3_variants_match_cuda_core_layer(ops, C, T, F, impls):
-    """Layer-level check of every tcgen05 3x3-conv kernel against the CUDA-core implicit GEMM (same bf16
+def test_conv3x3_variants_match_cuda_core_layer(ops, C, T, F, impls, name, dtype, tdtype):
+    """Layer-level check of every tcgen05 3x3-conv kernel against the CUDA-core implicit GEMM (same 16-bit
     inputs, fp32 accumulation): 1 streaming, 2 weight-stationary, 3 row-stacked (C=48) / CTA pair (C=96),
     4 CTA-pair streaming."""
     rng = np.random.default_rng(C)
-    x = torch.randn(3, T, F, C, device="cuda").bfloat16()
+    x = torch.randn(3, T, F, C, device="cuda").to(tdtype)
     w = (rng.standard_normal((C, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32)
     scale = torch.rand(C, device="cuda") + 0.5
     shift = torch.randn(C, device="cuda") * 0.1
@@ -341,15 +392,17 @@ def test_conv3x3_variants_match_cuda_core_layer(ops, C, T, F, impls):
         y, _ = ops.debug_conv3x3(x, w, scale, shift, impl)
         assert _tc_aborted() == 0
         s = sdr_db(ref.float().cpu().numpy(), y.float().cpu().numpy())
-        assert s > 60, (impl, s)
+        assert s > (75 if name == "fp16" else 60), (impl, s)
 
 
-def test_unet_tcgen05_full_geometry(ops):
+@pytest.mark.parametrize("name,dtype,tdtype", H16)
+def test_unet_tcgen05_full_geometry(ops, name, dtype, tdtype):
+    """The network alone at Kim_Vocal geometry on a white-noise spectrogram: fp16 63 dB, bf16 45 dB measured."""
     net, x, ref = _unet_case(ops, 3072, 256, 48, 1)
-    tc = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()).bfloat16())).float().cpu()
+    tc = ops.tfc_to_onnx(net.forward(ops.onnx_to_tfc(x.cuda()).to(tdtype))).float().cpu()
     assert _tc_aborted() == 0
     s = sdr_db(ref.numpy(), tc.numpy())
-    assert s > 30, s
+    assert s > (58 if name == "fp16" else 40), s
 
 
 def test_tempogram_stats_match_host_reference(ops):
@@ -427,9 +480,11 @@ def test_lpc_formants_match_oracle(ops):
     r_mags, r_counts = OF.lpc_formant_frames(y, SR, int(0.025 * SR), 441, 12)
     assert mags.shape == r_mags.shape == (len(range(0, len(y) - int(0.025 * SR), 441)), 3)
     same = counts == r_counts
-    assert same.mean() > 0.98, same.mean()
-    # Burg in fp64 on both sides; the 512-point response is fp32 on the GPU
-    np.testing.assert_allclose(mags[same], r_mags[same], rtol=2e-3, atol=1e-5)
+    print("lpc: peak counts equal in", same.mean(), "of", same.size, "frames; max rel magnitude error",
+          float(np.max(np.abs(mags[same] - r_mags[same]) / np.maximum(np.abs(r_mags[same]), 1e-12))))
+    # Burg recursion AND the 512-point response in fp64 on both sides (north_star: features within 1e-4 relative)
+    assert same.all(), np.nonzero(~same)[0][:10]
+    np.testing.assert_allclose(mags, r_mags, rtol=1e-4, atol=1e-7)
     # ragged track reconstruction follows the reference's append rule
     tr = ops.formant_tracks(mags, counts)
     assert len(tr[0]) >= len(tr[1]) >= len(tr[2])

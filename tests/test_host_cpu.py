@@ -226,3 +226,106 @@ def test_refine_host_logic_matches_oracle():
     times = [0.2, 0.49, 0.5, 0.51, 3.0, 3.4, 5.0, 9.6, 9.5, 9.51]
     assert R._filter_cut_times(times, duration_s=10.0, min_gap_s=1.0, min_boundary_s=0.5) == [0.51, 3.0, 5.0]
     assert R._filter_cut_times(times, duration_s=0.0, min_gap_s=1.0, min_boundary_s=0.5) == []
+
+
+# --------------------------------------------------------------------------- model files / drop-in hygiene
+def _export_onnx(net, x, path):
+    """torch's TorchScript ONNX exporter writes the protobuf itself; only its onnxscript post-pass imports `onnx`."""
+    import importlib
+    import warnings
+
+    import torch
+
+    mod = importlib.import_module("torch.onnx._internal.torchscript_exporter.onnx_proto_utils")
+    mod._add_onnxscript_fn = lambda proto, opsets: proto
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.onnx.export(net, (x,), path, input_names=["input"], output_names=["output"],
+                          dynamic_axes={"input": {0: "batch"}, "output": {0: "batch"}}, dynamo=False, opset_version=13)
+
+
+def test_onnx_model_file_is_read_like_the_reference_session(tmp_path):
+    """The reference hands a .onnx to onnxruntime (backends.py:137-181, 216-253); here the initializers are read straight
+    out of the protobuf and mapped onto the TFC-TDF parameter names.  A real ONNX file is produced with torch's exporter
+    (BatchNorm folded into the convolutions, as in Kim_Vocal_1.onnx) and must give the same network."""
+    import torch
+
+    from audio_cut_b200 import onnx_weights as ow
+    from audio_cut_b200 import unet_weights as uw
+    from oracle import unet as ounet
+
+    try:
+        import importlib
+
+        importlib.import_module("torch.onnx._internal.torchscript_exporter.onnx_proto_utils")
+    except Exception:
+        pytest.skip("this torch build has no TorchScript ONNX exporter")
+    geo = uw.UNetGeometry(dim_f=128, dim_t=32, g=16, n=2, l=2, bn=4)
+    st = uw.random_state(geo, gains=[])
+    net = ounet.build_net(st, geo.dim_f, geo.dim_t, geo.g, L=2 * geo.n + 1, l=geo.l, bn=geo.bn)
+    x = torch.randn(2, 4, geo.dim_f, geo.dim_t, generator=torch.Generator().manual_seed(0))
+    path = str(tmp_path / "Kim_Vocal_1.onnx")
+    _export_onnx(net, x, path)
+    nodes, inits = ow.read_onnx(path)
+    assert sum(n["op"] == "Conv" for n in nodes) == 1 + (2 * geo.n + 1) * geo.l + geo.n + 1
+    st2, geo2 = ow.load_onnx(path, dim_t=geo.dim_t)
+    assert geo2 == geo
+    assert set(st2) == set(uw.param_shapes(geo))
+    net2 = ounet.build_net(st2, geo.dim_f, geo.dim_t, geo.g, L=2 * geo.n + 1, l=geo.l, bn=geo.bn)
+    with torch.no_grad():
+        a, b = net(x), net2(x)
+    assert float((a - b).abs().max()) < 1e-5 * max(1.0, float(a.abs().max()))
+    # the packed blob the C ABI takes is the same function too (BN folded either by the exporter or by pack_blob)
+    assert uw.pack_blob(st2, geo).shape == uw.pack_blob(st, geo).shape
+    # a file that is not this architecture is rejected loudly
+    bad = tmp_path / "bad.onnx"
+    bad.write_bytes(b"\\x08\\x07")
+    with pytest.raises(ValueError):
+        ow.load_onnx(str(bad))
+
+
+def test_chunk_vad_adapter_matches_reference_semantics():
+    """B200ChunkVAD vs a hand-computed timeline: halo clipping, the straddling-left-edge rule, 120 ms merge, focus windows
+    (silero_chunk_vad.py:56-116, 118-188)."""
+    from audio_cut_b200.chunk_vad import B200ChunkVAD
+    from audio_cut_b200.gpu_pipeline import chunk_schedule
+
+    sr = 1000
+    plans = chunk_schedule(25.0, chunk_s=10.0, overlap_s=2.5, halo_s=0.5)
+    stamps = {0: [{"start": 1000, "end": 2000}, {"start": 9200, "end": 9900}],          # second one crosses eff_end 9.5
+              1: [{"start": 100, "end": 900}, {"start": 1900, "end": 1950}, {"start": 5000, "end": 5000}],
+              2: [{"start": 0, "end": 300}, {"start": 9900, "end": 10000}]}
+    vad = B200ChunkVAD(sr, inference_fn=None)
+    calls = []
+    for p in plans:
+        vad.inference_fn = lambda x, i=p.index: (calls.append(i), stamps.get(i, []))[1]
+        vad.process_chunk(p, np.zeros(int((p.end_s - p.start_s) * sr), np.float32), sr)
+    segs = vad.finalize()
+    # chunk 0: [1,2], [9.2,9.5]; chunk 1 (start 7.5, eff 8.0-17.0): [7.6,8.4] straddles the left edge -> keeps 7.6; [9.4,9.45] merges
+    # with [9.2,9.5]; chunk 2 (start 15, eff 15.5-25): [15,15.3] lies before its effective region -> dropped; [24.9,25.0]
+    got = [(round(s["start"], 6), round(s["end"], 6)) for s in segs]
+    assert got == [(1.0, 2.0), (7.6, 8.4), (9.2, 9.5), (24.9, 25.0)], got
+    assert all(abs(s["duration"] - (s["end"] - s["start"])) < 1e-12 for s in segs)
+    wins = vad.to_focus_windows(pad_s=0.5)
+    assert [(round(a, 6), round(b, 6)) for a, b in wins] == [(0.5, 2.5), (7.1, 10.0), (24.4, 25.0)]
+    with pytest.raises(ValueError):
+        vad.process_chunk(plans[0], np.zeros(10, np.float32), sr + 1)
+
+
+def test_separator_without_model_raises_like_the_reference(tmp_path, monkeypatch):
+    """enhanced_vocal_separator.py:136-137 / backends.py:154-160: no model file -> the constructor raises.  There is no
+    silent random-weight network and the default n_fft is the reference's 6144 (backends.py:264)."""
+    from audio_cut_b200.backends import B200Mdx23Backend
+    from audio_cut_b200.separator import B200VocalSeparator
+
+    monkeypatch.setenv("MDX23_MODELS_PATH", str(tmp_path))
+    monkeypatch.delenv("MDX23_N_FFT", raising=False)
+    with pytest.raises(RuntimeError, match="no usable separation backend"):
+        B200VocalSeparator(44100)
+    be = B200Mdx23Backend(str(tmp_path))
+    assert be.geom.n_fft == 6144 and be.align_hop == 4096
+    with pytest.raises(FileNotFoundError):
+        be.load_model()
+    monkeypatch.setenv("MDX23_MODEL_FILENAME", "Kim_Vocal_1.onnx")
+    with pytest.raises(FileNotFoundError, match="Kim_Vocal_1.onnx"):
+        B200Mdx23Backend(str(tmp_path)).load_model()
