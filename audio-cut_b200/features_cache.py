@@ -92,35 +92,63 @@ def compute_mdd_series(rms, flatness, onset_strength, weights=MDD_WEIGHTS) -> np
 
 
 def classify_bpm(bpm: float) -> str:
-    """adaptive_vad_enhancer.py:_classify_music_by_bpm categories (slow/medium/fast/very_fast)."""
-    if bpm < 80:
-        return "slow"
-    if bpm < 120:
-        return "medium"
-    if bpm < 160:
-        return "fast"
-    return "very_fast"
+    """BPMAnalyzer._classify_music_by_bpm (adaptive_vad_enhancer.py:170-186)."""
+    for name, lo, hi in (("slow", 50, 80), ("medium", 80, 120), ("fast", 120, 160), ("very_fast", 160, 200)):
+        if lo <= bpm < hi:
+            return name
+    return "very_slow" if bpm < 50 else "extreme_fast"
+
+
+# vocal_pause_splitting.bpm_adaptive_settings.pause_duration_multipliers.{slow,medium,fast}_song_multiplier defaults
+# (adaptive_vad_enhancer.py:204-228); a host that carries the reference's ConfigManager passes its own values
+PAUSE_MULTIPLIERS = (1.5, 1.0, 0.7)
+
+
+def bpm_adaptive_factors(bpm: float, stability: float, variance: float, multipliers=PAUSE_MULTIPLIERS) -> Dict:
+    """BPMAnalyzer._calculate_bpm_adaptive_factors / _calculate_analysis_window_size (adaptive_vad_enhancer.py:188-270)."""
+    slow_m, medium_m, fast_m = multipliers
+    if bpm < 70:
+        f = {"threshold_modifier": -0.05, "min_pause_modifier": slow_m, "min_speech_modifier": 1.2, "sensitivity": "high"}
+    elif bpm < 100:
+        f = {"threshold_modifier": 0.0, "min_pause_modifier": medium_m, "min_speech_modifier": 1.0, "sensitivity": "medium"}
+    elif bpm < 140:
+        f = {"threshold_modifier": 0.1, "min_pause_modifier": fast_m, "min_speech_modifier": 0.8, "sensitivity": "low"}
+    else:
+        f = {"threshold_modifier": 0.15, "min_pause_modifier": fast_m, "min_speech_modifier": 0.6, "sensitivity": "very_low"}
+    f["threshold_modifier"] += (1.0 - stability) * 0.1
+    f["threshold_modifier"] += variance * 0.05
+    window = 12.0 if bpm < 70 else (10.0 if bpm < 120 else 8.0)
+    f.update({"bpm_value": bpm, "stability_score": stability, "variance_score": variance, "recommended_window_size": window,
+              "beat_sync_important": bpm > 100})
+    return f
 
 
 def bpm_features_from_wave(wave_dev: torch.Tensor, sr: int) -> BPMFeatures:
     """BPMAnalyzer.extract_bpm_features (adaptive_vad_enhancer.py:48-168): onset envelope at hop 512
-    with the MEDIAN aggregate on the GPU, tempogram / DP beat tracker on the host."""
+    with the MEDIAN aggregate on the GPU (:61-67 via beat_track(y=...), :143-148), tempogram on the GPU, the DP beat
+    tracker as a C++ host scan."""
     hop = 512
     n = wave_dev.numel()
     total = 1 + n // hop
     env_d = ops.stft_features(wave_dev, [(0, n, 0)], hop, sr, total_frames=total, want=("onset_median",))["onset_median"]
     curve, bpm, _ = ops.tempogram_stats(env_d, sr, hop, start_bpm=120.0)
     env = env_d.cpu().numpy()
-    if not env.any():
-        return BPMFeatures(120.0, "medium", 0.5, 0.5, 0.1, {}, np.zeros(0, dtype=int))
-    bpm, beats = host_dsp.beat_track(env, sr, hop, start_bpm=120.0, tightness=100.0, bpm=bpm, dp=ops.host_beat_dp)
-    if len(beats) >= 3:
+    if not env.any():  # librosa.beat.beat_track: no onsets -> (0.0, [])
+        bpm, beats = 0.0, np.zeros(0, dtype=int)
+    else:
+        bpm, beats = host_dsp.beat_track(env, sr, hop, start_bpm=120.0, tightness=100.0, bpm=bpm, dp=ops.host_beat_dp)
+    if len(beats) >= 3:  # _calculate_beat_stability (:99-126)
         iv = np.diff(beats)
-        stability = float(np.clip(1.0 - np.std(iv) / np.mean(iv), 0.0, 1.0)) if np.mean(iv) > 0 else 0.5
+        stability = float(np.clip(1.0 - np.std(iv) / np.mean(iv), 0.0, 1.0)) if np.mean(iv) != 0 else 0.5
     else:
         stability = 0.5
-    variance = float(np.clip(np.std(curve) / (np.mean(curve) + 1e-8), 0.0, 1.0)) if len(curve) > 1 else 0.1
-    return BPMFeatures(float(bpm), classify_bpm(float(bpm)), stability, 0.8, variance, {}, beats)
+    if len(curve) > 1:  # _calculate_tempo_variance (:128-168)
+        c = np.asarray(curve, dtype=np.float64)
+        variance = float(np.clip(float(np.std(c)) / (float(np.mean(c)) + 1e-8), 0.0, 1.0))
+    else:
+        variance = 0.1
+    bpm = float(bpm)
+    return BPMFeatures(bpm, classify_bpm(bpm), stability, 0.8, variance, bpm_adaptive_factors(bpm, stability, variance), beats)
 
 
 class B200ChunkFeatureBuilder:

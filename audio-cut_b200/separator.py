@@ -206,7 +206,7 @@ class B200VocalSeparator:
     def __init__(self, sample_rate: int = 44100, *, backend: Optional[B200Mdx23Backend] = None,
                  pipeline_config: Optional[PipelineConfig] = None,
                  vad_fn: Optional[Callable[[object, np.ndarray, int], List[Dict[str, float]]]] = None,
-                 chunk_vad=None, marker_threshold_db: float = -50.0):
+                 chunk_vad=None, marker_threshold_db: float = -50.0, pure_music_min_s: float = 0.0):
         self.sample_rate = sample_rate
         self._pipeline_cfg = pipeline_config or PipelineConfig()
         if backend is None:
@@ -224,7 +224,10 @@ class B200VocalSeparator:
         # chunk_vad: a FACTORY ``(sample_rate) -> object with process_chunk(plan, vocal_chunk, sr) / finalize()`` (one
         # instance per track, like SileroChunkVAD at enhanced_vocal_separator.py:329-333), e.g. chunk_vad.B200ChunkVAD
         self._chunk_vad_factory = chunk_vad
+        # quality_control.segment_vocal_threshold_db / quality_control.pure_music_min_duration of the reference's config
+        # (vocal_separator.py:471-472); a host that carries the reference's ConfigManager passes get_config(...) here
         self._marker_threshold_db = marker_threshold_db
+        self._pure_music_min_s = float(pure_music_min_s)
         self.enable_fallback = False
         self.backend_pref = "mdx23"
         # stems are returned as numpy views of page-locked memory (no pinned -> pageable copy after the D2H);
@@ -370,7 +373,8 @@ class B200VocalSeparator:
             parallel_copy(vocal, v.pin_out_np[0])
             if instrumental is not None:
                 parallel_copy(instrumental, v.pin_out_np[1])
-        markers = vocal_presence_markers_from_rms(mark.pin.numpy()[:n_mark].copy(), total, sr, hop, self._marker_threshold_db)
+        markers = vocal_presence_markers_from_rms(mark.pin.numpy()[:n_mark].copy(), total, sr, hop, self._marker_threshold_db,
+                                                  self._pure_music_min_s)
         self._last_device = (v.mono, v.vocal, v.instr if any_instr else None)
         self._energies = (float(stats[0]) / max(total, 1), float(stats[1]) / max(total, 1) if any_instr else None,
                           float(stats[2]) / max(total, 1))

@@ -65,3 +65,46 @@ def synth_track(seconds: float, *, sr: int = SR, seed: int = 0, stereo: bool = T
     right = np.zeros(n)
     right[3:] = 0.9 * left[:-3]
     return np.stack([left, right]).astype(np.float32)
+
+
+def synth_song(seconds: float, *, sr: int = SR, seed: int = 0) -> np.ndarray:
+    """Mono "song" with phrase structure for the cut-point chain: sung phrases of 1.5-4 s separated by
+    rests of 0.3-1.4 s (the accompaniment drops out in every third rest), a quiet noise bed and a 96 BPM click track.
+    float32, shape (N,), peak 0.5."""
+    n = int(round(seconds * sr))
+    rng = np.random.default_rng(1000 + seed)
+    t = np.arange(n, dtype=np.float64) / sr
+    f0 = 196.0 * 2.0 ** (np.sin(2 * np.pi * 0.07 * t + seed) * 0.3)
+    phase = 2 * np.pi * np.cumsum(f0 * (1.0 + 0.008 * np.sin(2 * np.pi * 5.2 * t))) / sr
+    voc = np.zeros(n)
+    for k in range(1, 9):
+        voc += np.sin(k * phase + rng.uniform(0, 2 * np.pi)) / k**1.1
+    gate = np.zeros(n)
+    acc = np.ones(n)
+    pos, idx = int(0.4 * sr), 0
+    while pos < n:
+        ln = int(rng.uniform(1.5, 4.0) * sr)
+        gate[pos : pos + ln] = rng.uniform(0.6, 1.0)
+        rest = int(rng.uniform(0.3, 1.4) * sr)
+        if idx % 3 == 2:
+            acc[pos + ln : pos + ln + rest] = 0.05
+        pos += ln + rest
+        idx += 1
+    ramp = int(0.015 * sr)
+    kern = np.hanning(2 * ramp + 1)
+    kern /= kern.sum()
+    gate = np.convolve(gate, kern, mode="same")
+    acc = np.convolve(acc, kern, mode="same")
+    noise = rng.standard_normal(n)
+    noise = np.convolve(noise, np.ones(8) / 8.0, mode="same")
+    clicks = np.zeros(n)
+    bl = int(0.03 * sr)
+    bt = np.arange(bl) / sr
+    burst = np.sin(2 * np.pi * 800.0 * bt) * np.exp(-bt / 0.006)
+    for p0 in range(0, n, int(0.625 * sr)):
+        seg = min(bl, n - p0)
+        clicks[p0 : p0 + seg] += burst[:seg]
+    mix = 0.7 * voc * gate / (np.max(np.abs(voc)) + 1e-12) + acc * (0.02 * noise / (np.max(np.abs(noise)) + 1e-12) + 0.08 * clicks)
+    mix = mix + 2e-4 * rng.standard_normal(n)
+    mix *= 0.5 / (np.max(np.abs(mix)) + 1e-12)
+    return mix.astype(np.float32)

@@ -9,6 +9,10 @@ What is executed unmodified from /root/reference:
   * ``audio_cut.separation.backends.MDX23OnnxBackend.infer_chunk``       -> infer_chunk.npz
   * ``EnhancedVocalSeparator._separate_with_pipeline`` and, inside it,
     ``ChunkFeatureBuilder.add_chunk/finalize`` + ``_compute_mdd_series`` -> pipeline.npz
+  * ``BPMAnalyzer.extract_bpm_features`` (``--rhythm``)                  -> rhythm.json
+  * the whole cut-point chain of ``v2.2_mdd`` (``--cutchain``): separator driver, feature builder, presence markers,
+    ``PureVocalPauseDetector.detect_pure_vocal_pauses``, ``SeamlessSplitter._find_no_vocal_runs`` /
+    ``_finalize_and_filter_cuts_v2``, ``finalize_cut_points``            -> cutchain.json
 
 Third-party pieces that are absent from the image are stubbed, and the stubs are
 NOT the thing being pinned: ``onnxruntime`` -> a fake session computing a fixed linear
@@ -37,9 +41,10 @@ sys.path.insert(0, os.path.join(REF, "src"))
 
 from oracle import features as OF  # noqa: E402
 from oracle import mdx as OM  # noqa: E402
+from oracle import rhythm as ORH  # noqa: E402
 
 
-def install_librosa_shim():
+def install_librosa_shim(full_rhythm: bool = False):
     lib = types.ModuleType("librosa")
     feat = types.ModuleType("librosa.feature")
     rhythm = types.ModuleType("librosa.feature.rhythm")
@@ -52,19 +57,35 @@ def install_librosa_shim():
     )
     onset.onset_detect = lambda onset_envelope=None, sr=22050, hop_length=512, **k: OF.onset_detect(onset_envelope, sr, hop_length)
     lib.frames_to_time = lambda frames, sr=22050, hop_length=512, **k: np.asarray(frames) * hop_length / float(sr)
-    rhythm.tempo = lambda onset_envelope=None, **k: np.full(len(onset_envelope), 120.0)
+    if not full_rhythm:  # the round-1 fixtures (pipeline.npz) were generated with these placeholders
+        rhythm.tempo = lambda onset_envelope=None, **k: np.full(len(onset_envelope), 120.0)
 
-    def beat_track(y=None, onset_envelope=None, **k):
-        if y is not None:
-            raise RuntimeError("shim: beat_track(y=...) not provided")  # BPMAnalyzer falls back to defaults
-        return 120.0, np.zeros(0, dtype=int)
+        def beat_track(y=None, onset_envelope=None, **k):
+            if y is not None:
+                raise RuntimeError("shim: beat_track(y=...) not provided")  # BPMAnalyzer falls back to defaults
+            return 120.0, np.zeros(0, dtype=int)
+    else:
+        def _tempo(onset_envelope=None, sr=22050, hop_length=512, aggregate=np.mean, start_bpm=120.0, **k):
+            return ORH.tempo(onset_envelope, sr, hop_length, start_bpm=start_bpm, aggregate=None if aggregate is None else "mean")
+
+        rhythm.tempo = _tempo
+
+        def beat_track(y=None, onset_envelope=None, sr=22050, hop_length=512, start_bpm=120.0, tightness=100, **k):
+            return ORH.beat_track(onset_envelope, sr, hop_length, y=y, start_bpm=start_bpm, tightness=float(tightness))
 
     beat.beat_track = beat_track
     feat.rhythm = rhythm
     lib.feature, lib.onset, lib.beat = feat, onset, beat
     lib.load = None
+    lib.resample = None
     for m in (lib, feat, rhythm, onset, beat):
         sys.modules[m.__name__] = m
+    # the orchestrator module imports its I/O libraries at module level; nothing here calls them
+    for name in ("soundfile", "pydub"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["pydub"], "AudioSegment"):
+        sys.modules["pydub"].AudioSegment = object
 
 
 def gen_chunk_schedule():
@@ -177,8 +198,186 @@ def gen_pipeline():
     print("pipeline.npz", vocal.shape, cache.rms_series.shape, cache.onset_frames, ctx.gpu_meta)
 
 
+def gen_rhythm():
+    """BPMAnalyzer.extract_bpm_features of the REFERENCE (adaptive_vad_enhancer.py:48-298, unmodified) on top of the shim
+    whose librosa.beat / librosa.feature.rhythm forward to oracle.rhythm: pins the classification, stability, variance
+    and adaptive-factor arithmetic (the librosa algorithms themselves stay 'parity unpinned', see oracle/rhythm.py)."""
+    install_librosa_shim(full_rhythm=True)
+    from vocal_smart_splitter.core.adaptive_vad_enhancer import BPMAnalyzer
+
+    sys.path.insert(0, ROOT)
+    from audio_cut_b200 import synth
+
+    cases = []
+    sr = 44100
+    for tag, audio in (("track20", synth.synth_track(20.0, seed=2, stereo=False)), ("song24", synth.synth_song(24.0, seed=1)),
+                       ("clicks150", _click_wave(16.0, 150.0, sr)), ("clicks72", _click_wave(20.0, 72.0, sr)), ("silence", np.zeros(sr * 6, np.float32))):
+        bf = BPMAnalyzer(sr).extract_bpm_features(audio)
+        cases.append({"tag": tag, "main_bpm": float(np.squeeze(bf.main_bpm)), "bpm_category": bf.bpm_category,
+                      "beat_strength": float(bf.beat_strength), "bpm_confidence": float(bf.bpm_confidence),
+                      "tempo_variance": float(bf.tempo_variance),
+                      "adaptive_factors": {k: (float(v) if isinstance(v, (int, float, np.floating)) and not isinstance(v, bool) else v)
+                                           for k, v in (bf.adaptive_factors or {}).items()},
+                      "beat_positions": [int(b) for b in np.asarray(bf.beat_positions).ravel()]})
+    with open(os.path.join(HERE, "rhythm.json"), "w") as f:
+        json.dump(cases, f, indent=0)
+    print("rhythm.json", [(c["tag"], round(c["main_bpm"], 2), c["bpm_category"], len(c["beat_positions"])) for c in cases])
+
+
+def _click_wave(seconds, bpm, sr):
+    n = int(seconds * sr)
+    x = np.zeros(n, np.float32)
+    bl = int(0.02 * sr)
+    burst = (np.sin(2 * np.pi * 1000.0 * np.arange(bl) / sr) * np.exp(-np.arange(bl) / (0.004 * sr))).astype(np.float32)
+    step = 60.0 / bpm * sr
+    k = 0
+    while int(k * step) + bl < n:
+        p = int(k * step)
+        x[p:p + bl] += burst
+        k += 1
+    return x + 1e-4 * np.random.default_rng(5).standard_normal(n).astype(np.float32)
+
+
+CUTCHAIN_SECONDS = 40.0
+CUTCHAIN_N_FFT = 6144  # the reference hard-codes it (backends.py:264)
+
+
+def gen_cutchain(small: bool = False):
+    """SURVEY.md X1 fixture (``small``: the backend is a fixed linear map instead of the network, so that the CPU-only test
+    suite can rebuild the stems in no time - what that variant pins is the restated detector chain, not the separation): the reference's OWN chain - EnhancedVocalSeparator._separate_with_pipeline (oracle network as the
+    backend, Kim_Vocal geometry) -> ChunkFeatureBuilder -> VocalSeparator._compute_vocal_presence_markers ->
+    PureVocalPauseDetector.detect_pure_vocal_pauses -> candidate assembly of _process_pure_vocal_split ->
+    SeamlessSplitter._finalize_and_filter_cuts_v2 / finalize_cut_points - all unmodified, on the oracle-backed librosa shim.
+    Every configuration value the chain reads is recorded.  The stems themselves are not stored (tests recompute them with
+    the oracle from the seeded input); their checksums are."""
+    install_librosa_shim(full_rhythm=True)
+    import logging
+
+    logging.disable(logging.CRITICAL)
+    from audio_cut.separation.backends import IVocalSeparatorBackend, SeparationOutputs
+    from audio_cut.utils.gpu_pipeline import PipelineConfig
+    from vocal_smart_splitter.core import enhanced_vocal_separator as evs
+    from vocal_smart_splitter.core import pure_vocal_pause_detector as pv
+    from vocal_smart_splitter.core import seamless_splitter as ss
+    from vocal_smart_splitter.core.vocal_separator import VocalSeparator
+    from vocal_smart_splitter.utils import config_manager as cm
+
+    from audio_cut_b200 import synth, unet_weights as uw
+    from oracle import unet as ounet
+
+    recorded = {}
+    real_get = cm.get_config
+
+    def spy(key, default=None):
+        val = real_get(key, default)
+        recorded[key] = val
+        return val
+
+    for mod in (cm, pv, ss, evs):
+        if hasattr(mod, "get_config"):
+            mod.get_config = spy
+    import vocal_smart_splitter.core.vocal_separator as vsm
+    import vocal_smart_splitter.core.vocal_pause_detector as vpd
+
+    for mod in (vsm, vpd):
+        if hasattr(mod, "get_config"):
+            mod.get_config = spy
+
+    sr = 44100
+    seconds = 48.0 if small else CUTCHAIN_SECONDS
+    audio = synth.synth_song(seconds, sr=sr, seed=3 if small else 0)
+    geo = uw.UNetGeometry()
+    net = None if small else ounet.build_net(uw.random_state(geo), geo.dim_f, geo.dim_t, geo.g)
+    mg = OM.MdxGeometry(CUTCHAIN_N_FFT, 1024, 3072, 256)
+    align_hop = 4096
+
+    class OracleBackend(IVocalSeparatorBackend):
+        def load_model(self):
+            pass
+
+        def sample_rate(self):
+            return sr
+
+        def infer_chunk(self, mix_chunk, **kw):
+            if small:  # tests/helpers.py:linear_backend is the same map
+                v = (np.float32(0.7) * mix_chunk).astype(np.float32)
+                return SeparationOutputs(vocal=v, instrumental=(mix_chunk - v).astype(np.float32))
+            v, i = OM.infer_chunk(mix_chunk, net, mg, align_hop=align_hop)
+            return SeparationOutputs(vocal=v, instrumental=i)
+
+    sep = object.__new__(evs.EnhancedVocalSeparator)
+    sep.sample_rate = sr
+    sep._pipeline_cfg = PipelineConfig(enable=False)
+    ctx = sep._build_cpu_context(len(audio) / float(sr))
+    vocal, instr, cache, vad = sep._separate_with_pipeline(audio, OracleBackend(), ctx)
+    markers = VocalSeparator(sr)._compute_vocal_presence_markers(vocal)
+    det = pv.PureVocalPauseDetector(sr)
+    pauses = det.detect_pure_vocal_pauses(vocal, enable_mdd_enhancement=True, original_audio=audio, feature_cache=cache, vad_segments=vad)
+    assert not det._last_focus_windows, "the restated chain assumes no Silero model (empty focus windows)"
+    cands = [(float(p.cut_point), float(p.confidence)) for p in pauses]
+    fake = types.SimpleNamespace(sample_rate=sr, _set_guard_adjustments=lambda a: None)
+    min_pure = float(spy("quality_control.pure_music_min_duration", 0.0))
+    spans = ss.SeamlessSplitter._find_no_vocal_runs(fake, vocal, min_pure) if min_pure > 0 else []
+    for a, b in spans:
+        cands += [(float(a), 1.0), (float(b), 1.0)]
+    marker_times = [float(t) for t in markers.get("vocal_presence_cut_points_sec", [])]
+    duration = len(audio) / sr
+    protected = set()
+    for t in marker_times:
+        if t <= 0.0 or t >= duration:
+            continue
+        cands.append((t, 1.0))
+        protected.add(int(round(t * sr)))
+    res = ss.SeamlessSplitter._finalize_and_filter_cuts_v2(fake, list(cands), audio, pure_vocal_audio=vocal)
+    final = set(int(b) for b in res.sample_boundaries)
+    for s_ in protected:
+        s_ = int(min(max(s_, 0), len(audio)))
+        if s_ not in (0, len(audio)):
+            final.add(s_)
+
+    def js(v):
+        if isinstance(v, dict):
+            return {k: js(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [js(x) for x in v]
+        if isinstance(v, (np.floating, np.integer)):
+            return v.item()
+        return v
+
+    bf = cache.bpm_features
+    out = {
+        "seconds": seconds, "n_fft": mg.n_fft, "hop": mg.hop, "dim_f": mg.dim_f, "dim_t": mg.dim_t, "g": geo.g, "align_hop": align_hop,
+        "song_seed": 3 if small else 0, "sr": sr, "n_chunks": len(ctx.plans),
+        "config": js(recorded),
+        "vocal_sum": repr(float(np.sum(vocal.astype(np.float64)))), "vocal_abs_sum": repr(float(np.sum(np.abs(vocal.astype(np.float64))))),
+        "cache": {"global_mdd": repr(float(cache.global_mdd)), "main_bpm": repr(float(np.squeeze(bf.main_bpm))), "bpm_category": bf.bpm_category,
+                  "rms_max": repr(float(cache.rms_max)), "onset_max": repr(float(cache.onset_max)), "n_frames": int(cache.frame_count()),
+                  "onset_frames": [int(x) for x in cache.onset_frames], "beat_times": [repr(float(x)) for x in np.asarray(cache.beat_times)]},
+        "marker_times": [repr(t) for t in marker_times],
+        "pauses": [[repr(float(p.start_time)), repr(float(p.end_time)), repr(float(p.cut_point)), repr(float(p.confidence)), p.quality_grade, p.pause_type]
+                   for p in pauses],
+        "pure_music_spans": [[repr(float(a)), repr(float(b))] for a, b in spans],
+        "candidates": [[repr(t), repr(s)] for t, s in cands],
+        "refined_boundaries": [int(b) for b in res.sample_boundaries],
+        "final_times": [repr(float(p.t)) for p in res.final_points],
+        "adjustments": [[repr(float(a.raw_time)), repr(float(a.guard_time)), repr(float(a.final_time))] for a in res.adjustments],
+        "sample_boundaries": sorted(final),
+    }
+    name = "cutchain_small.json" if small else "cutchain.json"
+    with open(os.path.join(HERE, name), "w") as f:
+        json.dump(out, f, indent=0)
+    print(name, ": pauses", len(pauses), "candidates", len(cands), "spans", len(spans), "markers", marker_times,
+          "boundaries", out["sample_boundaries"], "config keys", len(recorded))
+
+
 def main():
-    torch.set_num_threads(4)
+    torch.set_num_threads(os.cpu_count() or 4)
+    if "--rhythm" in sys.argv:
+        return gen_rhythm()
+    if "--cutchain" in sys.argv:
+        return gen_cutchain()
+    if "--cutchain-small" in sys.argv:
+        return gen_cutchain(small=True)
     if "--cuts44k" in sys.argv:
         return gen_cuts_44k()
     if "--cuts" not in sys.argv:

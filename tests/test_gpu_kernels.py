@@ -405,9 +405,10 @@ def test_unet_tcgen05_full_geometry(ops, name, dtype, tdtype):
     assert s > (58 if name == "fp16" else 40), s
 
 
-def test_tempogram_stats_match_host_reference(ops):
-    """GPU tempogram (float32) vs the numpy restatement of librosa.feature.tempogram / rhythm.tempo."""
-    from audio_cut_b200 import host_dsp
+def test_tempogram_stats_match_oracle(ops):
+    """GPU tempogram / per-frame tempo / global tempo (float32) vs oracle.rhythm (the loop restatement of
+    librosa.feature.tempogram / rhythm.tempo, pinned by tests/test_oracle_golden.py) - rows A14 / N2."""
+    from oracle import rhythm as R
 
     for sr, hop, n, bpm_true in ((44100, 512, 5000, 100.0), (44100, 2205, 1203, 128.0)):
         period = 60.0 / bpm_true * sr / hop
@@ -416,13 +417,42 @@ def test_tempogram_stats_match_host_reference(ops):
             env[int(round(k * period))] = 1.0
         env += 0.05 * np.abs(np.random.default_rng(2).standard_normal(n)).astype(np.float32)
         win = int(np.floor(8.0 * sr / hop))
-        tg = host_dsp.tempogram(env, win)
-        ref_curve = host_dsp.tempo_from_tempogram(tg, sr, hop, aggregate=None)
-        ref_glob = host_dsp.tempo_from_tempogram(tg, sr, hop, aggregate="mean")[0]
+        tg = R.tempogram(env, win)
+        ref_curve = R.tempo(env, sr, hop, aggregate=None, tg=tg)
+        ref_glob = R.tempo(env, sr, hop, tg=tg)[0]
         curve, glob, tg_mean = ops.tempogram_stats(torch.from_numpy(env).cuda(), sr, hop)
         np.testing.assert_allclose(tg_mean, tg.mean(axis=1), rtol=0, atol=2e-5)
         assert glob == ref_glob
         assert np.mean(curve == ref_curve) > 0.995  # float32 vs float64 near-ties between adjacent lags
+
+
+def test_bpm_features_and_beats_match_oracle(ops):
+    """BPMAnalyzer.extract_bpm_features and the cache's tempo curve / beat times through the package (GPU onset envelope and
+    tempogram, C++ beat DP) vs oracle.rhythm on the same waveform: same BPM, class, beats, stability, variance, factors."""
+    from audio_cut_b200 import synth
+    from audio_cut_b200.features_cache import bpm_features_from_wave
+    from oracle import features as OF
+    from oracle import rhythm as R
+
+    for wave in (synth.synth_track(20.0, seed=2, stereo=False), synth.synth_song(24.0, seed=1)):
+        got = bpm_features_from_wave(torch.from_numpy(wave).cuda(), SR)
+        ref = R.extract_bpm_features(wave, SR)
+        assert got.main_bpm == ref.main_bpm and got.bpm_category == ref.bpm_category
+        assert [int(b) for b in got.beat_positions] == [int(b) for b in ref.beat_positions]
+        assert abs(got.beat_strength - ref.beat_strength) < 1e-9
+        assert abs(got.tempo_variance - ref.tempo_variance) < 2e-3  # per-frame argmax near-ties (float32 tempogram)
+        for k, v in ref.adaptive_factors.items():
+            g = got.adaptive_factors[k]
+            assert (abs(g - v) < 1e-3) if isinstance(v, float) else (g == v), k
+        # hop 2205 side (features_cache.py:283-294): beat_track on the cache's own onset envelope
+        env = OF.onset_strength(wave, SR, 2205)
+        curve, glob, _ = ops.tempogram_stats(torch.from_numpy(env).cuda(), SR, 2205)
+        assert glob == R.tempo(env, SR, 2205)[0]
+        from audio_cut_b200 import host_dsp
+
+        _, beats = host_dsp.beat_track(env, SR, 2205, bpm=glob, dp=ops.host_beat_dp)
+        _, ref_beats = R.beat_track(env, SR, 2205)
+        assert list(beats) == list(ref_beats)
 
 
 # --------------------------------------------------------------------------- pYIN / LPC formants (A17, A18)

@@ -3,7 +3,10 @@
 import json
 import os
 
+import sys
+
 import numpy as np
+import pytest
 import torch
 
 from oracle import mdx, pipeline, planner
@@ -167,3 +170,109 @@ def test_mel_db_matches_transformers_audio_utils():
         S = au.spectrogram(y.astype(np.float64), win, 2048, hop, power=2.0, center=True, pad_mode="constant", mel_filters=fb,
                            log_mel="dB", db_range=80.0, mel_floor=1e-10, dtype=np.float64)
         np.testing.assert_allclose(OF.mel_db(y, sr, 2048, hop, 128), S.T, rtol=0, atol=1e-5)
+
+
+# --------------------------------------------------------------------------- rhythm oracle (A14 / N2)
+def test_rhythm_oracle_autocorrelation_and_click_tracks():
+    from oracle import rhythm as R
+
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(160)
+    np.testing.assert_allclose(R.autocorrelate_direct(x), np.correlate(x, x, "full")[159:], rtol=0, atol=1e-12)
+    # the linear-ramp padding is numpy's
+    env = np.abs(rng.standard_normal(500))
+    tg = R.tempogram(env, 160)
+    assert tg.shape == (160, 500) and np.allclose(np.max(np.abs(tg), axis=0), 1.0)
+    # an impulse train with period P frames: tempo = 60 * sr / (hop * P), beats land on the impulses
+    sr, hop = 44100, 512
+    for period in (43, 36, 57):
+        env = np.zeros(1500, np.float32)
+        env[5::period] = 1.0
+        bpm = R.tempo(env, sr, hop)[0]
+        assert abs(bpm - 60.0 * sr / (hop * period)) < 1e-9, (period, bpm)
+        curve = R.tempo(env, sr, hop, aggregate=None)
+        assert np.all(curve[200:-200] == bpm)
+        _, beats = R.beat_track(env, sr, hop)
+        assert len(beats) > 20 and np.all(np.diff(beats) == period) and np.all((beats - 5) % period == 0)
+    t0, b0 = R.beat_track(np.zeros(100, np.float32), sr, hop)
+    assert t0 == 0.0 and len(b0) == 0
+
+
+def test_rhythm_oracle_reproduces_reference_bpm_analyzer(golden_dir):
+    """tests/golden/rhythm.json was produced by the reference's own BPMAnalyzer (adaptive_vad_enhancer.py:48-298)."""
+    import json
+
+    from audio_cut_b200 import synth
+    from oracle import rhythm as R
+
+    cases = json.load(open(os.path.join(golden_dir, "rhythm.json")))
+    sr = 44100
+
+    def click(seconds, bpm):
+        n = int(seconds * sr)
+        x = np.zeros(n, np.float32)
+        bl = int(0.02 * sr)
+        burst = (np.sin(2 * np.pi * 1000.0 * np.arange(bl) / sr) * np.exp(-np.arange(bl) / (0.004 * sr))).astype(np.float32)
+        step, k = 60.0 / bpm * sr, 0
+        while int(k * step) + bl < n:
+            x[int(k * step):int(k * step) + bl] += burst
+            k += 1
+        return x + 1e-4 * np.random.default_rng(5).standard_normal(n).astype(np.float32)
+
+    waves = {"track20": lambda: synth.synth_track(20.0, seed=2, stereo=False), "song24": lambda: synth.synth_song(24.0, seed=1),
+             "clicks150": lambda: click(16.0, 150.0), "clicks72": lambda: click(20.0, 72.0), "silence": lambda: np.zeros(sr * 6, np.float32)}
+    for c in cases:
+        bf = R.extract_bpm_features(waves[c["tag"]](), sr)
+        assert float(bf.main_bpm) == c["main_bpm"] and bf.bpm_category == c["bpm_category"], c["tag"]
+        assert bf.beat_strength == pytest.approx(c["beat_strength"], abs=1e-12)
+        assert bf.tempo_variance == pytest.approx(c["tempo_variance"], abs=1e-12)
+        assert [int(b) for b in bf.beat_positions] == c["beat_positions"]
+        for k, v in c["adaptive_factors"].items():
+            got = bf.adaptive_factors[k]
+            assert (got == pytest.approx(v, abs=1e-12)) if isinstance(v, float) else (got == v), (c["tag"], k)
+    # click tracks: the estimate is the grid point nearest to the true tempo
+    by = {c["tag"]: c for c in cases}
+    assert abs(by["clicks150"]["main_bpm"] - 150.0) < 3.0 and abs(by["clicks72"]["main_bpm"] - 72.0) < 1.0
+
+
+# --------------------------------------------------------------------------- cut-point chain (X1)
+def _check_chain(fx, res, exact=True):
+    """exact=False: the stems were rebuilt by a torch-CPU network whose last bits vary with the thread count / CPU (1e-6
+    relative), so continuous scores are compared with a tolerance; every discrete outcome must still be identical."""
+    got = [[repr(float(p.start_time)), repr(float(p.end_time)), repr(float(p.cut_point)), repr(float(p.confidence)), p.quality_grade,
+            p.pause_type] for p in res["pauses"]]
+    if exact:
+        assert got == fx["pauses"]
+        assert [[repr(float(t)), repr(float(s))] for t, s in res["candidates"]] == fx["candidates"]
+        assert [repr(t) for t in res["final_times"]] == fx["final_times"]
+    else:
+        assert [g[:3] + g[4:] for g in got] == [p[:3] + p[4:] for p in fx["pauses"]]
+        np.testing.assert_allclose([float(g[3]) for g in got], [float(p[3]) for p in fx["pauses"]], rtol=1e-4)
+        np.testing.assert_allclose([t for t, _ in res["candidates"]], [float(c[0]) for c in fx["candidates"]], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(res["final_times"], [float(t) for t in fx["final_times"]], rtol=0, atol=0.51 / fx["sr"])
+    assert [[repr(a), repr(b)] for a, b in res["pure_music_spans"]] == fx["pure_music_spans"]
+    assert res["refined_boundaries"] == fx["refined_boundaries"]
+    assert res["sample_boundaries"] == fx["sample_boundaries"]
+
+
+def test_detector_oracle_reproduces_reference_chain(golden_dir):
+    """The restated detector / candidate assembly / finalize chain (oracle/detector.py) against the fixture produced by the
+    reference's own PureVocalPauseDetector, SeamlessSplitter helpers and finalize_cut_points (make_golden.py --cutchain-small)."""
+    import json
+
+    from helpers import linear_backend, oracle_cutchain_inputs
+    from oracle import detector as D
+    from oracle import features as OF
+
+    fx = json.load(open(os.path.join(golden_dir, "cutchain_small.json")))
+    audio, vocal, cache = oracle_cutchain_inputs(fx, linear_backend)
+    assert repr(float(np.sum(vocal.astype(np.float64)))) == fx["vocal_sum"]
+    assert repr(float(cache.global_mdd)) == fx["cache"]["global_mdd"] and repr(float(cache.bpm_features.main_bpm)) == fx["cache"]["main_bpm"]
+    assert [int(x) for x in cache.onset_frames] == fx["cache"]["onset_frames"]
+    sr = fx["sr"]
+    hop = max(1, int(0.02 * sr))
+    markers = D.presence_marker_times(OF.rms(vocal, max(hop * 2, int(0.05 * sr)), hop), len(vocal), sr, D.Cfg(fx["config"]))
+    assert [repr(t) for t in markers] == fx["marker_times"]
+    res = D.cut_chain(audio, vocal, cache, markers, fx["config"], sr)
+    assert len(res["pauses"]) >= 10 and len(res["sample_boundaries"]) >= 10
+    _check_chain(fx, res)
