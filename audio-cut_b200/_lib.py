@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libaudiocut_b200.so")
 AC_F32, AC_BF16, AC_F16 = 0, 1, 2
 
 EXPORTS = [
-    "ac_init", "ac_last_error", "ac_abi_version", "ac_launch_count", "ac_frame_count", "ac_frame_rms",
+    "ac_init", "ac_last_error", "ac_abi_version", "ac_launch_count", "ac_frame_count", "ac_frame_rms", "ac_frame_rms_segments",
     "ac_stft_mdx", "ac_istft_mdx", "ac_unet_create", "ac_unet_destroy", "ac_unet_param_floats",
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
     "ac_track_workspace_bytes", "ac_separate_track", "ac_separate_track_ex", "ac_stft_features_workspace_bytes", "ac_stft_features",
@@ -76,6 +76,8 @@ def load() -> C.CDLL:
     lib.ac_launch_count.argtypes, lib.ac_launch_count.restype = [], ll
     lib.ac_frame_count.argtypes, lib.ac_frame_count.restype = [ll, i, i, i], ll
     lib.ac_frame_rms.argtypes, lib.ac_frame_rms.restype = [vp, ll, i, i, i, vp, vp], i
+    lib.ac_frame_rms_segments.argtypes = [vp, ll, C.POINTER(FeatSegment), i, i, i, i, vp, vp]
+    lib.ac_frame_rms_segments.restype = i
     lib.ac_zero_crossing_rate.argtypes, lib.ac_zero_crossing_rate.restype = [vp, ll, i, i, vp, vp], i
     lib.ac_stft_mdx.argtypes, lib.ac_stft_mdx.restype = [vp, vp, i, C.POINTER(MdxGeom), i, vp], i
     lib.ac_istft_mdx.argtypes, lib.ac_istft_mdx.restype = [vp, vp, i, C.POINTER(MdxGeom), i, vp], i

@@ -301,7 +301,9 @@ extern "C" int ac_refine_cut_points(const float* d_mix, const float* d_vocal, lo
   AC_REQUIRE(zero_cross_half >= 1 && search >= 1 && win >= 1, "window sizes must be >= 1 sample");
   if (n_points == 0) return AC_OK;
   const size_t smem = refine_smem_bytes(search, win);
-  AC_REQUIRE(smem <= 200 * 1024, "search + guard window does not fit one CTA's shared memory (max ~25k samples)");
+  // 227 KB of dynamic shared memory per CTA minus the kernel's small static arrays: search + win <= ~25.5k samples
+  // (the reference's shipped config, search_right_ms 450 + win_ms 80 at 44.1 kHz = 23 373 samples, needs 205.5 KB)
+  AC_REQUIRE(smem <= 225 * 1024, "search + guard window does not fit one CTA's shared memory (max ~25.5k samples)");
   static size_t attr = 0;
   if (smem > attr) {
     AC_CHECK_CUDA(cudaFuncSetAttribute(refine_cuts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

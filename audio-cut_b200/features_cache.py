@@ -177,11 +177,11 @@ class B200ChunkFeatureBuilder:
         feats = ops.stft_features(mix_dev, segs, hop, self.sr, total_frames=off, want=("flatness", "onset_mean"))
         # RMS frames: 1 + (l + 2*(frame//2) - frame)//hop per chunk, all chunks into one device buffer
         rms_counts = [ops.frame_count(l, self.frame_length, hop) for _, l, _ in segs]
-        rms_all = torch.empty(sum(rms_counts), dtype=torch.float32, device=mix_dev.device)
-        ro = 0
+        rms_segs, ro = [], 0
         for (s, l, _), cnt in zip(segs, rms_counts):
-            ops.frame_rms(mix_dev[s : s + l], self.frame_length, hop, out=rms_all[ro : ro + cnt])
+            rms_segs.append((s, l, ro))
             ro += cnt
+        rms_all = ops.frame_rms_segments(mix_dev, rms_segs, self.frame_length, hop, total_frames=ro)  # every chunk, one launch
         packed = torch.cat([feats["flatness"], feats["onset_mean"], rms_all]).cpu().numpy()  # one D2H
         flat, onset, rms_np = packed[:off], packed[off : 2 * off], packed[2 * off :]
         out = []

@@ -47,6 +47,22 @@ def frame_rms(x: torch.Tensor, frame_length: int, hop_length: int, center: bool 
     return out
 
 
+def frame_rms_segments(x: torch.Tensor, segments: Sequence[Tuple[int, int, int]], frame_length: int, hop_length: int, *,
+                       total_frames: int, center: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frame_rms of many slices of ``x`` in ONE launch; segments = (start, len, frame_off) as for ``stft_features``;
+    slice i's ``frame_count(len, ...)`` values land at ``out[frame_off:]``."""
+    lib = _lib.init(_dev_index(x))
+    x = x.contiguous().float()
+    if out is None:
+        out = torch.empty(total_frames, dtype=torch.float32, device=x.device)
+    assert out.numel() >= total_frames and out.is_contiguous() and out.dtype == torch.float32
+    if segments:
+        segs = (FeatSegment * len(segments))(*[FeatSegment(int(s), int(l), int(o)) for s, l, o in segments])
+        check(lib.ac_frame_rms_segments(ptr(x), x.numel(), segs, len(segments), frame_length, hop_length, int(center), ptr(out),
+                                        stream_ptr()), "ac_frame_rms_segments")
+    return out
+
+
 def zero_crossing_rate(x: torch.Tensor, frame_length: int = 2048, hop_length: int = 512) -> torch.Tensor:
     lib = _lib.init(_dev_index(x))
     x = x.contiguous().float()

@@ -185,7 +185,11 @@ def device_step(net_backend, mix_dev, plans, bounds, series_out):
         segs.append((cs, ce - cs, off))
         off += 1 + (ce - cs) // hop
     feats = ops.stft_features(mono, segs, hop, SR, total_frames=off, want=("flatness", "onset_mean"))
-    rms_c = [ops.frame_rms(mono[cs:ce], 4410, hop) for cs, ce, _, _ in bounds]
+    rsegs, roff = [], 0
+    for cs, ce, _, _ in bounds:
+        rsegs.append((cs, ce - cs, roff))
+        roff += ops.frame_count(ce - cs, 4410, hop)
+    rms_c = ops.frame_rms_segments(mono, rsegs, 4410, hop, total_frames=roff)  # all 32 chunks in one launch
     # BPM front end: onset envelope (median) at hop 512 over the effective-region concat
     bpm_wave = torch.cat([mono[es:ee] for _, _, es, ee in bounds])
     n_b = bpm_wave.numel()

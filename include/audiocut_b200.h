@@ -77,6 +77,13 @@ AC_API int ac_profile_collect(ac_kernel_stat* out, int max_classes); /* returns 
  * and :1848, vocal_separator.py:483.  d_out has ac_frame_count(n, frame, hop, center) floats. */
 AC_API long long ac_frame_count(long long n, int frame, int hop, int center);
 AC_API int ac_frame_rms(const float* d_x, long long n, int frame, int hop, int center, float* d_out, void* stream);
+/* The same for MANY slices of one signal in one launch (every pipeline chunk of a track: ChunkFeatureBuilder.add_chunk
+ * calls librosa.feature.rms once per chunk, features_cache.py:182).  Slice i = d_x[start, start + len) is framed and
+ * padded as if it were the whole signal; its ac_frame_count(len, ...) values go to d_out + frame_off.
+ * h_segs is a HOST array of ac_feat_segment (declared below). */
+struct ac_feat_segment;
+AC_API int ac_frame_rms_segments(const float* d_x, long long n, const struct ac_feat_segment* h_segs, int n_segs, int frame,
+                          int hop, int center, float* d_out, void* stream);
 
 /* ---- MDX23 STFT / iSTFT ---------------------------------------------------------------------
  * Conv_TDF_net_trim_model.stft / .istft of the external MVSEP-MDX23 inference.py, called at

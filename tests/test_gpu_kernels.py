@@ -660,3 +660,26 @@ def test_pyin_decode_on_very_short_inputs(ops, n):
     assert a[0].shape == (1 + n // 441,)
     for u, v in zip(a, b):
         np.testing.assert_array_equal(u, v)
+
+
+def test_frame_rms_segments_one_launch_equals_per_chunk_calls(ops, audio):
+    """ac_frame_rms_segments: every pipeline chunk of a track in one launch == librosa.feature.rms per chunk slice
+    (features_cache.py:182), including unaligned chunk starts, ragged tails and more segments than one launch carries."""
+    from oracle import features as OF
+
+    y = audio[0]
+    x = torch.from_numpy(y).cuda()
+    rng = np.random.default_rng(1)
+    for frame, hop, n_seg in ((4410, 2205, 5), (1102, 441, 7), (2048, 441, 130)):
+        segs, off = [], 0
+        for _ in range(n_seg):
+            ln = int(rng.integers(1, 60000))
+            st = int(rng.integers(0, len(y) - ln))
+            segs.append((st, ln, off))
+            off += ops.frame_count(ln, frame, hop)
+        l0 = ops._lib.load().ac_launch_count()
+        got = ops.frame_rms_segments(x, segs, frame, hop, total_frames=off).cpu().numpy()
+        assert ops._lib.load().ac_launch_count() - l0 == (n_seg + 95) // 96
+        for st, ln, o in segs:
+            ref = OF.rms(y[st:st + ln], frame, hop)
+            np.testing.assert_allclose(got[o:o + len(ref)], ref, rtol=1e-4, atol=1e-7)
