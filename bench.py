@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: x-realtime separation+features of the audio-cut hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp16|bf16|fp32]
 
 A "step" is one pass of the hot path over one synthetic 4-minute 44.1 kHz stereo track per GPU
 (BASELINE.json configs[1]; at N > 1 configs[3]: tracks sharded across ranks, no data-path collective,
@@ -15,7 +15,14 @@ weak scaling).  Prints ONE JSON line on rank 0 (see the task contract for the ke
          with HOST numpy buffers: pinned H2D of the mix, the kernels, D2H of both stems and all
          series, and the host-side rhythm scans (tempogram / beat DP) of TrackFeatureCache.
   --impl reference   times the CPU restatement of the reference path (oracle/: torch-CPU network +
-         numpy features; onnxruntime / librosa are not installable here) on a bounded sample.
+         numpy features; onnxruntime / librosa are not installable here): each step is BASELINE configs[0] in
+         full - one 30 s stereo track, 4 pipeline chunks / 8 model windows and their features.
+
+Beside the contract's keys the B200 line carries: ``stem_sdr_db`` (the timed 16-bit path's stems against the CPU oracle
+on the cpu_baseline sample), ``fp32_value`` / ``bf16_value`` (the same device-timed step on the other arithmetic paths),
+and ``configs`` = BASELINE configs[2] (one hour of mono audio, feature-only, host buffers in and out, per-kernel HBM
+fractions; N = 1) and configs[4] (one 60-minute stereo mix chunk-sharded over the N ranks with halo recompute, merged
+on the host, strong scaling, checked sample for sample against the single-GPU stitch).
 """
 from __future__ import annotations
 
@@ -88,7 +95,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle restatement of the reference's CPU path
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_pass(sample_seconds: float, n_fft: int, threads: int, state=None):
+def cpu_reference_pass(sample_seconds: float, n_fft: int, threads: int, state=None, want_stems: bool = False):
     """One bounded pass of the reference CPU path over `sample_seconds` of the workload: chunked
     MDX23 separation (backends.py:299-406 + enhanced_vocal_separator.py:366-458 restated) with the
     torch-CPU TFC-TDF net, ChunkFeatureBuilder features (features_cache.py:122-335 restated) and the
@@ -109,7 +116,7 @@ def cpu_reference_pass(sample_seconds: float, n_fft: int, threads: int, state=No
     n = audio.shape[-1]
     plans = planner.chunk_schedule(n / float(SR))
     t0 = time.perf_counter()
-    vocal, _ = pipeline.separate_track(audio, lambda ch: mdx.infer_chunk(ch, net, mg), sr=SR, plans=plans)
+    vocal, instr = pipeline.separate_track(audio, lambda ch: mdx.infer_chunk(ch, net, mg), sr=SR, plans=plans)
     mono = audio.mean(axis=0)
     cf = pipeline.ChunkFeatures(SR)
     for p in plans:
@@ -121,7 +128,10 @@ def cpu_reference_pass(sample_seconds: float, n_fft: int, threads: int, state=No
         OF.rms(vocal, fr, hop)
     OF.spectral_flatness(vocal, 2048, 441)
     OF.rms(mono, 2048, 441)
-    return n / float(SR), time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    if want_stems:
+        return n / float(SR), wall, (audio, plans, vocal, instr)
+    return n / float(SR), wall
 
 
 def bench_config(n_fft: int, world: int, chunks: int = 32, windows: int = 64) -> dict:
@@ -133,31 +143,45 @@ def bench_config(n_fft: int, world: int, chunks: int = 32, windows: int = 64) ->
             "parallelism": f"track-sharded x{world}, no collective"}
 
 
+REF_SAMPLE_S = 30.0  # BASELINE configs[0]: the reference's own CPU-runnable case, in full
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    sample_s = 10.0  # one pipeline chunk = 2 model windows per step
     from audio_cut_b200 import unet_weights as uw
+    from oracle import mdx, planner
 
     st = uw.random_state(uw.UNetGeometry())
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_pass(sample_s, args.n_fft, threads, st)
+        cpu_reference_pass(REF_SAMPLE_S, args.n_fft, threads, st)
     audio_s, wall = 0.0, 0.0
     for _ in range(args.steps):
-        a, w = cpu_reference_pass(sample_s, args.n_fft, threads, st)
+        a, w = cpu_reference_pass(REF_SAMPLE_S, args.n_fft, threads, st)
         audio_s += a
         wall += w
     value = audio_s / wall
+    plans = planner.chunk_schedule(REF_SAMPLE_S)
+    mg = mdx.MdxGeometry(n_fft=args.n_fft)
+    n_win = sum(mdx.n_windows(planner.sample_bounds(p, SR, int(REF_SAMPLE_S * SR))[1] - planner.sample_bounds(p, SR, int(REF_SAMPLE_S * SR))[0], mg)
+                for p in plans)
+    cfg = {"workload": "BASELINE configs[0] in full: one 30 s 44.1 kHz stereo track per step through the reference's CPU path "
+                       "(chunked MDX23 separation + ChunkFeatureBuilder features + the vocal RMS / flatness series); a bounded "
+                       "sample of the B200 arm's workload (4-min tracks, same chunk schedule and window geometry)",
+           "sample_s": REF_SAMPLE_S, "chunks_per_step": len(plans), "windows_per_step": int(n_win),
+           "n_fft": args.n_fft, "hop": 1024, "dim_f": 3072, "dim_t": 256, "chunk_s": 10.0, "overlap_s": 2.5, "halo_s": 0.5,
+           "weights": "random-init TFC-TDF (Kim_Vocal geometry, seed 1234)", "arithmetic": "fp32 (torch-CPU), the B200 arm's default is fp16 operands / fp32 accumulation",
+           "parallelism": f"{threads} host threads, rank 0 only"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(args.n_fft, max(1, args.gpus)),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample_s:.0f} s stereo (1 chunk, 2 MDX windows + its features) per step, {args.steps} steps; "
-                                   "oracle port: torch-CPU TFC-TDF net + numpy/scipy librosa restatement (onnxruntime/librosa absent)"},
+                         "sample": f"{REF_SAMPLE_S:.0f} s stereo (configs[0]: {len(plans)} chunks, {n_win} MDX windows + features) per step, "
+                                   f"{args.steps} steps; oracle port: torch-CPU TFC-TDF net + numpy/scipy librosa restatement "
+                                   "(onnxruntime / librosa absent from the image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -168,7 +192,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def device_step(net_backend, mix_dev, plans, bounds, series_out):
+def device_step(net_backend, mix_dev, plans, bounds, series_out, dtype=None):
     """One hot-path pass with inputs resident in HBM; every series stays on the device."""
     import torch
 
@@ -177,7 +201,7 @@ def device_step(net_backend, mix_dev, plans, bounds, series_out):
 
     be = net_backend
     vocal, instr, _ = ops.separate_track(be.net, mix_dev, bounds, be.geom, align_hop=be.align_hop,
-                                         output_is_vocal=True, dtype=be.dtype)
+                                         output_is_vocal=True, dtype=be.dtype if dtype is None else dtype)
     mono = mix_dev.mean(dim=0)
     hop = 2205
     segs, off = [], 0
@@ -199,6 +223,153 @@ def device_step(net_backend, mix_dev, plans, bounds, series_out):
     v_flat = ops.stft_features(vocal, [(0, vocal.numel(), 0)], 441, SR, total_frames=1 + vocal.numel() // 441, want=("flatness",))
     m_rms = ops.frame_rms(mono, 2048, 441)
     series_out[:] = [vocal, instr, feats, rms_c, bpm_env, v_rms, v_flat, m_rms]
+
+
+def time_device_steps(be, mix_dev, plans, bounds, dtype, steps, barrier):
+    """ms per step of ``device_step`` on another arithmetic path (same network, same kernels' schedule)."""
+    import torch
+
+    keep = []
+    device_step(be, mix_dev, plans, bounds, keep, dtype=dtype)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        device_step(be, mix_dev, plans, bounds, keep, dtype=dtype)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def sdr_db(ref, est):
+    ref, est = np.asarray(ref, np.float64), np.asarray(est, np.float64)
+    den = float(np.sum((ref - est) ** 2))
+    return float("inf") if den == 0 else 10.0 * np.log10(float(np.sum(ref ** 2)) / den + 1e-300)
+
+
+def features_1h_config(dev, peaks):
+    """BASELINE configs[2]: every framewise series over one hour of mono audio, HOST buffers in and out."""
+    import torch
+
+    from audio_cut_b200 import featbench, ops, synth
+
+    seconds = 3600.0
+    base = synth.synth_track(240.0, seed=3, stereo=False)
+    n = int(seconds * SR)
+    host = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    host.numpy()[:] = np.tile(base, n // base.size + 1)[:n]
+    nf441, nf512 = 1 + n // 441, 1 + n // 512
+    outs_pin = {}
+
+    def run():
+        x = host.to(dev, non_blocking=True)
+        res = {}
+        for fr, hp in ((4410, 2205), (1102, 441), (2048, 441), (2205, 882)):
+            res[f"rms_{fr}_{hp}"] = ops.frame_rms(x, fr, hp)
+        res["zcr"] = ops.zero_crossing_rate(x, 2048, 441)
+        res.update({"v_" + k: v for k, v in ops.stft_features(x, [(0, n, 0)], 441, SR, total_frames=nf441,
+                                                                   want=("flatness", "centroid", "low_ratio")).items()})
+        res.update({"b_" + k: v for k, v in ops.stft_features(x, [(0, n, 0)], 512, SR, total_frames=nf512,
+                                                                   want=("onset_mean", "onset_median")).items()})
+        f0, flag, vp = ops.pyin(x, SR, 441)
+        res["f0"], res["voiced_prob"], res["voiced_flag"] = f0, vp, flag.to(torch.float32)
+        mags, counts = ops.lpc_formants(x, SR, 441, 12)
+        res["formant_mags"], res["formant_counts"] = mags.reshape(-1), counts.to(torch.float32)
+        nbytes = 0
+        for k, v in res.items():
+            if k not in outs_pin:
+                outs_pin[k] = torch.empty(v.numel(), dtype=torch.float32, pin_memory=True)
+            outs_pin[k].copy_(v.reshape(-1), non_blocking=True)
+            nbytes += v.numel() * 4
+        torch.cuda.synchronize()
+        return nbytes
+
+    run()
+    t0 = time.perf_counter()
+    d2h = run()
+    wall = time.perf_counter() - t0
+    table = featbench.feature_only_bench(seconds, device=dev.index or 0, hbm_peak_gbs=peaks["hbm"])
+    return {"workload": "BASELINE configs[2]: RMS x4 geometries, ZCR, STFT-2048 flatness/centroid/band ratio @441, BPM onset envelope "
+                        "mean+median @512, pYIN (YIN + fp64 Viterbi), LPC formants over 1 h of synthetic mono audio",
+            "e2e": {"value": seconds / wall, "unit": UNIT, "ms": wall * 1000.0, "h2d_bytes": int(n * 4), "d2h_bytes": int(d2h),
+                    "call": "pinned host ndarray -> ops.* -> pinned host series"},
+            "device_resident": {"value": table["x_realtime_all_series"], "unit": UNIT, "ms": table["total_ms"]},
+            "kernels": table["kernels"], "hbm_peak_GBps": peaks["hbm"]}
+
+
+def chunk_sharded_config(be, rank, world, dev, barrier, dist):
+    """BASELINE configs[4]: ONE 60-minute stereo mix, pipeline chunks dealt to the ranks in contiguous blocks (halo
+    recomputed locally, each rank uploads only the samples its chunks touch), shards merged on the host with the
+    reference's accumulate / weight rule; strong scaling.  Rank 0 also runs the whole mix alone and compares."""
+    import torch
+
+    from audio_cut_b200 import ops, sharding, synth
+    from audio_cut_b200.gpu_pipeline import chunk_schedule
+
+    seconds = 3600.0
+    base = synth.synth_track(240.0, seed=11, stereo=True)
+    mix = np.ascontiguousarray(np.tile(base, (1, 15)))
+    n = mix.shape[1]
+    plans = chunk_schedule(n / float(SR))
+    bounds = [p.sample_bounds(SR, n) for p in plans]
+    kw = dict(align_hop=be.align_hop, output_is_vocal=True, dtype=be.dtype)
+    lo_c, hi_c = sharding.shard_chunks(len(bounds), world)[rank]
+    mine = list(bounds[lo_c:hi_c])
+    lo, hi = sharding.shard_sample_range(mine)
+    local_host = torch.from_numpy(np.ascontiguousarray(mix[:, lo:hi])).pin_memory()
+    local_bounds = sharding.localize_bounds(mine, lo)
+
+    def one_pass():
+        local = local_host.to(dev, non_blocking=True)
+        return ops.separate_track(be.net, local, local_bounds, be.geom, **kw)
+
+    one_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    v, i, w = one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1)
+    shard = {"lo": lo, "vocal": v.cpu().numpy(), "instr": i.cpu().numpy(), "weight": w.cpu().numpy()}
+    tag = os.environ.get("MASTER_PORT", "0")
+    path = f"/dev/shm/acb200_{tag}_{rank}.npz"
+    if world > 1 and rank != 0:
+        np.savez(path, **shard)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # timing only; doubles as the "shards are on the host" barrier
+    out = None
+    if rank == 0:
+        shards = [shard]
+        for r in range(1, world):
+            with np.load(f"/dev/shm/acb200_{tag}_{r}.npz") as z:
+                shards.append({k: z[k] for k in z.files})
+            os.remove(f"/dev/shm/acb200_{tag}_{r}.npz")
+        mv, mi = sharding.merge_chunk_shards(n, shards)
+        e2e_s = time.perf_counter() - t0
+        # the single-GPU stitch of the same mix, for the identity check and the strong-scaling denominator
+        full = torch.from_numpy(mix).to(dev)
+        ops.separate_track(be.net, full, bounds, be.geom, **kw)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        fv, fi, _ = ops.separate_track(be.net, full, bounds, be.geom, **kw)
+        s1.record()
+        torch.cuda.synchronize()
+        t1_ms = s0.elapsed_time(s1)
+        same = bool(np.array_equal(mv, fv.cpu().numpy()) and np.array_equal(mi, fi.cpu().numpy()))
+        tn_ms = float(t[0])
+        out = {"workload": "BASELINE configs[4]: one 60-min 44.1 kHz stereo mix, 480 chunks / 960 windows, chunk-sharded with halo recompute, "
+                           "host merge (no collective on the data path)", "scaling": "strong", "n_gpus": world,
+               "value": seconds / (tn_ms / 1000.0), "unit": UNIT, "ms": tn_ms, "timing": "CUDA events, max over ranks (upload of the rank's samples + separation)",
+               "e2e_value": seconds / e2e_s, "e2e_ms": e2e_s * 1000.0, "e2e_includes": "D2H of every shard, /dev/shm hand-over, host merge on rank 0",
+               "single_gpu_ms": t1_ms, "strong_scaling_efficiency": t1_ms / (world * tn_ms),
+               "merged_equals_single_gpu_stitch": same, "chunks_per_rank": [b - a for a, b in sharding.shard_chunks(len(bounds), world)]}
+    if world > 1:
+        dist.barrier()
+    return out
 
 
 def run_b200(args):
@@ -303,6 +474,20 @@ def run_b200(args):
     d2h = res.vocal_track.nbytes + (res.instrumental_track.nbytes if res.instrumental_track is not None else 0) + \
         4 * (fc.rms_series.size + fc.spectral_flatness.size + fc.onset_envelope.size) + 4 * (1 + (n + 1323000) // 512) + 4 * (1 + n // 882)
 
+    # ---- the other arithmetic paths (N = 1), configs[2] (N = 1) and configs[4] (every N)
+    other = {}
+    if world == 1 and not args.quick:
+        for name, dt in (("fp16", _lib.AC_F16), ("bf16", _lib.AC_BF16), ("fp32", _lib.AC_F32)):
+            if name != args.precision:
+                other[name] = time_device_steps(be, mix_dev, plans, bounds, dt, 2, barrier)
+    extra_cfgs = {}
+    if not args.quick:
+        if world == 1:
+            extra_cfgs["features_1h"] = features_1h_config(dev, _peaks())
+        cs = chunk_sharded_config(be, rank, world, dev, barrier, dist)
+        if cs is not None:
+            extra_cfgs["chunk_sharded_60min"] = cs
+
     t = torch.tensor([dev_ms, e2e_s * 1000.0, e2e_pageable_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,28 +505,41 @@ def run_b200(args):
             k["gbs"] = k["bytes"] / (k["total_ms"] * 1e6) if k["total_ms"] > 0 else 0.0
         top = kstats[0]
         tensor_bound = top["flops"] > 0
-        traffic = None  # DRAM bytes per launch of the dominant kernel class, from the committed ncu --set full capture
+        traffic, traffic_src = None, None  # DRAM bytes per launch of the dominant kernel class, from the committed ncu --set full capture
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                traffic = float(json.load(f)[top["name"]]["dram_bytes_per_launch"])
+            for name in ("r02_traffic.json", "r01_traffic.json"):
+                p = os.path.join(ROOT, "profiles", name)
+                if os.path.exists(p):
+                    with open(p) as f:
+                        traffic = float(json.load(f)[top["name"]]["dram_bytes_per_launch"])
+                    traffic_src = f"profiles/{name} (ncu --set full capture of the same kernels, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+                    break
         except Exception:
             traffic = None
         if tensor_bound:
             roof = {"bound": "tensor", "kernel": top["name"], "achieved": top["tflops"], "peak": peaks["bf16_sustained"],
                     "unit": "TFLOP/s", "frac": top["tflops"] / peaks["bf16_sustained"], "traffic": traffic,
-                    "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "traffic_source": traffic_src,
+                    "peak_source": peaks["src"] + ", sustained bf16 = f16 tensor-core rate (kernel timed inside a long step)",
                     "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"]}
         else:
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": top["gbs"] / peaks["hbm"], "traffic": traffic, "peak_source": peaks["src"],
                     "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"]}
         cpu_threads = os.cpu_count() or 1
-        cpu = None
+        cpu, stem_sdr = None, None
         if world == 1 and not args.no_cpu_baseline:
-            a, w = cpu_reference_pass(10.0, args.n_fft, cpu_threads, state)
+            a, w, (s_audio, s_plans, s_vocal, s_instr) = cpu_reference_pass(REF_SAMPLE_S, args.n_fft, cpu_threads, state, want_stems=True)
             cpu = {"value": a / w, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                   "sample": "10 s stereo (1 chunk, 2 MDX windows + its features), one pass; oracle port: torch-CPU TFC-TDF net + "
-                             "numpy/scipy librosa restatement (onnxruntime/librosa absent from the image)"}
+                   "sample": f"{REF_SAMPLE_S:.0f} s stereo (BASELINE configs[0]: {len(s_plans)} chunks, 8 MDX windows + features), one pass; oracle "
+                             "port: torch-CPU TFC-TDF net + numpy/scipy librosa restatement (onnxruntime / librosa absent from the image)"}
+            # the timed path's stems against that CPU pass (the oracle is the checker here, never the thing measured)
+            s_bounds = [p.sample_bounds(SR, s_audio.shape[-1]) for p in chunk_schedule(s_audio.shape[-1] / float(SR))]
+            gv, gi, _ = ops.separate_track(be.net, torch.from_numpy(s_audio).to(dev), s_bounds, be.geom, align_hop=be.align_hop,
+                                           output_is_vocal=True, dtype=be.dtype)
+            stem_sdr = {"vocal": sdr_db(s_vocal, gv.cpu().numpy()), "instrumental": sdr_db(s_instr, gi.cpu().numpy()),
+                        "path": args.precision, "vs": f"CPU oracle, {REF_SAMPLE_S:.0f} s stereo, n_fft {args.n_fft}",
+                        "gate": "north_star: >= 40 dB for the 16-bit path, >= 60 dB for fp32"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -357,7 +555,12 @@ def run_b200(args):
             "kernels": [{k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in k.items()} for k in kstats],
             "unet_tflops_overall": sum(k["flops"] for k in kstats) / (sum(k["total_ms"] for k in kstats if k["flops"] > 0) * 1e9 + 1e-9),
             "cpu_baseline": cpu,
+            "stem_sdr_db": stem_sdr,
+            "configs": extra_cfgs,
         }
+        for name, ms in other.items():
+            line[f"{name}_value"] = TRACK_SECONDS / (ms / 1000.0)
+            line[f"{name}_ms_per_step"] = ms
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -373,6 +576,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--n-fft", dest="n_fft", type=int, default=7680)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline workload only: skip the other precisions and BASELINE configs[2] / configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
