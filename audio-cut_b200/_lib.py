@@ -23,6 +23,7 @@ EXPORTS = [
     "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3", "ac_pyin_frame_count", "ac_pyin_workspace_bytes", "ac_pyin",
     "ac_lpc_frame_count", "ac_lpc_formants", "ac_refine_cut_points", "ac_quiet_lookup_db",
     "ac_host_is_pinned", "ac_copy_h2d_async",
+    "ac_pcm_decode", "ac_peak_normalize", "ac_pcm_pack", "ac_resample_out_len", "ac_resample_poly",
 ]
 
 
@@ -118,6 +119,12 @@ def load() -> C.CDLL:
     lib.ac_quiet_lookup_db.argtypes, lib.ac_quiet_lookup_db.restype = [vp, ll, i, vp, vp], i
     lib.ac_host_is_pinned.argtypes, lib.ac_host_is_pinned.restype = [vp, sz], i
     lib.ac_copy_h2d_async.argtypes, lib.ac_copy_h2d_async.restype = [vp, vp, sz, vp], i
+    lib.ac_pcm_decode.argtypes, lib.ac_pcm_decode.restype = [vp, ll, i, i, i, vp, vp], i
+    lib.ac_peak_normalize.argtypes, lib.ac_peak_normalize.restype = [vp, ll, vp, vp], i
+    lib.ac_pcm_pack.argtypes, lib.ac_pcm_pack.restype = [vp, ll, i, i, vp, vp], i
+    lib.ac_resample_out_len.argtypes, lib.ac_resample_out_len.restype = [ll, i, i], ll
+    lib.ac_resample_poly.argtypes = [vp, C.POINTER(ll), C.POINTER(ll), i, i, i, vp, i, i, i, ll, vp, vp]
+    lib.ac_resample_poly.restype = i
     lib.ac_profile_begin.argtypes, lib.ac_profile_begin.restype = [], i
     lib.ac_profile_collect.argtypes, lib.ac_profile_collect.restype = [C.POINTER(KernelStat), i], i
     _lib = lib

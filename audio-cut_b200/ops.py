@@ -275,6 +275,57 @@ def host_beat_dp(localscore: np.ndarray, period: int, tightness: float):
     return backlink, cumscore
 
 
+# ---- batched resampler in front of the per-chunk VAD ----------------------------------
+_RESAMPLE_TAPS: Dict[Tuple[int, int, str], Tuple[torch.Tensor, int, int, int, int]] = {}
+
+
+def resample_filter(up: int, down: int):
+    """(taps float32, n_pre_pad, n_pre_remove, up, down) exactly as scipy.signal.resample_poly designs them for float32 input:
+    firwin(2*half_len+1, 1/max_rate, window=('kaiser', 5.0)).astype(float32) * up, half_len = 10*max_rate."""
+    import math
+
+    import scipy.signal
+
+    g = math.gcd(int(up), int(down))
+    up, down = int(up) // g, int(down) // g
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    h = scipy.signal.firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)).astype(np.float32)
+    h = h * np.float32(up)
+    n_pre_pad = down - half_len % down
+    n_pre_remove = (half_len + n_pre_pad) // down
+    return h, n_pre_pad, n_pre_remove, up, down
+
+
+def resample_chunks(x: torch.Tensor, chunk_lens: Sequence[int], sr_in: int = 44100, sr_out: int = 16000, *, bucket: int = 4096):
+    """All chunks of ``x`` (float32 CUDA, chunks back to back) resampled sr_in -> sr_out in one launch.
+
+    Returns (batch [n_chunks, L] zero-padded to a multiple of ``bucket`` like advanced_vad.silero_length_bucket
+    (vocal_pause_detector.py:190-195), out_lens).  Semantics: scipy.signal.resample_poly(chunk, sr_out, sr_in) per chunk."""
+    lib = _lib.init(_dev_index(x))
+    x = x.contiguous().float()
+    key = (sr_out, sr_in, str(x.device))
+    if key not in _RESAMPLE_TAPS:
+        h, npp, npr, up, down = resample_filter(sr_out, sr_in)
+        _RESAMPLE_TAPS[key] = (torch.from_numpy(h).to(x.device), npp, npr, up, down)
+    taps, npp, npr, up, down = _RESAMPLE_TAPS[key]
+    n_seg = len(chunk_lens)
+    offs = np.concatenate([[0], np.cumsum(np.asarray(chunk_lens, dtype=np.int64))])[:-1].astype(np.int64) if n_seg else np.zeros(0, np.int64)
+    lens = np.asarray(chunk_lens, dtype=np.int64)
+    if n_seg and int(offs[-1] + lens[-1]) > x.numel():
+        raise ValueError("chunk lengths exceed the buffer")
+    out_lens = [int(lib.ac_resample_out_len(int(l), up, down)) for l in lens]
+    row = max(out_lens) if out_lens else 0
+    if bucket > 0:
+        row += (-row) % bucket
+    row = max(row, 1)
+    out = torch.empty((n_seg, row), dtype=torch.float32, device=x.device)
+    if n_seg:
+        check(lib.ac_resample_poly(ptr(x), offs.ctypes.data_as(C.POINTER(C.c_longlong)), lens.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                   n_seg, up, down, ptr(taps), taps.numel(), npp, npr, row, ptr(out), stream_ptr()), "ac_resample_poly")
+    return out, out_lens
+
+
 # ---- F0 / formants of the legacy pause-detector branch (pure_vocal_pause_detector.py:410-459, 961-1018)
 C2_HZ = 65.40639132514966   # librosa.note_to_hz("C2")
 C7_HZ = 2093.004522404789   # librosa.note_to_hz("C7")

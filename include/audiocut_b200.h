@@ -276,6 +276,28 @@ AC_API int ac_quiet_lookup_db(const float* d_wave, long long n, int win, double*
  * |y| <= 1e-10 -> 0): pure_vocal_pause_detector.py:444. */
 AC_API int ac_zero_crossing_rate(const float* d_x, long long n, int frame, int hop, float* d_out, void* stream);
 
+/* ---- data formats either side of the path -----------------------------------
+ * Decode side of AudioProcessor.load_audio (utils/audio_processor.py:32-60: librosa.load(mono=True) then audio / max|audio|):
+ * d_bytes = interleaved little-endian PCM frames [n_frames][channels], bits 16 or 24; libsndfile's float normalisation
+ * (/ 2^15, / 2^23).  mono != 0: d_out [n_frames] = channel mean (librosa.to_mono); else planar [channels][n_frames]. */
+AC_API int ac_pcm_decode(const void* d_bytes, long long n_frames, int channels, int bits, int mono, float* d_out, void* stream);
+/* x /= max|x| when the maximum is > 0 (audio_processor.py:54-56); d_scratch: one 32-bit word of device memory. */
+AC_API int ac_peak_normalize(float* d_x, long long n, unsigned int* d_scratch, void* stream);
+/* Encode side of export_audio (utils/audio_export.py:70-133): d_x planar [channels][n_frames] float32 -> interleaved frames.
+ * format 0: PCM_24 exactly as sf.write(subtype="PCM_24") = libsndfile f2let_array, lrintf(x * 0x7FFFFF), low 3 bytes LE, no
+ * clipping; 1: libsndfile's clipping variant (SFC_SET_CLIPPING: scale 2^31, saturate, top 3 bytes); 2: int16 of the MP3 path,
+ * np.round(clip(x, -1, 1) * 32767).  d_out: n_frames * channels * (3 | 3 | 2) bytes. */
+AC_API int ac_pcm_pack(const float* d_x, long long n_frames, int channels, int format, void* d_out, void* stream);
+/* Polyphase resampler in front of the per-chunk VAD (core/vocal_pause_detector.py:175-296 resamples every chunk 44.1 -> 16 kHz
+ * with librosa.resample and zero-pads it to a multiple of 4096): all segments (chunks) of d_x in one launch, semantics of
+ * scipy.signal.resample_poly(x, up, down) = librosa res_type="polyphase".  Segment s = d_x[off_s, off_s + len_s) goes to row s
+ * of d_out [n_segs][row_len], ac_resample_out_len(len_s) samples followed by zeros.  d_taps: the FIR (already multiplied
+ * by `up`), n_pre_pad / n_pre_remove as resample_poly derives them (down - half_len % down, (half_len + n_pre_pad) / down). */
+AC_API long long ac_resample_out_len(long long n_in, int up, int down);
+AC_API int ac_resample_poly(const float* d_x, const long long* h_seg_off, const long long* h_seg_len, int n_segs, int up, int down,
+                     const float* d_taps, int n_taps, int n_pre_pad, int n_pre_remove, long long row_len, float* d_out,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

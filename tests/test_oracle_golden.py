@@ -276,3 +276,55 @@ def test_detector_oracle_reproduces_reference_chain(golden_dir):
     res = D.cut_chain(audio, vocal, cache, markers, fx["config"], sr)
     assert len(res["pauses"]) >= 10 and len(res["sample_boundaries"]) >= 10
     _check_chain(fx, res)
+
+
+# --------------------------------------------------------------------------- PCM formats (N3)
+def test_pcm_oracle_against_python_wave_and_struct(tmp_path):
+    """The oracle's integer layouts against Python's own struct / wave modules, and the rounding rule on known answers."""
+    import struct
+    import wave
+
+    from oracle import audio_io as IO
+
+    x = np.array([0.0, 1.0, -1.0, 0.5, -0.5, 1e-7, 0.25 + 2.0 ** -24, 3.0 / 8388607.0, 2.5 / 8388607.0, 3.5 / 8388607.0], np.float32)
+    got = IO.pcm24_bytes(x)
+    want = [0, 8388607, -8388607, 4194304, -4194304, 1, 2097152, 3, 2, 4]  # lrintf: 4194303.5 -> even, 2.5 -> 2, 3.5 -> 4
+    assert got == b"".join(struct.pack("<i", v)[:3] for v in want)
+    assert IO.pcm24_bytes(np.array([1.5, -1.0, 1.0], np.float32), clip=True) == b"\xff\xff\x7f" + b"\x00\x00\x80" + b"\xff\xff\x7f"
+    assert IO.pcm24_bytes(np.array([0.5], np.float32), clip=True) == struct.pack("<i", 1 << 30)[1:]
+    assert IO.int16_bytes(np.array([2.0, -2.0, 0.5, 1.5 / 32767.0, 2.5 / 32767.0], np.float32)) == struct.pack("<5h", 32767, -32767, 16384, 2, 2)
+    # container round trip through wave: what write -> read of a 24-bit stereo file gives back
+    rng = np.random.default_rng(0)
+    st = (0.9 * rng.uniform(-1, 1, (1000, 2))).astype(np.float32)
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(3); w.setframerate(44100); w.writeframes(IO.pcm24_bytes(st))
+    with wave.open(path, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getnframes()) == (2, 3, 1000)
+        back = IO.decode_pcm(w.readframes(1000), 2, 24, mono=False)
+    assert back.shape == (2, 1000) and np.max(np.abs(back.T - st)) <= 0.5 / 8388607.0 + 1.2e-7
+    mono = IO.decode_pcm(IO.int16_bytes(st), 2, 16, mono=True, normalize=True)
+    assert mono.shape == (1000,) and abs(np.max(np.abs(mono)) - 1.0) < 1e-7
+
+
+def test_resampler_filter_design_matches_scipy():
+    """ops.resample_filter restates the FIR scipy.signal.resample_poly designs; applying it with the plain polyphase sum
+    (what the kernel computes) must give scipy's output."""
+    import scipy.signal
+
+    from audio_cut_b200 import ops
+
+    h, npp, npr, up, down = ops.resample_filter(16000, 44100)
+    assert (up, down) == (160, 441) and h.dtype == np.float32 and len(h) == 2 * 4410 + 1
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(3000).astype(np.float32)
+    ref = scipy.signal.resample_poly(x, 16000, 44100)
+    n_out = -(-len(x) * up // down)
+    assert len(ref) == n_out
+    m = np.arange(n_out)
+    y = np.zeros(n_out)
+    for k, mm in enumerate(m):
+        T = (mm + npr) * down - npp
+        j = np.arange(max(0, -(-(T - len(h) + 1) // up)), min(len(x) - 1, T // up) + 1)
+        y[k] = np.dot(h[T - j * up].astype(np.float64), x[j].astype(np.float64))
+    np.testing.assert_allclose(y, ref, rtol=0, atol=2e-5)
