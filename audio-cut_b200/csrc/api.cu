@@ -75,6 +75,25 @@ const FftPlan* get_fft_plan(int n) {
     tw[i] = make_float2((float)std::cos(a), (float)std::sin(a));
     hann[i] = (float)(0.5 - 0.5 * std::cos(two_pi * (double)i / (double)n));
   }
+  const int n_hi = (n + 63) / 64;
+  std::vector<float2> tw2(64 + n_hi);
+  for (int i = 0; i < 64; ++i) {
+    double a = -two_pi * (double)i / (double)n;
+    tw2[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  for (int i = 0; i < n_hi; ++i) {
+    double a = -two_pi * (double)(64 * i) / (double)n;
+    tw2[64 + i] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  float2* d_tw2 = nullptr;
+  if (cudaMalloc(&d_tw2, sizeof(float2) * tw2.size()) != cudaSuccess ||
+      cudaMemcpy(d_tw2, tw2.data(), sizeof(float2) * tw2.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error(std::string("fft plan upload: ") + cudaGetErrorString(cudaGetLastError()));
+    delete p;
+    return nullptr;
+  }
+  p->d_tw_lo = d_tw2;
+  p->d_tw_hi = d_tw2 + 64;
   float2* d_tw = nullptr;
   float* d_h = nullptr;
   if (cudaMalloc(&d_tw, sizeof(float2) * n) != cudaSuccess || cudaMalloc(&d_h, sizeof(float) * n) != cudaSuccess ||

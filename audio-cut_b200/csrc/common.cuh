@@ -141,6 +141,10 @@ struct FftPlan {
   int n_radix = 0;
   int radix[16];
   const float2* d_twiddle = nullptr;  // exp(-2*pi*i*k/n), k in [0,n)
+  // two-level twiddles: exp(-2*pi*i*m/n) = d_tw_lo[m & 63] * d_tw_hi[m >> 6]; 64 + ceil(n/64) entries that stay in L1
+  // (gathering from the n-entry table cost one L2 sector per butterfly input: 4 GB of L2 traffic per 16-window STFT launch)
+  const float2* d_tw_lo = nullptr;
+  const float2* d_tw_hi = nullptr;
   const float* d_hann = nullptr;      // periodic hann, n values
 };
 // returns nullptr (and sets the error) when n has a prime factor other than 2,3,5

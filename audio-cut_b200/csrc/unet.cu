@@ -403,24 +403,67 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
 }
 
 namespace ac {
+// Workspace of one forward over B windows (elements of the activation type):
+//   IO[i]   i = 1..n   level-i tensors for the whole batch: the encoder's input of level i, later reused for the decoder's
+//                      output of level i (the encoder input is dead by then)
+//   skip[i] i = 0..n-1 encoder outputs (multiplicative skips)
+//   A, Bf, H           ping-pong scratch of the TFC convs and the TDF bottleneck, sized for the largest SUB-BATCH
+// Sub-batching: level i runs sb[i] windows at a time through all the kernels of its block (first conv / up, 3 convs, TDF1,
+// TDF2, down) before the next sb[i] windows start.  The idea - keep the layer-to-layer hand-over (75 MB per window at level 0
+// in 16 bit) inside the 126 MB L2 instead of a 1.2 GB HBM round trip per layer - does NOT pay on B200: AC_UNET_SB=1 costs
+// 17.3 ms per 16 windows against 16.3 ms for the whole batch (persistent kernels lose more on short grids than L2 gives
+// back; two dies, 63 MB each).  Kept as a dev hook (AC_UNET_SB) with the negative result recorded; default sb = B.
 struct WsPlan {
-  size_t level0;       // elements of one level-0 activation tensor
-  size_t skip_off[8];  // element offsets of the skip tensors
-  size_t P, Q, H, total;
+  size_t e[8];        // elements of one window's level-i tensor
+  int sb[8];          // sub-batch of level i
+  size_t io_off[8];   // IO[i], i >= 1
+  size_t skip_off[8];
+  size_t A, Bf, H, total;
 };
-static WsPlan plan_ws(const ac_unet_geom& g, int B) {
-  WsPlan w;
-  w.level0 = (size_t)B * g.dim_t * g.dim_f * g.g;
+static void default_sub_batches(const ac_unet_geom& g, int B, int dtype, int* sb) {
+  // dev hook: AC_UNET_SB="1,2,4" = windows per pass at levels 0,1,2 (deeper levels: the whole batch)
+  static const char* env = getenv("AC_UNET_SB");
+  int cfg[8] = {B, B, B, B, B, B, B, B};
+  (void)dtype;  // measured on B200 (profiles/r02_subbatch_sweep.log): the whole batch per pass is fastest - per-window passes
+                // at level 0 (75 MB tensors, nominally L2-sized) are 6 % SLOWER, so the default stays sb = B everywhere
+  if (env && *env) {
+    int k = 0;
+    const char* p = env;
+    while (*p && k < 8) {
+      int v = atoi(p);
+      if (v > 0) cfg[k] = v;
+      ++k;
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+  }
+  int prev = 1;
+  for (int i = 0; i <= g.n; ++i) {
+    int v = cfg[i] < 1 ? 1 : (cfg[i] > B ? B : cfg[i]);
+    if (v < prev) v = prev;  // deeper levels never use a smaller sub-batch
+    sb[i] = v;
+    prev = v;
+  }
+}
+static WsPlan plan_ws(const ac_unet_geom& g, int B, int dtype) {
+  WsPlan w{};
+  default_sub_batches(g, B, dtype, w.sb);
   size_t off = 0;
   auto bump = [&](size_t n) {
     size_t o = off;
     off += (n + 127) / 128 * 128;
     return o;
   };
-  w.P = bump(w.level0);
-  w.Q = bump(w.level0);
-  w.H = bump(w.level0 / g.bn);
-  for (int i = 0; i < g.n; ++i) w.skip_off[i] = bump(((size_t)B * (g.dim_t >> i) * (g.dim_f >> i)) * g.g * (i + 1));
+  size_t scratch = 0;
+  for (int i = 0; i <= g.n; ++i) {
+    w.e[i] = (size_t)(g.dim_t >> i) * (g.dim_f >> i) * g.g * (i + 1);
+    if ((size_t)w.sb[i] * w.e[i] > scratch) scratch = (size_t)w.sb[i] * w.e[i];
+  }
+  w.A = bump(scratch);
+  w.Bf = bump(scratch);
+  w.H = bump(scratch / g.bn + 128);
+  for (int i = 0; i < g.n; ++i) w.skip_off[i] = bump((size_t)B * w.e[i]);
+  for (int i = 1; i <= g.n; ++i) w.io_off[i] = bump((size_t)B * w.e[i]);
   w.total = off;
   return w;
 }
@@ -428,7 +471,7 @@ static WsPlan plan_ws(const ac_unet_geom& g, int B) {
 
 extern "C" size_t ac_unet_workspace_bytes(const ac_unet* net, int B, int dtype) {
   if (!net || B <= 0) return 0;
-  return ac::plan_ws(net->g, B).total * (dtype == AC_F32 ? 4 : 2) + 256;
+  return ac::plan_ws(net->g, B, dtype).total * (dtype == AC_F32 ? 4 : 2) + 256;
 }
 
 extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int B, int dtype, void* d_ws,
@@ -449,28 +492,30 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
   cudaStream_t st = (cudaStream_t)stream;
   const ac_unet_geom& g = net->g;
   const size_t es = dtype == AC_F32 ? 4 : 2;
-  const WsPlan wp = plan_ws(g, B);
+  const WsPlan wp = plan_ws(g, B, dtype);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~uintptr_t(255));
   auto ptr = [&](size_t off) { return (void*)(base + off * es); };
-  void* P = ptr(wp.P);
-  void* Q = ptr(wp.Q);
+  auto at = [&](void* p, size_t elems) { return (void*)((char*)p + elems * es); };
+  auto cat = [&](const void* p, size_t elems) { return (const void*)((const char*)p + elems * es); };
+  void* A = ptr(wp.A);
+  void* Bf = ptr(wp.Bf);
   void* H = ptr(wp.H);
   auto wsel = [&](const float* w32, size_t w_off) { return dtype == AC_F32 ? (const void*)w32 : (const void*)(net->d_h16[fmt] + w_off); };
   int rc;
 
-  // bf16 runs on the tensor-core path (all activations in the CG8 layout) unless the geometry has a layer
+  // The 16-bit formats run on the tensor-core path (all activations in the CG8 layout) unless the geometry has a layer
   // without a tcgen05 kernel or the test hook forces the CUDA-core kernels (channels-last layout).
   const bool use_tc = dtype != AC_F32 && net->tc_ok[fmt] && net->force_simt != 1;
 
-  auto conv3x3 = [&](const ConvLayer& L, const void* x, void* y, int T, int F, int C) -> int {
+  auto conv3x3 = [&](const ConvLayer& L, const void* x, void* y, int T, int F, int C, int nb) -> int {
     if (use_tc) {
-      TcConvArgs ta{(const h16*)x, (h16*)y, B, T, F, C, L.tc[fmt], L.af.scale, L.af.shift};
+      TcConvArgs ta{(const h16*)x, (h16*)y, nb, T, F, C, L.tc[fmt], L.af.scale, L.af.shift};
       if (L.ws[fmt] && net->force_simt != 2 && tc_conv3x3_ws_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_ws(L.ws[fmt], ta, st);
       if (L.cp[fmt] && net->force_simt != 2 && tc_conv3x3_pair_supported(T, F, C) == AC_OK) return launch_tc_conv3x3_pair(L.cp[fmt], ta, st);
       return launch_tc_conv3x3(ta, st);
     }
     GemmArgs a{};
-    a.M = B * T * F; a.N = L.N; a.K = L.K; a.batch = 1;
+    a.M = nb * T * F; a.N = L.N; a.K = L.K; a.batch = 1;
     a.a_mode = A_CONV3; a.A = x; a.T = T; a.F = F; a.C = C;
     a.Bm = wsel(L.w32, L.w_off);
     a.epi = EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = L.N; a.out = y;
@@ -478,21 +523,21 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     return launch_gemm_simt(a, dtype, st);
   };
   // out = relu(affine(W * in)) (+ residual)
-  auto tdf = [&](const TdfLayer& L, const Block& b, const void* in, const void* residual, void* out) -> int {
+  auto tdf = [&](const TdfLayer& L, const Block& b, const void* in, const void* residual, void* out, int nb) -> int {
     if (use_tc) {
       if (L.pair[fmt] && residual && net->force_simt != 2)
-        return launch_tc_tdf2_pair(L.pair[fmt], (const h16*)in, (const h16*)residual, (h16*)out, B, b.T,
+        return launch_tc_tdf2_pair(L.pair[fmt], (const h16*)in, (const h16*)residual, (h16*)out, nb, b.T,
                                    L.af.scale, L.af.shift, st);
       if (L.pair1[fmt] && !residual && net->force_simt != 2)
-        return launch_tc_tdf1_pair(L.pair1[fmt], (const h16*)in, (h16*)out, B, b.T, L.af.scale, L.af.shift, st);
+        return launch_tc_tdf1_pair(L.pair1[fmt], (const h16*)in, (h16*)out, nb, b.T, L.af.scale, L.af.shift, st);
       if (L.tc[fmt])
-        return launch_tc_tdf(L.tc[fmt], (const h16*)in, (const h16*)residual, (h16*)out, B, b.T,
+        return launch_tc_tdf(L.tc[fmt], (const h16*)in, (const h16*)residual, (h16*)out, nb, b.T,
                              L.af.scale, L.af.shift, st);
-      return launch_tdf_small_cg8((const h16*)in, net->d_h16[fmt] + L.w_off, (const h16*)residual, (h16*)out, B, b.T,
+      return launch_tdf_small_cg8((const h16*)in, net->d_h16[fmt] + L.w_off, (const h16*)residual, (h16*)out, nb, b.T,
                                   b.c, L.M, L.K, L.af.scale, L.af.shift, fmt, st);
     }
     GemmArgs a{};
-    a.M = L.M; a.N = b.c; a.K = L.K; a.batch = B * b.T;
+    a.M = L.M; a.N = b.c; a.K = L.K; a.batch = nb * b.T;
     a.a_mode = A_PLAIN; a.A = wsel(L.w32, L.w_off); a.a_batch_stride = 0;
     a.Bm = in; a.b_batch_stride = (long long)L.K * b.c;
     a.epi = residual ? EPI_RESIDUAL : EPI_AFFINE_RELU; a.scale = L.af.scale; a.shift = L.af.shift; a.cmod = b.c;
@@ -500,90 +545,108 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
     a.kclass = KC_TDF_SIMT;
     return launch_gemm_simt(a, dtype, st);
   };
-  // The network's last TDF2 can apply the final 1x1 conv in its epilogue (debug mode 3 keeps them separate)
-  bool final_fused = false;
-  // X is clobbered, Y is scratch, result lands in Z (Z != Y); last = the block that feeds the final conv
-  auto run_block = [&](const Block& b, void* X, void* Y, void* Z, bool last = false) -> int {
-    void* src = X;
-    void* dst = Y;
+  // One TFC-TDF block on nb windows: the l convs go in -> A -> Bf -> A ...; `in` may alias Bf (it is dead after the first
+  // conv) but not A; the result lands in Z (anything but the conv chain's last buffer).  out4 != nullptr: the network's
+  // last block - the final 1x1 conv is applied in the TDF2 epilogue when the kernel can, else by a separate launch.
+  auto run_block = [&](const Block& b, const void* in, void* Z, int nb, void* out4) -> int {
+    const void* src = in;
+    void* dst = A;
     for (int j = 0; j < g.l; ++j) {
-      if ((rc = conv3x3(b.conv[j], src, dst, b.T, b.F, b.c))) return rc;
-      void* t = src; src = dst; dst = t;
+      if ((rc = conv3x3(b.conv[j], src, dst, b.T, b.F, b.c, nb))) return rc;
+      src = dst;
+      dst = dst == A ? Bf : A;
     }
-    // src now holds the TFC output; dst is free.  If Z aliases src the residual would be clobbered.
-    void* tfc = src;
+    const void* tfc = src;
     if (Z == tfc) return (set_error("internal: block output aliases TFC output"), AC_E_INVALID);
-    if ((rc = tdf(b.tdf1, b, tfc, nullptr, H))) return rc;
-    if (last && use_tc && net->force_simt == 0 && b.tdf2.pair[fmt] && tc_tdf2_pair_can_fuse_final(b.tdf2.pair[fmt]) && b.c == g.g &&
-        b.T == g.dim_t && b.tdf2.M == g.dim_f) {
-      final_fused = true;
-      return launch_tc_tdf2_pair(b.tdf2.pair[fmt], (const h16*)H, (const h16*)tfc, (h16*)d_out, B, b.T,
-                                 b.tdf2.af.scale, b.tdf2.af.shift, st, net->final_w, net->final_b);
+    if ((rc = tdf(b.tdf1, b, tfc, nullptr, H, nb))) return rc;
+    if (out4) {
+      if (use_tc && net->force_simt == 0 && b.tdf2.pair[fmt] && tc_tdf2_pair_can_fuse_final(b.tdf2.pair[fmt]) && b.c == g.g &&
+          b.T == g.dim_t && b.tdf2.M == g.dim_f)
+        return launch_tc_tdf2_pair(b.tdf2.pair[fmt], (const h16*)H, (const h16*)tfc, (h16*)out4, nb, b.T, b.tdf2.af.scale,
+                                   b.tdf2.af.shift, st, net->final_w, net->final_b);
+      if ((rc = tdf(b.tdf2, b, H, tfc, Z, nb))) return rc;
+      if (use_tc) return launch_final_conv_cg8(Z, out4, (long long)nb * g.dim_t, g.dim_f, g.g, net->final_w, net->final_b, fmt, st);
+      return launch_final_conv(Z, out4, (long long)nb * g.dim_t * g.dim_f, g.g, net->final_w, net->final_b, dtype, st);
     }
-    return tdf(b.tdf2, b, H, tfc, Z);
+    return tdf(b.tdf2, b, H, tfc, Z, nb);
+  };
+  auto down = [&](const ConvLayer& d, const Block& b, const void* skip, void* out, int nb) -> int {
+    if (use_tc) return launch_tc_resample(d.rs[fmt], (const h16*)skip, nullptr, (h16*)out, nb, b.T / 2, b.F / 2, d.af.scale, d.af.shift, st);
+    GemmArgs a{};
+    a.M = nb * (b.T / 2) * (b.F / 2); a.N = d.N; a.K = d.K; a.batch = 1;
+    a.a_mode = A_DOWN2; a.A = skip; a.T = b.T / 2; a.F = b.F / 2; a.C = b.c;
+    a.Bm = wsel(d.w32, d.w_off);
+    a.epi = EPI_AFFINE_RELU; a.scale = d.af.scale; a.shift = d.af.shift; a.cmod = d.N; a.out = out;
+    a.kclass = KC_RESAMPLE_SIMT;
+    return launch_gemm_simt(a, dtype, st);
+  };
+  // b = the block at the OUTPUT resolution; in = the level below
+  auto up = [&](const ConvLayer& u, const Block& b, const void* in, const void* skip, void* out, int nb) -> int {
+    if (use_tc) return launch_tc_resample(u.rs[fmt], (const h16*)in, (const h16*)skip, (h16*)out, nb, b.T / 2, b.F / 2, u.af.scale, u.af.shift, st);
+    GemmArgs a{};
+    a.M = nb * (b.T / 2) * (b.F / 2); a.N = u.N; a.K = u.K; a.batch = 1;
+    a.a_mode = A_PLAIN; a.A = in; a.a_batch_stride = 0;
+    a.Bm = wsel(u.w32, u.w_off);
+    a.epi = EPI_UP_SKIP; a.scale = u.af.scale; a.shift = u.af.shift; a.cmod = b.c; a.out = out; a.extra = skip;
+    a.up_T = b.T / 2; a.up_F = b.F / 2;
+    a.kclass = KC_RESAMPLE_SIMT;
+    return launch_gemm_simt(a, dtype, st);
   };
 
-  const long long P0 = (long long)B * g.dim_t * g.dim_f;
-  if (use_tc)
-    rc = launch_first_conv_cg8(d_in, P, (long long)B * g.dim_t, g.dim_f, g.g, net->first_w, net->first_af.scale,
-                               net->first_af.shift, fmt, st);
-  else
-    rc = launch_first_conv(d_in, P, P0, g.g, net->first_w, net->first_af.scale, net->first_af.shift, dtype, st);
-  if (rc) return rc;
-  void* cur = P;
-  void* oth = Q;
+  const size_t e_spec = (size_t)g.dim_t * g.dim_f * g.dim_c;  // one window of the input / output spectrogram
+  // ---- encoder: level i turns IO[i] (level 0: the spectrogram through the first 1x1 conv) into skip[i] and IO[i+1]
   for (int i = 0; i < g.n; ++i) {
     const Block& b = net->blocks[i];
     void* skip = ptr(wp.skip_off[i]);
-    // l convs ping-pong cur/oth; with odd l the TFC output is in oth, with even l in cur: either way != skip
-    if ((rc = run_block(b, cur, oth, skip))) return rc;
-    const ConvLayer& d = net->ds[i];
-    if (use_tc) {
-      if ((rc = launch_tc_resample(d.rs[fmt], (const h16*)skip, nullptr, (h16*)cur, B, b.T / 2, b.F / 2,
-                                   d.af.scale, d.af.shift, st)))
-        return rc;
-      continue;
+    void* next = ptr(wp.io_off[i + 1]);
+    for (int b0 = 0; b0 < B; b0 += wp.sb[i]) {
+      const int nb = B - b0 < wp.sb[i] ? B - b0 : wp.sb[i];
+      const void* in;
+      if (i == 0) {
+        const void* spec = cat(d_in, (size_t)b0 * e_spec);
+        if (use_tc)
+          rc = launch_first_conv_cg8(spec, Bf, (long long)nb * g.dim_t, g.dim_f, g.g, net->first_w, net->first_af.scale,
+                                     net->first_af.shift, fmt, st);
+        else
+          rc = launch_first_conv(spec, Bf, (long long)nb * g.dim_t * g.dim_f, g.g, net->first_w, net->first_af.scale,
+                                 net->first_af.shift, dtype, st);
+        if (rc) return rc;
+        in = Bf;
+      } else {
+        in = at(ptr(wp.io_off[i]), (size_t)b0 * wp.e[i]);
+      }
+      void* sk = at(skip, (size_t)b0 * wp.e[i]);
+      if ((rc = run_block(b, in, sk, nb, nullptr))) return rc;
+      if ((rc = down(net->ds[i], b, sk, at(next, (size_t)b0 * wp.e[i + 1]), nb))) return rc;
     }
-    GemmArgs a{};
-    a.M = B * (b.T / 2) * (b.F / 2); a.N = d.N; a.K = d.K; a.batch = 1;
-    a.a_mode = A_DOWN2; a.A = skip; a.T = b.T / 2; a.F = b.F / 2; a.C = b.c;
-    a.Bm = wsel(d.w32, d.w_off);
-    a.epi = EPI_AFFINE_RELU; a.scale = d.af.scale; a.shift = d.af.shift; a.cmod = d.N; a.out = cur;
-    a.kclass = KC_RESAMPLE_SIMT;
-    if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
   }
+  // ---- bottleneck: IO[n] -> IO[n] (the input is dead after the first conv)
   {
     const Block& b = net->blocks[g.n];
-    // result must not alias the TFC output: TFC output is in (l odd ? oth : cur); write to the other one
-    void* Z = (g.l & 1) ? cur : oth;
-    if ((rc = run_block(b, cur, oth, Z))) return rc;
-    if (Z != cur) { void* t = cur; cur = oth; oth = t; }
+    void* io = ptr(wp.io_off[g.n]);
+    for (int b0 = 0; b0 < B; b0 += wp.sb[g.n]) {
+      const int nb = B - b0 < wp.sb[g.n] ? B - b0 : wp.sb[g.n];
+      void* s = at(io, (size_t)b0 * wp.e[g.n]);
+      if ((rc = run_block(b, s, s, nb, nullptr))) return rc;
+    }
   }
+  // ---- decoder: level lvl = n-1 .. 0: up(IO[lvl+1]) * skip[lvl] -> block -> IO[lvl] (level 0: the output spectrogram)
   for (int i = 0; i < g.n; ++i) {
     const int lvl = g.n - 1 - i;
     const Block& b = net->blocks[g.n + 1 + i];
     const ConvLayer& u = net->us[i];
     void* skip = ptr(wp.skip_off[lvl]);
-    if (use_tc) {
-      if ((rc = launch_tc_resample(u.rs[fmt], (const h16*)cur, (const h16*)skip, (h16*)oth, B, b.T / 2,
-                                   b.F / 2, u.af.scale, u.af.shift, st)))
-        return rc;
-    } else {
-    GemmArgs a{};
-    a.M = B * (b.T / 2) * (b.F / 2); a.N = u.N; a.K = u.K; a.batch = 1;
-    a.a_mode = A_PLAIN; a.A = cur; a.a_batch_stride = 0;
-    a.Bm = wsel(u.w32, u.w_off);
-    a.epi = EPI_UP_SKIP; a.scale = u.af.scale; a.shift = u.af.shift; a.cmod = b.c; a.out = oth; a.extra = skip;
-    a.up_T = b.T / 2; a.up_F = b.F / 2;
-    a.kclass = KC_RESAMPLE_SIMT;
-    if ((rc = launch_gemm_simt(a, dtype, st))) return rc;
+    void* below = ptr(wp.io_off[lvl + 1]);
+    for (int b0 = 0; b0 < B; b0 += wp.sb[lvl]) {
+      const int nb = B - b0 < wp.sb[lvl] ? B - b0 : wp.sb[lvl];
+      if ((rc = up(u, b, at(below, (size_t)b0 * wp.e[lvl + 1]), at(skip, (size_t)b0 * wp.e[lvl]), Bf, nb))) return rc;
+      if (lvl == 0) {
+        // Z (only used when the final conv cannot be fused): the skip slice is dead after the up-conv consumed it
+        if ((rc = run_block(b, Bf, at(skip, (size_t)b0 * wp.e[0]), nb, at(d_out, (size_t)b0 * e_spec)))) return rc;
+      } else {
+        if ((rc = run_block(b, Bf, at(ptr(wp.io_off[lvl]), (size_t)b0 * wp.e[lvl]), nb, nullptr))) return rc;
+      }
     }
-    { void* t = cur; cur = oth; oth = t; }
-    void* Z = (g.l & 1) ? cur : oth;
-    if ((rc = run_block(b, cur, oth, Z, i == g.n - 1))) return rc;
-    if (Z != cur) { void* t = cur; cur = oth; oth = t; }
   }
-  if (final_fused) return AC_OK;
-  if (use_tc) return launch_final_conv_cg8(cur, d_out, (long long)B * g.dim_t, g.dim_f, g.g, net->final_w, net->final_b, fmt, st);
-  return launch_final_conv(cur, d_out, P0, g.g, net->final_w, net->final_b, dtype, st);
+  return AC_OK;
 }
