@@ -437,13 +437,7 @@ static void default_sub_batches(const ac_unet_geom& g, int B, int dtype, int* sb
       if (*p == ',') ++p;
     }
   }
-  int prev = 1;
-  for (int i = 0; i <= g.n; ++i) {
-    int v = cfg[i] < 1 ? 1 : (cfg[i] > B ? B : cfg[i]);
-    if (v < prev) v = prev;  // deeper levels never use a smaller sub-batch
-    sb[i] = v;
-    prev = v;
-  }
+  for (int i = 0; i <= g.n; ++i) sb[i] = cfg[i] < 1 ? 1 : (cfg[i] > B ? B : cfg[i]);  // levels are independent passes
 }
 static WsPlan plan_ws(const ac_unet_geom& g, int B, int dtype) {
   WsPlan w{};
