@@ -336,10 +336,12 @@ def chunk_sharded_config(be, rank, world, dev, barrier, dist):
     tag = os.environ.get("MASTER_PORT", "0")
     path = f"/dev/shm/acb200_{tag}_{rank}.npz"
     if world > 1 and rank != 0:
-        np.savez(path, **shard)
+        np.savez(path + ".tmp.npz", **shard)
+        os.replace(path + ".tmp.npz", path)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # timing only; doubles as the "shards are on the host" barrier
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # timing only
+        barrier()  # host-blocking: every rank's shard file is complete
     out = None
     if rank == 0:
         shards = [shard]
