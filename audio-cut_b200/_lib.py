@@ -20,7 +20,7 @@ EXPORTS = [
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
     "ac_track_workspace_bytes", "ac_separate_track", "ac_separate_track_ex", "ac_stft_features_workspace_bytes", "ac_stft_features",
     "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
-    "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3", "ac_pyin_frame_count", "ac_pyin_workspace_bytes", "ac_pyin",
+    "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3", "ac_debug_conv3x3_chain", "ac_pyin_frame_count", "ac_pyin_workspace_bytes", "ac_pyin",
     "ac_lpc_frame_count", "ac_lpc_formants", "ac_refine_cut_points", "ac_quiet_lookup_db",
     "ac_host_is_pinned", "ac_copy_h2d_async",
     "ac_pcm_decode", "ac_peak_normalize", "ac_pcm_pack", "ac_resample_out_len", "ac_resample_poly",
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     lib.ac_debug_tc_aborted.argtypes, lib.ac_debug_tc_aborted.restype = [], i
     lib.ac_debug_conv3x3.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, i, i, C.POINTER(C.c_float), vp]
     lib.ac_debug_conv3x3.restype = i
+    lib.ac_debug_conv3x3_chain.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, i, i, C.POINTER(C.c_float), vp]
+    lib.ac_debug_conv3x3_chain.restype = i
     lib.ac_track_window_count.argtypes = [C.POINTER(ChunkDesc), i, C.POINTER(TrackParams)]
     lib.ac_track_window_count.restype = i
     lib.ac_track_workspace_bytes.argtypes = [vp, C.POINTER(ChunkDesc), i, C.POINTER(TrackParams)]

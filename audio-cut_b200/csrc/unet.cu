@@ -37,6 +37,7 @@ struct Block {
   int c, T, F;
   ConvLayer conv[8];
   TdfLayer tdf1, tdf2;
+  TcConvF3Weights* f3[2] = {nullptr, nullptr};  // fused chain of the block's three 3x3 convs (C = 48 only)
 };
 
 }  // namespace ac
@@ -245,6 +246,7 @@ extern "C" void ac_unet_destroy(ac_unet* net) {
         if (b.conv[j].ws[f]) ac::tc_conv3x3_ws_free(b.conv[j].ws[f]);
         if (b.conv[j].cp[f]) ac::tc_conv3x3_pair_free(b.conv[j].cp[f]);
       }
+      ac::tc_conv3x3_f3_free(b.f3[f]);
       ac::tc_tdf_free(b.tdf1.tc[f]);
       ac::tc_tdf_free(b.tdf2.tc[f]);
       ac::tc_tdf2_pair_free(b.tdf2.pair[f]);
@@ -293,6 +295,10 @@ static int ensure_h16(ac_unet* net, int fmt) {
       if (!L.tc[fmt] && tc_conv3x3_supported(b.T, b.F, b.c) == AC_OK && (rc = tc_conv3x3_pack(raw, b.c, fmt, &L.tc[fmt]))) return rc;
       if (!L.cp[fmt] && tc_conv3x3_pair_supported(b.T, b.F, b.c) == AC_OK && (rc = tc_conv3x3_pair_pack(raw, b.c, fmt, &L.cp[fmt]))) return rc;
       if (!L.ws[fmt] && tc_conv3x3_ws_supported(b.T, b.F, b.c) == AC_OK && (rc = tc_conv3x3_ws_pack(raw, b.c, fmt, &L.ws[fmt]))) return rc;
+    }
+    if (!b.f3[fmt] && g.l == 3 && tc_conv3x3_f3_supported(b.T, b.F, b.c, g.l) == AC_OK) {
+      const float* raws[3] = {blob + b.conv[0].raw_off, blob + b.conv[1].raw_off, blob + b.conv[2].raw_off};
+      if ((rc = tc_conv3x3_f3_pack(raws, b.c, fmt, &b.f3[fmt]))) return rc;
     }
     TdfLayer& t1 = b.tdf1;
     TdfLayer& t2 = b.tdf2;
@@ -397,6 +403,72 @@ extern "C" int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int
   if (d_w16) cudaFree(d_w16);
   if (rc == AC_OK && ce != cudaSuccess) {
     set_error(std::string("ac_debug_conv3x3: ") + cudaGetErrorString(ce));
+    return AC_E_CUDA;
+  }
+  return rc;
+}
+
+// Test / profiling hook: a chain of three 3x3 conv layers (C = 48) on CG8 tensors; impl 0 = three launches of the
+// weight-stationary kernel, 1 = the fused kernel (unet_tc_conv_f3.cu).  impl + 16: IEEE-half operands.  d_tmp = scratch of the
+// tensor's size (impl 0 ping-pongs d_out / d_tmp).  h_w = 3 x W[C][C][3][3], d_scale / d_shift = 3 x [C].
+extern "C" int ac_debug_conv3x3_chain(const void* d_in, void* d_out, void* d_tmp, int B, int T, int F, int C, const float* h_w,
+                                      const float* d_scale, const float* d_shift, int impl, int iters, float* h_ms,
+                                      void* stream) {
+  using namespace ac;
+  AC_REQUIRE(d_in && d_out && d_tmp && h_w && d_scale && d_shift && iters >= 1, "null pointer / iters");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int fmt = (impl & 16) ? kFmtF16 : kFmtBF16;
+  impl &= 15;
+  const size_t wn = (size_t)C * C * 9;
+  TcConvWsWeights* ws[3] = {nullptr, nullptr, nullptr};
+  TcConvF3Weights* f3 = nullptr;
+  int rc = AC_OK;
+  if (impl == 1) {
+    AC_REQUIRE(tc_conv3x3_f3_supported(T, F, C, 3) == AC_OK, "fused conv chain does not support this shape");
+    const float* raws[3] = {h_w, h_w + wn, h_w + 2 * wn};
+    if ((rc = tc_conv3x3_f3_pack(raws, C, fmt, &f3))) return rc;
+  } else {
+    AC_REQUIRE(tc_conv3x3_ws_supported(T, F, C) == AC_OK, "ws tc conv does not support this shape");
+    for (int j = 0; j < 3 && rc == AC_OK; ++j) rc = tc_conv3x3_ws_pack(h_w + j * wn, C, fmt, &ws[j]);
+  }
+  auto once = [&]() -> int {
+    if (impl == 1) {
+      const float* sc[3] = {d_scale, d_scale + C, d_scale + 2 * C};
+      const float* sh[3] = {d_shift, d_shift + C, d_shift + 2 * C};
+      return launch_tc_conv3x3_f3(f3, (const h16*)d_in, (h16*)d_out, B, T, F, sc, sh, st);
+    }
+    const void* src = d_in;
+    void* bufs[3] = {d_out, d_tmp, d_out};
+    for (int j = 0; j < 3; ++j) {
+      TcConvArgs ta{(const h16*)src, (h16*)bufs[j], B, T, F, C, nullptr, d_scale + j * C, d_shift + j * C};
+      int r = launch_tc_conv3x3_ws(ws[j], ta, st);
+      if (r) return r;
+      src = bufs[j];
+    }
+    return AC_OK;
+  };
+  if (rc == AC_OK) rc = once();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (rc == AC_OK && iters > 1) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int i = 1; i < iters && rc == AC_OK; ++i) rc = once();
+    cudaEventRecord(e1, st);
+  }
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (e0) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (h_ms) *h_ms = ms / (iters - 1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  for (int j = 0; j < 3; ++j)
+    if (ws[j]) tc_conv3x3_ws_free(ws[j]);
+  if (f3) tc_conv3x3_f3_free(f3);
+  if (rc == AC_OK && ce != cudaSuccess) {
+    set_error(std::string("ac_debug_conv3x3_chain: ") + cudaGetErrorString(ce));
     return AC_E_CUDA;
   }
   return rc;
@@ -545,10 +617,18 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
   auto run_block = [&](const Block& b, const void* in, void* Z, int nb, void* out4) -> int {
     const void* src = in;
     void* dst = A;
-    for (int j = 0; j < g.l; ++j) {
-      if ((rc = conv3x3(b.conv[j], src, dst, b.T, b.F, b.c, nb))) return rc;
+    if (use_tc && net->force_simt == 0 && g.l == 3 && b.f3[fmt] && tc_conv3x3_f3_supported(b.T, b.F, b.c, g.l) == AC_OK) {
+      // level 0: the three convs in one kernel, intermediates in shared memory (bit-identical to the chain below)
+      const float* sc[3] = {b.conv[0].af.scale, b.conv[1].af.scale, b.conv[2].af.scale};
+      const float* sh[3] = {b.conv[0].af.shift, b.conv[1].af.shift, b.conv[2].af.shift};
+      if ((rc = launch_tc_conv3x3_f3(b.f3[fmt], (const h16*)src, (h16*)dst, nb, b.T, b.F, sc, sh, st))) return rc;
       src = dst;
-      dst = dst == A ? Bf : A;
+    } else {
+      for (int j = 0; j < g.l; ++j) {
+        if ((rc = conv3x3(b.conv[j], src, dst, b.T, b.F, b.c, nb))) return rc;
+        src = dst;
+        dst = dst == A ? Bf : A;
+      }
     }
     const void* tfc = src;
     if (Z == tfc) return (set_error("internal: block output aliases TFC output"), AC_E_INVALID);

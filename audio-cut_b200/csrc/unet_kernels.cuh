@@ -66,6 +66,15 @@ int launch_tc_conv3x3_ws(const TcConvWsWeights* w, const TcConvArgs& a, cudaStre
 void tc_conv3x3_ws_set_rs(int enabled);    // test hook: 0 = never use the row-stacked (N = 144) kernel for C = 48
 void tc_conv3x3_ws_set_pair(int enabled);  // test hook: 0 = never use the CTA-pair (cta_group::2) kernel
 
+// fused chain of three 3x3 convs for C = 48 (unet_tc_conv_f3.cu): intermediates stay in shared memory; *out stays nullptr
+// for other widths.  Output bit-identical to three launch_tc_conv3x3_ws calls.
+struct TcConvF3Weights;
+int tc_conv3x3_f3_supported(int T, int F, int C, int n_convs);
+int tc_conv3x3_f3_pack(const float* const h_w[3] /*[C][C][3][3] each*/, int C, int fmt, TcConvF3Weights** out);
+void tc_conv3x3_f3_free(TcConvF3Weights* w);
+int launch_tc_conv3x3_f3(const TcConvF3Weights* w, const h16* in, h16* out, int nB, int T, int F, const float* const scale[3],
+                         const float* const shift[3], cudaStream_t st);
+
 // CUDA-core pieces of the CG8 path (unet_cg8.cu)
 int cg8_ends_supported(int g);
 // spec [rows*F][4] bf16 -> CG8 [rows][g/8][F][8] (rows = nB*T);  and back with bias

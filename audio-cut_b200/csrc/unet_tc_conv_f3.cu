@@ -1,0 +1,470 @@
+// Fused TFC conv chain for the widest U-Net level (C = 48): conv3x3+BN+ReLU three times in ONE kernel,
+// the two intermediate activations never leave the SM.
+//
+// Why: at C = 48 a single 3x3 conv moves 2 x 1.2 GB (B = 16 windows) for 522 GFLOP - the HBM/tensor knee - and its
+// N = 48 MMA shape is shared-memory bound (44 cycles of operand reads for 24 of math).  The unfused block therefore
+// costs 3 x 583 us.  Here
+//   * every conv runs in the ROW-STACKED formulation of unet_tc_conv_ws.cu (tc_conv3x3_rs_kernel): the three vertical
+//     taps are stacked along N = 144, input row r adds its contributions to the accumulators of output rows r+1, r,
+//     r-1, which sit side by side in a ring of TMEM blocks.  9 tensor-bound MMAs per 128 positions instead of 27
+//     shared-memory-bound ones, AND an input row is used by exactly one step, so each stage only needs a short FIFO
+//     of rows instead of a 3-row window;
+//   * conv c's epilogue writes its finished row (folded BN + ReLU, rounded to the 16-bit operand format exactly like
+//     the unfused kernel's global store) straight into the next conv's A-operand FIFO in shared memory, in the
+//     canonical no-swizzle K-major order [C/8][130][8] - which is also the CG8 global order, so the store is 512
+//     contiguous bytes per warp instruction;
+//   * zero padding of conv c+1 = rows / positions outside the image are written as zeros;
+//   * horizontally a strip is ONE M = 128 tile: conv1 computes 128 positions from 130, conv2 126 valid from those,
+//     conv3 124 valid: strips advance by 124 positions (3 % recompute, F = 3072 -> 25 strips);
+//   * vertically a segment of `rows` output rows costs rows+6 / rows+4 / rows+2 steps of the three convs.
+// Shared memory: 3 x 41.5 KB weights + (4 + 2 + 2) row tiles of 12.25 KB = 222 KB.  TMEM: rings of 4 + 3 + 3 blocks
+// of 48 columns = 480.  One MMA-issuing warp interleaves the three convs (conv2 lags conv1 by 3 steps, conv3 by 6, so
+// the epilogue has a whole macro step to drain a row before its consumer needs it).
+// Output is bit-identical to three launches of the weight-stationary kernel (same accumulation order per element).
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2..13 = epilogue.
+#include <stdlib.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "tc_common.cuh"
+#include "unet_kernels.cuh"
+
+namespace ac {
+
+constexpr int kF3C = 48;
+constexpr int kF3EpiWarps = 12;                       // (TMEM lane quadrant) x (16-channel group)
+constexpr int kF3Threads = (2 + kF3EpiWarps) * 32;
+constexpr int kF3Valid = 124;                         // output positions per strip
+constexpr int kF3RowPos = 130;                        // rows of an A tile
+constexpr int kF3ALbo = kF3RowPos * 16;               // bytes between 8-channel planes of a tile
+constexpr int kF3ATile = ((kF3C / 8) * kF3ALbo + 127) / 128 * 128;
+constexpr int kF3InSlots = 4;
+constexpr int kF3MidSlots = 2;
+constexpr int kF3BLbo = 3 * kF3C * 16;                // B rows = (dt, co): 144 rows of 16 B per 8-channel K group
+constexpr int kF3DfBytes = (kF3C / 8) * kF3BLbo;      // one horizontal tap: [C/8][144][8]
+constexpr int kF3WBytes = 3 * kF3DfBytes;             // one conv
+constexpr int kF3Header = 2048;
+constexpr int kF3Smem = kF3Header + 3 * kF3WBytes + (kF3InSlots + 2 * kF3MidSlots) * kF3ATile;
+static_assert(kF3Smem <= 227 * 1024, "shared memory budget");
+
+__host__ __device__ constexpr int f3_rb(int c) { return c == 0 ? 4 : 3; }           // TMEM blocks of conv c's ring
+__host__ __device__ constexpr int f3_col(int c) { return c == 0 ? 0 : (c == 1 ? 4 * 48 : 7 * 48); }
+__host__ __device__ constexpr int f3_skew(int c) { return 3 * c; }                  // macro-step lag of conv c
+constexpr int kF3Cols = 10 * 48;
+
+struct F3Params {
+  int nB, T, F;
+  int n_strips;          // strips of kF3Valid positions per image row
+  long long total_rows;  // nB * n_strips * T
+  const h16* wpack;      // [conv][df][C/8][dt*48 + co][8]
+  const float* scale[3];
+  const float* shift[3];
+  h16* out;
+  int* abort_flag;
+};
+
+struct F3Seg {
+  int b, f0, t0, t1;
+};
+__device__ __forceinline__ F3Seg f3_segment(const F3Params& p, long long L, long long hi) {
+  F3Seg s;
+  const long long strip = L / p.T;
+  s.t0 = (int)(L - strip * p.T);
+  const long long left = hi - L;
+  s.t1 = (left < (long long)(p.T - s.t0)) ? s.t0 + (int)left : p.T;
+  s.b = (int)(strip / p.n_strips);
+  s.f0 = (int)(strip - (long long)s.b * p.n_strips) * kF3Valid;
+  return s;
+}
+
+__device__ __forceinline__ uint64_t f3_desc_at(uint32_t lo_base, uint32_t hi, uint32_t byte_off) {
+  return ((uint64_t)hi << 32) | (uint64_t)(lo_base + (byte_off >> 4));
+}
+__device__ __forceinline__ void f3_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kF3Threads, 1)
+tc_conv3x3_f3_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params p) {
+  constexpr int C = kF3C, NT = 48, K16 = C / 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);   // [4]
+  uint64_t* in_empty = in_full + 4;                         // [4]
+  uint64_t* mid_full = in_full + 8;                         // [2 stages][2 slots]
+  uint64_t* mid_empty = in_full + 12;                       // [2 stages][2 slots]
+  uint64_t* done = in_full + 16;                            // [3 convs][4 blocks]  MMA -> epilogue: block complete
+  uint64_t* bfree = in_full + 28;                           // [3 convs][4 blocks]  epilogue -> MMA: drained and zeroed
+  uint64_t* wbar = in_full + 40;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 41);
+  float* s_scale = reinterpret_cast<float*>(smem + 512);    // [3][48]
+  float* s_shift = s_scale + 3 * NT;                        // [3][48]
+  uint8_t* w_smem = smem + kF3Header;
+  uint8_t* in_ring = w_smem + 3 * kF3WBytes;
+  uint8_t* mid_ring = in_ring + kF3InSlots * kF3ATile;      // stage 0 (conv1 -> conv2): 2 slots, stage 1: 2 slots
+  volatile int* abort_flag = p.abort_flag;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long lo, hi;
+  lo = p.total_rows * blockIdx.x / gridDim.x;
+  hi = p.total_rows * (blockIdx.x + 1) / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kF3InSlots; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&in_empty[s], 1);
+    }
+    for (int s = 0; s < 2 * kF3MidSlots; ++s) {
+      mbar_init(&mid_full[s], kF3EpiWarps);
+      mbar_init(&mid_empty[s], 1);
+    }
+    for (int b = 0; b < 12; ++b) {
+      mbar_init(&done[b], 1);
+      mbar_init(&bfree[b], kF3EpiWarps);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 3 * NT; i += blockDim.x) {
+    s_scale[i] = p.scale[i / NT][i % NT];
+    s_shift[i] = p.shift[i / NT][i % NT];
+  }
+  // the intermediate tiles start as zeros (rows 128, 129 of a tile are read by the last MMA rows and never written)
+  for (int i = threadIdx.x; i < 2 * kF3MidSlots * kF3ATile / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(mid_ring)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its output is visible from here on
+
+  if (warp == 0) {
+    // ===================== TMA producer: the three weight sets once, then one slot per input row ==========
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)(3 * kF3WBytes));
+      for (int i = 0; i < 9; ++i)
+        bulk_load_1d(w_smem + i * kF3DfBytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)i * kF3DfBytes, kF3DfBytes, wbar);
+      int s = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (long long L = lo; L < hi && alive;) {
+        const F3Seg sg = f3_segment(p, L, hi);
+        for (int r = sg.t0 - 3; r < sg.t1 + 3; ++r) {
+          if (!mbar_wait(&in_empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+          mbar_expect_tx(&in_full[s], (uint32_t)((C / 8) * kF3RowPos * 16));
+          tma_load_5d(in_ring + (size_t)s * kF3ATile, &in_map, &in_full[s], 0, sg.f0 - 3, 0, r, sg.b);
+          if (++s == kF3InSlots) { s = 0; ph ^= 1; }
+        }
+        L += sg.t1 - sg.t0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc144 = make_idesc<FMT>(144), idesc96 = make_idesc<FMT>(96), idesc48 = make_idesc<FMT>(48);
+    const uint64_t a_proto = make_desc(0, kF3ALbo, 128), b_proto = make_desc(0, kF3BLbo, 128);
+    const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+    const uint32_t a_lo_in = (uint32_t)a_proto + (smem_u32(in_ring) >> 4);
+    const uint32_t a_lo_mid = (uint32_t)a_proto + (smem_u32(mid_ring) >> 4);
+    const uint32_t b_lo0 = (uint32_t)b_proto + (smem_u32(w_smem) >> 4);
+    auto wait_all = [&](uint64_t* bar, uint32_t parity) {
+      return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+    };
+    bool alive = wait_all(wbar, 0);
+    // the epilogue warps zero the block rings before the first MMA (named barrier 1: 12 epilogue warps + this warp)
+    asm volatile("bar.sync 1, %0;" ::"r"((kF3EpiWarps + 1) * 32) : "memory");
+    tc_fence_after();
+    int fs[3] = {0, 0, 0};         // FIFO slot each conv reads next
+    uint32_t fph[3] = {0, 0, 0};
+    int gm[3] = {0, 0, 0};         // virtual step g mod RB
+    uint32_t cyc[3] = {0, 0, 0};   // g / RB
+
+    // one virtual step of conv CI: (real) 9..18 MMAs of input row -> blocks of output rows g+1, g, g-1; then "block of
+    // row g-1 is complete"
+    auto step = [&](auto ci, bool real) -> bool {
+      constexpr int CI = decltype(ci)::value;
+      constexpr int RB = f3_rb(CI);
+      const int sb = RB - 1 - gm[CI];
+      // row g+1 enters block sb: its previous owners (n of them) must have been drained and zeroed
+      {
+        const uint32_t n = (gm[CI] + 2 >= RB) ? cyc[CI] + 1 : cyc[CI];
+        if (n > 0 && !wait_all(&bfree[CI * 4 + sb], (n - 1) & 1)) return false;
+      }
+      if (real) {
+        const int s = fs[CI];
+        uint64_t* fullb = CI == 0 ? &in_full[s] : &mid_full[(CI - 1) * kF3MidSlots + s];
+        uint64_t* emptyb = CI == 0 ? &in_empty[s] : &mid_empty[(CI - 1) * kF3MidSlots + s];
+        if (!wait_all(fullb, fph[CI])) return false;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = CI == 0 ? a_lo_in + (uint32_t)s * (kF3ATile >> 4)
+                                        : a_lo_mid + (uint32_t)((CI - 1) * kF3MidSlots + s) * (kF3ATile >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)CI * (kF3WBytes >> 4);
+          const int n1 = (sb + 3 <= RB) ? 3 : RB - sb;  // blocks before the ring wraps
+          const uint32_t d0 = tmem_base + (uint32_t)(f3_col(CI) + sb * NT);
+          const uint32_t d1 = tmem_base + (uint32_t)f3_col(CI);
+#pragma unroll
+          for (int df = 0; df < 3; ++df) {
+#pragma unroll
+            for (int k = 0; k < K16; ++k) {
+              const uint64_t ad = f3_desc_at(a_lo, a_hi, df * 16 + k * 2 * kF3ALbo);
+              const uint32_t boff = df * kF3DfBytes + k * 2 * kF3BLbo;
+              if (n1 == 3) {
+                f3_umma(d0, ad, f3_desc_at(b_lo, b_hi, boff), idesc144);
+              } else if (n1 == 2) {
+                f3_umma(d0, ad, f3_desc_at(b_lo, b_hi, boff), idesc96);
+                f3_umma(d1, ad, f3_desc_at(b_lo, b_hi, boff + 2 * NT * 16), idesc48);
+              } else {
+                f3_umma(d0, ad, f3_desc_at(b_lo, b_hi, boff), idesc48);
+                f3_umma(d1, ad, f3_desc_at(b_lo, b_hi, boff + NT * 16), idesc96);
+              }
+            }
+          }
+          umma_commit(emptyb);
+        }
+        __syncwarp();
+        if (++fs[CI] == (CI == 0 ? kF3InSlots : kF3MidSlots)) { fs[CI] = 0; fph[CI] ^= 1; }
+      }
+      if (elect_one()) umma_commit(&done[CI * 4 + (sb + 2) % RB]);
+      __syncwarp();
+      if (++gm[CI] == RB) { gm[CI] = 0; ++cyc[CI]; }
+      return true;
+    };
+
+    for (long long L = lo; L < hi && alive;) {
+      const F3Seg sg = f3_segment(p, L, hi);
+      const int rows = sg.t1 - sg.t0;
+      const int M = rows + 10;
+      for (int m = 0; m < M && alive; ++m) {
+        {
+          const int v = m;  // conv1: rows + 6 real input rows + 2 flush steps
+          if (v < rows + 8) alive = step(std::integral_constant<int, 0>{}, v < rows + 6);
+        }
+        if (alive) {
+          const int v = m - f3_skew(1);
+          if (v >= 0 && v < rows + 6) alive = step(std::integral_constant<int, 1>{}, v < rows + 4);
+        }
+        if (alive) {
+          const int v = m - f3_skew(2);
+          if (v >= 0 && v < rows + 4) alive = step(std::integral_constant<int, 2>{}, v < rows + 2);
+        }
+      }
+      L += rows;
+    }
+  } else {
+    // ===================== epilogue (warps 2..13): drain + zero one block per virtual step of each conv ==========
+    const int quad = warp & 3;          // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
+    const int grp = (warp - 2) >> 2;    // channels [16*grp, +16)
+    const int mrow = quad * 32 + lane;  // MMA row = position within the tile
+    const size_t plane = (size_t)p.F * 8;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 16);
+    {
+      const uint32_t z = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kF3Cols; c0 += NT)
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(lane_addr + c0),
+            "r"(z)
+            : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"((kF3EpiWarps + 1) * 32) : "memory");
+    int Gm[3] = {0, 0, 0};          // drained virtual steps of conv c: G mod RB, G / RB
+    uint32_t Gc[3] = {0, 0, 0};
+    int ws_[2] = {0, 0};            // FIFO slot the stage writes next
+    uint32_t wph[2] = {0, 0};
+    bool alive = true;
+
+    // drain the block completed by virtual step v of conv CI; `t_out` = the output row it holds, `valid` = keep it
+    auto drain = [&](auto ci, const F3Seg& sg, int t_out, bool valid) -> bool {
+      constexpr int CI = decltype(ci)::value;
+      constexpr int RB = f3_rb(CI);
+      int blk = 1 - Gm[CI];
+      if (blk < 0) blk += RB;
+      if (!mbar_wait(&done[CI * 4 + blk], Gc[CI] & 1, abort_flag)) return false;
+      tc_fence_after();
+      uint32_t r[16];
+      const uint32_t taddr = lane_addr + (uint32_t)(f3_col(CI) + blk * NT);
+      tmem_ld16(taddr, r);
+      tmem_ld_wait();
+      {
+        const uint32_t z = 0;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+            "r"(z)
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&bfree[CI * 4 + blk]);
+      if (++Gm[CI] == RB) { Gm[CI] = 0; ++Gc[CI]; }
+      if (!valid) return true;
+      // position of this thread's row: conv1 tile starts at f0 - 2, conv2 at f0 - 1, conv3 at f0
+      const int pos = sg.f0 - 2 + CI + mrow;
+      uint32_t pk[8];
+      const float* sc = s_scale + CI * NT + grp * 16;
+      const float* sh = s_shift + CI * NT + grp * 16;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), sc[2 * e], sh[2 * e]), 0.f);
+        const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
+        pk[e] = pack2<FMT>(v0, v1);
+      }
+      if constexpr (CI < 2) {
+        // next conv's zero padding: nothing outside the image
+        const bool inside = t_out >= 0 && t_out < p.T && pos >= 0 && pos < p.F;
+        if (!inside) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk[e] = 0u;
+        }
+        const int s = ws_[CI];
+        if (!mbar_wait(&mid_empty[CI * kF3MidSlots + s], wph[CI] ^ 1, abort_flag)) return false;
+        uint8_t* dst = mid_ring + (size_t)(CI * kF3MidSlots + s) * kF3ATile + (size_t)(grp * 2) * kF3ALbo + (size_t)mrow * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dst + kF3ALbo) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mid_full[CI * kF3MidSlots + s]);
+        if (++ws_[CI] == kF3MidSlots) { ws_[CI] = 0; wph[CI] ^= 1; }
+      } else {
+        if (mrow < kF3Valid && pos < p.F) {
+          h16* dst = p.out + cg8_index(sg.b, t_out, grp * 2, pos, p.T, C, p.F);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      return true;
+    };
+
+    for (long long L = lo; L < hi && alive;) {
+      const F3Seg sg = f3_segment(p, L, hi);
+      const int rows = sg.t1 - sg.t0;
+      const int M = rows + 10;
+      for (int m = 0; m < M && alive; ++m) {
+        {
+          // conv1, virtual step v: holds output row t0 - 4 + v; rows t0-2 .. t1+1 feed conv2
+          const int v = m;
+          if (v < rows + 8) alive = drain(std::integral_constant<int, 0>{}, sg, sg.t0 - 4 + v, v >= 2 && v < rows + 6);
+        }
+        if (alive) {
+          const int v = m - f3_skew(1);  // conv2: output row t0 - 3 + v; rows t0-1 .. t1 feed conv3
+          if (v >= 0 && v < rows + 6) alive = drain(std::integral_constant<int, 1>{}, sg, sg.t0 - 3 + v, v >= 2 && v < rows + 4);
+        }
+        if (alive) {
+          const int v = m - f3_skew(2);  // conv3: output row t0 - 2 + v; rows t0 .. t1-1 are stored
+          if (v >= 0 && v < rows + 4) alive = drain(std::integral_constant<int, 2>{}, sg, sg.t0 - 2 + v, v >= 2 && v < rows + 2);
+        }
+      }
+      L += rows;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TcConvF3Weights {
+  int fmt;
+  h16* d_pack;
+};
+
+int tc_conv3x3_f3_supported(int T, int F, int C, int n_convs) {
+  static const bool off = getenv("AC_NO_F3") && atoi(getenv("AC_NO_F3")) != 0;  // dev hook: A/B against the unfused kernels
+  return (!off && C == kF3C && n_convs == 3 && T >= 1 && F >= kF3RowPos) ? AC_OK : AC_E_INVALID;
+}
+
+// h_w[j] = W_j[C][C][3][3] (conv j of the chain); packing per conv: [df][C/8][dt*48 + co][8]
+int tc_conv3x3_f3_pack(const float* const h_w[3], int C, int fmt, TcConvF3Weights** out) {
+  *out = nullptr;
+  if (C != kF3C) return AC_OK;
+  std::vector<h16> pack((size_t)3 * 9 * C * C);
+  size_t o = 0;
+  for (int j = 0; j < 3; ++j)
+    for (int df = 0; df < 3; ++df)
+      for (int kg = 0; kg < C / 8; ++kg)
+        for (int dt = 0; dt < 3; ++dt)
+          for (int co = 0; co < C; ++co)
+            for (int e = 0; e < 8; ++e) pack[o++] = h16_rn(h_w[j][(((size_t)co * C + kg * 8 + e) * 3 + dt) * 3 + df], fmt);
+  TcConvF3Weights* w = new TcConvF3Weights();
+  w->fmt = fmt;
+  w->d_pack = nullptr;
+  if (cudaMalloc(&w->d_pack, pack.size() * 2) != cudaSuccess ||
+      cudaMemcpy(w->d_pack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tc f3 weight upload failed");
+    if (w->d_pack) cudaFree(w->d_pack);
+    delete w;
+    return AC_E_CUDA;
+  }
+  *out = w;
+  return AC_OK;
+}
+
+void tc_conv3x3_f3_free(TcConvF3Weights* w) {
+  if (!w) return;
+  if (w->d_pack) cudaFree(w->d_pack);
+  delete w;
+}
+
+int launch_tc_conv3x3_f3(const TcConvF3Weights* w, const h16* in, h16* out, int nB, int T, int F, const float* const scale[3],
+                         const float* const shift[3], cudaStream_t st) {
+  AC_REQUIRE(w && in && out, "tc f3 conv: null pointer");
+  AC_REQUIRE(tc_conv3x3_f3_supported(T, F, kF3C, 3) == AC_OK, "tc f3 conv: unsupported shape");
+  EncodeTiledFn enc = get_tensor_map_encoder();
+  AC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available");
+  AC_REQUIRE(tc_abort_flag() != nullptr, "abort flag allocation failed");
+  const int C = kF3C;
+  // 5-D view of the CG8 tensor [nB][T][C/8][F][8]: (c%8, f, c/8, t, b); one box = [C/8][130 positions][8 ch]
+  CUtensorMap map;
+  const cuuint64_t dims[5] = {8, (cuuint64_t)F, (cuuint64_t)(C / 8), (cuuint64_t)T, (cuuint64_t)nB};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)F * 16, (cuuint64_t)F * C * 2, (cuuint64_t)T * F * C * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)kF3RowPos, (cuuint32_t)(C / 8), 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<h16*>(in), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f3 conv) failed with code " + std::to_string((int)r));
+    return AC_E_CUDA;
+  }
+  F3Params p;
+  p.nB = nB; p.T = T; p.F = F;
+  p.n_strips = (F + kF3Valid - 1) / kF3Valid;
+  p.total_rows = (long long)nB * p.n_strips * T;
+  p.wpack = w->d_pack;
+  for (int j = 0; j < 3; ++j) {
+    p.scale[j] = scale[j];
+    p.shift[j] = shift[j];
+  }
+  p.out = out;
+  p.abort_flag = tc_abort_flag();
+  // algorithmic work of the fused op: three convs' FLOPs, one read + one write of the activation
+  ProfScope ps(KC_CONV_TC, 3 * 2.0 * 9.0 * nB * (double)T * F * C * C, 4.0 * nB * (double)T * F * C, st);
+  auto kern = w->fmt == kFmtBF16 ? tc_conv3x3_f3_kernel<kFmtBF16> : tc_conv3x3_f3_kernel<kFmtF16>;
+  AC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int grid = device_sm_count();
+  if ((long long)grid > p.total_rows) grid = (int)p.total_rows;
+  AC_CHECK_CUDA(tc_launch(kern, grid, kF3Threads, kF3Smem, st, 1, map, p));
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+}  // namespace ac

@@ -184,6 +184,28 @@ def debug_conv3x3(x: torch.Tensor, w: np.ndarray, scale: torch.Tensor, shift: to
     return y, float(ms.value)
 
 
+def debug_conv3x3_chain(x: torch.Tensor, w: np.ndarray, scale: torch.Tensor, shift: torch.Tensor, impl: int, iters: int = 1):
+    """Three chained 16-bit 3x3 conv layers (test hook, C = 48): x [B,T,F,C], w [3,C,C,3,3] float32, scale / shift [3,C]
+    -> (y, mean ms per pass).  impl 0 = three weight-stationary launches, 1 = the fused kernel."""
+    lib = _lib.init(_dev_index(x))
+    assert x.dtype in (torch.bfloat16, torch.float16) and x.dim() == 4
+    B, T, F, Cc = x.shape
+    x = x.view(B, T, F, Cc // 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    assert w.shape == (3, Cc, Cc, 3, 3)
+    y = torch.empty_like(x)
+    tmp = torch.empty_like(x)
+    ms = C.c_float(0.0)
+    sc = scale.float().contiguous()
+    sh = shift.float().contiguous()
+    assert tuple(sc.shape) == (3, Cc) and tuple(sh.shape) == (3, Cc)
+    check(lib.ac_debug_conv3x3_chain(ptr(x), ptr(y), ptr(tmp), B, T, F, Cc, w.ctypes.data_as(C.c_void_p), ptr(sc), ptr(sh),
+                                     impl | (16 if x.dtype == torch.float16 else 0), iters, C.byref(ms), stream_ptr()),
+          "ac_debug_conv3x3_chain")
+    y = y.view(B, T, Cc // 8, F, 8).permute(0, 1, 3, 2, 4).contiguous().view(B, T, F, Cc)
+    return y, float(ms.value)
+
+
 def make_chunk_descs(bounds: Sequence[Tuple[int, int, int, int]]):
     """bounds: (chunk_start, chunk_end, eff_start, eff_end) per chunk, in samples."""
     arr = (ChunkDesc * max(1, len(bounds)))()

@@ -141,6 +141,13 @@ AC_API int ac_unet_set_debug(ac_unet* net, int force_simt);
  * host.  Runs `iters` launches; *h_ms (optional) = mean ms of launches 2..iters.  Synchronises. */
 AC_API int ac_debug_conv3x3(const void* d_in, void* d_out, int B, int T, int F, int C, const float* h_w,
                      const float* d_scale, const float* d_shift, int impl, int iters, float* h_ms, void* stream);
+/* Test / profiling hook: a chain of three 3x3 convolution layers (C = 48, the block shape of U-Net level 0) on
+ * [B][T][C/8][F][8] tensors.  impl 0 = three launches of the weight-stationary kernel (d_out / d_tmp ping-pong),
+ * 1 = the fused kernel that keeps both intermediates in shared memory; impl + 16 = IEEE-half operands.
+ * h_w = 3 x W[C][C][3][3] float32 on the host, d_scale / d_shift = 3 x [C] on the device, d_tmp = scratch of the
+ * tensor's size.  Runs `iters` launches; *h_ms (optional) = mean ms of launches 2..iters.  Synchronises. */
+AC_API int ac_debug_conv3x3_chain(const void* d_in, void* d_out, void* d_tmp, int B, int T, int F, int C, const float* h_w,
+                           const float* d_scale, const float* d_shift, int impl, int iters, float* h_ms, void* stream);
 /* Test hook: synchronises and returns 1 when a tensor-core kernel gave up on an mbarrier wait
  * (a pipeline bug; the watchdog keeps such a bug from hanging the GPU), 0 otherwise. */
 AC_API int ac_debug_tc_aborted(void);

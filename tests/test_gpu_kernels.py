@@ -396,6 +396,34 @@ def test_conv3x3_variants_match_cuda_core_layer(ops, C, T, F, impls, name, dtype
 
 
 @pytest.mark.parametrize("name,dtype,tdtype", H16)
+@pytest.mark.parametrize("B,T,F", [(2, 24, 640), (1, 7, 130), (3, 40, 3072)])
+def test_fused_conv_chain_is_bit_identical_to_three_launches(ops, B, T, F, name, dtype, tdtype):
+    """The level-0 TFC conv chain (3 x conv3x3 + BN + ReLU, C = 48) in one kernel with both intermediates in shared
+    memory (unet_tc_conv_f3.cu) vs three launches of the weight-stationary kernel: same accumulation order per element,
+    same 16-bit rounding of the intermediates -> identical bits.  Shapes: several strips with a ragged last one, a single
+    130-position strip with segments shorter than the pipeline depth, and the full frequency axis."""
+    C = 48
+    rng = np.random.default_rng(B * 1000 + T)
+    x = torch.randn(B, T, F, C, device="cuda").to(tdtype)
+    w = (rng.standard_normal((3, C, C, 3, 3)) / np.sqrt(9 * C) * 1.6).astype(np.float32)
+    scale = torch.rand(3, C, device="cuda") + 0.5
+    shift = torch.randn(3, C, device="cuda") * 0.1
+    ref, _ = ops.debug_conv3x3_chain(x, w, scale, shift, 0)
+    assert _tc_aborted() == 0
+    y, _ = ops.debug_conv3x3_chain(x, w, scale, shift, 1)
+    assert _tc_aborted() == 0
+    assert float(ref.float().abs().max()) > 0.1
+    assert torch.equal(ref.view(torch.int16), y.view(torch.int16)), (
+        int((ref.view(torch.int16) != y.view(torch.int16)).sum()), sdr_db(ref.float().cpu().numpy(), y.float().cpu().numpy()))
+    # and against the CUDA-core implicit GEMM, layer by layer (independent implementation)
+    z = x
+    for j in range(3):
+        z, _ = ops.debug_conv3x3(z, w[j], scale[j], shift[j], 0)
+    s = sdr_db(z.float().cpu().numpy(), y.float().cpu().numpy())
+    assert s > (70 if name == "fp16" else 50), s
+
+
+@pytest.mark.parametrize("name,dtype,tdtype", H16)
 def test_unet_tcgen05_full_geometry(ops, name, dtype, tdtype):
     """The network alone at Kim_Vocal geometry on a white-noise spectrogram: fp16 63 dB, bf16 45 dB measured."""
     net, x, ref = _unet_case(ops, 3072, 256, 48, 1)
