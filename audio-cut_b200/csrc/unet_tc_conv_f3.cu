@@ -18,10 +18,10 @@
 //     conv3 124 valid: strips advance by 124 positions (3 % recompute, F = 3072 -> 25 strips);
 //   * vertically a segment of `rows` output rows costs rows+6 / rows+4 / rows+2 steps of the three convs.
 // Shared memory: 3 x 41.5 KB weights + (4 + 2 + 2) row tiles of 12.25 KB = 222 KB.  TMEM: rings of 4 + 3 + 3 blocks
-// of 48 columns = 480.  One MMA-issuing warp interleaves the three convs (conv2 lags conv1 by 3 steps, conv3 by 6, so
-// the epilogue has a whole macro step to drain a row before its consumer needs it).
+// of 48 columns = 480.  Every conv is its own pipeline stage (one MMA-issuing warp + four epilogue warps), coupled to its
+// neighbours only through the row FIFOs.
 // Output is bit-identical to three launches of the weight-stationary kernel (same accumulation order per element).
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2..13 = epilogue.
+// Roles: warp 0 = TMA producer, warps 1..3 = MMA issuers of conv 1..3 (warp 1 owns TMEM), warps 4..15 = epilogue (4 per conv).
 #include <stdlib.h>
 
 #include <type_traits>
@@ -33,8 +33,8 @@
 namespace ac {
 
 constexpr int kF3C = 48;
-constexpr int kF3EpiWarps = 12;                       // (TMEM lane quadrant) x (16-channel group)
-constexpr int kF3Threads = (2 + kF3EpiWarps) * 32;
+constexpr int kF3EpiWarps = 12;                       // (conv) x (TMEM lane quadrant)
+constexpr int kF3Threads = (4 + kF3EpiWarps) * 32;   // producer + 3 MMA issuers + 12 epilogue warps
 constexpr int kF3Valid = 124;                         // output positions per strip
 constexpr int kF3RowPos = 130;                        // rows of an A tile
 constexpr int kF3ALbo = kF3RowPos * 16;               // bytes between 8-channel planes of a tile
@@ -50,7 +50,6 @@ static_assert(kF3Smem <= 227 * 1024, "shared memory budget");
 
 __host__ __device__ constexpr int f3_rb(int c) { return c == 0 ? 4 : 3; }           // TMEM blocks of conv c's ring
 __host__ __device__ constexpr int f3_col(int c) { return c == 0 ? 0 : (c == 1 ? 4 * 48 : 7 * 48); }
-__host__ __device__ constexpr int f3_skew(int c) { return 3 * c; }                  // macro-step lag of conv c
 constexpr int kF3Cols = 10 * 48;
 
 struct F3Params {
@@ -89,6 +88,23 @@ __device__ __forceinline__ void f3_umma(uint32_t tmem_d, uint64_t adesc, uint64_
       : "memory");
 }
 
+// The 9 (df, k) MMAs of one input row: N1 columns at d0 (+ N2 columns at d1 with the B rows after the first N1 when the
+// 3-block window wraps around the ring).  Straight-line code: per MMA two descriptor adds and the instruction.
+template <int N1, int N2, int FMT>
+__device__ __forceinline__ void f3_issue(uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t d0, uint32_t d1) {
+  const uint32_t idesc1 = make_idesc<FMT>(N1);
+#pragma unroll
+  for (int df = 0; df < 3; ++df) {
+#pragma unroll
+    for (int k = 0; k < kF3C / 16; ++k) {
+      const uint64_t ad = f3_desc_at(a_lo, a_hi, df * 16 + k * 2 * kF3ALbo);
+      const uint32_t boff = df * kF3DfBytes + k * 2 * kF3BLbo;
+      f3_umma(d0, ad, f3_desc_at(b_lo, b_hi, boff), idesc1);
+      if constexpr (N2 > 0) f3_umma(d1, ad, f3_desc_at(b_lo, b_hi, boff + N1 * 16), make_idesc<FMT>(N2));
+    }
+  }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kF3Threads, 1)
 tc_conv3x3_f3_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params p) {
@@ -103,8 +119,7 @@ tc_conv3x3_f3_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params 
   uint64_t* bfree = in_full + 28;                           // [3 convs][4 blocks]  epilogue -> MMA: drained and zeroed
   uint64_t* wbar = in_full + 40;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 41);
-  float* s_scale = reinterpret_cast<float*>(smem + 512);    // [3][48]
-  float* s_shift = s_scale + 3 * NT;                        // [3][48]
+  float* s_ss = reinterpret_cast<float*>(smem + 512);       // [3][48] {scale, shift}
   uint8_t* w_smem = smem + kF3Header;
   uint8_t* in_ring = w_smem + 3 * kF3WBytes;
   uint8_t* mid_ring = in_ring + kF3InSlots * kF3ATile;      // stage 0 (conv1 -> conv2): 2 slots, stage 1: 2 slots
@@ -121,19 +136,22 @@ tc_conv3x3_f3_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params 
       mbar_init(&in_empty[s], 1);
     }
     for (int s = 0; s < 2 * kF3MidSlots; ++s) {
-      mbar_init(&mid_full[s], kF3EpiWarps);
+      mbar_init(&mid_full[s], 4);
       mbar_init(&mid_empty[s], 1);
     }
     for (int b = 0; b < 12; ++b) {
       mbar_init(&done[b], 1);
-      mbar_init(&bfree[b], kF3EpiWarps);
+      mbar_init(&bfree[b], 4);
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 3 * NT; i += blockDim.x) {
-    s_scale[i] = p.scale[i / NT][i % NT];
-    s_shift[i] = p.shift[i / NT][i % NT];
+    const int j = i / NT, ch = i - j * NT;
+    const float* sc = j == 0 ? p.scale[0] : (j == 1 ? p.scale[1] : p.scale[2]);
+    const float* sh = j == 0 ? p.shift[0] : (j == 1 ? p.shift[1] : p.shift[2]);
+    s_ss[2 * i] = sc[ch];
+    s_ss[2 * i + 1] = sh[ch];
   }
   // the intermediate tiles start as zeros (rows 128, 129 of a tile are read by the last MMA rows and never written)
   for (int i = threadIdx.x; i < 2 * kF3MidSlots * kF3ATile / 16; i += blockDim.x)
@@ -170,206 +188,193 @@ tc_conv3x3_f3_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params 
         L += sg.t1 - sg.t0;
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t idesc144 = make_idesc<FMT>(144), idesc96 = make_idesc<FMT>(96), idesc48 = make_idesc<FMT>(48);
-    const uint64_t a_proto = make_desc(0, kF3ALbo, 128), b_proto = make_desc(0, kF3BLbo, 128);
-    const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
-    const uint32_t a_lo_in = (uint32_t)a_proto + (smem_u32(in_ring) >> 4);
-    const uint32_t a_lo_mid = (uint32_t)a_proto + (smem_u32(mid_ring) >> 4);
-    const uint32_t b_lo0 = (uint32_t)b_proto + (smem_u32(w_smem) >> 4);
+  } else if (warp <= 3) {
+    // ===================== MMA issuers: warp 1 + c issues conv c (warp-uniform loop, one elected lane issues) ==========
+    // One issuing warp for all three convs was the bottleneck of the first build (ncu: 711 SASS instructions per macro
+    // step of ~45 MMAs at ~8 cycles each, every other role waiting): the three convs are independent pipeline stages
+    // coupled only by the row FIFOs, so each gets its own issuer, and the ring-wrap case is chosen OUTSIDE the unrolled
+    // tap loops so that an MMA is two descriptor adds and the instruction.
     auto wait_all = [&](uint64_t* bar, uint32_t parity) {
       return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
     };
     bool alive = wait_all(wbar, 0);
-    // the epilogue warps zero the block rings before the first MMA (named barrier 1: 12 epilogue warps + this warp)
-    asm volatile("bar.sync 1, %0;" ::"r"((kF3EpiWarps + 1) * 32) : "memory");
+    // the epilogue warps zero the block rings before the first MMA (named barrier 1: 12 epilogue warps + 3 issuers)
+    asm volatile("bar.sync 1, %0;" ::"r"((kF3EpiWarps + 3) * 32) : "memory");
     tc_fence_after();
-    int fs[3] = {0, 0, 0};         // FIFO slot each conv reads next
-    uint32_t fph[3] = {0, 0, 0};
-    int gm[3] = {0, 0, 0};         // virtual step g mod RB
-    uint32_t cyc[3] = {0, 0, 0};   // g / RB
-
-    // one virtual step of conv CI: (real) 9..18 MMAs of input row -> blocks of output rows g+1, g, g-1; then "block of
-    // row g-1 is complete"
-    auto step = [&](auto ci, bool real) -> bool {
+    auto run = [&](auto ci) {
       constexpr int CI = decltype(ci)::value;
       constexpr int RB = f3_rb(CI);
-      const int sb = RB - 1 - gm[CI];
-      // row g+1 enters block sb: its previous owners (n of them) must have been drained and zeroed
-      {
-        const uint32_t n = (gm[CI] + 2 >= RB) ? cyc[CI] + 1 : cyc[CI];
-        if (n > 0 && !wait_all(&bfree[CI * 4 + sb], (n - 1) & 1)) return false;
-      }
-      if (real) {
-        const int s = fs[CI];
-        uint64_t* fullb = CI == 0 ? &in_full[s] : &mid_full[(CI - 1) * kF3MidSlots + s];
-        uint64_t* emptyb = CI == 0 ? &in_empty[s] : &mid_empty[(CI - 1) * kF3MidSlots + s];
-        if (!wait_all(fullb, fph[CI])) return false;
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_lo = CI == 0 ? a_lo_in + (uint32_t)s * (kF3ATile >> 4)
-                                        : a_lo_mid + (uint32_t)((CI - 1) * kF3MidSlots + s) * (kF3ATile >> 4);
-          const uint32_t b_lo = b_lo0 + (uint32_t)CI * (kF3WBytes >> 4);
-          const int n1 = (sb + 3 <= RB) ? 3 : RB - sb;  // blocks before the ring wraps
-          const uint32_t d0 = tmem_base + (uint32_t)(f3_col(CI) + sb * NT);
-          const uint32_t d1 = tmem_base + (uint32_t)f3_col(CI);
-#pragma unroll
-          for (int df = 0; df < 3; ++df) {
-#pragma unroll
-            for (int k = 0; k < K16; ++k) {
-              const uint64_t ad = f3_desc_at(a_lo, a_hi, df * 16 + k * 2 * kF3ALbo);
-              const uint32_t boff = df * kF3DfBytes + k * 2 * kF3BLbo;
-              if (n1 == 3) {
-                f3_umma(d0, ad, f3_desc_at(b_lo, b_hi, boff), idesc144);
-              } else if (n1 == 2) {
-                f3_umma(d0, ad, f3_desc_at(b_lo, b_hi, boff), idesc96);
-                f3_umma(d1, ad, f3_desc_at(b_lo, b_hi, boff + 2 * NT * 16), idesc48);
-              } else {
-                f3_umma(d0, ad, f3_desc_at(b_lo, b_hi, boff), idesc48);
-                f3_umma(d1, ad, f3_desc_at(b_lo, b_hi, boff + NT * 16), idesc96);
-              }
-            }
+      constexpr int kSlots = CI == 0 ? kF3InSlots : kF3MidSlots;
+      const uint64_t a_proto = make_desc(0, kF3ALbo, 128), b_proto = make_desc(0, kF3BLbo, 128);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(CI == 0 ? in_ring : mid_ring + (CI - 1) * kF3MidSlots * kF3ATile) >> 4);
+      const uint32_t b_lo = (uint32_t)b_proto + (smem_u32(w_smem + CI * kF3WBytes) >> 4);
+      uint64_t* fullb = CI == 0 ? in_full : mid_full + (CI - 1) * kF3MidSlots;
+      uint64_t* emptyb = CI == 0 ? in_empty : mid_empty + (CI - 1) * kF3MidSlots;
+      const uint32_t ring0 = tmem_base + (uint32_t)f3_col(CI);
+      int s = 0;          // FIFO slot read next
+      uint32_t ph = 0;
+      int gm = 0;         // virtual step g mod RB
+      uint32_t cyc = 0;   // g / RB
+      for (long long L = lo; L < hi && alive;) {
+        const F3Seg sg = f3_segment(p, L, hi);
+        const int rows = sg.t1 - sg.t0;
+        const int real = rows + 6 - 2 * CI;  // input rows of this conv in the segment; + 2 flush steps
+        for (int v = 0; v < real + 2 && alive; ++v) {
+          // virtual step g: input row -> blocks of output rows g+1, g, g-1 = ring blocks sb, sb+1, sb+2 (mod RB)
+          const int sb = RB - 1 - gm;
+          {
+            // row g+1 enters block sb: its previous owners (n of them) must have been drained and zeroed
+            const uint32_t n = (gm + 2 >= RB) ? cyc + 1 : cyc;
+            if (n > 0 && !wait_all(&bfree[CI * 4 + sb], (n - 1) & 1)) { alive = false; break; }
           }
-          umma_commit(emptyb);
+          if (v < real) {
+            if (!wait_all(&fullb[s], ph)) { alive = false; break; }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)s * (kF3ATile >> 4);
+              const uint32_t d0 = ring0 + (uint32_t)(sb * NT);
+              if (sb + 3 <= RB) {
+                f3_issue<144, 0, FMT>(a_lo, a_hi, b_lo, b_hi, d0, ring0);
+              } else if (sb + 2 == RB) {
+                f3_issue<96, 48, FMT>(a_lo, a_hi, b_lo, b_hi, d0, ring0);
+              } else {
+                f3_issue<48, 96, FMT>(a_lo, a_hi, b_lo, b_hi, d0, ring0);
+              }
+              umma_commit(&emptyb[s]);
+              umma_commit(&done[CI * 4 + (sb + 2) % RB]);
+            }
+            __syncwarp();
+            if (++s == kSlots) { s = 0; ph ^= 1; }
+          } else {
+            if (elect_one()) umma_commit(&done[CI * 4 + (sb + 2) % RB]);
+            __syncwarp();
+          }
+          if (++gm == RB) { gm = 0; ++cyc; }
         }
-        __syncwarp();
-        if (++fs[CI] == (CI == 0 ? kF3InSlots : kF3MidSlots)) { fs[CI] = 0; fph[CI] ^= 1; }
+        L += rows;
       }
-      if (elect_one()) umma_commit(&done[CI * 4 + (sb + 2) % RB]);
-      __syncwarp();
-      if (++gm[CI] == RB) { gm[CI] = 0; ++cyc[CI]; }
-      return true;
     };
-
-    for (long long L = lo; L < hi && alive;) {
-      const F3Seg sg = f3_segment(p, L, hi);
-      const int rows = sg.t1 - sg.t0;
-      const int M = rows + 10;
-      for (int m = 0; m < M && alive; ++m) {
-        {
-          const int v = m;  // conv1: rows + 6 real input rows + 2 flush steps
-          if (v < rows + 8) alive = step(std::integral_constant<int, 0>{}, v < rows + 6);
-        }
-        if (alive) {
-          const int v = m - f3_skew(1);
-          if (v >= 0 && v < rows + 6) alive = step(std::integral_constant<int, 1>{}, v < rows + 4);
-        }
-        if (alive) {
-          const int v = m - f3_skew(2);
-          if (v >= 0 && v < rows + 4) alive = step(std::integral_constant<int, 2>{}, v < rows + 2);
-        }
-      }
-      L += rows;
-    }
+    if (warp == 1) run(std::integral_constant<int, 0>{});
+    else if (warp == 2) run(std::integral_constant<int, 1>{});
+    else run(std::integral_constant<int, 2>{});
   } else {
-    // ===================== epilogue (warps 2..13): drain + zero one block per virtual step of each conv ==========
-    const int quad = warp & 3;          // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
-    const int grp = (warp - 2) >> 2;    // channels [16*grp, +16)
-    const int mrow = quad * 32 + lane;  // MMA row = position within the tile
+    // ===================== epilogue (warps 4..15): four warps (one per TMEM lane quadrant) per conv ==========
+    // A drain is a chain of latencies (barrier wake-up, tcgen05.ld, zeroing tcgen05.st, shared-memory stores, proxy
+    // fence, arrive: ~1500 cycles); with every warp draining all three convs in turn that chain, three times per macro
+    // step, was the critical path (first build: 2023 us against 1736 us unfused).  Specialised by conv the three drains
+    // of a macro step run side by side and each thread carries all 48 channels of its position.
+    const int quad = warp & 3;           // hardware rule: warp w may read TMEM lanes 32*(w%4) .. +31
+    const int conv = (warp - 4) >> 2;    // which conv this warp drains
+    const int mrow = quad * 32 + lane;   // MMA row = position within the tile
     const size_t plane = (size_t)p.F * 8;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 16);
     {
+      // zero this conv's ring (4 warps x 32 lanes x all its columns)
       const uint32_t z = 0;
+      const int c0 = conv == 0 ? f3_col(0) : (conv == 1 ? f3_col(1) : f3_col(2));
+      const int c1 = conv == 0 ? f3_col(1) : (conv == 1 ? f3_col(2) : kF3Cols);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kF3Cols; c0 += NT)
+      for (int c = c0; c < c1; c += 16)
         asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(lane_addr + c0),
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+                tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c),
             "r"(z)
             : "memory");
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
     }
-    asm volatile("bar.sync 1, %0;" ::"r"((kF3EpiWarps + 1) * 32) : "memory");
-    int Gm[3] = {0, 0, 0};          // drained virtual steps of conv c: G mod RB, G / RB
-    uint32_t Gc[3] = {0, 0, 0};
-    int ws_[2] = {0, 0};            // FIFO slot the stage writes next
-    uint32_t wph[2] = {0, 0};
-    bool alive = true;
+    asm volatile("bar.sync 1, %0;" ::"r"((kF3EpiWarps + 3) * 32) : "memory");
 
-    // drain the block completed by virtual step v of conv CI; `t_out` = the output row it holds, `valid` = keep it
-    auto drain = [&](auto ci, const F3Seg& sg, int t_out, bool valid) -> bool {
+    auto run = [&](auto ci) {
       constexpr int CI = decltype(ci)::value;
       constexpr int RB = f3_rb(CI);
-      int blk = 1 - Gm[CI];
-      if (blk < 0) blk += RB;
-      if (!mbar_wait(&done[CI * 4 + blk], Gc[CI] & 1, abort_flag)) return false;
-      tc_fence_after();
-      uint32_t r[16];
-      const uint32_t taddr = lane_addr + (uint32_t)(f3_col(CI) + blk * NT);
-      tmem_ld16(taddr, r);
-      tmem_ld_wait();
-      {
-        const uint32_t z = 0;
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
-            "r"(z)
-            : "memory");
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(&bfree[CI * 4 + blk]);
-      if (++Gm[CI] == RB) { Gm[CI] = 0; ++Gc[CI]; }
-      if (!valid) return true;
-      // position of this thread's row: conv1 tile starts at f0 - 2, conv2 at f0 - 1, conv3 at f0
-      const int pos = sg.f0 - 2 + CI + mrow;
-      uint32_t pk[8];
-      const float* sc = s_scale + CI * NT + grp * 16;
-      const float* sh = s_shift + CI * NT + grp * 16;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)f3_col(CI);
+      const float2* ss = reinterpret_cast<const float2*>(s_ss) + CI * NT;  // {scale, shift} per channel
+      int Gm = 0;          // drained virtual steps: G mod RB, G / RB
+      uint32_t Gc = 0;
+      int ws_ = 0;         // FIFO slot written next (CI < 2)
+      uint32_t wph = 0;
+      bool alive = true;
+      for (long long L = lo; L < hi && alive;) {
+        const F3Seg sg = f3_segment(p, L, hi);
+        const int rows = sg.t1 - sg.t0;
+        // conv CI: rows + 6 - 2*CI real steps + 2 flush steps; step v completes output row t0 - 4 + CI + v; the rows
+        // v in [2, real) are kept (conv1: t0-2 .. t1+1 feed conv2, conv2: t0-1 .. t1 feed conv3, conv3: t0 .. t1-1)
+        const int real = rows + 6 - 2 * CI;
+        const int pos = sg.f0 - 2 + CI + mrow;  // conv1's tile starts at f0 - 2, conv2's at f0 - 1, conv3's at f0
+        for (int v = 0; v < real + 2 && alive; ++v) {
+          const int t_out = sg.t0 - 4 + CI + v;
+          const bool valid = v >= 2 && v < real;
+          int blk = 1 - Gm;
+          if (blk < 0) blk += RB;
+          if (!mbar_wait(&done[CI * 4 + blk], Gc & 1, abort_flag)) { alive = false; break; }
+          tc_fence_after();
+          uint32_t r[NT];
+          const uint32_t taddr = lane_addr + (uint32_t)(blk * NT);
+          tmem_ld16(taddr, r);
+          tmem_ld16(taddr + 16, r + 16);
+          tmem_ld16(taddr + 32, r + 32);
+          tmem_ld_wait();
+          {
+            const uint32_t z = 0;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), sc[2 * e], sh[2 * e]), 0.f);
-        const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), sc[2 * e + 1], sh[2 * e + 1]), 0.f);
-        pk[e] = pack2<FMT>(v0, v1);
-      }
-      if constexpr (CI < 2) {
-        // next conv's zero padding: nothing outside the image
-        const bool inside = t_out >= 0 && t_out < p.T && pos >= 0 && pos < p.F;
-        if (!inside) {
+            for (int j = 0; j < NT; j += 16)
+              asm volatile(
+                  "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr + j),
+                  "r"(z)
+                  : "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_relaxed(&bfree[CI * 4 + blk]);
+          if (++Gm == RB) { Gm = 0; ++Gc; }
+          if (!valid) continue;
+          if constexpr (CI < 2) {
+            // next conv's zero padding: nothing outside the image
+            const bool inside = t_out >= 0 && t_out < p.T && pos >= 0 && pos < p.F;
+            if (!mbar_wait(&mid_empty[CI * kF3MidSlots + ws_], wph ^ 1, abort_flag)) { alive = false; break; }
+            uint8_t* dst = mid_ring + (size_t)(CI * kF3MidSlots + ws_) * kF3ATile + (size_t)mrow * 16;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) pk[e] = 0u;
+            for (int cg = 0; cg < NT / 8; ++cg) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 q = *reinterpret_cast<const float4*>(ss + cg * 8 + 2 * e);  // {sc0, sh0, sc1, sh1}
+                const float v0 = fmaxf(fmaf(__uint_as_float(r[cg * 8 + 2 * e]), q.x, q.y), 0.f);
+                const float v1 = fmaxf(fmaf(__uint_as_float(r[cg * 8 + 2 * e + 1]), q.z, q.w), 0.f);
+                pk[e] = inside ? pack2<FMT>(v0, v1) : 0u;
+              }
+              *reinterpret_cast<uint4*>(dst + cg * kF3ALbo) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mid_full[CI * kF3MidSlots + ws_]);
+            if (++ws_ == kF3MidSlots) { ws_ = 0; wph ^= 1; }
+          } else {
+            if (mrow < kF3Valid && pos < p.F) {
+              h16* dst = p.out + cg8_index(sg.b, t_out, 0, pos, p.T, C, p.F);
+#pragma unroll
+              for (int cg = 0; cg < NT / 8; ++cg) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float4 q = *reinterpret_cast<const float4*>(ss + cg * 8 + 2 * e);
+                  const float v0 = fmaxf(fmaf(__uint_as_float(r[cg * 8 + 2 * e]), q.x, q.y), 0.f);
+                  const float v1 = fmaxf(fmaf(__uint_as_float(r[cg * 8 + 2 * e + 1]), q.z, q.w), 0.f);
+                  pk[e] = pack2<FMT>(v0, v1);
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)cg * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
         }
-        const int s = ws_[CI];
-        if (!mbar_wait(&mid_empty[CI * kF3MidSlots + s], wph[CI] ^ 1, abort_flag)) return false;
-        uint8_t* dst = mid_ring + (size_t)(CI * kF3MidSlots + s) * kF3ATile + (size_t)(grp * 2) * kF3ALbo + (size_t)mrow * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dst + kF3ALbo) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mid_full[CI * kF3MidSlots + s]);
-        if (++ws_[CI] == kF3MidSlots) { ws_[CI] = 0; wph[CI] ^= 1; }
-      } else {
-        if (mrow < kF3Valid && pos < p.F) {
-          h16* dst = p.out + cg8_index(sg.b, t_out, grp * 2, pos, p.T, C, p.F);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        L += rows;
       }
-      return true;
     };
-
-    for (long long L = lo; L < hi && alive;) {
-      const F3Seg sg = f3_segment(p, L, hi);
-      const int rows = sg.t1 - sg.t0;
-      const int M = rows + 10;
-      for (int m = 0; m < M && alive; ++m) {
-        {
-          // conv1, virtual step v: holds output row t0 - 4 + v; rows t0-2 .. t1+1 feed conv2
-          const int v = m;
-          if (v < rows + 8) alive = drain(std::integral_constant<int, 0>{}, sg, sg.t0 - 4 + v, v >= 2 && v < rows + 6);
-        }
-        if (alive) {
-          const int v = m - f3_skew(1);  // conv2: output row t0 - 3 + v; rows t0-1 .. t1 feed conv3
-          if (v >= 0 && v < rows + 6) alive = drain(std::integral_constant<int, 1>{}, sg, sg.t0 - 3 + v, v >= 2 && v < rows + 4);
-        }
-        if (alive) {
-          const int v = m - f3_skew(2);  // conv3: output row t0 - 2 + v; rows t0 .. t1-1 are stored
-          if (v >= 0 && v < rows + 4) alive = drain(std::integral_constant<int, 2>{}, sg, sg.t0 - 2 + v, v >= 2 && v < rows + 2);
-        }
-      }
-      L += rows;
-    }
+    if (conv == 0) run(std::integral_constant<int, 0>{});
+    else if (conv == 1) run(std::integral_constant<int, 1>{});
+    else run(std::integral_constant<int, 2>{});
   }
   tc_fence_before();
   __syncthreads();
