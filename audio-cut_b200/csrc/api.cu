@@ -105,6 +105,31 @@ const FftPlan* get_fft_plan(int n) {
   }
   p->d_twiddle = d_tw;
   p->d_hann = d_h;
+  if (n == 7680 || n == 6144) {
+    // tables of the three-pass FFT (fft3.cuh): radices 16 x 20 x 24 (7680) / 16 x 16 x 24 (6144)
+    const int r1 = 16, r2 = n == 7680 ? 20 : 16, r3 = 24;
+    std::vector<float2> t2((size_t)r1 * r2), t3((size_t)r1 * r2 * r3);
+    for (int k = 0; k < r1; ++k)
+      for (int r = 0; r < r2; ++r) {
+        double a = -two_pi * (double)((k * r) % (r1 * r2)) / (double)(r1 * r2);
+        t2[(size_t)k * r2 + r] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+    for (int k = 0; k < r1 * r2; ++k)
+      for (int r = 0; r < r3; ++r) {
+        double a = -two_pi * (double)((k * r) % n) / (double)n;
+        t3[(size_t)k * r3 + r] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+    float2 *d2 = nullptr, *d3 = nullptr;
+    if (cudaMalloc(&d2, sizeof(float2) * t2.size()) != cudaSuccess || cudaMalloc(&d3, sizeof(float2) * t3.size()) != cudaSuccess ||
+        cudaMemcpy(d2, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d3, t3.data(), sizeof(float2) * t3.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error(std::string("fft plan upload: ") + cudaGetErrorString(cudaGetLastError()));
+      delete p;
+      return nullptr;
+    }
+    p->d_tw3_p2 = d2;
+    p->d_tw3_p3 = d3;
+  }
   g_plans[n] = p;
   return p;
 }

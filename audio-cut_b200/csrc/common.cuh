@@ -146,6 +146,9 @@ struct FftPlan {
   const float2* d_tw_lo = nullptr;
   const float2* d_tw_hi = nullptr;
   const float* d_hann = nullptr;      // periodic hann, n values
+  // three-pass FFT (fft3.cuh; n = 7680 / 6144 only): W_{R1 R2}^{k r} as [R1][R2] and W_n^{k r} as [R1 R2][R3]
+  const float2* d_tw3_p2 = nullptr;
+  const float2* d_tw3_p3 = nullptr;
 };
 // returns nullptr (and sets the error) when n has a prime factor other than 2,3,5
 const FftPlan* get_fft_plan(int n);

@@ -14,11 +14,14 @@
 // keeps the ceil(n_fft/hop) hop-blocks that are still receiving contributions in a shared-memory
 // ring, and emits a hop-block as soon as its last frame has been added - the overlap-add never
 // touches HBM.  Strips re-compute nb-1 warm-up frames.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <vector>
 
 #include "fft.cuh"
+#include "fft3.cuh"
 #include "stft_mdx.cuh"
 
 namespace ac {
@@ -255,6 +258,142 @@ __global__ void __launch_bounds__(kIstftThreads) istft_mdx_kernel(const T* __res
   }
 }
 
+// ---- three-pass kernels for n_fft = 7680 / 6144 (fft3.cuh) -----------------------------------------------------------
+// Same arithmetic as the kernels above around a different FFT: the frame is loaded from the track (STFT) / built from the
+// kept bins (iSTFT) by pass 1 itself, and the iSTFT's windowed overlap-add is pass 3's sink.  One 61 KB buffer.
+template <typename T, int N>
+__global__ void __launch_bounds__(kFft3Threads, 1) stft_mdx3_kernel(const float* __restrict__ src, long long ch_stride, int n_ch,
+                                                                    const WinDesc* __restrict__ wins, Fft3Tw tw,
+                                                                    const float* __restrict__ hann, int hop, int dim_f, int dim_t,
+                                                                    int W, T* __restrict__ spec) {
+  extern __shared__ float2 smem_f2[];
+  float2* buf = smem_f2;
+  constexpr int nb3 = N / Fft3Geom<N>::R3;
+  const int t = blockIdx.x;
+  const WinDesc wd = wins[blockIdx.y];
+  const float* s0 = src + wd.base;
+  const float* s1 = src + (n_ch > 1 ? ch_stride : 0) + wd.base;
+  const int p0 = t * hop - N / 2;
+  auto load = [&](int m) {
+    int p = p0 + m;
+    p = p < 0 ? -p : p;
+    p = p >= W ? 2 * (W - 1) - p : p;  // torch.stft center=True, pad_mode="reflect"
+    float l = 0.f, r = 0.f;
+    if (p >= wd.p_lo && p < wd.p_hi) {
+      l = __ldg(s0 + p);
+      r = __ldg(s1 + p);
+    }
+    const float w = __ldg(hann + m);
+    return make_float2(l * w, r * w);
+  };
+  float2* zrow = buf + threadIdx.x + (threadIdx.x >> 5);
+  auto sink = [&](int, int r, float2 v) { zrow[r * (nb3 + nb3 / 32)] = v; };
+  fft3_run<N, false>(buf, tw, load, sink);
+  __syncthreads();
+  T* out = spec + ((size_t)blockIdx.y * dim_t + t) * (size_t)dim_f * 4;
+  for (int k = threadIdx.x; k < dim_f; k += kFft3Threads) {
+    const float2 a = buf[fpad(k)];
+    const float2 b = buf[fpad(k == 0 ? 0 : N - k)];
+    store_spec4<T>(out + (size_t)k * 4, 0.5f * (a.x + b.x), 0.5f * (a.y - b.y), 0.5f * (a.y + b.y),
+                   -0.5f * (a.x - b.x));
+  }
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(kFft3Threads, 1) istft_mdx3_kernel(const T* __restrict__ spec, IstftArgs a, Fft3Tw tw,
+                                                                     unsigned hop_magic) {
+  extern __shared__ float2 smem_f2[];
+  float2* buf = smem_f2;
+  float2* ring = buf + fpad(N) + 1;  // [nb][hop]
+  constexpr int nb3 = N / Fft3Geom<N>::R3;
+  const int hop = a.hop;
+  const int e0 = a.blk_lo + blockIdx.x * a.strip;
+  const int e1 = min(a.blk_hi, e0 + a.strip);
+  if (e0 >= e1) return;
+  const WinDesc wd = a.wins[blockIdx.y];
+  const int half = N / 2;
+  const float inv_n = 1.0f / (float)N;
+  for (int i = threadIdx.x; i < a.nb * hop; i += kFft3Threads) ring[i] = make_float2(0.f, 0.f);
+  __syncthreads();
+  const int t_first = max(0, e0 - a.nb + 1);
+  int tmod = t_first % a.nb;  // t mod nb
+  for (int t = t_first; t < e1; ++t) {
+    if (t < a.dim_t) {
+      // ---- pass 1 builds the full-length spectrum of z = L + iR from the kept bins (Hermitian extension) on the fly
+      const T* in = spec + ((size_t)blockIdx.y * a.dim_t + t) * (size_t)a.dim_f * 4;
+      auto load = [&](int m) {
+        const int k = m < half ? m : N - m;
+        if (k >= a.dim_f) return make_float2(0.f, 0.f);
+        const float4 v = load_spec4(in + (size_t)k * 4);  // L_re, L_im, R_re, R_im
+        if (m == 0) return make_float2(v.x, v.z);          // c2r ignores the imaginary part of DC
+        return m < half ? make_float2(v.x - v.w, v.y + v.z) : make_float2(v.x + v.w, v.z - v.y);
+      };
+      // ---- pass 3 hands every output sample to the windowed overlap-add (frame t covers padded positions [t*hop, t*hop+N))
+      auto sink = [&](int j, int r, float2 v) {
+        const int m = j + r * nb3;
+        const float w = __ldg(a.hann + m) * inv_n;
+        const int q = (int)__umulhi((unsigned)m, hop_magic);  // m / hop
+        int blk = tmod + q;
+        if (blk >= a.nb) blk -= a.nb;
+        float2* dst = ring + blk * hop + (m - q * hop);
+        float2 acc = *dst;
+        acc.x = fmaf(v.x, w, acc.x);
+        acc.y = fmaf(v.y, w, acc.y);
+        *dst = acc;
+      };
+      fft3_run<N, true>(buf, tw, load, sink);
+      __syncthreads();
+    }
+    // ---- hop-block t is complete: emit (or discard during warm-up) and recycle its slot
+    float2* blk = ring + tmod * hop;
+    if (t >= e0) {
+      for (int i = threadIdx.x; i < hop; i += kFft3Threads) {
+        const int pos = t * hop + i;
+        const int n = pos - half;  // sample index in the torch.istft output
+        if (n < 0 || n >= a.W) continue;
+        const float e = __ldg(a.env + pos);
+        const float2 acc = blk[i];
+        const float y0 = acc.x / e, y1 = acc.y / e;
+        if (a.mode == 0) {
+          float* w0 = a.wave + (size_t)blockIdx.y * 2 * a.W;
+          w0[n] = y0;
+          w0[a.W + n] = y1;
+        } else {
+          const int o = n - half;  // trim = n_fft/2 on both sides (backends.py:377)
+          if (o < 0 || o >= wd.out_len || n >= a.W - half) continue;
+          const long long tp = wd.out_base + o;
+          const bool in_eff = tp >= wd.eff_start && tp < wd.eff_end;
+          if (!in_eff && !a.side_vocal) continue;
+          const float m0 = __ldg(a.mix + tp);
+          const float m1 = __ldg(a.mix + (a.n_ch > 1 ? a.mix_stride : 0) + tp);
+          float v, ins;
+          if (a.output_is_vocal) {
+            v = (y0 + y1) * 0.5f;
+            ins = ((m0 - y0) + (m1 - y1)) * 0.5f;
+          } else {
+            ins = (y0 + y1) * 0.5f;
+            v = ((m0 - y0) + (m1 - y1)) * 0.5f;
+          }
+          if (a.side_vocal) a.side_vocal[wd.side_base + o] = v;
+          if (!in_eff) continue;
+          atomicAdd(a.vocal + tp, v);
+          atomicAdd(a.instr + tp, ins);
+          atomicAdd(a.weight + tp, 1.0f);
+        }
+      }
+    }
+    for (int i = threadIdx.x; i < hop; i += kFft3Threads) blk[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+    if (++tmod == a.nb) tmod = 0;
+  }
+}
+
+// dev hook: AC_NO_FFT3=1 keeps the generic mixed-radix kernels for every size (A/B timing)
+static bool use_fft3(const MdxPlan* plan) {
+  static const bool off = getenv("AC_NO_FFT3") && atoi(getenv("AC_NO_FFT3")) != 0;
+  return !off && fft3_supported(plan->g.n_fft) && plan->fft->d_tw3_p2 && plan->fft->d_tw3_p3 && plan->g.hop <= 32768;
+}
+
 static size_t stft_smem_bytes(int n_fft) { return sizeof(float2) * 2 * (fft_smem_floats2(n_fft)); }
 
 int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, int n_ch, const WinDesc* d_wins,
@@ -268,6 +407,28 @@ int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, in
   dim3 grid(g.dim_t, n_win);
   const double es = dtype == AC_F32 ? 4.0 : 2.0;
   ProfScope ps(KC_STFT, 0.0, n_win * (2.0 * plan->W * 4 + (double)g.dim_t * g.dim_f * 4 * es), st);
+  if (use_fft3(plan)) {
+    const Fft3Tw tw{plan->fft->d_tw3_p2, plan->fft->d_tw3_p3};
+    const size_t smem3 = sizeof(float2) * fft_smem_floats2(g.n_fft);
+#define AC_STFT3_LAUNCH(TYPE, NN)                                                                                             \
+  do {                                                                                                                        \
+    AC_CHECK_CUDA(cudaFuncSetAttribute(stft_mdx3_kernel<TYPE, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+    stft_mdx3_kernel<TYPE, NN><<<grid, kFft3Threads, smem3, st>>>(d_src, ch_stride, n_ch, d_wins, tw, plan->fft->d_hann, g.hop, \
+                                                                  g.dim_f, g.dim_t, plan->W, (TYPE*)d_spec);                   \
+  } while (0)
+#define AC_STFT3_TYPE(TYPE)                                  \
+  do {                                                       \
+    if (g.n_fft == 7680) AC_STFT3_LAUNCH(TYPE, 7680);        \
+    else AC_STFT3_LAUNCH(TYPE, 6144);                        \
+  } while (0)
+    if (dtype == AC_F32) AC_STFT3_TYPE(float);
+    else if (dtype == AC_F16) AC_STFT3_TYPE(__half);
+    else AC_STFT3_TYPE(__nv_bfloat16);
+#undef AC_STFT3_TYPE
+#undef AC_STFT3_LAUNCH
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+  }
 #define AC_STFT_LAUNCH(TYPE, INPLACE)                                                                                        \
   do {                                                                                                                       \
     AC_CHECK_CUDA(cudaFuncSetAttribute(stft_mdx_kernel<TYPE, INPLACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -333,6 +494,29 @@ int launch_istft(const MdxPlan* plan, const void* d_spec, int dtype, const WinDe
   const double gen = plan->W - g.n_fft;
   // read spec + (stems: read mix 2ch, read-modify-write 3 accumulators | raw: write 2ch wave)
   ProfScope ps(KC_ISTFT, 0.0, n_win * ((double)g.dim_t * g.dim_f * 4 * es + (mode == 1 ? gen * (8 + 24) : plan->W * 8.0)), st);
+  if (use_fft3(plan)) {
+    const Fft3Tw tw{plan->fft->d_tw3_p2, plan->fft->d_tw3_p3};
+    const size_t smem3 = sizeof(float2) * (fft_smem_floats2(g.n_fft) + (size_t)a.nb * g.hop);
+    AC_REQUIRE(smem3 <= 227 * 1024, "n_fft too large for shared memory");
+    const unsigned hop_magic = (unsigned)((0x100000000ull + (unsigned)g.hop - 1) / (unsigned)g.hop);  // m / hop = umulhi(m, magic), m < 2^16
+#define AC_ISTFT3_LAUNCH(TYPE, NN)                                                                                             \
+  do {                                                                                                                         \
+    AC_CHECK_CUDA(cudaFuncSetAttribute(istft_mdx3_kernel<TYPE, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+    istft_mdx3_kernel<TYPE, NN><<<grid, kFft3Threads, smem3, st>>>((const TYPE*)d_spec, a, tw, hop_magic);                     \
+  } while (0)
+#define AC_ISTFT3_TYPE(TYPE)                                  \
+  do {                                                        \
+    if (g.n_fft == 7680) AC_ISTFT3_LAUNCH(TYPE, 7680);        \
+    else AC_ISTFT3_LAUNCH(TYPE, 6144);                        \
+  } while (0)
+    if (dtype == AC_F32) AC_ISTFT3_TYPE(float);
+    else if (dtype == AC_F16) AC_ISTFT3_TYPE(__half);
+    else AC_ISTFT3_TYPE(__nv_bfloat16);
+#undef AC_ISTFT3_TYPE
+#undef AC_ISTFT3_LAUNCH
+    AC_LAUNCH_CHECK();
+    return AC_OK;
+  }
   if (dtype == AC_F32) {
     AC_CHECK_CUDA(cudaFuncSetAttribute(istft_mdx_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_mdx_kernel<float><<<grid, kIstftThreads, smem, st>>>((const float*)d_spec, a);
