@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_mdx_kernel(const T* __res
 // Same arithmetic as the kernels above around a different FFT: the frame is loaded from the track (STFT) / built from the
 // kept bins (iSTFT) by pass 1 itself, and the iSTFT's windowed overlap-add is pass 3's sink.  One 61 KB buffer.
 template <typename T, int N>
-__global__ void __launch_bounds__(kFft3Threads, 1) stft_mdx3_kernel(const float* __restrict__ src, long long ch_stride, int n_ch,
+__global__ void __launch_bounds__(kFft3Threads, 2) stft_mdx3_kernel(const float* __restrict__ src, long long ch_stride, int n_ch,
                                                                     const WinDesc* __restrict__ wins, Fft3Tw tw,
                                                                     const float* __restrict__ hann, int hop, int dim_f, int dim_t,
                                                                     int W, T* __restrict__ spec) {
