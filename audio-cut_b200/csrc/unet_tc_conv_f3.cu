@@ -454,7 +454,7 @@ tc_conv3x3_f3p_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params
   pdl_launch_dependents();
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);   // [2]      leader: bytes of both CTAs' tiles
   uint64_t* in_empty = in_full + 4;                         // [2]      both (multicast commit)
-  uint64_t* mid_full = in_full + 8;                         // [2][2]   leader: 4 epilogue warps x 2 CTAs
+  uint64_t* mid_full = in_full + 8;                         // [2][2]   own 4 epilogue warps (+ leader: the peer's forwarder)
   uint64_t* mid_empty = in_full + 12;                       // [2][2]   both (multicast commit)
   uint64_t* done = in_full + 16;                            // [3][4]   both (multicast commit): block complete
   uint64_t* bfree = in_full + 28;                           // [3][4]   leader: 4 epilogue warps x 2 CTAs: drained and zeroed
@@ -480,7 +480,7 @@ tc_conv3x3_f3p_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params
       mbar_init(&in_empty[s], 1);
     }
     for (int s = 0; s < 2 * kF3MidSlots; ++s) {
-      mbar_init(&mid_full[s], 8);
+      mbar_init(&mid_full[s], leader ? 5 : 4);  // own 4 epilogue warps (+ leader: the peer's forwarder)
       mbar_init(&mid_empty[s], 1);
     }
     for (int b = 0; b < 12; ++b) {
@@ -553,12 +553,33 @@ tc_conv3x3_f3p_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params
     }
   } else if (warp <= 3) {
     // ===================== MMA issuers (leader CTA): warp 1 + c issues conv c ==========
+    // (cta-scope acquire: the leader never reads the peer's shared memory itself - the peer's tensor core does - and the
+    // peer's forwarder released at cluster scope; a cluster-scope acquire in this polling loop costs a CCTL.IVALL per poll)
     auto wait_all = [&](uint64_t* bar, uint32_t parity) {
-      return __all_sync(0xffffffffu, mbar_wait_cluster(bar, parity, abort_flag)) != 0;
+      return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
     };
     bool alive = wait_all(wbar, 0);
     if (!leader) {
       if (warp == 1 && alive && lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(wbar_peer), 0));  // "my weights are in place"
+      // Forwarders (warps 1, 2 of the peer, otherwise idle): the peer's epilogue warps signal a finished FIFO row on the
+      // peer's LOCAL barrier (a cluster-scope release per epilogue warp and row showed up as MEMBAR / ERRBAR stalls, 20 % of
+      // all samples); one thread here relays it to the leader's barrier, off everybody's critical path.
+      if (warp <= 2 && lane == 0) {
+        const int stage = warp - 1;
+        const uint32_t remote0 = mapa_u32(smem_u32(&mid_full[stage * kF3MidSlots]), 0);
+        int s = 0;
+        uint32_t ph = 0;
+        for (long long L = lo; L < hi && alive;) {
+          const F3pSeg sg = f3p_segment(p, L, hi, 0);
+          const int rows = sg.t1 - sg.t0;
+          for (int e = 0; e < rows + 4 - 2 * stage && alive; ++e) {
+            if (!mbar_wait(&mid_full[stage * kF3MidSlots + s], ph, abort_flag)) { alive = false; break; }
+            mbar_arrive_cluster(remote0 + (uint32_t)s * 8);
+            if (++s == kF3MidSlots) { s = 0; ph ^= 1; }
+          }
+          L += rows;
+        }
+      }
     } else {
       alive = alive && wait_all(wbar_peer, 0);
       auto run = [&](auto ci) {
@@ -631,7 +652,6 @@ tc_conv3x3_f3p_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params
     const int mrow = quad * 32 + lane;
     const size_t plane = (size_t)p.F * 8;
     const uint32_t bfree0 = mapa_u32(smem_u32(&bfree[0]), 0);
-    const uint32_t mid_full0 = mapa_u32(smem_u32(&mid_full[0]), 0);
     auto run = [&](auto ci) {
       constexpr int CI = decltype(ci)::value;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(CI * RB * NT);
@@ -691,7 +711,7 @@ tc_conv3x3_f3p_kernel(const __grid_constant__ CUtensorMap in_map, const F3Params
             }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mid_full0 + (uint32_t)(CI * kF3MidSlots + ws_) * 8);
+            if (lane == 0) mbar_arrive(&mid_full[CI * kF3MidSlots + ws_]);  // local; the peer's forwarder relays it
             if (++ws_ == kF3MidSlots) { ws_ = 0; wph ^= 1; }
           } else {
             if (sg.valid && mrow < kF3Valid && pos < p.F) {
