@@ -52,6 +52,36 @@ __device__ __forceinline__ void cp_tma_load_2d_2sm(void* dst, const CUtensorMap*
       : "memory");
 }
 
+constexpr int kCpKC = 48;                               // input channels per pipeline stage
+constexpr int kCpALbo = kCpRowPos * 16;
+constexpr int kCpATile = ((kCpKC / 8) * kCpALbo + 127) / 128 * 128;
+
+__device__ __forceinline__ void cp_umma_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  const uint64_t ad = ((uint64_t)a_hi << 32) | a_lo, bd = ((uint64_t)b_hi << 32) | b_lo;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the 9 * MT MMAs of one pipeline stage: 3 horizontal taps x MT tiles x KC/16 K steps
+template <int MT>
+__device__ __forceinline__ void cp_issue_stage(uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t tap16,
+                                               uint32_t bk16, uint32_t acc0, uint32_t NT, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int df = 0; df < 3; ++df) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int k = 0; k < kCpKC / 16; ++k) {
+        cp_umma_2sm(acc0 + (uint32_t)mt * NT, a_lo + (uint32_t)((mt * kCpATile + df * 16 + k * 2 * kCpALbo) >> 4),
+                    a_hi, b_lo + (uint32_t)df * tap16 + (uint32_t)k * bk16, b_hi, idesc, (df == 0 && k == 0) ? acc_first : 1u);
+      }
+    }
+  }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kCpThreads, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map, const CpParams p) {
@@ -161,9 +191,17 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader; warp-uniform loop, one elected lane issues) =====================
     if (leader) {
+      // Straight-line issue: ncu (profiles/r02_conv_pair_issue.md) had this warp as the kernel's bottleneck - 26 SASS
+      // instructions per MMA (runtime loop bounds from the parameter struct, 64-bit descriptor arithmetic), 139 cycles per
+      // 72-cycle MMA, producers waiting on full stages, tensor pipe 54 %.  The tap loops are unrolled per MT with 32-bit
+      // descriptor words: two adds and the instruction per MMA.
       const uint32_t idesc = make_idesc_2sm<FMT>(c.NT);
-      const uint32_t a_lbo = kCpRowPos * 16, b_lbo = (uint32_t)(c.NT / 2) * 16;
-      const uint64_t a_proto = make_desc(0, a_lbo, 128), b_proto = make_desc(0, b_lbo, 128);
+      const uint32_t b_lbo = (uint32_t)(c.NT / 2) * 16;
+      const uint64_t a_proto = make_desc(0, kCpALbo, 128), b_proto = make_desc(0, b_lbo, 128);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(stage0) >> 4);
+      const uint32_t b_lo0 = (uint32_t)b_proto + ((smem_u32(stage0) + (uint32_t)(c.MT * kCpATile)) >> 4);
+      const uint32_t stage16 = (uint32_t)(c.stage_bytes >> 4), tap16 = (uint32_t)(c.b_tap_bytes >> 4), bk16 = (2 * b_lbo) >> 4;
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
         return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
       };
@@ -180,21 +218,14 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
         for (int step = 0; step < steps; ++step) {
           if (!wait_all(&full[s], ph)) { alive = false; break; }
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage0 + (size_t)s * c.stage_bytes);
-          const uint32_t sb = sa + (uint32_t)(c.MT * c.a_tile_bytes);
           if (elect_one()) {
-            for (int df = 0; df < 3; ++df) {
-              for (int mt = 0; mt < c.MT; ++mt) {
-                const uint64_t ad0 = a_proto + ((sa + mt * c.a_tile_bytes + df * 16) >> 4);
-                const uint64_t bd0 = b_proto + ((sb + df * c.b_tap_bytes) >> 4);
-                const uint32_t acc = acc0 + (uint32_t)(mt * c.NT);
-                for (int k = 0; k < c.KC / 16; ++k) {
-                  if ((step | df | k) == 0)
-                    umma_f16_2sm<false>(acc, ad0 + (uint64_t)((k * 2 * a_lbo) >> 4), bd0 + (uint64_t)((k * 2 * b_lbo) >> 4), idesc);
-                  else
-                    umma_f16_2sm<true>(acc, ad0 + (uint64_t)((k * 2 * a_lbo) >> 4), bd0 + (uint64_t)((k * 2 * b_lbo) >> 4), idesc);
-                }
-              }
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16, b_lo = b_lo0 + (uint32_t)s * stage16;
+            const uint32_t acc_first = step == 0 ? 0u : 1u;  // the unit's first MMA per tile overwrites the accumulator
+            switch (c.MT) {
+              case 1: cp_issue_stage<1>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
+              case 2: cp_issue_stage<2>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
+              case 3: cp_issue_stage<3>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
+              default: cp_issue_stage<4>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
             }
             umma_commit_2sm(&empty[s]);
             if (step == steps - 1) umma_commit_2sm(&tfull[buf]);
@@ -288,7 +319,7 @@ static bool cp_make_cfg(int C, int F, CpCfg& c) {
   if (c.MT > pair_tiles) c.MT = pair_tiles;
   if (c.MT < 1) return false;
   c.nbuf = (2 * c.MT * c.NT <= 512) ? 2 : 1;
-  c.KC = 48;
+  c.KC = kCpKC;  // fixed: the kernel's stage issue code is unrolled for it
   c.nkc = C / c.KC;
   c.a_tile_bytes = (int)align_up((size_t)(c.KC / 8) * kCpRowPos * 16, 128);
   c.b_tap_bytes = c.KC * (c.NT / 2) * 2;
