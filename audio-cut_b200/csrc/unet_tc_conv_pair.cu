@@ -19,8 +19,9 @@ namespace ac {
 
 constexpr int kCpEpiGroups = 3;
 constexpr int kCpEpiWarps = 4 * kCpEpiGroups;
-constexpr int kCpWeightWarp = 2 + kCpEpiWarps;  // warps: 0 activation producer, 1 MMA, 2..13 epilogue, 14 weight producer
-constexpr int kCpThreads = (3 + kCpEpiWarps) * 32;
+constexpr int kCpProducers = 4;
+constexpr int kCpWeightWarp = 2 + kCpEpiWarps;  // warps: 0 producer, 1 MMA, 2..13 epilogue, 14..16 producers
+constexpr int kCpThreads = (2 + kCpEpiWarps + kCpProducers - 1) * 32;
 constexpr int kCpHeader = 5120;
 constexpr int kCpTileM = 128;
 constexpr int kCpRowPos = kCpTileM + 2;
@@ -140,8 +141,14 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
     f0 = fg * (2 * c.MT * kCpTileM);
   };
 
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs): own tiles + own half of the weights =====================
+  if (warp == 0 || warp >= kCpWeightWarp) {
+    // ===================== TMA producers (both CTAs): four issuing threads share the requests of every stage ==========
+    // A stage is MT activation tiles + 3 weight taps (this CTA's half of the slab) = 58 KB at C = 144, consumed by 1944
+    // cycles of MMAs.  One issuing thread moves ~14 B/clk (scripts/microbench/tma_box.cu), two moved 29 B/clk - exactly the
+    // consumption rate, and ncu had the MMA warp waiting on `full` a third of its time.  Request i of a stage goes to
+    // producer i mod 4; producer 0 of the leader posts the expect_tx for the whole stage (a complete_tx that lands first just
+    // runs the count negative).
+    const int role = warp == 0 ? 0 : warp - kCpWeightWarp + 1;
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
@@ -152,37 +159,20 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
         for (int dt = 0; dt < 3 && alive; ++dt) {
           for (int kc = 0; kc < c.nkc; ++kc) {
             if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
-            if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)(c.MT * (c.KC / 8) * (kCpRowPos * 16) + 3 * c.b_tap_bytes));
-            const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
-            uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
-            for (int mt = 0; mt < c.MT; ++mt)
-              tma_load_5d_2sm(st + mt * c.a_tile_bytes, &in_map, bar, 0, f0 + (2 * mt + (int)rank) * kCpTileM - 1, kc * (c.KC / 8),
-                              t + dt - 1, b);
-            if (++s == c.stages) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == kCpWeightWarp) {
-    // ===================== second TMA producer: this CTA's half of the weight slab of every stage ==============
-    // (one issuing thread moves ~14 B/clk, scripts/microbench/tma_box.cu; a stage needs twice that.  Its bytes are
-    //  part of the expect_tx the activation producer posts; a complete_tx that lands first just runs the count negative)
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      bool alive = true;
-      for (int u = pair; u < p.n_units && alive; u += n_pairs) {
-        int nt, b, t, f0;
-        decode(u, nt, b, t, f0);
-        for (int dt = 0; dt < 3 && alive; ++dt) {
-          for (int kc = 0; kc < c.nkc; ++kc) {
-            if (!mbar_wait(&empty[s], ph ^ 1, abort_flag)) { alive = false; break; }
+            if (leader && role == 0)
+              mbar_expect_tx(&full[s], 2u * (uint32_t)(c.MT * (c.KC / 8) * (kCpRowPos * 16) + 3 * c.b_tap_bytes));
             const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
             uint8_t* st = stage0 + (size_t)s * c.stage_bytes;
             // weights: slab (nt, rank, dt, kc) = 3 taps of b_rows rows each
             const int slab = ((nt * 2 + (int)rank) * 3 + dt) * c.nkc + kc;
-            for (int df = 0; df < 3; ++df)
-              cp_tma_load_2d_2sm(st + c.MT * c.a_tile_bytes + df * c.b_tap_bytes, &w_map, bar, 0, (slab * 3 + df) * b_rows);
+            for (int i = role; i < c.MT + 3; i += kCpProducers) {
+              if (i < c.MT)
+                tma_load_5d_2sm(st + i * c.a_tile_bytes, &in_map, bar, 0, f0 + (2 * i + (int)rank) * kCpTileM - 1, kc * (c.KC / 8),
+                                t + dt - 1, b);
+              else
+                cp_tma_load_2d_2sm(st + c.MT * c.a_tile_bytes + (i - c.MT) * c.b_tap_bytes, &w_map, bar, 0,
+                                   (slab * 3 + (i - c.MT)) * b_rows);
+            }
             if (++s == c.stages) { s = 0; ph ^= 1; }
           }
         }
@@ -250,32 +240,58 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
       const int n0 = nt * c.NT;
       if (!mbar_wait(&tfull[buf], use & 1, abort_flag)) break;
       tc_fence_after();
-      for (int mt = 0; mt < c.MT; ++mt) {
+      // This warp's 16-column chunks of the unit: (tile mt, columns (grp + 3 q) * 16).  With a single accumulator set (C >= 144)
+      // the next unit's MMAs wait for this loop, so the TMEM load of chunk i+1 is in flight while chunk i is scaled, packed
+      // and stored, and the set is handed back as soon as the last load has landed (before its math and stores).
+      const int per_tile = (c.NT / 16 - grp + kCpEpiGroups - 1) / kCpEpiGroups;
+      const int n_chunks = c.MT * per_tile;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT);
+      uint32_t ra[16], rb[16];
+      auto chunk_addr = [&](int i) {
+        const int mt = i / per_tile, q = i - mt * per_tile;
+        return tbase + (uint32_t)(mt * c.NT + (grp + kCpEpiGroups * q) * 16);
+      };
+      auto finish = [&](int i, const uint32_t* r) {
+        const int mt = i / per_tile, q = i - mt * per_tile;
+        const int j = (grp + kCpEpiGroups * q) * 16;
         const int f = f0 + (2 * mt + (int)rank) * kCpTileM + quad * 32 + lane;
-        const bool valid = f < p.F;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
-        h16* dst = p.out + cg8_index(b, t, n0 >> 3, valid ? f : 0, p.T, c.C, p.F);
-        for (int j = grp * 16; j < c.NT; j += 16 * kCpEpiGroups) {
-          uint32_t r[16];
-          tmem_ld16(taddr + j, r);
-          tmem_ld_wait();
-          if (valid) {
-            uint32_t pk[8];
+        if (f < p.F) {
+          h16* dst = p.out + cg8_index(b, t, (n0 + j) >> 3, f, p.T, c.C, p.F);
+          uint32_t pk[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int ch = n0 + j + 2 * e;
-              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
-              const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
-              pk[e] = pack2<FMT>(v0, v1);
-            }
-            *reinterpret_cast<uint4*>(dst + (size_t)(j >> 3) * plane) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + (size_t)((j >> 3) + 1) * plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          for (int e = 0; e < 8; ++e) {
+            const int ch = n0 + j + 2 * e;
+            const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
+            const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
+            pk[e] = pack2<FMT>(v0, v1);
+          }
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      };
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
+      };
+      if (n_chunks == 0) {
+        release();
+      } else {
+        tmem_ld16(chunk_addr(0), ra);
+        tmem_ld_wait();
+        for (int i = 0; i < n_chunks; i += 2) {
+          if (i + 1 < n_chunks) tmem_ld16(chunk_addr(i + 1), rb);
+          else release();
+          finish(i, ra);
+          if (i + 1 < n_chunks) {
+            tmem_ld_wait();
+            if (i + 2 < n_chunks) tmem_ld16(chunk_addr(i + 2), ra);
+            else release();
+            finish(i + 1, rb);
+            if (i + 2 < n_chunks) tmem_ld_wait();
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
     }
   }
   tc_fence_before();
