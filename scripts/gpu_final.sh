@@ -18,8 +18,15 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
     python scripts/dev_unet_tc_once.py 16 > /dev/null 2>&1
 python scripts/launch_table.py gpurun_out/${R}_launches_unet.csv > gpurun_out/${R}_unet_launches.txt
 # full-set capture of every tensor-core kernel of one forward (second forward), report kept on the box, summary exported
-ncu --set full --clock-control none --import-source on -k regex:"tc_conv3x3|tc_tdf|tc_resample" -s 59 -c 59 -o /tmp/prof_unet \
+# (55 tensor-core launches per forward since the level-0 conv chains are one launch each)
+ncu --set full --clock-control none --import-source on -k regex:"tc_conv3x3|tc_tdf|tc_resample" -s 55 -c 55 -o /tmp/prof_unet \
     python scripts/dev_unet_tc_once.py 16 > gpurun_out/${R}_ncu_unet_full.log 2>&1
 python scripts/ncu_summary.py rep /tmp/prof_unet.ncu-rep > gpurun_out/${R}_unet_ncu_full.md
+python scripts/make_traffic_json.py gpurun_out/${R}_unet_ncu_full.md gpurun_out/${R}_traffic.json
+# full-set capture of the MDX STFT / fused iSTFT (three-pass FFT) and the feature kernels
+python scripts/dev_hbm_once.py > gpurun_out/${R}_hbm_plain.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"stft_mdx|istft_mdx|frame_reduce|stft_feat|onset_flux" -c 40 -o /tmp/prof_hbm \
+    python scripts/dev_hbm_once.py > gpurun_out/${R}_ncu_hbm.log 2>&1
+python scripts/ncu_hbm_summary.py /tmp/prof_hbm.ncu-rep > gpurun_out/${R}_hbm_ncu_full.md 2>/dev/null || python scripts/ncu_summary.py rep /tmp/prof_hbm.ncu-rep > gpurun_out/${R}_hbm_ncu_full.md
 rm -f gpurun_out/${R}_launches_bench.csv
 cat gpurun_out/${R}_bench_final.json | head -c 600; echo; cat gpurun_out/${R}_plain_unet16.log
