@@ -18,7 +18,7 @@ EXPORTS = [
     "ac_init", "ac_last_error", "ac_abi_version", "ac_launch_count", "ac_frame_count", "ac_frame_rms", "ac_frame_rms_segments",
     "ac_stft_mdx", "ac_istft_mdx", "ac_unet_create", "ac_unet_destroy", "ac_unet_param_floats",
     "ac_unet_workspace_bytes", "ac_unet_forward", "ac_unet_set_debug", "ac_track_window_count",
-    "ac_track_workspace_bytes", "ac_separate_track", "ac_separate_track_ex", "ac_stft_features_workspace_bytes", "ac_stft_features",
+    "ac_track_workspace_bytes", "ac_separate_track", "ac_separate_track_ex", "ac_separate_track_pipelined", "ac_stft_features_workspace_bytes", "ac_stft_features",
     "ac_zero_crossing_rate", "ac_debug_tc_aborted", "ac_profile_begin", "ac_profile_collect",
     "ac_tempogram_stats", "ac_host_beat_dp", "ac_downmix_mono", "ac_track_stats", "ac_debug_conv3x3", "ac_debug_conv3x3_chain", "ac_pyin_frame_count", "ac_pyin_workspace_bytes", "ac_pyin",
     "ac_lpc_frame_count", "ac_lpc_formants", "ac_refine_cut_points", "ac_quiet_lookup_db",
@@ -102,6 +102,9 @@ def load() -> C.CDLL:
     lib.ac_separate_track.restype = i
     lib.ac_separate_track_ex.argtypes = [vp, vp, ll, C.POINTER(ChunkDesc), i, C.POINTER(TrackParams), vp, vp, vp, vp, vp, sz, vp]
     lib.ac_separate_track_ex.restype = i
+    lib.ac_separate_track_pipelined.argtypes = [vp, vp, vp, ll, C.POINTER(ChunkDesc), i, C.POINTER(TrackParams), vp, vp, vp, vp, vp, vp,
+                                                vp, sz, vp, vp, vp]
+    lib.ac_separate_track_pipelined.restype = i
     lib.ac_stft_features_workspace_bytes.argtypes = [C.POINTER(FeatSegment), i, i]
     lib.ac_stft_features_workspace_bytes.restype = sz
     lib.ac_stft_features.argtypes = [vp, C.POINTER(FeatSegment), i, i, i, vp, vp, vp, vp, vp, vp, sz, vp]

@@ -6,6 +6,7 @@
 // zero padding are index arithmetic, not copies) and that the fused iSTFT kernel uses to map its
 // output back to track samples (trim, concat, crop, halo trim).  Windows are independent, so they
 // are simply batched through STFT -> U-Net -> iSTFT max_batch at a time.
+#include <algorithm>
 #include <vector>
 
 #include "stft_mdx.cuh"
@@ -61,10 +62,12 @@ static void build_windows(const ac_chunk_desc* ch, int n_chunks, const ac_track_
   }
 }
 
+// divides samples [lo, lo + n) of both stems by their window count
 __global__ void finalize_stems_kernel(float* __restrict__ vocal, float* __restrict__ instr,
-                                      const float* __restrict__ weight, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                      const float* __restrict__ weight, long long lo, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  i += lo;
   float w = weight[i];
   w = w == 0.f ? 1.f : w;
   vocal[i] = vocal[i] / w;
@@ -174,15 +177,35 @@ extern "C" int ac_separate_track(ac_unet* net, const float* d_mix, long long n_s
                               stream);
 }
 
-extern "C" int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
-                                    int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr,
-                                    float* d_weight, float* d_chunk_vocal, void* d_ws, size_t ws_bytes, void* stream) {
-  using namespace ac;
+namespace ac {
+// events of the copy pipeline (one device per process; re-recording an event a stream already waited on is safe: a wait
+// refers to the record that preceded it)
+struct CopyEvents {
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t get(size_t i) {
+    while (ev.size() <= i) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      ev.push_back(e);
+    }
+    return ev[i];
+  }
+};
+static thread_local CopyEvents g_copy_events;
+
+// h_mix / h_vocal / h_instr (optional, page-locked): the host<->device copies of the track are pipelined against the window
+// batches on `cs` - the samples batch k reads are uploaded before it (later pieces while earlier batches compute), and every
+// stretch of the stems that no later window can touch is finalised and downloaded while the next batch runs.
+static int separate_track_impl(ac_unet* net, float* d_mix, const float* h_mix, long long n_samples, const ac_chunk_desc* h_chunks,
+                               int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr, float* d_weight,
+                               float* d_chunk_vocal, float* h_vocal, float* h_instr, void* d_ws, size_t ws_bytes, cudaStream_t st,
+                               cudaStream_t cs, cudaEvent_t uploaded) {
   AC_REQUIRE(net && d_mix && h_chunks && p && d_vocal && d_instr && d_weight && d_ws, "null pointer");
   AC_REQUIRE(track_geom_ok(*p), "MDX geometry: hop*(dim_t-1) must exceed n_fft, all sizes positive");
   AC_REQUIRE(n_samples > 0 && n_chunks >= 0, "bad sizes");
   AC_REQUIRE(p->n_channels == 1 || p->n_channels == 2, "n_channels must be 1 or 2");
   AC_REQUIRE(p->dtype == AC_F32 || p->dtype == AC_BF16 || p->dtype == AC_F16, "dtype");
+  AC_REQUIRE((h_vocal == nullptr) == (h_instr == nullptr), "host stems: both or none");
   for (int c = 0; c < n_chunks; ++c) {
     AC_REQUIRE(h_chunks[c].chunk_start >= 0 && h_chunks[c].chunk_start + h_chunks[c].chunk_len <= n_samples,
                "chunk outside the track");
@@ -192,7 +215,6 @@ extern "C" int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long 
     set_error("track workspace too small");
     return AC_E_WORKSPACE;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   const MdxPlan* plan = get_mdx_plan(p->mdx);
   if (!plan) return AC_E_INVALID;
   std::vector<WinDesc> wins;
@@ -207,6 +229,38 @@ extern "C" int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long 
   const size_t spec_bytes = align_up((size_t)mb * p->mdx.dim_t * p->mdx.dim_f * 4 * es, 256);
   char* d_uws = d_spec + spec_bytes;
   const size_t uws_bytes = ws_bytes - (size_t)(d_uws - reinterpret_cast<char*>(d_ws));
+  const int n_batches = nw > 0 ? (nw + mb - 1) / mb : 0;
+
+  // ---- upload plan: batch k reads track samples below up_end[k] (window position p of window w = sample base + p)
+  size_t n_ev = 0;
+  std::vector<cudaEvent_t> up_ev((size_t)n_batches, nullptr);
+  if (h_mix) {
+    long long done = 0;
+    auto upload = [&](long long to) -> int {
+      if (to > n_samples) to = n_samples;
+      if (to <= done) return AC_OK;
+      for (int c = 0; c < p->n_channels; ++c)
+        AC_CHECK_CUDA(cudaMemcpyAsync(d_mix + (size_t)c * n_samples + done, h_mix + (size_t)c * n_samples + done,
+                                      sizeof(float) * (size_t)(to - done), cudaMemcpyHostToDevice, cs));
+      done = to;
+      return AC_OK;
+    };
+    for (int k = 0; k < n_batches; ++k) {
+      long long need = 0;
+      for (int w = k * mb; w < nw && w < (k + 1) * mb; ++w) need = std::max(need, wins[w].base + (long long)wins[w].p_hi);
+      int rc = upload(need);
+      if (rc) return rc;
+      up_ev[k] = g_copy_events.get(n_ev++);
+      AC_REQUIRE(up_ev[k] != nullptr, "event creation failed");
+      AC_CHECK_CUDA(cudaEventRecord(up_ev[k], cs));
+    }
+    int rc = upload(n_samples);  // whatever no window reads (the feature kernels still do)
+    if (rc) return rc;
+    if (uploaded) AC_CHECK_CUDA(cudaEventRecord(uploaded, cs));
+  }
+  // ---- download plan: after windows [0, w) no later window writes below fin_lo[w] = min eff_start of windows >= w
+  std::vector<long long> fin_lo((size_t)nw + 1, n_samples);
+  for (int w = nw - 1; w >= 0; --w) fin_lo[w] = std::min(fin_lo[w + 1], (long long)wins[w].eff_start);
 
   AC_CHECK_CUDA(cudaMemsetAsync(d_vocal, 0, sizeof(float) * n_samples, st));
   AC_CHECK_CUDA(cudaMemsetAsync(d_instr, 0, sizeof(float) * n_samples, st));
@@ -223,8 +277,28 @@ extern "C" int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long 
     AC_CHECK_CUDA(cudaMemcpyAsync(d_wins, h_pin, sizeof(WinDesc) * nw, cudaMemcpyHostToDevice, st));
     AC_CHECK_CUDA(cudaEventRecord(g_win_stage.ev[slot], st));
   }
-  for (int w0 = 0; w0 < nw; w0 += mb) {
+  long long fin_done = 0;
+  auto finish_to = [&](long long to) -> int {  // finalise [fin_done, to) and send it home
+    if (to > n_samples) to = n_samples;
+    if (to <= fin_done) return AC_OK;
+    const long long n = to - fin_done;
+    finalize_stems_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_vocal, d_instr, d_weight, fin_done, n);
+    AC_LAUNCH_CHECK();
+    if (h_vocal) {
+      cudaEvent_t e = g_copy_events.get(n_ev++);
+      AC_REQUIRE(e != nullptr, "event creation failed");
+      AC_CHECK_CUDA(cudaEventRecord(e, st));
+      AC_CHECK_CUDA(cudaStreamWaitEvent(cs, e, 0));
+      AC_CHECK_CUDA(cudaMemcpyAsync(h_vocal + fin_done, d_vocal + fin_done, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, cs));
+      AC_CHECK_CUDA(cudaMemcpyAsync(h_instr + fin_done, d_instr + fin_done, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, cs));
+    }
+    fin_done = to;
+    return AC_OK;
+  };
+  int k = 0;
+  for (int w0 = 0; w0 < nw; w0 += mb, ++k) {
     const int b = nw - w0 < mb ? nw - w0 : mb;
+    if (h_mix) AC_CHECK_CUDA(cudaStreamWaitEvent(st, up_ev[k], 0));
     int rc = launch_stft(plan, d_mix, n_samples, p->n_channels, d_wins + w0, b, d_spec, p->dtype, st);
     if (rc) return rc;
     rc = ac_unet_forward(net, d_spec, d_spec, b, p->dtype, d_uws, uws_bytes, st);
@@ -232,10 +306,28 @@ extern "C" int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long 
     rc = launch_istft(plan, d_spec, p->dtype, d_wins + w0, b, 1, nullptr, d_mix, n_samples, p->n_channels,
                       p->output_is_vocal, d_vocal, d_instr, d_weight, st, d_chunk_vocal);
     if (rc) return rc;
+    if (h_vocal && (rc = finish_to(fin_lo[w0 + b]))) return rc;  // without a host target one finalise at the end is cheaper
   }
-  finalize_stems_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, st>>>(d_vocal, d_instr, d_weight, n_samples);
-  AC_LAUNCH_CHECK();
-  return AC_OK;
+  if (h_mix && n_batches == 0 && uploaded) AC_CHECK_CUDA(cudaStreamWaitEvent(st, uploaded, 0));
+  return finish_to(n_samples);
+}
+}  // namespace ac
+
+extern "C" int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
+                                    int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr,
+                                    float* d_weight, float* d_chunk_vocal, void* d_ws, size_t ws_bytes, void* stream) {
+  return ac::separate_track_impl(net, const_cast<float*>(d_mix), nullptr, n_samples, h_chunks, n_chunks, p, d_vocal, d_instr, d_weight,
+                                 d_chunk_vocal, nullptr, nullptr, d_ws, ws_bytes, (cudaStream_t)stream, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int ac_separate_track_pipelined(ac_unet* net, float* d_mix, const float* h_mix, long long n_samples,
+                                           const ac_chunk_desc* h_chunks, int n_chunks, const ac_track_params* p, float* d_vocal,
+                                           float* d_instr, float* d_weight, float* d_chunk_vocal, float* h_vocal, float* h_instr,
+                                           void* d_ws, size_t ws_bytes, void* stream, void* copy_stream, void* uploaded_event) {
+  AC_REQUIRE(copy_stream != stream || (!h_mix && !h_vocal), "the copy stream must differ from the compute stream");
+  return ac::separate_track_impl(net, d_mix, h_mix, n_samples, h_chunks, n_chunks, p, d_vocal, d_instr, d_weight, d_chunk_vocal,
+                                 h_vocal, h_instr, d_ws, ws_bytes, (cudaStream_t)stream, (cudaStream_t)copy_stream,
+                                 (cudaEvent_t)uploaded_event);
 }
 
 extern "C" int ac_downmix_mono(const float* d_mix, int n_channels, long long n, float* d_out, void* stream) {

@@ -216,9 +216,14 @@ def make_chunk_descs(bounds: Sequence[Tuple[int, int, int, int]]):
 
 def separate_track(net: UNet, mix: torch.Tensor, bounds: Sequence[Tuple[int, int, int, int]], geom: MdxGeom, *,
                    align_hop: int = 4096, output_is_vocal: bool = True, dtype: int = AC_F32, max_batch: int = 0, out=None,
-                   chunk_vocal: Optional[torch.Tensor] = None):
+                   chunk_vocal: Optional[torch.Tensor] = None, host_mix: int = 0, host_out: Optional[Tuple[int, int]] = None,
+                   copy_stream: Optional[torch.cuda.Stream] = None, uploaded_event: Optional[torch.cuda.Event] = None):
     """mix [n_ch, N] f32 on the GPU -> (vocal [N], instrumental [N], weight [N]); ``out`` = preallocated triple.
-    ``chunk_vocal`` (optional, float32 [sum of chunk lengths]): receives every chunk's own pre-stitch vocal output."""
+    ``chunk_vocal`` (optional, float32 [sum of chunk lengths]): receives every chunk's own pre-stitch vocal output.
+    With ``copy_stream``: the copies are pipelined against the window batches (ac_separate_track_pipelined) - ``host_mix`` =
+    address of the page-locked [n_ch, N] float32 source that is uploaded INTO ``mix`` piece by piece (0: ``mix`` is already
+    resident), ``host_out`` = addresses of two page-locked [N] float32 arrays receiving the stems as they become final,
+    ``uploaded_event`` is recorded on ``copy_stream`` when the whole mix is on the device."""
     assert mix.dim() == 2 and mix.shape[0] in (1, 2)
     mix = mix.contiguous().float()
     n = mix.shape[1]
@@ -238,6 +243,17 @@ def separate_track(net: UNet, mix: torch.Tensor, bounds: Sequence[Tuple[int, int
     if chunk_vocal is not None:
         need = sum(max(0, ce - cs) for cs, ce, _, _ in bounds)
         assert chunk_vocal.is_cuda and chunk_vocal.dtype == torch.float32 and chunk_vocal.is_contiguous() and chunk_vocal.numel() >= need
+    if copy_stream is not None:
+        hv, hi = host_out if host_out is not None else (0, 0)
+        if uploaded_event is not None and not uploaded_event.cuda_event:  # torch creates the CUDA event lazily
+            uploaded_event.record(copy_stream)
+        check(lib.ac_separate_track_pipelined(net.handle, ptr(mix), C.c_void_p(host_mix or None), n, descs, len(bounds), C.byref(tp),
+                                              ptr(vocal), ptr(instr), ptr(weight), ptr(chunk_vocal), C.c_void_p(hv or None),
+                                              C.c_void_p(hi or None), ptr(ws), ws.numel(), stream_ptr(),
+                                              C.c_void_p(copy_stream.cuda_stream),
+                                              C.c_void_p(uploaded_event.cuda_event if uploaded_event is not None else None)),
+              "ac_separate_track_pipelined")
+        return vocal, instr, weight
     check(lib.ac_separate_track_ex(net.handle, ptr(mix), n, descs, len(bounds), C.byref(tp), ptr(vocal), ptr(instr), ptr(weight),
                                    ptr(chunk_vocal), ptr(ws), ws.numel(), stream_ptr()), "ac_separate_track_ex")
     return vocal, instr, weight

@@ -167,6 +167,7 @@ class _TrackBuffers:
         self.cap = 0
         self.s_sep = torch.cuda.Stream(device=dev)
         self.s_feat = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_copy = torch.cuda.Stream(device=dev)  # H2D pieces / D2H of finished stretches beside the window batches
         self.events = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         self.stats_dev = torch.zeros(5, dtype=torch.float64, device=dev)
         self.stats_pin = torch.zeros(5, dtype=torch.float64, pin_memory=True)
@@ -310,24 +311,30 @@ class B200VocalSeparator:
             if not direct:
                 parallel_copy(v.pin_in_np, audio.reshape(n_ch, total))
             caller = torch.cuda.current_stream(dev)
+            copy_stream = bufs.s_copy
             stream.wait_stream(caller)
+            copy_stream.wait_stream(caller)
+            # The copies are pipelined against the window batches (ac_separate_track_pipelined): the mix goes up in pieces,
+            # each before the batch that reads it, and every stretch of the stems that no later window can touch comes
+            # home while the next batch runs - only the first upload piece and the last download piece are exposed.
+            host_mix = audio.ctypes.data if direct else v.pin_in_np.ctypes.data
+            host_out = ((out_pin[0].data_ptr(), out_pin[1].data_ptr()) if out_pin is not None
+                        else (v.pin_out[0].data_ptr(), v.pin_out[1].data_ptr()))
             with torch.cuda.stream(stream):
                 ev[0].record()
-                if direct:
-                    ops.check(lib.ac_copy_h2d_async(ops.ptr(v.mix), audio.ctypes.data, audio.nbytes, ops.stream_ptr()),
-                              "ac_copy_h2d_async")
-                else:
-                    v.mix.copy_(v.pin_in, non_blocking=True)
-                ev[1].record()
+            with torch.cuda.stream(copy_stream):
+                ev[1].record()  # creates the CUDA event; the library re-records it once the whole mix is resident
+            with torch.cuda.stream(stream):
+                ops.separate_track(backend.net, v.mix, [b for _, b in live], backend.geom, align_hop=backend.align_hop,
+                                   output_is_vocal=backend.get_output_type() == "vocal", dtype=backend.dtype,
+                                   out=(v.vocal, v.instr, v.weight), chunk_vocal=side_dev, host_mix=host_mix, host_out=host_out,
+                                   copy_stream=copy_stream, uploaded_event=ev[1])
+                ev[2].record()
             feat_stream.wait_event(ev[1])
             with torch.cuda.stream(feat_stream):
                 ops.check(lib.ac_downmix_mono(ops.ptr(v.mix), n_ch, total, ops.ptr(v.mono), ops.stream_ptr()), "ac_downmix_mono")
                 ev[4].record()
             with torch.cuda.stream(stream):
-                ops.separate_track(backend.net, v.mix, [b for _, b in live], backend.geom, align_hop=backend.align_hop,
-                                   output_is_vocal=backend.get_output_type() == "vocal", dtype=backend.dtype,
-                                   out=(v.vocal, v.instr, v.weight), chunk_vocal=side_dev)
-                ev[2].record()
                 if self.capture_device_metrics:  # NVML sample taken while the network runs, off the critical path
                     finish_metrics = ctx.capture_device_metrics_async()
                 # tail, all asynchronous: presence-marker RMS, energies, D2H of the stems and the scalars
@@ -339,11 +346,6 @@ class B200VocalSeparator:
                 stream.wait_event(ev[4])
                 ops.check(lib.ac_track_stats(ops.ptr(v.vocal), ops.ptr(v.instr), ops.ptr(v.mono), total, ops.ptr(bufs.stats_dev),
                                              ops.stream_ptr()), "ac_track_stats")
-                if out_pin is not None:  # D2H straight into the arrays the caller will own
-                    out_pin[0].copy_(v.vocal, non_blocking=True)
-                    out_pin[1].copy_(v.instr, non_blocking=True)
-                else:
-                    v.pin_out.copy_(v.stems2, non_blocking=True)
                 if side_dev is not None:
                     side_pin.copy_(side_dev, non_blocking=True)
                 mark.pin.copy_(mark.dev, non_blocking=True)
@@ -356,8 +358,10 @@ class B200VocalSeparator:
                 builder.add_track(v.mono, [p for p, _ in live])
                 cache = builder.finalize(audio)
             ev[3].synchronize()
+            copy_stream.synchronize()  # the last stretch of the stems
             caller.wait_stream(stream)
             caller.wait_stream(feat_stream)
+            caller.wait_stream(copy_stream)
         stats = bufs.stats_pin.numpy().copy()
         if stats[4] != 0:  # tc_common.cuh:mbar_wait watchdog: the tensor-core kernels drained out early, the stems are invalid
             raise _lib.AudioCutError("a tcgen05 kernel hit its mbarrier watchdog during this track: separation output is invalid")

@@ -190,6 +190,18 @@ AC_API int ac_separate_track(ac_unet* net, const float* d_mix, long long n_sampl
 AC_API int ac_separate_track_ex(ac_unet* net, const float* d_mix, long long n_samples, const ac_chunk_desc* h_chunks,
                          int n_chunks, const ac_track_params* p, float* d_vocal, float* d_instr, float* d_weight,
                          float* d_chunk_vocal, void* d_ws, size_t ws_bytes, void* stream);
+/* ac_separate_track_ex with the host<->device copies of the track pipelined against the window batches (what the
+ * reference's chunk loop does with its per-chunk pinned copies, enhanced_vocal_separator.py:366-458, gpu_pipeline.py
+ * PinnedBufferPool).  h_mix (optional, page-locked, [n_channels][n_samples] float32): uploaded into d_mix in pieces on
+ * copy_stream, each piece before the window batch that reads it; uploaded_event (optional cudaEvent_t) is recorded on
+ * copy_stream once the whole mix is resident.  h_vocal / h_instr (optional, page-locked, [n_samples] each): every stretch of
+ * the stems that no later window can touch is finalised and downloaded on copy_stream while the next batch runs.  On
+ * return everything is enqueued: wait for `stream` (compute) AND `copy_stream` (last download).  copy_stream must not be
+ * `stream`. */
+AC_API int ac_separate_track_pipelined(ac_unet* net, float* d_mix, const float* h_mix, long long n_samples,
+                                const ac_chunk_desc* h_chunks, int n_chunks, const ac_track_params* p, float* d_vocal,
+                                float* d_instr, float* d_weight, float* d_chunk_vocal, float* h_vocal, float* h_instr,
+                                void* d_ws, size_t ws_bytes, void* stream, void* copy_stream, void* uploaded_event);
 
 /* Stereo -> mono mean (np.mean(mix, axis=0) at features_cache.py:137-139 / enhanced_vocal_separator.py
  * mono handling); n_channels == 1 copies.  d_mix [n_channels][n] -> d_out [n]. */

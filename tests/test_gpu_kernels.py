@@ -192,6 +192,42 @@ def test_separate_track_small_geometry(ops, stereo, output_is_vocal):
     assert w.max() == 2 and w.min() == 1
 
 
+@pytest.mark.parametrize("n_samples,max_batch", [(138400, 4), (138400, 0), (641, 0), (16001, 3)])
+def test_separate_track_pipelined_copies_equal_the_plain_call(ops, n_samples, max_batch):
+    """ac_separate_track_pipelined (mix uploaded in pieces ahead of the batch that reads them, every finished stretch of
+    the stems finalised and downloaded while the next batch runs) against ac_separate_track_ex on a resident mix with one
+    download at the end: same kernels on the same data, so the stems must be bit-identical - with several batches per track
+    (max_batch 3 / 4: 11+ windows), one batch, and tracks shorter than a window / a chunk."""
+    import torch
+
+    from audio_cut_b200 import unet_weights as uw
+    from oracle import planner
+
+    sr, n_fft, hop, dim_f, dim_t, g = 8000, 640, 128, 256, 32, 16
+    geo = uw.UNetGeometry(dim_f=dim_f, dim_t=dim_t, g=g)
+    net = ops.UNet(uw.random_state(geo, seed=1234), geo)
+    rng = np.random.default_rng(n_samples + max_batch)
+    audio = (0.3 * rng.standard_normal((2, n_samples))).astype(np.float32)
+    plans = planner.chunk_schedule(n_samples / float(sr), 2.0, 0.5, 0.1)
+    bounds = [planner.sample_bounds(p, sr, n_samples) for p in plans]
+    geom = ops.mdx_geom(n_fft, hop, dim_f, dim_t)
+    v0, i0, w0 = ops.separate_track(net, torch.from_numpy(audio).cuda(), bounds, geom, align_hop=256, max_batch=max_batch)
+    v0, i0, w0 = v0.cpu(), i0.cpu(), w0.cpu()
+    host_mix = torch.from_numpy(audio).pin_memory()
+    host_out = torch.full((2, n_samples), float("nan")).pin_memory()
+    d_mix = torch.full((2, n_samples), float("nan"), device="cuda")  # filled by the call
+    copy_stream, up = torch.cuda.Stream(), torch.cuda.Event()
+    copy_stream.wait_stream(torch.cuda.current_stream())
+    v1, i1, w1 = ops.separate_track(net, d_mix, bounds, geom, align_hop=256, max_batch=max_batch, host_mix=host_mix.data_ptr(),
+                                    host_out=(host_out[0].data_ptr(), host_out[1].data_ptr()), copy_stream=copy_stream,
+                                    uploaded_event=up)
+    up.synchronize()
+    assert torch.equal(d_mix.cpu(), torch.from_numpy(audio))  # the whole mix is resident once the event has fired
+    torch.cuda.synchronize()
+    assert torch.equal(v1.cpu(), v0) and torch.equal(i1.cpu(), i0) and torch.equal(w1.cpu(), w0)
+    assert torch.equal(host_out[0], v0) and torch.equal(host_out[1], i0)
+
+
 @pytest.mark.parametrize("n_samples", [1, 100, 641, 5000, 16001])
 def test_separate_track_short_and_ragged_inputs(ops, n_samples):
     """Tracks shorter than one model window / one chunk / not a multiple of anything: the planner returns a single
