@@ -66,19 +66,15 @@ __device__ __forceinline__ void cp_umma_2sm(uint32_t tmem_d, uint32_t a_lo, uint
       "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// the 9 * MT MMAs of one pipeline stage: 3 horizontal taps x MT tiles x KC/16 K steps
-template <int MT>
-__device__ __forceinline__ void cp_issue_stage(uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t tap16,
-                                               uint32_t bk16, uint32_t acc0, uint32_t NT, uint32_t idesc, uint32_t acc_first) {
+// the 9 MMAs of one tile in one pipeline stage: 3 horizontal taps x KC/16 K steps (a_lo = the tile's descriptor word)
+__device__ __forceinline__ void cp_issue_tile(uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t tap16,
+                                              uint32_t bk16, uint32_t acc, uint32_t idesc, uint32_t acc_first) {
 #pragma unroll
   for (int df = 0; df < 3; ++df) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-      for (int k = 0; k < kCpKC / 16; ++k) {
-        cp_umma_2sm(acc0 + (uint32_t)mt * NT, a_lo + (uint32_t)((mt * kCpATile + df * 16 + k * 2 * kCpALbo) >> 4),
-                    a_hi, b_lo + (uint32_t)df * tap16 + (uint32_t)k * bk16, b_hi, idesc, (df == 0 && k == 0) ? acc_first : 1u);
-      }
+    for (int k = 0; k < kCpKC / 16; ++k) {
+      cp_umma_2sm(acc, a_lo + (uint32_t)((df * 16 + k * 2 * kCpALbo) >> 4), a_hi, b_lo + (uint32_t)df * tap16 + (uint32_t)k * bk16,
+                  b_hi, idesc, (df == 0 && k == 0) ? acc_first : 1u);
     }
   }
 }
@@ -91,9 +87,9 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
   const CpCfg& c = p.cfg;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [stages]  leader: both CTAs' stage landed
   uint64_t* empty = full + kCpMaxStages;                // [stages]
-  uint64_t* tfull = empty + kCpMaxStages;               // [2]
-  uint64_t* tempty = tfull + 2;                         // [2]       leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tfull = empty + kCpMaxStages;               // [2 sets][4 tiles]  tile complete
+  uint64_t* tempty = tfull + 8;                         // [2 sets][4 tiles]  leader: tile drained by both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 8);
   float* s_scale = reinterpret_cast<float*>(smem + 1024);  // [C] (<= 512)
   float* s_shift = s_scale + 512;
   uint8_t* stage0 = smem + kCpHeader;
@@ -112,7 +108,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 8; ++b) {
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 2 * kCpEpiWarps);
     }
@@ -199,28 +195,31 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
       uint32_t ph = 0;
       uint32_t n_acc = 0;
       bool alive = true;
+      // Tiles are issued one after the other inside a stage (tile-major: the accumulation order per output is unchanged), with
+      // one complete / drained barrier pair PER TILE: with a single accumulator set (C >= 144: MT * NT > 256 columns) the drain
+      // of a unit used to stop the MMAs for three tile drains; now tile 0 drains under the last stage's MMAs of tiles 1 and 2, and
+      // the next unit's first stage starts on tile 0 while tile 2 is still draining.
       for (int u = pair; u < p.n_units && alive; u += n_pairs, ++n_acc) {
         const int buf = c.nbuf == 2 ? (int)(n_acc & 1) : 0;
         const uint32_t use = c.nbuf == 2 ? (n_acc >> 1) : n_acc;
-        if (!wait_all(&tempty[buf], (use & 1) ^ 1)) break;
-        tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * c.MT * c.NT);
-        for (int step = 0; step < steps; ++step) {
+        for (int step = 0; step < steps && alive; ++step) {
           if (!wait_all(&full[s], ph)) { alive = false; break; }
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16, b_lo = b_lo0 + (uint32_t)s * stage16;
-            const uint32_t acc_first = step == 0 ? 0u : 1u;  // the unit's first MMA per tile overwrites the accumulator
-            switch (c.MT) {
-              case 1: cp_issue_stage<1>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
-              case 2: cp_issue_stage<2>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
-              case 3: cp_issue_stage<3>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
-              default: cp_issue_stage<4>(a_lo, a_hi, b_lo, b_hi, tap16, bk16, acc0, (uint32_t)c.NT, idesc, acc_first); break;
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * stage16, b_lo = b_lo0 + (uint32_t)s * stage16;
+          for (int mt = 0; mt < c.MT; ++mt) {
+            if (step == 0) {
+              if (!wait_all(&tempty[buf * 4 + mt], (use & 1) ^ 1)) { alive = false; break; }
+              tc_fence_after();
             }
-            umma_commit_2sm(&empty[s]);
-            if (step == steps - 1) umma_commit_2sm(&tfull[buf]);
+            if (elect_one()) {
+              cp_issue_tile(a_lo + (uint32_t)mt * (kCpATile >> 4), a_hi, b_lo, b_hi, tap16, bk16, acc0 + (uint32_t)(mt * c.NT), idesc,
+                            step == 0 ? 0u : 1u);  // the unit's first MMA per tile overwrites the accumulator
+              if (step == steps - 1) umma_commit_2sm(&tfull[buf * 4 + mt]);
+              if (mt == c.MT - 1) umma_commit_2sm(&empty[s]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (++s == c.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -238,60 +237,58 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_
       int nt, b, t, f0;
       decode(u, nt, b, t, f0);
       const int n0 = nt * c.NT;
-      if (!mbar_wait(&tfull[buf], use & 1, abort_flag)) break;
-      tc_fence_after();
-      // This warp's 16-column chunks of the unit: (tile mt, columns (grp + 3 q) * 16).  With a single accumulator set (C >= 144)
-      // the next unit's MMAs wait for this loop, so the TMEM load of chunk i+1 is in flight while chunk i is scaled, packed
-      // and stored, and the set is handed back as soon as the last load has landed (before its math and stores).
+      // This warp's 16-column chunks of a tile: columns (grp + 3 q) * 16.  Tile by tile: wait for the tile, pull its chunks
+      // (the TMEM load of chunk q+1 in flight while chunk q is scaled, packed and stored), hand the tile back after the last load.
       const int per_tile = (c.NT / 16 - grp + kCpEpiGroups - 1) / kCpEpiGroups;
-      const int n_chunks = c.MT * per_tile;
-      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT);
-      uint32_t ra[16], rb[16];
-      auto chunk_addr = [&](int i) {
-        const int mt = i / per_tile, q = i - mt * per_tile;
-        return tbase + (uint32_t)(mt * c.NT + (grp + kCpEpiGroups * q) * 16);
-      };
-      auto finish = [&](int i, const uint32_t* r) {
-        const int mt = i / per_tile, q = i - mt * per_tile;
-        const int j = (grp + kCpEpiGroups * q) * 16;
+      bool alive = true;
+      for (int mt = 0; mt < c.MT && alive; ++mt) {
+        if (!mbar_wait(&tfull[buf * 4 + mt], use & 1, abort_flag)) { alive = false; break; }
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * c.MT * c.NT + mt * c.NT);
         const int f = f0 + (2 * mt + (int)rank) * kCpTileM + quad * 32 + lane;
-        if (f < p.F) {
-          h16* dst = p.out + cg8_index(b, t, (n0 + j) >> 3, f, p.T, c.C, p.F);
-          uint32_t pk[8];
+        uint32_t ra[16], rb[16];
+        auto chunk_addr = [&](int q) { return tbase + (uint32_t)((grp + kCpEpiGroups * q) * 16); };
+        auto finish = [&](int q, const uint32_t* r) {
+          const int j = (grp + kCpEpiGroups * q) * 16;
+          if (f < p.F) {
+            h16* dst = p.out + cg8_index(b, t, (n0 + j) >> 3, f, p.T, c.C, p.F);
+            uint32_t pk[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ch = n0 + j + 2 * e;
-            const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
-            const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
-            pk[e] = pack2<FMT>(v0, v1);
+            for (int e = 0; e < 8; ++e) {
+              const int ch = n0 + j + 2 * e;
+              const float v0 = fmaxf(fmaf(__uint_as_float(r[2 * e]), s_scale[ch], s_shift[ch]), 0.f);
+              const float v1 = fmaxf(fmaf(__uint_as_float(r[2 * e + 1]), s_scale[ch + 1], s_shift[ch + 1]), 0.f);
+              pk[e] = pack2<FMT>(v0, v1);
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(dst + plane) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        };
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)(buf * 4 + mt) * 8);
+        };
+        if (per_tile == 0) {
+          release();
+          continue;
         }
-      };
-      auto release = [&]() {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + (uint32_t)buf * 8);
-      };
-      if (n_chunks == 0) {
-        release();
-      } else {
         tmem_ld16(chunk_addr(0), ra);
         tmem_ld_wait();
-        for (int i = 0; i < n_chunks; i += 2) {
-          if (i + 1 < n_chunks) tmem_ld16(chunk_addr(i + 1), rb);
+        for (int i = 0; i < per_tile; i += 2) {
+          if (i + 1 < per_tile) tmem_ld16(chunk_addr(i + 1), rb);
           else release();
           finish(i, ra);
-          if (i + 1 < n_chunks) {
+          if (i + 1 < per_tile) {
             tmem_ld_wait();
-            if (i + 2 < n_chunks) tmem_ld16(chunk_addr(i + 2), ra);
+            if (i + 2 < per_tile) tmem_ld16(chunk_addr(i + 2), ra);
             else release();
             finish(i + 1, rb);
-            if (i + 2 < n_chunks) tmem_ld_wait();
+            if (i + 2 < per_tile) tmem_ld_wait();
           }
         }
       }
+      if (!alive) break;
     }
   }
   tc_fence_before();
