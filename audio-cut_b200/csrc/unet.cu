@@ -1,5 +1,6 @@
 // TFC-TDF U-Net: parameter upload / repacking and the forward schedule.
 // Replaces self._session.run(...) at backends.py:358 (onnxruntime executing Kim_Vocal_1.onnx).
+#include <algorithm>
 #include <vector>
 
 #include "unet_kernels.cuh"
@@ -304,6 +305,22 @@ static int ensure_h16(ac_unet* net, int fmt) {
     TdfLayer& t2 = b.tdf2;
     if (!t1.tc[fmt] && (rc = tc_tdf_pack(blob + t1.raw_off, t1.M, t1.K, b.c, b.T, fmt, &t1.tc[fmt]))) return rc;
     if (!t2.tc[fmt] && (rc = tc_tdf_pack(blob + t2.raw_off, t2.M, t2.K, b.c, b.T, fmt, &t2.tc[fmt]))) return rc;
+    if (!t1.tc[fmt] && !t2.tc[fmt] && (t1.M < 32 || t1.M % 16)) {
+      // Bottleneck width below a UMMA tile's granularity (Kim_Vocal level 4: F/8 = 24): run the pair on the tensor cores with the
+      // hidden tensor padded to Mp rows - TDF1 gets Mp - M zero weight rows (its extra outputs are relu(shift), finite), TDF2 gets
+      // Mp - M zero weight columns (so they contribute nothing).  Both layers or neither: they share the hidden layout.
+      const int Mp = t1.M < 32 ? 32 : (t1.M + 15) / 16 * 16;
+      std::vector<float> w1p((size_t)Mp * t1.K, 0.f), w2p((size_t)t2.M * Mp, 0.f);
+      for (int m = 0; m < t1.M; ++m) std::copy(blob + t1.raw_off + (size_t)m * t1.K, blob + t1.raw_off + (size_t)(m + 1) * t1.K, w1p.begin() + (size_t)m * t1.K);
+      for (int m = 0; m < t2.M; ++m) std::copy(blob + t2.raw_off + (size_t)m * t2.K, blob + t2.raw_off + (size_t)(m + 1) * t2.K, w2p.begin() + (size_t)m * Mp);
+      if ((rc = tc_tdf_pack(w1p.data(), Mp, t1.K, b.c, b.T, fmt, &t1.tc[fmt]))) return rc;
+      if ((rc = tc_tdf_pack(w2p.data(), t2.M, Mp, b.c, b.T, fmt, &t2.tc[fmt]))) return rc;
+      if (!t1.tc[fmt] || !t2.tc[fmt]) {
+        tc_tdf_free(t1.tc[fmt]);
+        tc_tdf_free(t2.tc[fmt]);
+        t1.tc[fmt] = t2.tc[fmt] = nullptr;
+      }
+    }
     if (!t2.pair[fmt] && (rc = tc_tdf2_pair_pack(blob + t2.raw_off, t2.M, t2.K, b.c, b.T, fmt, &t2.pair[fmt]))) return rc;
     if (!t1.pair1[fmt] && (rc = tc_tdf1_pair_pack(blob + t1.raw_off, t1.M, t1.K, b.c, b.T, fmt, &t1.pair1[fmt]))) return rc;
   }
@@ -527,7 +544,7 @@ static WsPlan plan_ws(const ac_unet_geom& g, int B, int dtype) {
   }
   w.A = bump(scratch);
   w.Bf = bump(scratch);
-  w.H = bump(scratch / g.bn + 128);
+  w.H = bump(2 * (scratch / g.bn) + 128);  // x2: levels whose bottleneck is padded to a UMMA-friendly row count (ensure_h16)
   for (int i = 0; i < g.n; ++i) w.skip_off[i] = bump((size_t)B * w.e[i]);
   for (int i = 1; i <= g.n; ++i) w.io_off[i] = bump((size_t)B * w.e[i]);
   w.total = off;

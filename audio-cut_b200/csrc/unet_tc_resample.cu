@@ -10,6 +10,8 @@
 //         (t,f) to out[b][2t+dt][2f+df][:] and multiplies by the encoder skip tensor.
 // These layers are HBM bound (<= 8 FLOP/B), so the design goal is streaming: one pass over the
 // input, one over the skip, one write - the MMA work hides under the memory time.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "tc_common.cuh"
@@ -307,6 +309,11 @@ static bool make_rs_cfg(int mode, int Cin, int Cout, RsCfg& c) {
     c.NT = Cout;
     c.ntap = 4;
     while (c.ntap > 1 && 2 * c.ntap * c.NT > 512) c.ntap /= 2;
+    // Two accumulator sets force one tap per unit at C_out = 144 (2 x 2 x 144 columns > 512): the 49 KB input tile is then
+    // fetched four times and the units are too short to stream.  Two taps on ONE set (MMA and drain of a unit serialised, both
+    // small next to its memory time) took that layer from 255 to 161 us; at C_out = 96 (401 -> 465 us) and at C_out >= 192
+    // (79 -> 82, 28 -> 30 us) the single set loses, so they keep the double-buffered configuration.
+    if (c.ntap == 1 && 2 * c.NT <= 320) c.ntap = 2;
     c.nsplit = 4 / c.ntap;  // tap groups
     c.MT = 1;
     c.nbuf = (2 * c.ntap * c.NT <= 512) ? 2 : 1;
