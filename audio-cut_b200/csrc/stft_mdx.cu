@@ -299,6 +299,96 @@ __global__ void __launch_bounds__(kFft3Threads, 2) stft_mdx3_kernel(const float*
   }
 }
 
+// STFT + the network's first 1x1 conv: the frame's 4 spectrogram values per bin never go to HBM as a [f][4] tensor; each
+// thread turns its bins into the 48-channel CG8 row the level-0 conv chain reads (6 x 16-byte stores per bin, lanes walk f).
+template <int FMT, int N>
+__global__ void __launch_bounds__(kFft3Threads, 2) stft_mdx3_first_kernel(const float* __restrict__ src, long long ch_stride, int n_ch,
+                                                                          const WinDesc* __restrict__ wins, Fft3Tw tw,
+                                                                          const float* __restrict__ hann, int hop, int dim_f, int dim_t,
+                                                                          int W, h16* __restrict__ out, const float* __restrict__ cw,
+                                                                          const float* __restrict__ cscale,
+                                                                          const float* __restrict__ cshift) {
+  constexpr int G = 48;
+  extern __shared__ float2 smem_f2[];
+  float2* buf = smem_f2;
+  float* sw = reinterpret_cast<float*>(buf + ((fpad(N) + 2) & ~1));  // 16-byte aligned: [G][4] weights, [G] scale, [G] shift
+  float* ssc = sw + G * 4;
+  float* ssh = ssc + G;
+  constexpr int nb3 = N / Fft3Geom<N>::R3;
+  for (int i = threadIdx.x; i < G * 4; i += kFft3Threads) sw[i] = cw[i];
+  for (int i = threadIdx.x; i < G; i += kFft3Threads) {
+    ssc[i] = cscale[i];
+    ssh[i] = cshift[i];
+  }
+  const int t = blockIdx.x;
+  const WinDesc wd = wins[blockIdx.y];
+  const float* s0 = src + wd.base;
+  const float* s1 = src + (n_ch > 1 ? ch_stride : 0) + wd.base;
+  const int p0 = t * hop - N / 2;
+  auto load = [&](int m) {
+    int p = p0 + m;
+    p = p < 0 ? -p : p;
+    p = p >= W ? 2 * (W - 1) - p : p;  // torch.stft center=True, pad_mode="reflect"
+    float l = 0.f, r = 0.f;
+    if (p >= wd.p_lo && p < wd.p_hi) {
+      l = __ldg(s0 + p);
+      r = __ldg(s1 + p);
+    }
+    const float w = __ldg(hann + m);
+    return make_float2(l * w, r * w);
+  };
+  float2* zrow = buf + threadIdx.x + (threadIdx.x >> 5);
+  auto sink = [&](int, int r, float2 v) { zrow[r * (nb3 + nb3 / 32)] = v; };
+  fft3_run<N, false>(buf, tw, load, sink);
+  __syncthreads();
+  // row = (window, t); CG8: out[((row * G/8 + cg) * F + f) * 8 + c%8].  Three bins per thread and round share every weight /
+  // scale / shift load (the conv is ~2600 instructions per thread and frame, more than the FFT itself).
+  h16* orow = out + ((size_t)blockIdx.y * dim_t + t) * (size_t)(G / 8) * dim_f * 8;
+  for (int k0 = threadIdx.x; k0 < dim_f; k0 += 3 * kFft3Threads) {
+    float2 x01[3], x23[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int k = k0 + j * kFft3Threads;
+      const int kk = k < dim_f ? k : 0;
+      const float2 a = buf[fpad(kk)];
+      const float2 b = buf[fpad(kk == 0 ? 0 : N - kk)];
+      // the spectrogram values exactly as the [f][4] store would round them
+      x01[j] = unpack2<FMT>(pack2<FMT>(0.5f * (a.x + b.x), 0.5f * (a.y - b.y)));
+      x23[j] = unpack2<FMT>(pack2<FMT>(0.5f * (a.y + b.y), -0.5f * (a.x - b.x)));
+    }
+#pragma unroll 1  // (unrolled, the 48-channel body spills under the 64-register budget of two CTAs per SM)
+    for (int cg = 0; cg < G / 8; ++cg) {
+      uint32_t pk[3][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v[3][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = cg * 8 + 2 * e + h;
+          const float4 wv = *reinterpret_cast<const float4*>(sw + c * 4);
+          const float sc = ssc[c], sh = ssh[c];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            float s = wv.x * x01[j].x;
+            s = fmaf(wv.y, x01[j].y, s);
+            s = fmaf(wv.z, x23[j].x, s);
+            s = fmaf(wv.w, x23[j].y, s);
+            v[j][h] = fmaxf(fmaf(s, sc, sh), 0.f);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pk[j][e] = pack2<FMT>(v[j][0], v[j][1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int k = k0 + j * kFft3Threads;
+        if (k < dim_f)
+          *reinterpret_cast<uint4*>(orow + ((size_t)cg * dim_f + k) * 8) = make_uint4(pk[j][0], pk[j][1], pk[j][2], pk[j][3]);
+      }
+    }
+  }
+}
+
 template <typename T, int N>
 __global__ void __launch_bounds__(kFft3Threads, 1) istft_mdx3_kernel(const T* __restrict__ spec, IstftArgs a, Fft3Tw tw,
                                                                      unsigned hop_magic) {
@@ -392,6 +482,38 @@ __global__ void __launch_bounds__(kFft3Threads, 1) istft_mdx3_kernel(const T* __
 static bool use_fft3(const MdxPlan* plan) {
   static const bool off = getenv("AC_NO_FFT3") && atoi(getenv("AC_NO_FFT3")) != 0;
   return !off && fft3_supported(plan->g.n_fft) && plan->fft->d_tw3_p2 && plan->fft->d_tw3_p3 && plan->g.hop <= 32768;
+}
+
+bool stft_first_conv_supported(const MdxPlan* plan, int g, int dtype) {
+  return use_fft3(plan) && g == 48 && (dtype == AC_F16 || dtype == AC_BF16);
+}
+
+int launch_stft_first_conv(const MdxPlan* plan, const float* d_src, long long ch_stride, int n_ch, const WinDesc* d_wins, int n_win,
+                           void* d_cg8, int g, const float* d_w, const float* d_scale, const float* d_shift, int dtype,
+                           cudaStream_t st) {
+  if (n_win <= 0) return AC_OK;
+  if (!stft_first_conv_supported(plan, g, dtype)) return AC_E_INVALID;
+  const ac_mdx_geom& gm = plan->g;
+  const Fft3Tw tw{plan->fft->d_tw3_p2, plan->fft->d_tw3_p3};
+  const size_t smem = sizeof(float2) * fft_smem_floats2(gm.n_fft) + sizeof(float) * (48 * 4 + 2 * 48) + 16;
+  dim3 grid(gm.dim_t, n_win);
+  // algorithmic bytes: the window's samples in, the 48-channel 16-bit tensor out
+  ProfScope ps(KC_STFT, 2.0 * n_win * (double)gm.dim_t * gm.dim_f * g * 4,
+               n_win * (2.0 * plan->W * 4 + (double)gm.dim_t * gm.dim_f * g * 2.0), st);
+#define AC_STFT3F_LAUNCH(FMT, NN)                                                                                                 \
+  do {                                                                                                                            \
+    AC_CHECK_CUDA(cudaFuncSetAttribute(stft_mdx3_first_kernel<FMT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    stft_mdx3_first_kernel<FMT, NN><<<grid, kFft3Threads, smem, st>>>(d_src, ch_stride, n_ch, d_wins, tw, plan->fft->d_hann, gm.hop,  \
+                                                                     gm.dim_f, gm.dim_t, plan->W, (h16*)d_cg8, d_w, d_scale, d_shift); \
+  } while (0)
+  if (dtype == AC_F16) {
+    if (gm.n_fft == 7680) AC_STFT3F_LAUNCH(kFmtF16, 7680); else AC_STFT3F_LAUNCH(kFmtF16, 6144);
+  } else {
+    if (gm.n_fft == 7680) AC_STFT3F_LAUNCH(kFmtBF16, 7680); else AC_STFT3F_LAUNCH(kFmtBF16, 6144);
+  }
+#undef AC_STFT3F_LAUNCH
+  AC_LAUNCH_CHECK();
+  return AC_OK;
 }
 
 static size_t stft_smem_bytes(int n_fft) { return sizeof(float2) * 2 * (fft_smem_floats2(n_fft)); }

@@ -28,6 +28,15 @@ const MdxPlan* get_mdx_plan(const ac_mdx_geom& g);
 int launch_stft(const MdxPlan* plan, const float* d_src, long long ch_stride, int n_ch, const WinDesc* d_wins,
                 int n_win, void* d_spec, int dtype, cudaStream_t st);
 
+// STFT with the network's first 1x1 conv (4 -> 48 channels, folded BN + ReLU) applied in the epilogue: writes the CG8 tensor
+// [n_win][dim_t][48/8][dim_f][8] the level-0 conv chain reads, bit-identical to launch_stft + first_conv_cg8_kernel (the four
+// spectrogram values are rounded to the 16-bit format first, as the separate store would).  AC_E_INVALID when the shape has no
+// fused kernel (n_fft other than 7680 / 6144, g != 48, fp32): the caller then runs the two launches.
+int launch_stft_first_conv(const MdxPlan* plan, const float* d_src, long long ch_stride, int n_ch, const WinDesc* d_wins, int n_win,
+                           void* d_cg8, int g, const float* d_w /*[g][4]*/, const float* d_scale, const float* d_shift, int dtype,
+                           cudaStream_t st);
+bool stft_first_conv_supported(const MdxPlan* plan, int g, int dtype);
+
 // mode 0: raw torch.istft output into d_wave [n_win][2][W].
 // mode 1: stems: trims n_fft/2 per side, maps to the track through WinDesc, subtracts from the
 //         mix, averages the two channels and atomically accumulates vocal / instrumental / weight.

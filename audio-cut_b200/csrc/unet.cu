@@ -557,8 +557,52 @@ extern "C" size_t ac_unet_workspace_bytes(const ac_unet* net, int B, int dtype) 
   return ac::plan_ws(net->g, B, dtype).total * (dtype == AC_F32 ? 4 : 2) + 256;
 }
 
+namespace ac {
+static int unet_forward_impl(ac_unet* net, const void* d_in, void* d_out, int B, int dtype, void* d_ws, size_t ws_bytes,
+                             void* stream, bool first_done);
+static bool unet_first_fusable(const ac_unet* net, int B, int dtype) {
+  if (!net || dtype == AC_F32 || net->force_simt != 0) return false;
+  const int fmt = fmt_of_dtype(dtype);
+  if (!net->h16_ready[fmt] || !net->tc_ok[fmt]) return false;
+  return plan_ws(net->g, B, dtype).sb[0] >= B;  // the whole batch goes through level 0 in one pass
+}
+// Where the network expects the output of its first 1x1 conv for a batch of B windows (CG8 [B][T][g/8][F][8]) and that
+// conv's parameters - for a producer that applies it itself (the fused STFT epilogue, stft_mdx.cu).  AC_E_INVALID when
+// this network / dtype / batch cannot take it (fp32, CUDA-core debug modes, sub-batched level 0).
+int unet_first_conv_target(ac_unet* net, int B, int dtype, void* d_ws, size_t ws_bytes, void** d_target, const float** w,
+                           const float** scale, const float** shift) {
+  AC_REQUIRE(net && d_ws && d_target && w && scale && shift, "null pointer");
+  if (dtype != AC_F32) {
+    int rc0 = ensure_h16(net, fmt_of_dtype(dtype));
+    if (rc0) return rc0;
+  }
+  if (!unet_first_fusable(net, B, dtype)) return AC_E_INVALID;
+  if (ws_bytes < ac_unet_workspace_bytes(net, B, dtype)) {
+    set_error("unet workspace too small");
+    return AC_E_WORKSPACE;
+  }
+  const WsPlan wp = plan_ws(net->g, B, dtype);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~uintptr_t(255));
+  *d_target = base + wp.Bf * 2;
+  *w = net->first_w;
+  *scale = net->first_af.scale;
+  *shift = net->first_af.shift;
+  return AC_OK;
+}
+int unet_base_channels(const ac_unet* net) { return net ? net->g.g : 0; }
+int unet_forward_after_first(ac_unet* net, void* d_out, int B, int dtype, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+  AC_REQUIRE(unet_first_fusable(net, B, dtype), "the first conv of this network / dtype cannot be applied by the caller");
+  return unet_forward_impl(net, d_out, d_out, B, dtype, d_ws, ws_bytes, (void*)st, true);
+}
+}  // namespace ac
+
 extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int B, int dtype, void* d_ws,
                                size_t ws_bytes, void* stream) {
+  return ac::unet_forward_impl(net, d_in, d_out, B, dtype, d_ws, ws_bytes, stream, false);
+}
+
+static int ac::unet_forward_impl(ac_unet* net, const void* d_in, void* d_out, int B, int dtype, void* d_ws, size_t ws_bytes,
+                                 void* stream, bool first_done) {
   using namespace ac;
   AC_REQUIRE(net && d_in && d_out && d_ws, "null pointer");
   AC_REQUIRE(B > 0, "batch must be positive");
@@ -695,7 +739,9 @@ extern "C" int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int 
       const void* in;
       if (i == 0) {
         const void* spec = cat(d_in, (size_t)b0 * e_spec);
-        if (use_tc)
+        if (first_done)
+          rc = AC_OK;  // the caller's producer (fused STFT epilogue) has already written Bf
+        else if (use_tc)
           rc = launch_first_conv_cg8(spec, Bf, (long long)nb * g.dim_t, g.dim_f, g.g, net->first_w, net->first_af.scale,
                                      net->first_af.shift, fmt, st);
         else

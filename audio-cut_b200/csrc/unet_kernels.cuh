@@ -41,6 +41,12 @@ int launch_first_conv(const void* in, void* out, long long P, int g, const float
 int launch_final_conv(const void* in, void* out, long long P, int g, const float* w /*[4][g]*/, const float* bias,
                       int dtype, cudaStream_t st);
 
+// ---- hooks for a producer that applies the network's first 1x1 conv itself (track.cu + the fused STFT epilogue) -----------------
+int unet_first_conv_target(ac_unet* net, int B, int dtype, void* d_ws, size_t ws_bytes, void** d_target, const float** w,
+                           const float** scale, const float** shift);
+int unet_base_channels(const ac_unet* net);  // g: channels after the first conv
+int unet_forward_after_first(ac_unet* net, void* d_out, int B, int dtype, void* d_ws, size_t ws_bytes, cudaStream_t st);
+
 // ---- tcgen05 path (f16 / bf16 operands: every *_pack takes the format, kFmtF16 / kFmtBF16) -------------------------------------------------------------------
 struct TcConvWeights;  // opaque: packed smem images for one 3x3 conv layer
 struct TcConvArgs {

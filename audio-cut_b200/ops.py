@@ -138,7 +138,7 @@ class UNet:
                 pass
             self.handle = None
 
-    def set_debug(self, force_simt: bool) -> None:
+    def set_debug(self, force_simt: int) -> None:
         check(self._lib.ac_unet_set_debug(self.handle, int(force_simt)))
 
     def workspace(self, nbytes: int) -> torch.Tensor:

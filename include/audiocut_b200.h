@@ -130,7 +130,9 @@ AC_API int ac_unet_forward(ac_unet* net, const void* d_in, void* d_out, int B, i
                     void* stream);
 /* Test hook: 0 = let the library choose, 1 = force the CUDA-core kernels for every layer (bf16
  * storage kept), so the tcgen05 kernels can be checked layer by layer, 2 = tcgen05 kernels but
- * without the weight-stationary convolution (A/B timing). */
+ * without the weight-stationary convolution (A/B timing), 3 = the same kernels as 0 but without the
+ * cross-kernel fusions (level-0 conv chain in one launch, final 1x1 conv in the last TDF2, first 1x1 conv in
+ * the STFT epilogue): every fusion is bit-identical to its unfused form, so 0 and 3 must give identical bits. */
 AC_API int ac_unet_set_debug(ac_unet* net, int force_simt);
 /* Test / profiling hook: one bf16 3x3 convolution layer y = relu(scale * conv(x, W) + shift).
  * impl: 0 = CUDA-core implicit GEMM on channels-last [B][T][F][C] tensors; 1 = streaming tcgen05

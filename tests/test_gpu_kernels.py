@@ -228,6 +228,38 @@ def test_separate_track_pipelined_copies_equal_the_plain_call(ops, n_samples, ma
     assert torch.equal(host_out[0], v0) and torch.equal(host_out[1], i0)
 
 
+@pytest.mark.parametrize("name,dtype,tdtype", H16)
+def test_fused_forms_are_bit_identical_to_the_unfused_kernels(ops, name, dtype, tdtype):
+    """Kim_Vocal geometry, 12 s stereo (3 windows): the production schedule (level-0 conv chains as one CTA-pair launch each, the
+    final 1x1 conv inside the last TDF2, the first 1x1 conv inside the STFT epilogue) against debug mode 3 = the same kernels
+    without those fusions.  Each fusion keeps the arithmetic and the 16-bit rounding points of what it replaces, so the stems
+    and the weights must be identical bit for bit."""
+    import torch
+
+    from audio_cut_b200 import synth, unet_weights as uw
+    from oracle import planner
+
+    sr = 44100
+    geo = uw.UNetGeometry()
+    net = ops.UNet(uw.random_state(geo, seed=1234), geo)
+    audio = synth.synth_track(12.0, sr=sr, seed=5, stereo=True)
+    n = audio.shape[-1]
+    plans = planner.chunk_schedule(n / float(sr), 10.0, 2.5, 0.5)
+    bounds = [planner.sample_bounds(p, sr, n) for p in plans]
+    geom = ops.mdx_geom(7680, 1024, 3072, 256)
+    mix = torch.from_numpy(audio).cuda()
+    out = []
+    for mode in (0, 3):
+        net.set_debug(mode)
+        v, i, w = ops.separate_track(net, mix, bounds, geom, dtype=dtype)
+        assert _tc_aborted() == 0
+        out.append((v.cpu(), i.cpu(), w.cpu()))
+    net.set_debug(0)
+    assert float(out[0][0].abs().max()) > 1e-3
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b), float((a - b).abs().max())
+
+
 @pytest.mark.parametrize("n_samples", [1, 100, 641, 5000, 16001])
 def test_separate_track_short_and_ragged_inputs(ops, n_samples):
     """Tracks shorter than one model window / one chunk / not a multiple of anything: the planner returns a single
