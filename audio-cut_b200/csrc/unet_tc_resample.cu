@@ -48,6 +48,26 @@ struct RsParams {
   int* abort_flag;
 };
 
+// 256-bit accesses (sm_100): one lane moves the two horizontally adjacent output positions of one CG8 plane
+struct U8 { uint32_t v[8]; };
+__device__ __forceinline__ U8 ldg_stream_u8(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_u8(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid_constant__ CUtensorMap in_map, const RsParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -196,9 +216,74 @@ __global__ void __launch_bounds__(kRsThreads, 1) tc_resample_kernel(const __grid
     const bool fast = n_my <= kMaxMy;
     const bool pre_ok = fast && !down;
     const size_t plane = down ? (size_t)p.F * 8 : (size_t)(2 * p.F) * 8;  // elements between 8-channel groups of `out`
+    // ---- UP with both horizontal taps in the unit (ntap >= 2): a thread owns BOTH output positions 2f, 2f+1 of its input
+    // position, so one plane is 32 contiguous bytes per lane = one 256-bit skip load and one 256-bit store (the per-tap form
+    // writes 16 bytes at a 32-byte stride: every sector filled by two different instructions).  Item = (vertical tap, plane).
+    bool paired_done = false;
+    if (!down && c.ntap >= 2) {
+      const int n_cg = c.Cout >> 3;
+      const int n_items = (c.ntap >> 1) * n_cg;
+      const int n_mine = n_items > grp ? (n_items - grp + kRsEpiGroups - 1) / kRsEpiGroups : 0;
+      constexpr int kMaxPair = 6;
+      if ((n_items + kRsEpiGroups - 1) / kRsEpiGroups <= kMaxPair) {  // the same decision in every warp (the two forms enumerate differently)
+        int buf = 0;
+        uint32_t tph = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+          int ns, b, t, f0;
+          decode(u, ns, b, t, f0);
+          const int f = f0 + quad * 32 + lane;
+          // element index of (row 2t + dt, plane cg, position 2f)
+          auto addr = [&](int it) {
+            const int idx = grp + kRsEpiGroups * it;
+            const int dtl = idx / n_cg, cg = idx - dtl * n_cg;
+            const int tap0 = ns * c.ntap + 2 * dtl;
+            return cg8_index(b, 2 * t + (tap0 >> 1), cg, 2 * f, 2 * p.T, c.Cout, 2 * p.F);
+          };
+          U8 pre[kMaxPair];
+          if (f < p.F) {
+#pragma unroll
+            for (int it = 0; it < kMaxPair; ++it)
+              if (it < n_mine) pre[it] = ldg_stream_u8(p.skip + addr(it));
+          }
+          if (!mbar_wait(&tfull[buf], tph, abort_flag)) break;
+          tc_fence_after();
+          const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_per_unit * c.NT);
+#pragma unroll
+          for (int it = 0; it < kMaxPair; ++it) {
+            if (it < n_mine) {
+              const int idx = grp + kRsEpiGroups * it;
+              const int dtl = idx / n_cg, cg = idx - dtl * n_cg;
+              uint32_t r0[8], r1[8];
+              tmem_ld8(tb + (uint32_t)((2 * dtl) * c.NT + cg * 8), r0);      // tap (dt, df = 0): position 2f
+              tmem_ld8(tb + (uint32_t)((2 * dtl + 1) * c.NT + cg * 8), r1);  // tap (dt, df = 1): position 2f + 1
+              tmem_ld_wait();
+              if (f < p.F) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int ch = cg * 8 + 2 * e;
+                  const float sc0 = s_scale[ch], sh0 = s_shift[ch], sc1 = s_scale[ch + 1], sh1 = s_shift[ch + 1];
+                  const float2 m0 = unpack2<FMT>(pre[it].v[e]), m1 = unpack2<FMT>(pre[it].v[4 + e]);
+                  pk[e] = pack2<FMT>(fmaxf(fmaf(__uint_as_float(r0[2 * e]), sc0, sh0), 0.f) * m0.x,
+                                     fmaxf(fmaf(__uint_as_float(r0[2 * e + 1]), sc1, sh1), 0.f) * m0.y);
+                  pk[4 + e] = pack2<FMT>(fmaxf(fmaf(__uint_as_float(r1[2 * e]), sc0, sh0), 0.f) * m1.x,
+                                         fmaxf(fmaf(__uint_as_float(r1[2 * e + 1]), sc1, sh1), 0.f) * m1.y);
+                }
+                stg_u8(p.out + addr(it), pk);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_relaxed(&tempty[buf]);
+          if (++buf == c.nbuf) { buf = 0; tph ^= 1; }
+        }
+        paired_done = true;
+      }
+    }
     int buf = 0;
     uint32_t tph = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = blockIdx.x; u < p.n_units && !paired_done; u += gridDim.x) {
       int ns, b, t, f0;
       decode(u, ns, b, t, f0);
       // CG8 index of channel 0 (of this unit's N slice) for accumulator a
