@@ -55,6 +55,16 @@ __device__ __forceinline__ void t1_tma_load_2d_2sm(void* dst, const CUtensorMap*
       : "memory");
 }
 
+__device__ __forceinline__ void t1_umma_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  const uint64_t ad = ((uint64_t)a_hi << 32) | a_lo, bd = ((uint64_t)b_hi << 32) | b_lo;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kT1Threads, 1)
 tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map, const T1Params p) {
@@ -151,38 +161,41 @@ tc_tdf1_pair_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
         return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
       };
+      // ring stage / phase carried incrementally and 32-bit descriptor words (the 64-bit division and modulo per stage and
+      // the 64-bit descriptor sums cost this warp more instructions per MMA than a 96-cycle MMA leaves room for)
       const uint32_t idesc = make_idesc_2sm<FMT>(c.N) | (1u << 16);  // B is MN-major
       const uint64_t a_proto = make_desc(0, 128 * 16, 128);
       const uint64_t b_proto = make_desc_mn(0, 128, (uint32_t)c.Kt * 16);
-      long long i = 0;
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
+      const uint32_t b_lo0 = (uint32_t)b_proto + ((smem_u32(ring) + (uint32_t)(c.n_mp * c.a_blob_bytes)) >> 4);
+      const uint32_t stage16 = (uint32_t)c.stage_bytes >> 4, blob16 = (uint32_t)c.a_blob_bytes >> 4;
+      const int ksteps = c.Kt / 16;
+      int s = 0;
+      uint32_t ph = 0;
       bool alive = true;
       for (int lu = 0; lu < n_my && alive; ++lu) {
         const int buf = c.nbuf == 2 ? (lu & 1) : 0;
         const uint32_t use = c.nbuf == 2 ? (uint32_t)(lu >> 1) : (uint32_t)lu;
         if (!wait_all(&tempty[buf], (use & 1) ^ 1)) break;
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * acc_cols);
-        for (int kc = 0; kc < c.nk; ++kc, ++i) {
-          const int s = (int)(i % c.stages);
-          if (!wait_all(&full[s], (uint32_t)((i / c.stages) & 1))) { alive = false; break; }
+        for (int kc = 0; kc < c.nk; ++kc) {
+          if (!wait_all(&full[s], ph)) { alive = false; break; }
           tc_fence_after();
-          const uint32_t sa = smem_u32(ring + (size_t)s * c.stage_bytes);
-          const uint32_t sb = sa + (uint32_t)(c.n_mp * c.a_blob_bytes);
           if (elect_one()) {
+            const uint32_t sa = a_lo0 + (uint32_t)s * stage16, sb = b_lo0 + (uint32_t)s * stage16;
             for (int mp = 0; mp < c.n_mp; ++mp) {
-              const uint64_t ad0 = a_proto + (uint64_t)((sa + (uint32_t)mp * c.a_blob_bytes) >> 4);
-              const uint64_t bd0 = b_proto + (uint64_t)(sb >> 4);
+              const uint32_t a_lo = sa + (uint32_t)mp * blob16;
               const uint32_t acc = acc0 + (uint32_t)(mp * c.N);
-              for (int k = 0; k < c.Kt / 16; ++k) {
-                if (kc == 0 && k == 0)
-                  umma_f16_2sm<false>(acc, ad0 + (uint64_t)(k * 2 * 128), bd0 + (uint64_t)(k * 16), idesc);
-                else
-                  umma_f16_2sm<true>(acc, ad0 + (uint64_t)(k * 2 * 128), bd0 + (uint64_t)(k * 16), idesc);
-              }
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k)
+                t1_umma_2sm(acc, a_lo + (uint32_t)k * 256u, a_hi, sb + (uint32_t)k * 16u, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
             }
             umma_commit_2sm(&empty[s]);
             if (kc == c.nk - 1) umma_commit_2sm(&tfull[buf]);
           }
           __syncwarp();
+          if (++s == c.stages) { s = 0; ph ^= 1; }
         }
       }
     }

@@ -68,6 +68,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       : "memory");
 }
 
+__device__ __forceinline__ void t2_umma_2sm(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  const uint64_t ad = ((uint64_t)a_hi << 32) | a_lo, bd = ((uint64_t)b_hi << 32) | b_lo;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <bool FINAL, int FMT>
 __global__ void __launch_bounds__(t2_threads(FINAL), 1)
 tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_constant__ CUtensorMap w_map, const T2Params p) {
@@ -175,38 +185,50 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
       auto wait_all = [&](uint64_t* bar, uint32_t parity) {
         return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
       };
+      // ncu (profiles/r02_tdf2_issue.md): this warp never waited - 34 SASS instructions per MMA (64-bit ring-stage division
+      // and modulo, a division per K step for the H box, 64-bit descriptor sums) = 206 cycles per 96-cycle MMA, tensor pipe
+      // 38 %, the epilogue idle a third of its time.  Ring stage, phase and the H-box position are now carried incrementally
+      // and the descriptors are 32-bit words: two adds and the instruction per MMA.
       const uint32_t idesc = make_idesc_2sm<FMT>(c.N) | (1u << 16);  // B is MN-major
       const uint64_t a_proto = make_desc(0, 128 * 16, 128);
       const uint64_t b_proto = make_desc_mn(0, 128, (uint32_t)c.Kb * 16);
-      const uint32_t hbox_bytes = (uint32_t)(c.h_bytes / c.nkb);
-      long long i = 0;   // ring stage counter
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_proto + (smem_u32(ring) >> 4);
+      const uint32_t stage16 = (uint32_t)c.a_stage_bytes >> 4;
+      const uint32_t hbox16 = (uint32_t)(c.h_bytes / c.nkb) >> 4;
+      const int ksteps = c.Kt / 16;
+      int s = 0;          // ring stage
+      uint32_t ph = 0;
       uint32_t acc_n = 0;  // accumulator tiles issued
       bool alive = true;
       for (int lu = 0; lu < n_my && alive; ++lu) {
         const int hb = c.n_hbuf == 2 ? (lu & 1) : 0;
         const uint32_t use = c.n_hbuf == 2 ? (uint32_t)(lu >> 1) : (uint32_t)lu;
         if (!wait_all(&hfull[hb], use & 1)) break;
-        const uint32_t h_addr = smem_u32(h_smem + (size_t)hb * c.h_bytes);
+        const uint32_t b_lo0 = (uint32_t)b_proto + (smem_u32(h_smem + (size_t)hb * c.h_bytes) >> 4);
         for (int mp = 0; mp < c.n_mp && alive; ++mp, ++acc_n) {
           const int buf = acc_n & 1;
           if (!wait_all(&tempty[buf], ((acc_n >> 1) & 1) ^ 1)) { alive = false; break; }
           const uint32_t acc = tmem_base + (uint32_t)(buf * c.N);
-          for (int kc = 0; kc < c.nk; ++kc, ++i) {
-            const int s = (int)(i % c.stages);
-            if (!wait_all(&afull[s], (uint32_t)((i / c.stages) & 1))) { alive = false; break; }
+          // position inside the H tile: box kb (hbox16 apart), K offset kin inside it (16 bytes per K row in the MN-major box)
+          uint32_t box_lo = b_lo0;
+          int kin = 0;
+          for (int kc = 0; kc < c.nk; ++kc) {
+            if (!wait_all(&afull[s], ph)) { alive = false; break; }
             tc_fence_after();
-            const uint32_t sa = smem_u32(ring + (size_t)s * c.a_stage_bytes);
-            if (elect_one()) {
-              for (int k = 0; k < c.Kt / 16; ++k) {
-                const int kk = kc * c.Kt + k * 16;  // K offset inside the H tile
-                const int kb = kk / c.Kb, kin = kk - kb * c.Kb;
-                const uint64_t ad = a_proto + (uint64_t)((sa + (uint32_t)k * 2 * 128 * 16) >> 4);
-                const uint64_t bd = b_proto + (uint64_t)((h_addr + (uint32_t)kb * hbox_bytes + (uint32_t)kin * 16) >> 4);
-                if (kc == 0 && k == 0)
-                  umma_f16_2sm<false>(acc, ad, bd, idesc);
-                else
-                  umma_f16_2sm<true>(acc, ad, bd, idesc);
+            const bool el = elect_one();
+            uint32_t a_lo = a_lo0 + (uint32_t)s * stage16;
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k) {
+              if (el) t2_umma_2sm(acc, a_lo, a_hi, box_lo + (uint32_t)kin, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+              a_lo += (2 * 128 * 16) >> 4;
+              kin += 16;  // 16 K rows x 16 bytes >> 4
+              if (kin == c.Kb) {
+                kin = 0;
+                box_lo += hbox16;
               }
+            }
+            if (el) {
               umma_commit_2sm(&aempty[s]);
               if (kc == c.nk - 1) {
                 umma_commit_2sm(&tfull[buf]);
@@ -214,6 +236,7 @@ tc_tdf2_pair_kernel(const __grid_constant__ CUtensorMap h_map, const __grid_cons
               }
             }
             __syncwarp();
+            if (++s == c.stages) { s = 0; ph ^= 1; }
           }
         }
       }
